@@ -1,0 +1,120 @@
+/* librotmv_sm100.so -- C ABI of the B200-native Rot-MVGaze multi-view hot path.
+ *
+ * The reference (ut-vision/Rot-MVGaze) is pure PyTorch and has no FFI of its own: the drop-in
+ * boundary its callers see is the nn.Module contract of models/rot_mv.py:102-269
+ * (`FeatRotationSymm`), mirrored by rot-mvgaze_b200/rotmv_b200/module.py. This header is the
+ * C boundary underneath that module: each entry point replaces the ATen/cuDNN/cuBLAS dispatches
+ * the cited reference lines perform today. INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never allocates or frees
+ *     device memory and never synchronises the host (every call is CUDA-graph capturable);
+ *   - activations are NHWC (channels innermost); "strides" are in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 = OK, <0 = invalid argument / unsupported shape, >0 = cudaError_t;
+ *     rmv_last_error() returns a thread-local description of the last failure;
+ *   - dtype codes: RMV_DTYPE_F32 = 0 (fp32 storage, FFMA kernels), RMV_DTYPE_BF16 = 1
+ *     (bf16 storage, tcgen05 tensor-core kernels with fp32 accumulation in TMEM).
+ */
+#ifndef ROTMV_SM100_H_
+#define ROTMV_SM100_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMV_VERSION 100
+#define RMV_DTYPE_F32 0
+#define RMV_DTYPE_BF16 1
+
+#define RMV_ENGINE_AUTO 0 /* bf16 storage -> tcgen05 when the shape allows, else FFMA */
+#define RMV_ENGINE_SIMT 1 /* hand-written FFMA kernels (fp32 parity mode; on-device reference) */
+#define RMV_ENGINE_TC 2   /* tcgen05/TMEM/TMA implicit GEMM; error if the shape is unsupported */
+
+int rmv_version(void);
+const char* rmv_last_error(void);
+/* 0 when `device` is compute capability 10.x (B200); negative otherwise. */
+int rmv_device_check(int device);
+
+/* ----------------------------------------------------------------------------------------------
+ * Convolution / linear layer with fused epilogue:
+ *     y = act( scale[k] * conv(x, w)[..., k] + shift[k] + residual )
+ * Replaces nn.Conv2d + nn.BatchNorm2d(eval) + residual add + nn.ReLU of
+ * models/resnet.py:128-148,261-266 and nn.Linear(+ReLU) of models/backbones/blocks.py:41-60.
+ * A Linear layer is the 1x1 case with n_img=1, in_h=1, in_w=rows, x_sw=lda, y_sw=ldc.
+ * -------------------------------------------------------------------------------------------- */
+typedef struct rmv_conv_args {
+  int x_dtype;            /* RMV_DTYPE_*; weights have the same dtype */
+  int y_dtype;            /* RMV_DTYPE_* of y */
+  int engine;             /* RMV_ENGINE_* */
+  int block_n;            /* 0 = auto; tcgen05 N tile (64/128/256) */
+  const void* x;          /* input, element (n,h,w,c) at x[n*x_sn + h*x_sh + w*x_sw + c*x_sc] */
+  long long x_sn, x_sh, x_sw, x_sc;
+  int n_img, in_h, in_w, c_in;
+  const void* w;          /* filters [c_out][kh][kw][c_in], contiguous */
+  int c_out, kh, kw, stride, pad;
+  void* y;                /* output, element (n,oh,ow,k) at y[n*y_sn + oh*y_sh + ow*y_sw + k] */
+  long long y_sn, y_sh, y_sw;
+  int out_h, out_w;
+  const float* scale;     /* [c_out] or NULL (=1) */
+  const float* shift;     /* [c_out] or NULL (=0): folded BN shift or Linear bias */
+  const void* residual;   /* same dtype as y, or NULL */
+  long long r_sn, r_sh, r_sw;
+  int relu;
+} rmv_conv_args;
+
+int rmv_conv2d_fwd(const rmv_conv_args* args, void* stream);
+
+/* Stem im2col: x fp32 NCHW [n,3,224,224]-like -> A[n*out_h*out_w, k_pad] (bf16 or fp32), row =
+ * (kh,kw,c)-ordered 7x7x3 patch (stride 2, pad 3) zero-padded to k_pad columns. Feeds the stem
+ * conv (models/resnet.py:184-186,262) to the tensor-core GEMM. */
+int rmv_stem_im2col(const float* x, void* a, int n_img, int c_in, int in_h, int in_w, int kh,
+                    int kw, int stride, int pad, int out_h, int out_w, int k_pad, int a_dtype,
+                    void* stream);
+
+/* fp32 NCHW -> NHWC (fp32 or bf16) layout change (the reference keeps NCHW, trainer.py:100-106). */
+int rmv_nchw_to_nhwc(const float* x, void* y, int n_img, int c, int h, int w, int y_dtype,
+                     void* stream);
+
+/* MaxPool2d(kernel 3, stride 2, pad 1), NHWC. models/resnet.py:189,265. */
+int rmv_maxpool3x3s2_fwd(const void* x, void* y, int n_img, int in_h, int in_w, int c, int dtype,
+                         void* stream);
+
+/* AdaptiveAvgPool2d(1) + Flatten: x NHWC [n, hw, c] -> y0[n, c] (row stride ld0) and, if y1 !=
+ * NULL, the same values to y1 (row stride ld1). models/resnet.py:272-273, models/rot_mv.py:124-128. */
+int rmv_avgpool_fwd(const void* x, int n_img, int hw, int c, int dtype, void* y0, long long ld0,
+                    void* y1, long long ld1, void* stream);
+
+/* Rotation-constrained cross-view gather (models/rot_mv.py:193-194,234,238; SURVEY D1 for V>2):
+ *   dst[(b*V+v), r*nvec + k] = 1/(V-1) * sum_{u != v} sum_c rot[b,v,u,r,c] * feat[(b*V+u), c*nvec + k]
+ * feat rows have stride ld_feat, dst rows ld_dst (both in elements); rot is fp32 [B,V,V,3,3] with
+ * rot[b,i,j] = R_i R_j^T. With apply_rot == 0 the rotation is skipped (ignore_rotmat=True). */
+int rmv_rotate_gather_fwd(const void* feat, long long ld_feat, const float* rot, void* dst,
+                          long long ld_dst, int batch, int views, int nvec, int dtype,
+                          int apply_rot, void* stream);
+
+/* Gaze head tail + loss (models/rot_mv.py:249-254 last Linear; utils/math.py:52-60;
+ * losses/gaze_loss.py:42-52; losses/stereo_loss.py:46-54,65-84):
+ *   pred[m, 0:2] = hidden[m, :] . w2[0:2, :]^T + b2           (hidden: [rows, hid] fp32/bf16)
+ *   if gt != NULL: loss_out[0] += loss_scale * sum_m angular_deg(pred[m], gt[m])  (fp32 atomics)
+ * The caller folds StereoL1Loss.rel_weight, the IterationLoss decay of this iteration and the
+ * 1/batch of the mean into loss_scale. pred is fp32 [rows, 2]; gt fp32 [rows, 2]; w2/b2 fp32. */
+int rmv_head_loss_fwd(const void* hidden, long long ld_hidden, int hid_dtype, const float* w2,
+                      const float* b2, int rows, int hid, float* pred, const float* gt,
+                      float loss_scale, float* loss_out, void* stream);
+
+/* Mean angular error in degrees between pitch-yaw predictions and labels, clamped cosine
+ * (utils/math.py:96-137; the on-device replacement for the per-step D2H at trainer.py:128).
+ * Adds sum of per-row errors to err_sum[0] and rows to err_sum[1]. */
+int rmv_angular_error_accum(const float* pred, long long ld_pred, const float* gt, long long ld_gt,
+                            int rows, float* err_sum, void* stream);
+
+/* head pose (pitch,yaw) [B,V,2] -> rotations [B,V,V,3,3], rot[b,i,j] = R_i R_j^T with
+ * R = R_y(yaw) R_x(-pitch) (utils/math.py:188-219, trainer.py:110-111, models/rot_mv.py:193-194). */
+int rmv_pose_to_rotations(const float* head_pose, float* rotations, int batch, int views,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROTMV_SM100_H_ */

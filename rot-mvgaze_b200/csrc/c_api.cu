@@ -1,0 +1,68 @@
+// extern "C" surface of librotmv_sm100.so that is not tied to one kernel file: version, error
+// string, device check and the convolution dispatcher.
+#include "common.cuh"
+#include "ops.h"
+
+#include <stdarg.h>
+
+namespace rmv {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace rmv
+
+using namespace rmv;
+
+extern "C" int rmv_version(void) { return RMV_VERSION; }
+extern "C" const char* rmv_last_error(void) { return last_error(); }
+
+extern "C" int rmv_device_check(int device) {
+  int major = 0, minor = 0;
+  RMV_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  RMV_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  RMV_CHECK_ARG(major == 10, "device %d is sm_%d%d; librotmv_sm100 contains sm_100a code only",
+                device, major, minor);
+  return 0;
+}
+
+extern "C" int rmv_conv2d_fwd(const rmv_conv_args* args, void* stream) {
+  RMV_CHECK_ARG(args != nullptr, "conv2d_fwd: null args");
+  const ConvArgs& p = *args;
+  RMV_CHECK_ARG(p.x && p.w && p.y, "conv2d_fwd: null tensor pointer");
+  RMV_CHECK_ARG(p.n_img >= 0 && p.in_h > 0 && p.in_w > 0 && p.c_in > 0 && p.c_out > 0,
+                "conv2d_fwd: bad shape");
+  RMV_CHECK_ARG(p.out_h == (p.in_h + 2 * p.pad - p.kh) / p.stride + 1 &&
+                    p.out_w == (p.in_w + 2 * p.pad - p.kw) / p.stride + 1,
+                "conv2d_fwd: out size %dx%d inconsistent with in %dx%d k%dx%d s%d p%d", p.out_h,
+                p.out_w, p.in_h, p.in_w, p.kh, p.kw, p.stride, p.pad);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool tc_ok = p.x_dtype == RMV_DTYPE_BF16 && p.c_in % 64 == 0 && p.c_out % 8 == 0 &&
+                     (p.x_sc == 0 || p.x_sc == 1) && (p.stride == 1 || p.stride == 2);
+  if (p.engine == RMV_ENGINE_TC) {
+    RMV_CHECK_ARG(tc_ok, "conv2d_fwd: shape/dtype not supported by the tcgen05 engine");
+    return conv_fwd_tc(p, s);
+  }
+  if (p.engine == RMV_ENGINE_AUTO && tc_ok) return conv_fwd_tc(p, s);
+  return conv_fwd_simt(p, s);
+}

@@ -1,0 +1,458 @@
+// HBM-bound kernels of the Rot-MV path: layout changes, pooling, the rotation-constrained
+// cross-view gather, the gaze-head tail + angular loss, metrics and pose->rotation conversion.
+// All are one-pass, 128-bit vectorised along the contiguous (channel / feature) axis.
+#include "common.cuh"
+#include "ops.h"
+
+#include <math_constants.h>
+
+namespace rmv {
+namespace {
+
+constexpr float kRadToDeg = 57.29577951308232f;  // 180 / pi
+
+// ---- 8-wide vector helpers: bf16 x8 (16 B) or fp32 x8 (2 x 16 B) -> float[8] ----------------
+template <typename T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 v = unpack_bf16x2(w[i]);
+      f[2 * i] = v.x; f[2 * i + 1] = v.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* f) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float* f) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* f) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Stem im2col (fp32 NCHW -> [pixels, k_pad])
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void stem_im2col_kernel(const float* __restrict__ x, T* __restrict__ a, int n_img,
+                                   int c_in, int in_h, int in_w, int kh, int kw, int stride,
+                                   int pad, int out_h, int out_w, int k_pad, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int chunks = k_pad / 8;
+  const int chunk = (int)(idx % chunks);
+  const long long m = idx / chunks;
+  const int ow = (int)(m % out_w);
+  const long long t = m / out_w;
+  const int oh = (int)(t % out_h);
+  const int n = (int)(t / out_h);
+  const int k_real = kh * kw * c_in;
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = chunk * 8 + i;
+    float v = 0.f;
+    if (k < k_real) {
+      const int tap = k / c_in, c = k - tap * c_in;
+      const int r = tap / kw, s = tap - r * kw;
+      const int ih = oh * stride - pad + r, iw = ow * stride - pad + s;
+      if (ih >= 0 && ih < in_h && iw >= 0 && iw < in_w)
+        v = __ldg(x + (((long long)n * c_in + c) * in_h + ih) * in_w + iw);
+    }
+    f[i] = v;
+  }
+  Vec8<T>::store(a + m * k_pad + chunk * 8, f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int c,
+                                    long long hw, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
+  if (idx >= total) return;
+  const long long n = idx / hw, p = idx % hw;
+  for (int ch = 0; ch < c; ++ch) {
+    const float v = __ldg(x + (n * c + ch) * hw + p);
+    if constexpr (sizeof(T) == 2) y[idx * c + ch] = __float2bfloat16_rn(v);
+    else y[idx * c + ch] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool 3x3 s2 p1, NHWC, 8 channels per thread
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int in_h, int in_w,
+                               int c, int out_h, int out_w, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = c / 8;
+  const int cc = (int)(idx % cv) * 8;
+  long long t = idx / cv;
+  const int ow = (int)(t % out_w); t /= out_w;
+  const int oh = (int)(t % out_h);
+  const long long n = t / out_h;
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -CUDART_INF_F;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int ih = oh * 2 - 1 + r;
+    if (ih < 0 || ih >= in_h) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int iw = ow * 2 - 1 + s;
+      if (iw < 0 || iw >= in_w) continue;
+      float f[8];
+      Vec8<T>::load(x + ((n * in_h + ih) * in_w + iw) * c + cc, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
+    }
+  }
+  Vec8<T>::store(y + ((n * out_h + oh) * out_w + ow) * c + cc, m);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Global average pool, NHWC [n, hw, c] -> [n, c] (one or two destinations, row strides ld0/ld1)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void avgpool_kernel(const T* __restrict__ x, int hw, int c, T* __restrict__ y0,
+                               long long ld0, T* __restrict__ y1, long long ld1, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = c / 8;
+  const int cc = (int)(idx % cv) * 8;
+  const long long n = idx / cv;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const T* p = x + n * hw * c + cc;
+  for (int i = 0; i < hw; ++i) {
+    float f[8];
+    Vec8<T>::load(p + (long long)i * c, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += f[j];
+  }
+  const float inv = 1.f / (float)hw;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] *= inv;
+  Vec8<T>::store(y0 + n * ld0 + cc, s);
+  if (y1 != nullptr) Vec8<T>::store(y1 + n * ld1 + cc, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rotation-constrained cross-view gather
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void rotate_gather_kernel(const T* __restrict__ feat, long long ld_feat,
+                                     const float* __restrict__ rot, T* __restrict__ dst,
+                                     long long ld_dst, int views, int nvec, int apply_rot,
+                                     long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int kv = nvec / 8;
+  const int k0 = (int)(idx % kv) * 8;
+  const long long row = idx / kv;  // b*V + v
+  const int v = (int)(row % views);
+  const long long b = row / views;
+  float o[3][8];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[r][i] = 0.f;
+  for (int u = 0; u < views; ++u) {
+    if (u == v) continue;
+    const T* fp = feat + (b * views + u) * ld_feat + k0;
+    float f[3][8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Vec8<T>::load(fp + (long long)c * nvec, f[c]);
+    float R[9];
+    if (apply_rot) {
+      const float* rp = rot + ((b * views + v) * views + u) * 9;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.f : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t = R[r * 3 + 0] * f[0][i];
+        t = fmaf(R[r * 3 + 1], f[1][i], t);
+        t = fmaf(R[r * 3 + 2], f[2][i], t);
+        o[r][i] += t;
+      }
+  }
+  if (views > 2) {
+    const float inv = 1.f / (float)(views - 1);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[r][i] *= inv;
+  }
+  T* dp = dst + row * ld_dst + k0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) Vec8<T>::store(dp + (long long)r * nvec, o[r]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gaze head tail (hid -> 2 GEMV) + pitch-yaw -> vector + angular loss
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pitchyaw_to_vec(float p, float y, float* v) {
+  float sp, cp, sy, cy;
+  sincosf(p, &sp, &cp);
+  sincosf(y, &sy, &cy);
+  v[0] = cp * sy; v[1] = sp; v[2] = cp * cy;
+}
+// F.cosine_similarity(a, b, eps) of torch >= 1.12: normalise each vector first.
+__device__ __forceinline__ float cos_sim_torch(const float* a, const float* b, float eps) {
+  const float na = fmaxf(sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), eps);
+  const float nb = fmaxf(sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]), eps);
+  return (a[0] / na) * (b[0] / nb) + (a[1] / na) * (b[1] / nb) + (a[2] / na) * (b[2] / nb);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __restrict__ w2,
+                 const float* __restrict__ b2, int rows, int hid, float* __restrict__ pred,
+                 const float* __restrict__ gt, float loss_scale, float* __restrict__ loss_out) {
+  __shared__ float s_part[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  float ang = 0.f;
+  if (row < rows) {
+    float d0 = 0.f, d1 = 0.f;
+    const T* hp = hidden + (long long)row * ld;
+    for (int k = lane * 8; k < hid; k += 256) {
+      float h[8], a[8], b[8];
+      Vec8<T>::load(hp + k, h);
+      Vec8<float>::load(w2 + k, a);
+      Vec8<float>::load(w2 + hid + k, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { d0 = fmaf(h[i], a[i], d0); d1 = fmaf(h[i], b[i], d1); }
+    }
+    d0 = warp_sum(d0) + __ldg(b2);
+    d1 = warp_sum(d1) + __ldg(b2 + 1);
+    if (lane == 0) {
+      pred[row * 2] = d0; pred[row * 2 + 1] = d1;
+      if (gt != nullptr) {
+        float vg[3], vp[3];
+        pitchyaw_to_vec(__ldg(gt + row * 2), __ldg(gt + row * 2 + 1), vg);
+        pitchyaw_to_vec(d0, d1, vp);
+        float sim = cos_sim_torch(vg, vp, 1e-6f);
+        sim = fminf(fmaxf(sim, -1.f), 1.f);
+        ang = acosf(sim) * kRadToDeg;
+      }
+    }
+  }
+  if (gt != nullptr) {
+    if (lane == 0) s_part[warp] = ang;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += s_part[i];
+      atomicAdd(loss_out, s * loss_scale);
+    }
+  }
+}
+
+__global__ void angular_error_kernel(const float* __restrict__ pred, long long ld_pred,
+                                     const float* __restrict__ gt, long long ld_gt, int rows,
+                                     float* __restrict__ err_sum) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  float e = 0.f;
+  if (row < rows) {
+    float a[3], b[3];
+    pitchyaw_to_vec(__ldg(pred + row * ld_pred), __ldg(pred + row * ld_pred + 1), a);
+    pitchyaw_to_vec(__ldg(gt + row * ld_gt), __ldg(gt + row * ld_gt + 1), b);
+    const float ab = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+    const float na = fmaxf(sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), 1e-7f);
+    const float nb = fmaxf(sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]), 1e-7f);
+    // The reference metric does not clamp (utils/math.py:118-120,135-137) and can return NaN
+    // when rounding pushes the similarity past 1; the device metric clamps.
+    const float sim = fminf(fmaxf(ab / (na * nb), -1.f), 1.f);
+    e = acosf(sim) * kRadToDeg;
+  }
+  e = warp_sum(e);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(err_sum, e);
+    const int first = blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+    const int cnt = max(0, min(32, rows - first));
+    atomicAdd(err_sum + 1, (float)cnt);
+  }
+}
+
+__global__ void pose_to_rot_kernel(const float* __restrict__ pose, float* __restrict__ rot,
+                                   int views, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, i, j)
+  if (idx >= total) return;
+  const int j = (int)(idx % views);
+  const int i = (int)((idx / views) % views);
+  const long long b = idx / ((long long)views * views);
+  float R[2][9];
+  const int vi[2] = {i, j};
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const float* p = pose + (b * views + vi[t]) * 2;
+    float sp, cp, sy, cy;
+    sincosf(-__ldg(p), &sp, &cp);   // head-pose convention: pitch enters negated
+    sincosf(__ldg(p + 1), &sy, &cy);
+    // R = R_y(yaw) * R_x(-pitch)
+    R[t][0] = cy;  R[t][1] = sy * sp;  R[t][2] = sy * cp;
+    R[t][3] = 0.f; R[t][4] = cp;       R[t][5] = -sp;
+    R[t][6] = -sy; R[t][7] = cy * sp;  R[t][8] = cy * cp;
+  }
+  float* o = rot + idx * 9;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s = R[0][r * 3 + 0] * R[1][c * 3 + 0];
+      s = fmaf(R[0][r * 3 + 1], R[1][c * 3 + 1], s);
+      s = fmaf(R[0][r * 3 + 2], R[1][c * 3 + 2], s);
+      o[r * 3 + c] = s;
+    }
+}
+
+inline unsigned blocks_for(long long total, int threads) {
+  return (unsigned)((total + threads - 1) / threads);
+}
+
+}  // namespace
+}  // namespace rmv
+
+using namespace rmv;
+
+extern "C" int rmv_stem_im2col(const float* x, void* a, int n_img, int c_in, int in_h, int in_w,
+                               int kh, int kw, int stride, int pad, int out_h, int out_w,
+                               int k_pad, int a_dtype, void* stream) {
+  RMV_CHECK_ARG(k_pad % 8 == 0 && k_pad >= kh * kw * c_in, "stem_im2col: bad k_pad %d", k_pad);
+  const long long total = (long long)n_img * out_h * out_w * (k_pad / 8);
+  if (total == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (a_dtype == RMV_DTYPE_BF16)
+    stem_im2col_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, s>>>(
+        x, (__nv_bfloat16*)a, n_img, c_in, in_h, in_w, kh, kw, stride, pad, out_h, out_w, k_pad, total);
+  else
+    stem_im2col_kernel<float><<<blocks_for(total, 256), 256, 0, s>>>(
+        x, (float*)a, n_img, c_in, in_h, in_w, kh, kw, stride, pad, out_h, out_w, k_pad, total);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_nchw_to_nhwc(const float* x, void* y, int n_img, int c, int h, int w,
+                                int y_dtype, void* stream) {
+  const long long hw = (long long)h * w, total = hw * n_img;
+  if (total == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (y_dtype == RMV_DTYPE_BF16)
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, s>>>(x, (__nv_bfloat16*)y, c, hw, total);
+  else
+    nchw_to_nhwc_kernel<float><<<blocks_for(total, 256), 256, 0, s>>>(x, (float*)y, c, hw, total);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_maxpool3x3s2_fwd(const void* x, void* y, int n_img, int in_h, int in_w, int c,
+                                    int dtype, void* stream) {
+  RMV_CHECK_ARG(c % 8 == 0, "maxpool: c=%d must be a multiple of 8", c);
+  const int out_h = (in_h + 2 - 3) / 2 + 1, out_w = (in_w + 2 - 3) / 2 + 1;
+  const long long total = (long long)n_img * out_h * out_w * (c / 8);
+  if (total == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == RMV_DTYPE_BF16)
+    maxpool_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, s>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, in_h, in_w, c, out_h, out_w, total);
+  else
+    maxpool_kernel<float><<<blocks_for(total, 256), 256, 0, s>>>((const float*)x, (float*)y, in_h, in_w, c, out_h, out_w, total);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_avgpool_fwd(const void* x, int n_img, int hw, int c, int dtype, void* y0,
+                               long long ld0, void* y1, long long ld1, void* stream) {
+  RMV_CHECK_ARG(c % 8 == 0 && ld0 % 8 == 0 && ld1 % 8 == 0, "avgpool: c/ld must be multiples of 8");
+  const long long total = (long long)n_img * (c / 8);
+  if (total == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == RMV_DTYPE_BF16)
+    avgpool_kernel<__nv_bfloat16><<<blocks_for(total, 128), 128, 0, s>>>(
+        (const __nv_bfloat16*)x, hw, c, (__nv_bfloat16*)y0, ld0, (__nv_bfloat16*)y1, ld1, total);
+  else
+    avgpool_kernel<float><<<blocks_for(total, 128), 128, 0, s>>>((const float*)x, hw, c, (float*)y0, ld0, (float*)y1, ld1, total);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_rotate_gather_fwd(const void* feat, long long ld_feat, const float* rot,
+                                     void* dst, long long ld_dst, int batch, int views, int nvec,
+                                     int dtype, int apply_rot, void* stream) {
+  RMV_CHECK_ARG(views >= 2, "rotate_gather: need >= 2 views, got %d", views);
+  RMV_CHECK_ARG(nvec % 8 == 0 && ld_feat % 8 == 0 && ld_dst % 8 == 0,
+                "rotate_gather: nvec/ld must be multiples of 8");
+  const long long total = (long long)batch * views * (nvec / 8);
+  if (total == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == RMV_DTYPE_BF16)
+    rotate_gather_kernel<__nv_bfloat16><<<blocks_for(total, 128), 128, 0, s>>>(
+        (const __nv_bfloat16*)feat, ld_feat, rot, (__nv_bfloat16*)dst, ld_dst, views, nvec, apply_rot, total);
+  else
+    rotate_gather_kernel<float><<<blocks_for(total, 128), 128, 0, s>>>(
+        (const float*)feat, ld_feat, rot, (float*)dst, ld_dst, views, nvec, apply_rot, total);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_head_loss_fwd(const void* hidden, long long ld_hidden, int hid_dtype,
+                                 const float* w2, const float* b2, int rows, int hid, float* pred,
+                                 const float* gt, float loss_scale, float* loss_out,
+                                 void* stream) {
+  RMV_CHECK_ARG(hid % 8 == 0 && ld_hidden % 8 == 0, "head_loss: hid/ld must be multiples of 8");
+  RMV_CHECK_ARG(gt == nullptr || loss_out != nullptr, "head_loss: gt given without loss_out");
+  if (rows == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (hid_dtype == RMV_DTYPE_BF16)
+    head_loss_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)hidden, ld_hidden, w2, b2, rows, hid, pred, gt, loss_scale, loss_out);
+  else
+    head_loss_kernel<float><<<grid, 256, 0, s>>>((const float*)hidden, ld_hidden, w2, b2, rows, hid, pred, gt, loss_scale, loss_out);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_angular_error_accum(const float* pred, long long ld_pred, const float* gt,
+                                       long long ld_gt, int rows, float* err_sum, void* stream) {
+  if (rows == 0) return 0;
+  angular_error_kernel<<<blocks_for(rows, 128), 128, 0, (cudaStream_t)stream>>>(pred, ld_pred, gt, ld_gt, rows, err_sum);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_pose_to_rotations(const float* head_pose, float* rotations, int batch,
+                                     int views, void* stream) {
+  const long long total = (long long)batch * views * views;
+  if (total == 0) return 0;
+  pose_to_rot_kernel<<<blocks_for(total, 128), 128, 0, (cudaStream_t)stream>>>(head_pose, rotations, views, total);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,197 @@
+"""Tensor-level wrappers over the C ABI. Activations are NHWC; every function launches on the
+current CUDA stream and returns without synchronising."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.RotmvError("rotmv_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+def conv2d(x, w, *, stride=1, pad=0, scale=None, shift=None, residual=None, relu=False,
+           out=None, out_dtype=None, engine=L.ENGINE_AUTO, block_n=0):
+    """y = act(scale * conv(x, w) + shift + residual).
+
+    x: [N, H, W, C] (any pixel strides, channel stride 1); w: [K, kh, kw, C] contiguous, same
+    dtype as x; scale/shift: fp32 [K]; residual/out: [N, OH, OW, K].
+    Mirrors nn.Conv2d+BatchNorm2d(eval)+ReLU of reference models/resnet.py:128-148.
+    """
+    _need_cuda(x, w, scale, shift, residual, out)
+    n, h, wd, c = x.shape
+    k, kh, kw, c2 = w.shape
+    assert c == c2 and w.is_contiguous() and w.dtype == x.dtype and x.stride(3) == 1
+    oh = (h + 2 * pad - kh) // stride + 1
+    ow = (wd + 2 * pad - kw) // stride + 1
+    if out is None:
+        out = torch.empty((n, oh, ow, k), dtype=out_dtype or x.dtype, device=x.device)
+    assert tuple(out.shape) == (n, oh, ow, k) and out.stride(3) == 1
+    a = L.ConvArgs()
+    a.x_dtype = L.dtype_code(x.dtype)
+    a.y_dtype = L.dtype_code(out.dtype)
+    a.engine = engine
+    a.block_n = block_n
+    a.x = x.data_ptr()
+    a.x_sn, a.x_sh, a.x_sw, a.x_sc = x.stride(0), x.stride(1), x.stride(2), 1
+    a.n_img, a.in_h, a.in_w, a.c_in = n, h, wd, c
+    a.w = w.data_ptr()
+    a.c_out, a.kh, a.kw, a.stride, a.pad = k, kh, kw, stride, pad
+    a.y = out.data_ptr()
+    a.y_sn, a.y_sh, a.y_sw = out.stride(0), out.stride(1), out.stride(2)
+    a.out_h, a.out_w = oh, ow
+    for t in (scale, shift):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == k)
+    a.scale = L.ptr(scale)
+    a.shift = L.ptr(shift)
+    if residual is not None:
+        assert tuple(residual.shape) == tuple(out.shape) and residual.dtype == out.dtype
+        assert residual.stride(3) == 1
+        a.residual = residual.data_ptr()
+        a.r_sn, a.r_sh, a.r_sw = residual.stride(0), residual.stride(1), residual.stride(2)
+    a.relu = int(relu)
+    L.check(L.load().rmv_conv2d_fwd(C.byref(a), L.stream_ptr()), "rmv_conv2d_fwd")
+    return out
+
+
+def conv2d_nchw_input(x_nchw, w, *, stride, pad, scale=None, shift=None, relu=False,
+                      out_dtype=None):
+    """FFMA conv that consumes the caller's NCHW fp32 tensor directly through strides
+    (fp32 parity mode stem; reference models/resnet.py:184-188,262-264)."""
+    _need_cuda(x_nchw, w)
+    xv = x_nchw.permute(0, 2, 3, 1)  # logical NHWC view of NCHW storage
+    n, h, wd, c = xv.shape
+    k, kh, kw, _ = w.shape
+    oh = (h + 2 * pad - kh) // stride + 1
+    ow = (wd + 2 * pad - kw) // stride + 1
+    out = torch.empty((n, oh, ow, k), dtype=out_dtype or x_nchw.dtype, device=x_nchw.device)
+    a = L.ConvArgs()
+    a.x_dtype = L.dtype_code(x_nchw.dtype)
+    a.y_dtype = L.dtype_code(out.dtype)
+    a.engine = L.ENGINE_SIMT
+    a.x = xv.data_ptr()
+    a.x_sn, a.x_sh, a.x_sw, a.x_sc = xv.stride(0), xv.stride(1), xv.stride(2), xv.stride(3)
+    a.n_img, a.in_h, a.in_w, a.c_in = n, h, wd, c
+    a.w = w.data_ptr()
+    a.c_out, a.kh, a.kw, a.stride, a.pad = k, kh, kw, stride, pad
+    a.y = out.data_ptr()
+    a.y_sn, a.y_sh, a.y_sw = out.stride(0), out.stride(1), out.stride(2)
+    a.out_h, a.out_w = oh, ow
+    a.scale = L.ptr(scale)
+    a.shift = L.ptr(shift)
+    a.relu = int(relu)
+    L.check(L.load().rmv_conv2d_fwd(C.byref(a), L.stream_ptr()), "rmv_conv2d_fwd")
+    return out
+
+
+def linear(x, w, bias=None, *, relu=False, out=None, out_dtype=None, engine=L.ENGINE_AUTO,
+           block_n=0):
+    """y = act(x @ w.T + bias); x [M, K] (row stride free), w [N, K] contiguous, out [M, N] (row
+    stride free). Mirrors nn.Linear(+ReLU) of reference models/backbones/blocks.py:41-60."""
+    m, kdim = x.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((m, n), dtype=out_dtype or x.dtype, device=x.device)
+    x4 = x.as_strided((1, 1, m, kdim), (x.stride(0) * max(m, 1), x.stride(0) * max(m, 1), x.stride(0), 1),
+                      x.storage_offset())
+    o4 = out.as_strided((1, 1, m, n), (out.stride(0) * max(m, 1), out.stride(0) * max(m, 1), out.stride(0), 1),
+                        out.storage_offset())
+    conv2d(x4, w.view(n, 1, 1, kdim), shift=bias, relu=relu, out=o4, engine=engine, block_n=block_n)
+    return out
+
+
+def stem_im2col(x_nchw, k_pad=192, dtype=torch.bfloat16, kh=7, kw=7, stride=2, pad=3):
+    _need_cuda(x_nchw)
+    assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    n, c, h, w = x_nchw.shape
+    oh = (h + 2 * pad - kh) // stride + 1
+    ow = (w + 2 * pad - kw) // stride + 1
+    a = torch.empty((n * oh * ow, k_pad), dtype=dtype, device=x_nchw.device)
+    L.check(L.load().rmv_stem_im2col(x_nchw.data_ptr(), a.data_ptr(), n, c, h, w, kh, kw, stride,
+                                     pad, oh, ow, k_pad, L.dtype_code(dtype), L.stream_ptr()),
+            "rmv_stem_im2col")
+    return a, oh, ow
+
+
+def nchw_to_nhwc(x_nchw, dtype):
+    _need_cuda(x_nchw)
+    assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    n, c, h, w = x_nchw.shape
+    y = torch.empty((n, h, w, c), dtype=dtype, device=x_nchw.device)
+    L.check(L.load().rmv_nchw_to_nhwc(x_nchw.data_ptr(), y.data_ptr(), n, c, h, w,
+                                      L.dtype_code(dtype), L.stream_ptr()), "rmv_nchw_to_nhwc")
+    return y
+
+
+def maxpool3x3s2(x):
+    _need_cuda(x)
+    assert x.is_contiguous()
+    n, h, w, c = x.shape
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = torch.empty((n, oh, ow, c), dtype=x.dtype, device=x.device)
+    L.check(L.load().rmv_maxpool3x3s2_fwd(x.data_ptr(), y.data_ptr(), n, h, w, c,
+                                          L.dtype_code(x.dtype), L.stream_ptr()),
+            "rmv_maxpool3x3s2_fwd")
+    return y
+
+
+def avgpool(x, out0, out1=None):
+    """x [N, H, W, C] contiguous -> out0[:, :C] (and out1[:, :C]); out* are [N, >=C] row-strided."""
+    _need_cuda(x, out0, out1)
+    assert x.is_contiguous()
+    n, h, w, c = x.shape
+    assert out0.dtype == x.dtype and (out1 is None or out1.dtype == x.dtype)
+    L.check(L.load().rmv_avgpool_fwd(x.data_ptr(), n, h * w, c, L.dtype_code(x.dtype),
+                                     out0.data_ptr(), out0.stride(0), L.ptr(out1),
+                                     0 if out1 is None else out1.stride(0), L.stream_ptr()),
+            "rmv_avgpool_fwd")
+
+
+def rotate_gather(feat, rot, dst, batch, views, nvec=512, apply_rot=True):
+    """dst[b*V+v, r*nvec+k] = 1/(V-1) sum_{u!=v} sum_c rot[b,v,u,r,c] feat[b*V+u, c*nvec+k].
+    feat/dst: [B*V, 3*nvec] row-strided views. Reference models/rot_mv.py:234,238."""
+    _need_cuda(feat, rot, dst)
+    assert feat.dtype == dst.dtype and feat.stride(1) == 1 and dst.stride(1) == 1
+    assert rot.dtype == torch.float32 and rot.is_contiguous()
+    assert tuple(rot.shape) == (batch, views, views, 3, 3)
+    L.check(L.load().rmv_rotate_gather_fwd(feat.data_ptr(), feat.stride(0), rot.data_ptr(),
+                                           dst.data_ptr(), dst.stride(0), batch, views, nvec,
+                                           L.dtype_code(feat.dtype), int(apply_rot),
+                                           L.stream_ptr()), "rmv_rotate_gather_fwd")
+
+
+def head_loss(hidden, w2, b2, pred, gt=None, loss_scale=0.0, loss_out=None):
+    _need_cuda(hidden, w2, b2, pred, gt, loss_out)
+    rows, hid = hidden.shape
+    assert w2.dtype == torch.float32 and w2.is_contiguous() and tuple(w2.shape) == (2, hid)
+    assert pred.dtype == torch.float32 and pred.is_contiguous()
+    assert gt is None or (gt.dtype == torch.float32 and gt.is_contiguous())
+    L.check(L.load().rmv_head_loss_fwd(hidden.data_ptr(), hidden.stride(0),
+                                       L.dtype_code(hidden.dtype), w2.data_ptr(), b2.data_ptr(),
+                                       rows, hid, pred.data_ptr(), L.ptr(gt), float(loss_scale),
+                                       L.ptr(loss_out), L.stream_ptr()), "rmv_head_loss_fwd")
+
+
+def angular_error_accum(pred, gt, err_sum):
+    _need_cuda(pred, gt, err_sum)
+    assert pred.dtype == gt.dtype == err_sum.dtype == torch.float32
+    L.check(L.load().rmv_angular_error_accum(pred.data_ptr(), pred.stride(0), gt.data_ptr(),
+                                             gt.stride(0), pred.shape[0], err_sum.data_ptr(),
+                                             L.stream_ptr()), "rmv_angular_error_accum")
+
+
+def pose_to_rotations(head_pose):
+    """[B, V, 2] (pitch, yaw) -> [B, V, V, 3, 3]; reference utils/math.py:188-219 + rot_mv.py:193-194."""
+    _need_cuda(head_pose)
+    assert head_pose.dtype == torch.float32 and head_pose.is_contiguous()
+    b, v, _ = head_pose.shape
+    rot = torch.empty((b, v, v, 3, 3), dtype=torch.float32, device=head_pose.device)
+    L.check(L.load().rmv_pose_to_rotations(head_pose.data_ptr(), rot.data_ptr(), b, v,
+                                           L.stream_ptr()), "rmv_pose_to_rotations")
+    return rot
