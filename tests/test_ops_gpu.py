@@ -1,0 +1,177 @@
+"""Per-kernel parity on the GPU: each sm_100a kernel against the single torch op it replaces
+(fp32, TF32 disabled), on the same seeded inputs. Calls go through the C ABI (ctypes)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _ref_conv(x_nhwc, w_krsc, stride, pad, scale, shift, residual, relu):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    w = w_krsc.float().permute(0, 3, 1, 2)
+    y = F.conv2d(x, w, stride=stride, padding=pad)
+    if scale is not None:
+        y = y * scale.view(1, -1, 1, 1)
+    if shift is not None:
+        y = y + shift.view(1, -1, 1, 1)
+    y = y.permute(0, 2, 3, 1)
+    if residual is not None:
+        y = y + residual.float()
+    if relu:
+        y = torch.relu(y)
+    return y.contiguous()
+
+
+CONV_CASES = [
+    # n, h, w, c_in, c_out, k, stride, pad, residual, relu
+    (4, 56, 56, 64, 64, 1, 1, 0, False, True),
+    (4, 56, 56, 64, 256, 1, 1, 0, True, True),
+    (3, 56, 56, 64, 64, 3, 1, 1, False, True),
+    (5, 28, 28, 128, 128, 3, 1, 1, False, True),
+    (7, 14, 14, 256, 256, 3, 1, 1, False, True),
+    (3, 7, 7, 512, 512, 3, 1, 1, False, False),
+    (4, 56, 56, 128, 128, 3, 2, 1, False, True),
+    (2, 28, 28, 256, 256, 3, 2, 1, False, True),
+    (6, 14, 14, 512, 512, 3, 2, 1, False, True),
+    (4, 56, 56, 256, 512, 1, 2, 0, False, False),
+    (9, 14, 14, 1024, 2048, 1, 2, 0, False, False),
+    (16, 7, 7, 2048, 512, 1, 1, 0, False, True),
+    (33, 7, 7, 512, 2048, 1, 1, 0, True, True),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("engine", ["tc", "simt_bf16", "simt_f32"])
+def test_conv_parity(case, engine):
+    from rotmv_b200 import functional as RF, _lib as L
+
+    n, h, w, ci, co, k, stride, pad, use_res, relu = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case) * 7 + 1)
+    dt = torch.float32 if engine == "simt_f32" else torch.bfloat16
+    x = torch.randn((n, h, w, ci), device="cuda", generator=g).to(dt)
+    wt = (torch.randn((co, k, k, ci), device="cuda", generator=g) / math.sqrt(k * k * ci)).to(dt)
+    scale = torch.rand((co,), device="cuda", generator=g) + 0.5
+    shift = torch.randn((co,), device="cuda", generator=g)
+    oh = (h + 2 * pad - k) // stride + 1
+    res = torch.randn((n, oh, oh, co), device="cuda", generator=g).to(dt) if use_res else None
+    eng = L.ENGINE_TC if engine == "tc" else L.ENGINE_SIMT
+    y = RF.conv2d(x, wt, stride=stride, pad=pad, scale=scale, shift=shift, residual=res,
+                  relu=relu, engine=eng)
+    ref = _ref_conv(x, wt, stride, pad, scale, shift, res, relu)
+    torch.cuda.synchronize()
+    err = (y.float() - ref).abs().max().item()
+    tol = (2e-5 if dt == torch.float32 else 1.2e-2) * ref.abs().max().item()
+    assert err <= tol, f"{engine} {case}: max err {err} > {tol}"
+
+
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+def test_conv_tc_fp32_out_tight(block_n):
+    """fp32 output removes the bf16 rounding of y: tcgen05 accumulation must agree with the fp32
+    reference to accumulation-order noise."""
+    from rotmv_b200 import functional as RF, _lib as L
+
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn((6, 14, 14, 256), device="cuda", generator=g).bfloat16()
+    wt = (torch.randn((512, 3, 3, 256), device="cuda", generator=g) / 48).bfloat16()
+    y = RF.conv2d(x, wt, stride=1, pad=1, out_dtype=torch.float32, engine=L.ENGINE_TC,
+                  block_n=block_n)
+    ref = _ref_conv(x, wt, 1, 1, None, None, None, False)
+    err = (y - ref).abs().max().item()
+    assert err <= 2e-5 * ref.abs().max().item() + 1e-5, err
+
+
+LINEAR_CASES = [(300, 2048, 1536), (16, 3584, 3584), (513, 3584, 512), (128, 1536, 1536),
+                (1024, 3584, 1536)]
+
+
+@pytest.mark.parametrize("m,k,n", LINEAR_CASES)
+@pytest.mark.parametrize("engine", ["tc", "simt_f32"])
+def test_linear_parity(m, k, n, engine):
+    from rotmv_b200 import functional as RF, _lib as L
+
+    g = torch.Generator(device="cuda").manual_seed(m + k + n)
+    dt = torch.float32 if engine == "simt_f32" else torch.bfloat16
+    # strided input and output views, as the fusion block uses them (concat-free buffers)
+    xbuf = torch.randn((m, k + 64), device="cuda", generator=g).to(dt)
+    x = xbuf[:, 64:]
+    wt = (torch.randn((n, k), device="cuda", generator=g) / math.sqrt(k)).to(dt)
+    b = torch.randn((n,), device="cuda", generator=g)
+    obuf = torch.zeros((m, n + 128), device="cuda", dtype=dt)
+    out = obuf[:, 128:]
+    RF.linear(x, wt, b, relu=True, out=out,
+              engine=L.ENGINE_TC if engine == "tc" else L.ENGINE_SIMT)
+    ref = torch.relu(x.float() @ wt.float().t() + b)
+    err = (out.float() - ref).abs().max().item()
+    tol = (2e-5 if dt == torch.float32 else 1.2e-2) * ref.abs().max().item()
+    assert err <= tol, (err, tol)
+    assert obuf[:, :128].abs().max().item() == 0.0  # nothing written outside the view
+
+
+def test_maxpool_avgpool():
+    from rotmv_b200 import functional as RF
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for dt in (torch.float32, torch.bfloat16):
+        x = torch.randn((3, 112, 112, 64), device="cuda", generator=g).to(dt)
+        y = RF.maxpool3x3s2(x)
+        ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+        assert torch.equal(y.float(), ref)
+        z = torch.randn((5, 7, 7, 2048), device="cuda", generator=g).to(dt)
+        o0 = torch.zeros((5, 3584), device="cuda", dtype=dt)
+        o1 = torch.zeros((5, 3584), device="cuda", dtype=dt)
+        RF.avgpool(z, o0, o1)
+        refm = z.float().mean(dim=(1, 2))
+        tol = 1e-6 if dt == torch.float32 else 1e-2
+        assert (o0[:, :2048].float() - refm).abs().max().item() <= tol
+        assert torch.equal(o0, o1) and o0[:, 2048:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("views", [2, 4])
+def test_rotate_gather(views):
+    from rotmv_b200 import functional as RF
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    b = 9
+    pose = (torch.rand((b, views, 2), device="cuda", generator=g) - 0.5)
+    rot = RF.pose_to_rotations(pose)
+    feat = torch.randn((b * views, 1536), device="cuda", generator=g)
+    dst = torch.zeros((b * views, 3584), device="cuda")
+    RF.rotate_gather(feat, rot, dst[:, 2048:], b, views)
+    f3 = feat.view(b, views, 3, 512)
+    ref = torch.zeros_like(f3)
+    for v in range(views):
+        for u in range(views):
+            if u != v:
+                ref[:, v] += rot[:, v, u] @ f3[:, u]
+    ref /= (views - 1)
+    assert (dst[:, 2048:].reshape(b, views, 3, 512) - ref).abs().max().item() < 1e-5
+    assert dst[:, :2048].abs().max().item() == 0
+
+
+def test_stem_im2col_matches_conv():
+    from rotmv_b200 import functional as RF, _lib as L
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((2, 3, 224, 224), device="cuda", generator=g)
+    w = torch.randn((64, 3, 7, 7), device="cuda", generator=g) / 12
+    a, oh, ow = RF.stem_im2col(x)
+    wk = torch.zeros((64, 192), device="cuda")
+    wk[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147)
+    y = RF.linear(a, wk.bfloat16(), None, engine=L.ENGINE_TC, out_dtype=torch.float32)
+    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), stride=2, padding=3)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, 64)
+    assert (y - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-5
+    # fp32 engine straight from NCHW strides
+    y32 = RF.conv2d_nchw_input(x, w.permute(0, 2, 3, 1).contiguous(), stride=2, pad=3)
+    ref32 = F.conv2d(x, w, stride=2, padding=3).permute(0, 2, 3, 1)
+    assert (y32 - ref32).abs().max().item() <= 2e-5 * ref32.abs().max().item()
