@@ -96,12 +96,15 @@ int rmv_rotate_gather_fwd(const void* feat, long long ld_feat, const float* rot,
 /* Gaze head tail + loss (models/rot_mv.py:249-254 last Linear; utils/math.py:52-60;
  * losses/gaze_loss.py:42-52; losses/stereo_loss.py:46-54,65-84):
  *   pred[m, 0:2] = hidden[m, :] . w2[0:2, :]^T + b2           (hidden: [rows, hid] fp32/bf16)
- *   if gt != NULL: loss_out[0] += loss_scale * sum_m angular_deg(pred[m], gt[m])  (fp32 atomics)
+ *   if gt != NULL: loss_out[0] += loss_scale * sum_m d_m * angular_deg(pred[m], gt[m])  (fp32 atomics)
+ *                  with d_m = 1 for view 0 rows (m % views == 0) and aux_decay otherwise
+ *                  (StereoL1Loss.reference_decay).
  * The caller folds StereoL1Loss.rel_weight, the IterationLoss decay of this iteration and the
  * 1/batch of the mean into loss_scale. pred is fp32 [rows, 2]; gt fp32 [rows, 2]; w2/b2 fp32. */
 int rmv_head_loss_fwd(const void* hidden, long long ld_hidden, int hid_dtype, const float* w2,
                       const float* b2, int rows, int hid, float* pred, const float* gt,
-                      float loss_scale, float* loss_out, void* stream);
+                      float loss_scale, int views, float aux_decay, float* loss_out,
+                      void* stream);
 
 /* Mean angular error in degrees between pitch-yaw predictions and labels, clamped cosine
  * (utils/math.py:96-137; the on-device replacement for the per-step D2H at trainer.py:128).
@@ -113,6 +116,11 @@ int rmv_angular_error_accum(const float* pred, long long ld_pred, const float* g
  * R = R_y(yaw) R_x(-pitch) (utils/math.py:188-219, trainer.py:110-111, models/rot_mv.py:193-194). */
 int rmv_pose_to_rotations(const float* head_pose, float* rotations, int batch, int views,
                           void* stream);
+
+/* per-view rotations rot[B,V,3,3] -> rotations[B,V,V,3,3], [b,i,j] = rot[b,i] rot[b,j]^T
+ * (models/rot_mv.py:193-194: rot_10 = rot_0 rot_1^T, rot_01 = rot_1 rot_0^T). */
+int rmv_relative_rotations(const float* rot, float* rotations, int batch, int views,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -234,7 +234,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __restrict__ w2,
                  const float* __restrict__ b2, int rows, int hid, float* __restrict__ pred,
-                 const float* __restrict__ gt, float loss_scale, float* __restrict__ loss_out) {
+                 const float* __restrict__ gt, float loss_scale, int views, float aux_decay,
+                 float* __restrict__ loss_out) {
   __shared__ float s_part[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -260,7 +261,7 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
         pitchyaw_to_vec(d0, d1, vp);
         float sim = cos_sim_torch(vg, vp, 1e-6f);
         sim = fminf(fmaxf(sim, -1.f), 1.f);
-        ang = acosf(sim) * kRadToDeg;
+        ang = acosf(sim) * kRadToDeg * ((row % views) == 0 ? 1.f : aux_decay);
       }
     }
   }
@@ -330,6 +331,27 @@ __global__ void pose_to_rot_kernel(const float* __restrict__ pose, float* __rest
       float s = R[0][r * 3 + 0] * R[1][c * 3 + 0];
       s = fmaf(R[0][r * 3 + 1], R[1][c * 3 + 1], s);
       s = fmaf(R[0][r * 3 + 2], R[1][c * 3 + 2], s);
+      o[r * 3 + c] = s;
+    }
+}
+
+__global__ void relative_rot_kernel(const float* __restrict__ rot, float* __restrict__ out,
+                                    int views, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, i, j)
+  if (idx >= total) return;
+  const int j = (int)(idx % views);
+  const int i = (int)((idx / views) % views);
+  const long long b = idx / ((long long)views * views);
+  const float* ri = rot + (b * views + i) * 9;
+  const float* rj = rot + (b * views + j) * 9;
+  float* o = out + idx * 9;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s = __ldg(ri + r * 3) * __ldg(rj + c * 3);
+      s = fmaf(__ldg(ri + r * 3 + 1), __ldg(rj + c * 3 + 1), s);
+      s = fmaf(__ldg(ri + r * 3 + 2), __ldg(rj + c * 3 + 2), s);
       o[r * 3 + c] = s;
     }
 }
@@ -425,17 +447,18 @@ extern "C" int rmv_rotate_gather_fwd(const void* feat, long long ld_feat, const 
 
 extern "C" int rmv_head_loss_fwd(const void* hidden, long long ld_hidden, int hid_dtype,
                                  const float* w2, const float* b2, int rows, int hid, float* pred,
-                                 const float* gt, float loss_scale, float* loss_out,
-                                 void* stream) {
+                                 const float* gt, float loss_scale, int views,
+                                 float aux_decay, float* loss_out, void* stream) {
   RMV_CHECK_ARG(hid % 8 == 0 && ld_hidden % 8 == 0, "head_loss: hid/ld must be multiples of 8");
   RMV_CHECK_ARG(gt == nullptr || loss_out != nullptr, "head_loss: gt given without loss_out");
+  RMV_CHECK_ARG(views >= 1, "head_loss: views must be >= 1");
   if (rows == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (hid_dtype == RMV_DTYPE_BF16)
-    head_loss_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)hidden, ld_hidden, w2, b2, rows, hid, pred, gt, loss_scale, loss_out);
+    head_loss_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)hidden, ld_hidden, w2, b2, rows, hid, pred, gt, loss_scale, views, aux_decay, loss_out);
   else
-    head_loss_kernel<float><<<grid, 256, 0, s>>>((const float*)hidden, ld_hidden, w2, b2, rows, hid, pred, gt, loss_scale, loss_out);
+    head_loss_kernel<float><<<grid, 256, 0, s>>>((const float*)hidden, ld_hidden, w2, b2, rows, hid, pred, gt, loss_scale, views, aux_decay, loss_out);
   RMV_LAUNCH_CHECK();
   return 0;
 }
@@ -453,6 +476,15 @@ extern "C" int rmv_pose_to_rotations(const float* head_pose, float* rotations, i
   const long long total = (long long)batch * views * views;
   if (total == 0) return 0;
   pose_to_rot_kernel<<<blocks_for(total, 128), 128, 0, (cudaStream_t)stream>>>(head_pose, rotations, views, total);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_relative_rotations(const float* rot, float* rotations, int batch, int views,
+                                      void* stream) {
+  const long long total = (long long)batch * views * views;
+  if (total == 0) return 0;
+  relative_rot_kernel<<<blocks_for(total, 128), 128, 0, (cudaStream_t)stream>>>(rot, rotations, views, total);
   RMV_LAUNCH_CHECK();
   return 0;
 }

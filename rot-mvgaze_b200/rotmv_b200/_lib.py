@@ -57,9 +57,10 @@ SIGNATURES = {
     "rmv_maxpool3x3s2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rmv_avgpool_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp]),
     "rmv_rotate_gather_fwd": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
-    "rmv_head_loss_fwd": (_i, [_vp, _ll, _i, _vp, _vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
+    "rmv_head_loss_fwd": (_i, [_vp, _ll, _i, _vp, _vp, _i, _i, _vp, _vp, _f, _i, _f, _vp, _vp]),
     "rmv_angular_error_accum": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp]),
     "rmv_pose_to_rotations": (_i, [_vp, _vp, _i, _i, _vp]),
+    "rmv_relative_rotations": (_i, [_vp, _vp, _i, _i, _vp]),
 }
 
 

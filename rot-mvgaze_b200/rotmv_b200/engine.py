@@ -1,0 +1,230 @@
+"""Inference engine: turns the parameter tree of `FeatRotationSymm` into prepared device weights
+(BatchNorm folded into per-channel scale/shift, filters in KRSC layout, bf16 or fp32 storage) and
+runs the multi-view forward as a sequence of librotmv_sm100 kernel launches on the current stream.
+
+precision "bf16": tcgen05/TMEM/TMA implicit-GEMM kernels, bf16 storage, fp32 accumulation.
+precision "fp32": FFMA kernels, fp32 storage (parity mode: rtol 1e-4 against the CPU oracle).
+
+Data layout in HBM (per trunk chunk of n images): activations NHWC; the fusion stage keeps two
+[M, 2048+1536] row-major buffers X and Y (M = B*V rows, row m = b*V+v) whose first 2048 columns hold
+the image feature (written once by the average-pool kernel) so that the reference's torch.cat
+(models/rot_mv.py:47,250,253) never materialises: the rotate kernel writes X[:, 2048:], the fuser's
+second GEMM writes Y[:, 2048:], and the GEMMs read the 3584-wide rows in place.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import functional as RF
+
+_DT = {"bf16": torch.bfloat16, "fp32": torch.float32}
+
+
+def _bn_fold(bn):
+    """BatchNorm2d(eval) -> (scale, shift): models/resnet.py:187 etc., eps from the module."""
+    inv = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+    scale = bn.weight.detach().float() * inv
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def _krsc(conv, dtype):
+    return conv.weight.detach().permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+class _ConvSpec:
+    __slots__ = ("w", "scale", "shift", "stride", "pad")
+
+    def __init__(self, conv, bn, dtype):
+        self.w = _krsc(conv, dtype)
+        self.scale, self.shift = _bn_fold(bn)
+        self.stride, self.pad = conv.stride[0], conv.padding[0]
+
+
+class _LinSpec:
+    __slots__ = ("w", "b")
+
+    def __init__(self, lin, dtype):
+        self.w = lin.weight.detach().to(dtype).contiguous()
+        self.b = lin.bias.detach().float().contiguous()
+
+
+class InferenceEngine:
+    def __init__(self, model, precision: str):
+        if precision not in _DT:
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        L.load()  # fail loudly when the CUDA library is missing
+        self.precision = precision
+        self.dtype = _DT[precision]
+        self.model = model
+        self.num_iter = model._num_iter
+        self.fc_dim = model._fc_dim
+        self.nvec = model._num_feat_vec
+        self.apply_rot = not model._ignore_rotmat
+        self.chunk = max(1, int(model.trunk_chunk))
+        trunk = model._feat_extractor[0]
+        dev = trunk.conv1.weight.device
+        if dev.type != "cuda":
+            raise L.RotmvError("FeatRotationSymm parameters must live on a CUDA device "
+                               "(model.cuda()); there is no CPU path")
+        L.check(L.load().rmv_device_check(dev.index or 0), "rmv_device_check")
+        self.device = dev
+        self._stamp = self._version_stamp()
+        dt = self.dtype
+        # ---- trunk ----
+        self.stem_scale, self.stem_shift = _bn_fold(trunk.bn1)
+        w7 = trunk.conv1.weight.detach().permute(0, 2, 3, 1).contiguous()  # [64,7,7,3]
+        if precision == "bf16":
+            self.stem_kpad = 192
+            wk = torch.zeros((64, self.stem_kpad), device=dev, dtype=torch.float32)
+            wk[:, :147] = w7.reshape(64, 147)
+            self.stem_w = wk.to(dt)
+        else:
+            self.stem_w = w7.float()
+        self.kind = trunk.kind
+        self.blocks: List[Dict[str, Any]] = []
+        for blk in trunk.blocks():
+            spec = {"c1": _ConvSpec(blk.conv1, blk.bn1, dt), "c2": _ConvSpec(blk.conv2, blk.bn2, dt)}
+            if self.kind == "bottleneck":
+                spec["c3"] = _ConvSpec(blk.conv3, blk.bn3, dt)
+            if blk.downsample is not None:
+                spec["ds"] = _ConvSpec(blk.downsample[0], blk.downsample[1], dt)
+            self.blocks.append(spec)
+        # ---- fusion stage ----
+        lif = model._lifter._lifter.blocks
+        self.lift = [_LinSpec(lif[0][0], dt), _LinSpec(lif[1][0], dt)]
+        self.fusers, self.heads = [], []
+        for i in range(self.num_iter):
+            fb = model._img_fusers[i]._fuser.blocks
+            self.fusers.append([_LinSpec(fb[0][0], dt), _LinSpec(fb[1][0], dt)])
+            hb = model._gaze_estimators[i].blocks
+            self.heads.append((_LinSpec(hb[0][0], dt),
+                               hb[1][0].weight.detach().float().contiguous(),
+                               hb[1][0].bias.detach().float().contiguous()))
+        self._bufs: Dict[Any, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _version_stamp(self):
+        return tuple(t._version for t in list(self.model.parameters()) + list(self.model.buffers()))
+
+    def stale(self) -> bool:
+        return self._stamp != self._version_stamp()
+
+    def _buf(self, tag, shape, dtype=None):
+        key = (tag, tuple(shape), dtype or self.dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, device=self.device, dtype=dtype or self.dtype)
+            self._bufs[key] = t
+        return t
+
+    # ------------------------------------------------------------------------------------------
+    def _conv(self, x, spec, tag, relu, residual=None):
+        n, h, w, _ = x.shape
+        oh = (h + 2 * spec.pad - spec.w.shape[1]) // spec.stride + 1
+        ow = (w + 2 * spec.pad - spec.w.shape[2]) // spec.stride + 1
+        out = self._buf(tag, (n, oh, ow, spec.w.shape[0]))
+        return RF.conv2d(x, spec.w, stride=spec.stride, pad=spec.pad, scale=spec.scale,
+                         shift=spec.shift, residual=residual, relu=relu, out=out)
+
+    def trunk(self, imgs: torch.Tensor, feat0: torch.Tensor, feat1: torch.Tensor) -> None:
+        """imgs [n,3,H,W] fp32 NCHW -> global-average-pooled features into feat0[:, :C], feat1[:, :C]
+        (reference `_feat_extractor`, models/rot_mv.py:124-128,196-197)."""
+        n = imgs.shape[0]
+        if self.precision == "bf16":
+            a, oh, ow = RF.stem_im2col(imgs, k_pad=self.stem_kpad, dtype=self.dtype)
+            y = self._buf("stem", (n * oh * ow, 64))
+            RF.conv2d(a.view(1, 1, n * oh * ow, self.stem_kpad), self.stem_w.view(64, 1, 1, -1),
+                      scale=self.stem_scale, shift=self.stem_shift, relu=True,
+                      out=y.view(1, 1, n * oh * ow, 64))
+            y = y.view(n, oh, ow, 64)
+        else:
+            y = RF.conv2d_nchw_input(imgs, self.stem_w, stride=2, pad=3, scale=self.stem_scale,
+                                     shift=self.stem_shift, relu=True)
+        x = RF.maxpool3x3s2(y)
+        for bi, spec in enumerate(self.blocks):
+            out_tag = ("out", bi & 1)
+            if self.kind == "bottleneck":
+                t = self._conv(x, spec["c1"], "t1", True)
+                t = self._conv(t, spec["c2"], "t2", True)
+                skip = self._conv(x, spec["ds"], "ds", False) if "ds" in spec else x
+                x = self._conv(t, spec["c3"], out_tag, True, residual=skip)
+            else:
+                t = self._conv(x, spec["c1"], "t1", True)
+                skip = self._conv(x, spec["ds"], "ds", False) if "ds" in spec else x
+                x = self._conv(t, spec["c2"], out_tag, True, residual=skip)
+        RF.avgpool(x, feat0, feat1)
+
+    # ------------------------------------------------------------------------------------------
+    def run(self, images: torch.Tensor, rotations: torch.Tensor, *, want_all: bool = True,
+            gt: Optional[torch.Tensor] = None) -> Dict[str, Any]:
+        if not images.is_cuda:
+            raise L.RotmvError("images must be a CUDA tensor (there is no CPU path)")
+        b, v = images.shape[0], images.shape[1]
+        if v < 2:
+            raise ValueError("Rot-MV needs at least two views")
+        if tuple(rotations.shape) != (b, v, v, 3, 3):
+            raise ValueError(f"rotations must be [B,V,V,3,3] = {(b, v, v, 3, 3)}, got {tuple(rotations.shape)}")
+        m = b * v
+        imgs = images.reshape(m, *images.shape[2:])
+        if imgs.dtype != torch.float32 or not imgs.is_contiguous():
+            imgs = imgs.float().contiguous()
+        rot = rotations.float().contiguous()
+        wide = self.fc_dim + 3 * self.nvec
+        x_buf = self._buf("X", (m, wide))
+        y_buf = self._buf("Y", (m, wide))
+        for s in range(0, m, self.chunk):
+            e = min(m, s + self.chunk)
+            self.trunk(imgs[s:e], x_buf[s:e], y_buf[s:e])
+        feat_y = y_buf[:, self.fc_dim:]
+        # lifter (models/rot_mv.py:91-98,198-199): 2048 -> 1536 (+ReLU) -> 1536
+        l1 = self._buf("L1", (m, 3 * self.nvec))
+        RF.linear(x_buf[:, :self.fc_dim], self.lift[0].w, self.lift[0].b, relu=True, out=l1)
+        RF.linear(l1, self.lift[1].w, self.lift[1].b, out=feat_y)
+        out: Dict[str, Any] = {"num_iter": self.num_iter}
+
+        def per_view(t2d, tail):
+            t = t2d.float().reshape(b, v, *tail)
+            return [t[:, k].contiguous() for k in range(v)]
+
+        if want_all:
+            for k, t in enumerate(per_view(x_buf[:, :self.fc_dim], (self.fc_dim,))):
+                out[f"img_feat_{k}"] = t
+            for k, t in enumerate(per_view(feat_y, (3, self.nvec))):
+                out[f"initial_rot_feat_{k}"] = t
+        hid = self._buf("H", (m, wide))
+        g = self._buf("G", (m, 512))
+        gt_flat = None
+        loss = None
+        if gt is not None:
+            gt_flat = gt.float().reshape(m, 2).contiguous()
+            loss = torch.zeros((1,), device=self.device, dtype=torch.float32)
+            out["loss"] = loss
+        for i in range(self.num_iter):
+            # A_v = mean_{u != v} R_vu F_u(old)  -> X[:, 2048:]   (models/rot_mv.py:234,238)
+            RF.rotate_gather(feat_y, rot, x_buf[:, self.fc_dim:], b, v, self.nvec, self.apply_rot)
+            f1, f2 = self.fusers[i]
+            RF.linear(x_buf, f1.w, f1.b, relu=True, out=hid)          # Linear(3584,3584)+ReLU
+            RF.linear(hid, f2.w, f2.b, out=feat_y)                    # Linear(3584,1536) -> new F
+            h1, w2, b2 = self.heads[i]
+            RF.linear(y_buf, h1.w, h1.b, relu=True, out=g)            # Linear(3584,512)+ReLU
+            pred = torch.empty((m, 2), device=self.device, dtype=torch.float32)
+            # IterationLoss weight of iteration i (losses/stereo_loss.py:77): decay^(n-1-i) * rel_weight / B
+            cfg = self.model.loss_cfg
+            scale = (cfg["iter_decay"] ** (self.num_iter - 1 - i)) * cfg["rel_weight"] / b
+            RF.head_loss(g, w2, b2, pred, gt_flat, scale, loss, views=v,
+                         aux_decay=cfg["reference_decay"])            # Linear(512,2) (+ loss)
+            if want_all or i == self.num_iter - 1:
+                it: Dict[str, Any] = {}
+                pv = pred.view(b, v, 2)
+                for k in range(v):
+                    it[f"pred_gaze_{k}"] = pv[:, k].contiguous()
+                if want_all:
+                    for k, t in enumerate(per_view(feat_y, (3, self.nvec))):
+                        it[f"feat_{k}"] = t
+                out[f"iter_{i}"] = it
+        out["pred_gaze"] = out[f"iter_{self.num_iter - 1}"]["pred_gaze_0"]
+        return out

@@ -166,7 +166,8 @@ def rotate_gather(feat, rot, dst, batch, views, nvec=512, apply_rot=True):
                                            L.stream_ptr()), "rmv_rotate_gather_fwd")
 
 
-def head_loss(hidden, w2, b2, pred, gt=None, loss_scale=0.0, loss_out=None):
+def head_loss(hidden, w2, b2, pred, gt=None, loss_scale=0.0, loss_out=None, views=1,
+              aux_decay=1.0):
     _need_cuda(hidden, w2, b2, pred, gt, loss_out)
     rows, hid = hidden.shape
     assert w2.dtype == torch.float32 and w2.is_contiguous() and tuple(w2.shape) == (2, hid)
@@ -175,7 +176,8 @@ def head_loss(hidden, w2, b2, pred, gt=None, loss_scale=0.0, loss_out=None):
     L.check(L.load().rmv_head_loss_fwd(hidden.data_ptr(), hidden.stride(0),
                                        L.dtype_code(hidden.dtype), w2.data_ptr(), b2.data_ptr(),
                                        rows, hid, pred.data_ptr(), L.ptr(gt), float(loss_scale),
-                                       L.ptr(loss_out), L.stream_ptr()), "rmv_head_loss_fwd")
+                                       int(views), float(aux_decay), L.ptr(loss_out),
+                                       L.stream_ptr()), "rmv_head_loss_fwd")
 
 
 def angular_error_accum(pred, gt, err_sum):
@@ -195,3 +197,15 @@ def pose_to_rotations(head_pose):
     L.check(L.load().rmv_pose_to_rotations(head_pose.data_ptr(), rot.data_ptr(), b, v,
                                            L.stream_ptr()), "rmv_pose_to_rotations")
     return rot
+
+
+def relative_rotations(rot):
+    """[B, V, 3, 3] per-view rotations -> [B, V, V, 3, 3] with [b,i,j] = R_i R_j^T
+    (reference models/rot_mv.py:193-194)."""
+    _need_cuda(rot)
+    rot = rot.float().contiguous()
+    b, v = rot.shape[0], rot.shape[1]
+    out = torch.empty((b, v, v, 3, 3), dtype=torch.float32, device=rot.device)
+    L.check(L.load().rmv_relative_rotations(rot.data_ptr(), out.data_ptr(), b, v, L.stream_ptr()),
+            "rmv_relative_rotations")
+    return out

@@ -1,0 +1,188 @@
+"""`FeatRotationSymm` -- host-side mirror of the reference operator (models/rot_mv.py:102-269).
+
+Same constructor, same 348 state_dict keys (so reference checkpoints load with strict=True), same
+dict-in/dict-out `forward(data)` contract that `IterationLoss` and `Trainer` consume
+(losses/stereo_loss.py:46-50,66-76; trainer.py:122-126,176-181), plus the tensor form
+`forward(images[B,V,3,H,W], rotations[B,V,V,3,3]) -> pred_gaze[B,2]` for any V >= 2.
+
+The torch.nn layers built here are PARAMETER CONTAINERS ONLY (they give the reference's key names,
+shapes and random-init stream); their `forward` is never called. All compute goes through
+librotmv_sm100.so (see engine.py); there is no PyTorch/CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Union
+
+import torch
+import torch.nn as nn
+
+from . import engine as E
+
+NUM_FEAT_VEC = 512
+
+
+def _mlp_params(c_in: int, widths: List[int]) -> nn.Module:
+    """Key layout of reference `Mlp` (models/backbones/blocks.py:26-82): blocks.{i}.0.{weight,bias}."""
+    holder = nn.Module()
+    dims = [c_in] + list(widths)
+    holder.blocks = nn.ModuleList(
+        [nn.Sequential(nn.Linear(dims[i], dims[i + 1])) for i in range(len(widths))])
+    return holder
+
+
+def _wrap(name: str, child: nn.Module) -> nn.Module:
+    holder = nn.Module()
+    setattr(holder, name, child)
+    return holder
+
+
+class _BlockParams(nn.Module):
+    def __init__(self, kind: str, c_in: int, width: int, stride: int, downsample):
+        super().__init__()
+        self.kind, self.stride = kind, stride
+        if kind == "bottleneck":  # models/resnet.py:99-126
+            self.conv1 = nn.Conv2d(c_in, width, 1, bias=False)
+            self.bn1 = nn.BatchNorm2d(width)
+            self.conv2 = nn.Conv2d(width, width, 3, stride=stride, padding=1, bias=False)
+            self.bn2 = nn.BatchNorm2d(width)
+            self.conv3 = nn.Conv2d(width, width * 4, 1, bias=False)
+            self.bn3 = nn.BatchNorm2d(width * 4)
+        else:  # models/resnet.py:50-75
+            self.conv1 = nn.Conv2d(c_in, width, 3, stride=stride, padding=1, bias=False)
+            self.bn1 = nn.BatchNorm2d(width)
+            self.conv2 = nn.Conv2d(width, width, 3, padding=1, bias=False)
+            self.bn2 = nn.BatchNorm2d(width)
+        self.downsample = downsample
+
+
+class _TrunkParams(nn.Module):
+    """Parameter/buffer tree of the reference ResNet (models/resnet.py:151-218), incl. the unused
+    `fc` (Q4) so checkpoints round-trip."""
+
+    def __init__(self, depth: int):
+        super().__init__()
+        kind, counts, expansion = {50: ("bottleneck", [3, 4, 6, 3], 4),
+                                   18: ("basic", [2, 2, 2, 2], 1)}[depth]
+        self.kind = kind
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        c_in = 64
+        for idx, (width, n_blocks) in enumerate(zip([64, 128, 256, 512], counts)):
+            blocks = []
+            for b in range(n_blocks):
+                s = (1 if idx == 0 else 2) if b == 0 else 1
+                ds = None
+                if b == 0 and (s != 1 or c_in != width * expansion):
+                    ds = nn.Sequential(nn.Conv2d(c_in, width * expansion, 1, stride=s, bias=False),
+                                       nn.BatchNorm2d(width * expansion))
+                blocks.append(_BlockParams(kind, c_in, width, s, ds))
+                c_in = width * expansion
+            setattr(self, f"layer{idx + 1}", nn.Sequential(*blocks))
+        self.fc = nn.Linear(c_in, 1000)
+        self.out_dim = c_in
+        for m in self.modules():  # models/resnet.py:203-208
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    def blocks(self):
+        for li in range(1, 5):
+            for blk in getattr(self, f"layer{li}"):
+                yield blk
+
+
+class FeatRotationSymm(nn.Module):
+    def __init__(self, backbone_depth: int = 50, num_iter: Optional[int] = None,
+                 share_weights: bool = False, encode_rotmat: bool = False,
+                 share_feature: bool = False, ignore_rotmat: bool = False, *,
+                 precision: str = "bf16", trunk_chunk: int = 32):
+        super().__init__()
+        self._num_iter = num_iter
+        self._output_index = num_iter - 1  # TypeError when num_iter is None, as in the reference
+        self._num_feat_vec = NUM_FEAT_VEC
+        if backbone_depth not in (18, 50):
+            raise ValueError(f"backbone_depth must be 18 or 50, got {backbone_depth}")
+        trunk = _TrunkParams(backbone_depth)
+        self._feat_extractor = nn.ModuleList([trunk])  # keys "_feat_extractor.0.*" (:124-128)
+        self._fc_dim = trunk.out_dim
+        self._lifter = _wrap("_lifter", _mlp_params(self._fc_dim, [NUM_FEAT_VEC * 3] * 2))
+        assert not (ignore_rotmat and encode_rotmat)
+        self._ignore_rotmat, self._encode_rotmat = ignore_rotmat, encode_rotmat
+        self._share_feature, self._share_weights = share_feature, share_weights
+        if share_feature:
+            raise NotImplementedError(
+                "share_feature=True (RotFeatFuser + IntensityBatchNorm, models/rot_mv.py:13-32,"
+                "70-85) is not built yet; it is not reachable from the reference main.py")
+        if encode_rotmat:
+            raise NotImplementedError(
+                "encode_rotmat=True (ImageRotmatFeatFuser, models/rot_mv.py:53-67) is not built "
+                "yet; it is not reachable from the reference main.py")
+        fuse_in = self._fc_dim + 3 * NUM_FEAT_VEC
+
+        def fuser():
+            return _wrap("_fuser", _mlp_params(fuse_in, [fuse_in, 3 * NUM_FEAT_VEC]))
+
+        def head():
+            return _mlp_params(fuse_in, [512, 2])
+
+        if share_weights:  # one module aliased num_iter times (:150-158, Q10)
+            self._img_fusers = nn.ModuleList([fuser()] * num_iter)
+            self._gaze_estimators = nn.ModuleList([head()] * num_iter)
+        else:
+            self._img_fusers = nn.ModuleList([fuser() for _ in range(num_iter)])
+            self._gaze_estimators = nn.ModuleList([head() for _ in range(num_iter)])
+        self.precision = precision
+        self.trunk_chunk = trunk_chunk
+        # main.py:239-240: StereoL1Loss(rel_weight=0.01, reference_decay=1.0), IterationLoss(0.5)
+        self.loss_cfg = {"rel_weight": 0.01, "reference_decay": 1.0, "iter_decay": 0.5}
+        self.fuse_loss = False  # dict API: also return data["loss"] from the fused head+loss kernel
+        self._engines: Dict[str, E.InferenceEngine] = {}
+
+    # -- engine management ---------------------------------------------------------------------
+    def engine(self, precision: Optional[str] = None) -> "E.InferenceEngine":
+        precision = precision or self.precision
+        eng = self._engines.get(precision)
+        if eng is None or eng.stale():
+            eng = E.InferenceEngine(self, precision)
+            self._engines[precision] = eng
+        return eng
+
+    def invalidate(self) -> None:
+        """Drop cached folded/converted weights (call after changing parameters in place)."""
+        self._engines.clear()
+
+    def train(self, mode: bool = True):
+        self._engines.clear()
+        return super().train(mode)
+
+    # -- forward -------------------------------------------------------------------------------
+    def forward(self, data_or_images: Union[Dict[str, Any], torch.Tensor],
+                rotations: Optional[torch.Tensor] = None, *, precision: Optional[str] = None):
+        if isinstance(data_or_images, dict):
+            return self._forward_dict(data_or_images, precision)
+        out = self.forward_views(data_or_images, rotations, precision=precision, want_all=False)
+        return out["pred_gaze"]
+
+    def forward_views(self, images: torch.Tensor, rotations: torch.Tensor, *,
+                      precision: Optional[str] = None, want_all: bool = True,
+                      gt: Optional[torch.Tensor] = None) -> Dict[str, Any]:
+        if self.training:
+            raise NotImplementedError(
+                "train-mode forward runs through rotmv_b200.trainer.TrainStep (batch-statistic "
+                "BatchNorm + backward); module.forward is the inference path")
+        if images.dim() != 5 or rotations is None or rotations.dim() != 5:
+            raise ValueError("expected images[B,V,3,H,W] and rotations[B,V,V,3,3]")
+        return self.engine(precision).run(images, rotations, want_all=want_all, gt=gt)
+
+    def _forward_dict(self, data: Dict[str, Any], precision) -> Dict[str, Any]:
+        """Reference dict contract for two views (models/rot_mv.py:187-269); mutates `data`."""
+        from . import functional as RF
+
+        images = torch.stack([data["img_0"], data["img_1"]], dim=1)
+        # rot_10 = rot_0 rot_1^T, rot_01 = rot_1 rot_0^T (:193-194) -> rotations[b,i,j] = R_i R_j^T
+        rotations = RF.relative_rotations(torch.stack([data["rot_0"], data["rot_1"]], dim=1))
+        gt = None
+        if "gt_gaze" in data and "gt_gaze_1" in data and self.fuse_loss:
+            gt = torch.stack([data["gt_gaze"], data["gt_gaze_1"]], dim=1)
+        out = self.forward_views(images, rotations, precision=precision, want_all=True, gt=gt)
+        data.update(out)
+        return data
