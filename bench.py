@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Headline benchmark: Rot-MV multi-view inference throughput (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+A "step" is one forward pass of `FeatRotationSymm` (ResNet-50 trunk -> rotation-constrained
+cross-view fusion x3 -> gaze heads) over one batch of 256 two-view samples (512 images, 224x224),
+random-init weights, synthetic inputs. Prints ONE JSON line (rank 0):
+  value      whole-job multi-view samples/s, inputs resident in HBM, CUDA-graph replay, CUDA events
+  e2e        same metric through the host-buffer entry (pinned host -> HBM copy of images+rotations
+             and device -> host read of pred_gaze inside the timed region, every step)
+  roofline   tcgen05 implicit-GEMM kernel: algorithmic FLOPs / measured launch time vs measured peak
+  cpu_baseline  the CPU oracle (port of the reference's PyTorch path) on the host cores
+`--impl reference` times the reference's own CPU path (oracle port; /root/reference does not travel
+to the GPU box) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "rot-mvgaze_b200"))
+
+import torch  # noqa: E402
+
+METRIC = "multi-view samples/sec (224^2, fwd)"
+UNIT = "samples/s"
+# SURVEY 8d / BASELINE.md: forward FLOPs per view (2*MAC, conv + linear), default config
+FLOPS_PER_VIEW = 8.306399e9
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "src": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def workload(args):
+    return {"workload": "configs[1]: Rot-MV 2-view inference, synthetic batch 256 bf16 on 1xB200 "
+                        "(xgaze2mpiinv_known shape)" if (args.batch, args.views) == (256, 2)
+            else f"Rot-MV {args.views}-view inference, synthetic batch {args.batch}",
+            "batch_per_gpu": args.batch, "views": args.views, "image": "3x224x224 fp32 NCHW",
+            "backbone": "resnet50", "num_iter": 3, "weights": "random-init (seed 0)",
+            "mode": "eval forward (no_grad)", "precision": args.precision,
+            "parallelism": f"dp{args.gpus} (batch sharded, no collective)",
+            "l2": "inputs %.0f MB/step per GPU exceed the 126 MB L2; no flush needed"
+                  % (args.batch * args.views * 3 * 224 * 224 * 4 / 1e6)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU oracle legs
+# --------------------------------------------------------------------------------------------
+def time_cpu_oracle(views: int, sample_batch: int, min_seconds: float, max_iters: int,
+                    warmup: int = 1):
+    from oracle import rotmv_oracle as O
+
+    torch.set_num_threads(os.cpu_count())
+    model = O.build_model(num_iter=3, depth=50, seed=0).eval()
+    images, pose, _ = O.synthetic_batch(sample_batch, views, seed=1)
+    rot = O.pairwise_rotations(pose)
+    times = []
+    with torch.no_grad():
+        for _ in range(warmup):
+            model.forward_views(images, rot)
+        t_all = time.perf_counter()
+        while len(times) < max_iters and (time.perf_counter() - t_all < min_seconds or len(times) < 2):
+            t0 = time.perf_counter()
+            model.forward_views(images, rot)
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 8
+    from oracle import rotmv_oracle as O
+
+    torch.set_num_threads(os.cpu_count())
+    model = O.build_model(num_iter=3, depth=50, seed=0).eval()
+    images, pose, _ = O.synthetic_batch(sample, args.views, seed=1)
+    rot = O.pairwise_rotations(pose)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            model.forward_views(images, rot)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            model.forward_views(images, rot)
+        dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = (f"oracle port of the reference PyTorch CPU path; each step = {sample} of the "
+            f"{args.batch} samples of the workload batch ({args.views} views, fp32, eval)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(),
+                             "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from rotmv_b200 import _lib as L
+    from rotmv_b200 import functional as RF
+    from rotmv_b200.engine import GraphedForward
+    from rotmv_b200.module import FeatRotationSymm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    torch.manual_seed(0)
+    model = FeatRotationSymm(50, 3, precision=args.precision, trunk_chunk=args.chunk)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(1 + rank)
+    B, V = args.batch, args.views
+    images_host = torch.randn((B, V, 3, 224, 224), generator=g).pin_memory()
+    pose_host = torch.rand((B, V, 2), generator=g) - 0.5
+    rot_dev = RF.pose_to_rotations(pose_host.to(dev))
+    rot_host = rot_dev.cpu().pin_memory()
+    images_dev = images_host.to(dev)
+
+    sess = GraphedForward(model, B, V, precision=args.precision)
+    sess.images.copy_(images_dev)
+    sess.rotations.copy_(rot_dev)
+    del images_dev
+
+    # ---- device-resident throughput: warm-up, then K timed replays ---------------------------
+    for _ in range(max(args.warmup, 3)):
+        sess()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = 0
+    e0.record()
+    for _ in range(args.steps):
+        sess()
+        launches0 += sess.launches_per_replay
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = n_gpus * B * args.steps / (ms_total * 1e-3)
+    pred_check = sess.pred.float().abs().sum().item()
+    if not (pred_check == pred_check):
+        raise SystemExit("bench.py: non-finite predictions")
+
+    # ---- end to end: host buffers in, prediction out, every step -----------------------------
+    for _ in range(2):
+        sess.run_host(images_host, rot_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sess.run_host(images_host, rot_host)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n_gpus * B * args.steps / e2e_s
+    h2d = images_host.numel() * 4 + rot_host.numel() * 4
+    d2h = B * 2 * 4
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": workload(args), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": launches0}
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit GEMM), measured live ----------------
+    if rank == 0:
+        RF.PROFILE = []
+        with torch.no_grad():
+            model.engine(args.precision).run(sess.images, sess.rotations, want_all=False)
+        torch.cuda.synchronize()
+        recs, RF.PROFILE = RF.PROFILE, None
+        tc = [(r[1], r[2].elapsed_time(r[3])) for r in recs if r[0] == "tcgen05"]
+        pk = peaks()
+        if tc:
+            flops = sum(f for f, _ in tc)
+            ms = sum(t for _, t in tc)
+            achieved = flops / (ms * 1e-3) / 1e12
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "igemm_traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            line["roofline"] = {
+                "kernel": "igemm_kernel (tcgen05.mma + TMA implicit GEMM: all 53 convs + 14 linears)",
+                "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tflops"], "traffic": traffic, "peak_source": pk["src"],
+                "launches_per_step": len(tc), "flops_per_launch": flops / len(tc),
+                "avg_launch_ms": ms / len(tc), "kernel_share_of_step": ms / ms_step,
+                "whole_step_frac": (B * V * FLOPS_PER_VIEW / (ms_step * 1e-3) / 1e12) / pk["tflops"]}
+        # ---- CPU baseline: the oracle on this box's host cores, bounded sample -----------------
+        if n_gpus == 1 and not args.no_cpu:
+            times = time_cpu_oracle(V, 8, min_seconds=12.0, max_iters=40)
+            cpu_value = 8 / (sum(times) / len(times))
+            line["cpu_baseline"] = {
+                "value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                "sample": f"{len(times)} eval forwards of 8 of the {B} samples ({V} views, fp32, "
+                          f"oracle port of the reference PyTorch CPU path), {sum(times):.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="multi-view samples per GPU per step")
+    ap.add_argument("--views", type=int, default=2)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("ROTMV_CHUNK", "64")),
+                    help="images per trunk micro-batch")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

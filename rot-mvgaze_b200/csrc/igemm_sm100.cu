@@ -28,13 +28,15 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kMaxTaps = 49;
-constexpr int kNumThreads = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kNumThreads = 224;  // warp0 TMA(A,B), warp1 MMA, warps2-5 epilogue, warp6 TMA(residual)
 constexpr int kABytes = kBlockM * kBlockK * 2;
+constexpr int kChunkBytes = kBlockM * 128;  // one staged output / residual chunk: 128 rows x 128 B
 
 struct IgemmArgs {
   CUtensorMap tmap_a[4];
   CUtensorMap tmap_b;
-  int out_w, out_h, n_img;
+  CUtensorMap tmap_out;  // store map: (c_out, W, H, N), box (128 B of channels, box_w, box_h, box_n)
+  CUtensorMap tmap_res;  // residual load map, same geometry (bf16)
   int box_w, box_h, box_n;
   int tiles_w, tiles_h, tiles_n;
   int n_tiles, n_total;
@@ -42,40 +44,71 @@ struct IgemmArgs {
   signed char tap_map[kMaxTaps];
   signed char tap_dw[kMaxTaps];
   signed char tap_dh[kMaxTaps];
-  void* out;
-  long long os_n, os_h, os_w;
-  const __nv_bfloat16* residual;
-  long long rs_n, rs_h, rs_w;
   const float* scale;
   const float* shift;
   int relu;
-  int out_fp32;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool HAS_RES>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kStages = (BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? (HAS_RES ? 5 : 6) : 6);
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kOutBytes = 2 * kChunkBytes;
+  static constexpr int kResBytes = HAS_RES ? 2 * kChunkBytes : 0;
+  static constexpr int kVecBytes = 2 * BLOCK_N * 4;  // scale + shift of the current N tile
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kOutBytes + kResBytes + kVecBytes + 256 /*barriers*/ + 1024 /*align*/;
+  static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 };
 
-template <int BLOCK_N>
+__device__ __forceinline__ void tma_store_4d(const void* tmap, const void* src, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(tmap)),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync(int id) {
+  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+}
+
+// OUT_F32: 32 fp32 columns per staged chunk; otherwise 64 bf16 columns (both 128 B per row).
+template <int BLOCK_N, bool HAS_RES, bool OUT_F32>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmArgs args) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, HAS_RES>;
+  constexpr int kChunkCols = OUT_F32 ? 32 : 64;
+  constexpr int kChunks = BLOCK_N / kChunkCols;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + C::kStages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* smem_b = smem_a + C::kStages * kABytes;
+  uint8_t* smem_out = smem_b + C::kStages * C::kBBytes;  // [2][128 rows][128 B], SW128
+  uint8_t* smem_res = smem_out + C::kOutBytes;           // [2][128 rows][128 B], SW128
+  float* s_scale = reinterpret_cast<float*>(smem_res + C::kResBytes);
+  float* s_shift = s_scale + BLOCK_N;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BLOCK_N);
   uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + C::kStages;        // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * C::kStages;    // [2]        MMA -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;           // [2]        epilogue -> MMA
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;            // [2]        TMA(residual) -> epilogue
+  uint64_t* res_empty = res_full + 2;             // [2]        epilogue -> TMA(residual)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -83,6 +116,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&args.tmap_b);
     tma_prefetch_desc(&args.tmap_a[0]);
+    tma_prefetch_desc(&args.tmap_out);
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -90,6 +124,8 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 128);
+      mbar_init(&res_full[i], 1);
+      mbar_init(&res_empty[i], 128);
     }
     fence_mbar_init();
   }
@@ -107,7 +143,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   const int num_kb = args.num_taps * args.c_blocks;
 
   if (warp == 0) {
-    // ------------------------------- TMA producer -------------------------------
+    // ------------------------------- TMA producer (A, B) ------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -161,14 +197,38 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
+  } else if (warp == 6) {
+    // ------------------------------- TMA producer (residual) --------------------
+    if (HAS_RES && lane == 0) {
+      tma_prefetch_desc(&args.tmap_res);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % args.n_tiles;
+        const int m_tile = tile / args.n_tiles;
+        const int tw = m_tile % args.tiles_w;
+        const int th = (m_tile / args.tiles_w) % args.tiles_h;
+        const int tn = m_tile / (args.tiles_w * args.tiles_h);
+        for (int c = 0; c < kChunks; ++c) {
+          mbar_wait(&res_empty[slot], phase ^ 1);
+          mbar_expect_tx(&res_full[slot], kChunkBytes);
+          tma_load_4d(smem_res + slot * kChunkBytes, &args.tmap_res, &res_full[slot],
+                      n_tile * BLOCK_N + c * kChunkCols, tw * args.box_w, th * args.box_h,
+                      tn * args.box_n);
+          if (++slot == 2) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
   } else {
-    // ------------------------------- epilogue -----------------------------------
+    // ------------------------------- epilogue (warps 2..5) ----------------------
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
     const int row = quarter * 32 + lane;
-    const int dw = row % args.box_w;
-    const int dh = (row / args.box_w) % args.box_h;
-    const int dn = row / (args.box_w * args.box_h);
+    const int tid_e = threadIdx.x - 64;  // 0..127
+    const uint32_t sw = (uint32_t)(row & 7);
     int local = 0;
+    int cc = 0;  // running chunk counter: staging buffer = cc & 1
+    int rslot = 0;
+    uint32_t rphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -177,37 +237,52 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       const int tw = m_tile % args.tiles_w;
       const int th = (m_tile / args.tiles_w) % args.tiles_h;
       const int tn = m_tile / (args.tiles_w * args.tiles_h);
-      const int ow = tw * args.box_w + dw, oh = th * args.box_h + dh, n = tn * args.box_n + dn;
-      const bool valid = (ow < args.out_w) && (oh < args.out_h) && (n < args.n_img);
-      const long long o_off = n * args.os_n + oh * args.os_h + ow * args.os_w;
-      const long long r_off = n * args.rs_n + oh * args.rs_h + ow * args.rs_w;
-
+      // per-channel scale/shift of this N tile -> smem (all readers of the previous tile's values
+      // are behind the last epi_bar_sync(2) of that tile)
+      for (int i = tid_e; i < BLOCK_N; i += 128) {
+        const int col = n_tile * BLOCK_N + i;
+        const bool ok = col < args.n_total;
+        s_scale[i] = (ok && args.scale != nullptr) ? __ldg(args.scale + col) : 1.f;
+        s_shift[i] = (ok && args.shift != nullptr) ? __ldg(args.shift + col) : 0.f;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32,
-                           v);
-        tmem_ld_wait();
-        const int col0 = n_tile * BLOCK_N + c * 32;
-        if (valid && col0 < args.n_total) {
+      for (int c = 0; c < kChunks; ++c, ++cc) {
+        uint8_t* obuf = smem_out + (cc & 1) * kChunkBytes;
+        // (1) staging buffer free: the store issued two chunks ago has finished reading it
+        if (tid_e == 0) tma_store_wait_read<1>();
+        epi_bar_sync(1);
+        if (HAS_RES) mbar_wait(&res_full[rslot], rphase);
+        const uint8_t* rbuf = smem_res + rslot * kChunkBytes;
+        // (2) TMEM -> registers -> scale/shift(/residual)/ReLU -> swizzled smem
+#pragma unroll
+        for (int half = 0; half < (OUT_F32 ? 1 : 2); ++half) {
+          uint32_t v[32];
+          const int col_in_tile = c * kChunkCols + half * 32;
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N +
+                                 col_in_tile, v);
+          tmem_ld_wait();
+          if (c == kChunks - 1 && half == (OUT_F32 ? 0 : 1)) {
+            // accumulator fully read: hand the TMEM buffer back to the MMA warp early
+            tc_fence_before_sync();
+            mbar_arrive(&tmem_empty[acc]);
+          }
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (args.scale != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= __ldg(args.scale + col0 + j);
+          for (int q = 0; q < 8; ++q) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + col_in_tile + q * 4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + col_in_tile + q * 4);
+            f[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]), sc.x, sh.x);
+            f[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]), sc.y, sh.y);
+            f[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]), sc.z, sh.z);
+            f[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]), sc.w, sh.w);
           }
-          if (args.shift != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += __ldg(args.shift + col0 + j);
-          }
-          if (args.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(args.residual + r_off + col0);
+          if (HAS_RES) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 r = __ldg(rp + q);
+              const uint32_t j = (uint32_t)(half * 4 + q);  // 16-byte unit within the 128-byte row
+              const uint4 r = *reinterpret_cast<const uint4*>(rbuf + row * 128 + ((j ^ sw) << 4));
               const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
@@ -221,13 +296,12 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          if (args.out_fp32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + o_off + col0);
+          if (OUT_F32) {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+              *reinterpret_cast<float4*>(obuf + row * 128 + (((uint32_t)q ^ sw) << 4)) =
+                  make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
           } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + o_off + col0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 o;
@@ -235,14 +309,26 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
               o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
               o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
               o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-              op[q] = o;
+              const uint32_t j = (uint32_t)(half * 4 + q);
+              *reinterpret_cast<uint4*>(obuf + row * 128 + ((j ^ sw) << 4)) = o;
             }
           }
         }
+        if (HAS_RES) {
+          mbar_arrive(&res_empty[rslot]);
+          if (++rslot == 2) { rslot = 0; rphase ^= 1; }
+        }
+        // (3) make the generic-proxy smem writes visible to the TMA store, then (4) store
+        fence_proxy_async_smem();
+        epi_bar_sync(2);
+        if (tid_e == 0) {
+          tma_store_4d(&args.tmap_out, obuf, n_tile * BLOCK_N + c * kChunkCols, tw * args.box_w,
+                       th * args.box_h, tn * args.box_n);
+          tma_store_commit();
+        }
       }
-      tc_fence_before_sync();
-      mbar_arrive(&tmem_empty[acc]);
     }
+    if (tid_e == 0) tma_store_wait_all();
   }
 
   tc_fence_before_sync();
@@ -276,14 +362,14 @@ EncodeTiledFn get_encode_fn() {
 }
 
 int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
-               const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+               const cuuint64_t* strides_bytes, const cuuint32_t* box, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   RMV_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
-                  dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RMV_CHECK_ARG(r == CUDA_SUCCESS,
                 "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] strides "
                 "[%llu %llu %llu] box [%u %u %u %u] base %p",
@@ -298,24 +384,33 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dim
 
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool HAS_RES, bool OUT_F32>
 int launch(const IgemmArgs& a, int total_tiles, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, HAS_RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    RMV_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::kSmemBytes));
+    RMV_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, HAS_RES, OUT_F32>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  igemm_kernel<BLOCK_N><<<grid, kNumThreads, C::kSmemBytes, stream>>>(a);
+  igemm_kernel<BLOCK_N, HAS_RES, OUT_F32><<<grid, kNumThreads, C::kSmemBytes, stream>>>(a);
   RMV_LAUNCH_CHECK();
   return 0;
+}
+
+template <int BLOCK_N>
+int dispatch(const IgemmArgs& a, int total, bool has_res, bool out_f32, cudaStream_t stream) {
+  if (out_f32) return launch<BLOCK_N, false, true>(a, total, stream);
+  if (has_res) return launch<BLOCK_N, true, false>(a, total, stream);
+  return launch<BLOCK_N, false, false>(a, total, stream);
 }
 
 }  // namespace
 
 int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) {
+  const bool out_f32 = (p.y_dtype == RMV_DTYPE_F32);
+  const int y_es = out_f32 ? 4 : 2;
   RMV_CHECK_ARG(p.c_in % kBlockK == 0, "tcgen05 conv: c_in=%d must be a multiple of 64", p.c_in);
   RMV_CHECK_ARG(p.c_out % 8 == 0, "tcgen05 conv: c_out=%d must be a multiple of 8", p.c_out);
   RMV_CHECK_ARG(p.stride == 1 || p.stride == 2, "tcgen05 conv: stride %d unsupported", p.stride);
@@ -324,18 +419,23 @@ int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) {
                 "tcgen05 conv: input pixel strides must be multiples of 8 elements");
   RMV_CHECK_ARG((reinterpret_cast<uintptr_t>(p.x) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(p.w) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(p.y) & 15) == 0,
+                    (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0,
                 "tcgen05 conv: pointers must be 16-byte aligned");
   RMV_CHECK_ARG(p.y_sw % 8 == 0 && p.y_sh % 8 == 0 && p.y_sn % 8 == 0,
                 "tcgen05 conv: output pixel strides must be multiples of 8 elements");
+  RMV_CHECK_ARG(p.residual == nullptr || (p.r_sw % 8 == 0 && p.r_sh % 8 == 0 && p.r_sn % 8 == 0),
+                "tcgen05 conv: residual pixel strides must be multiples of 8 elements");
+  RMV_CHECK_ARG(!(out_f32 && p.residual != nullptr),
+                "tcgen05 conv: residual add with fp32 output is not supported");
 
   IgemmArgs a;
   memset(&a, 0, sizeof(a));
   int out_w = p.out_w, out_h = p.out_h, n_img = p.n_img;
   long long x_sw = p.x_sw, x_sh = p.x_sh, x_sn = p.x_sn;
+  long long y_sw = p.y_sw, y_sh = p.y_sh, y_sn = p.y_sn;
+  long long r_sw = p.r_sw, r_sh = p.r_sh, r_sn = p.r_sn;
   int in_w = p.in_w, in_h = p.in_h;
-  a.os_n = p.y_sn; a.os_h = p.y_sh; a.os_w = p.y_sw;
-  a.rs_n = p.r_sn; a.rs_h = p.r_sh; a.rs_w = p.r_sw;
 
   // 1x1 stride-1 over a dense pixel grid is a plain GEMM: flatten (n, h, w) into one axis.
   const bool pointwise = (p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0);
@@ -348,8 +448,8 @@ int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) {
     out_h = in_h = 1;
     n_img = 1;
     x_sh = x_sw * in_w; x_sn = x_sh;
-    a.os_h = a.os_n = 0;
-    a.rs_h = a.rs_n = 0;
+    y_sh = y_sw * out_w; y_sn = y_sh;
+    r_sh = r_sw * out_w; r_sn = r_sh;
   }
 
   // Pick the (box_w, box_h, box_n) factorisation of the 128-row M tile with the least padding.
@@ -364,7 +464,6 @@ int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) {
       if (eff > best_eff + 1e-9) { best_eff = eff; best_w = bw; best_h = bh; best_n = bn; }
     }
   a.box_w = best_w; a.box_h = best_h; a.box_n = best_n;
-  a.out_w = out_w; a.out_h = out_h; a.n_img = n_img;
   a.tiles_w = ceil_div(out_w, a.box_w);
   a.tiles_h = ceil_div(out_h, a.box_h);
   a.tiles_n = ceil_div(n_img, a.box_n);
@@ -398,9 +497,10 @@ int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) {
       a.tap_dw[t] = (signed char)floordiv(q - p.pad, s);
     }
 
+  const long m_tiles = (long)a.tiles_w * a.tiles_h * a.tiles_n;
   const int block_n = (p.block_n > 0) ? p.block_n
                       : (p.c_out <= 64) ? 64
-                      : (p.c_out % 256 == 0 && (long)a.tiles_w * a.tiles_h * a.tiles_n * (p.c_out / 256) >= 2L * num_sms()) ? 256
+                      : (p.c_out % 256 == 0 && m_tiles * (p.c_out / 256) >= 2L * num_sms()) ? 256
                       : 128;
   RMV_CHECK_ARG(block_n == 64 || block_n == 128 || block_n == 256, "bad block_n %d", block_n);
   {
@@ -411,21 +511,35 @@ int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) {
     int rc = encode_map(&a.tmap_b, p.w, 2, dims, strides, box);
     if (rc) return rc;
   }
+  {
+    // Output (store) and residual (load) maps share the M-tile box; 128 bytes of channels per row.
+    cuuint64_t dims[4] = {(cuuint64_t)p.c_out, (cuuint64_t)out_w, (cuuint64_t)out_h,
+                          (cuuint64_t)n_img};
+    cuuint32_t box[4] = {(cuuint32_t)(128 / y_es), (cuuint32_t)a.box_w, (cuuint32_t)a.box_h,
+                         (cuuint32_t)a.box_n};
+    cuuint64_t ystr[3] = {(cuuint64_t)(y_sw * y_es), (cuuint64_t)(y_sh * y_es),
+                          (cuuint64_t)(y_sn * y_es)};
+    int rc = encode_map(&a.tmap_out, p.y, 4, dims, ystr, box, out_f32);
+    if (rc) return rc;
+    if (p.residual != nullptr) {
+      cuuint64_t rstr[3] = {(cuuint64_t)(r_sw * 2), (cuuint64_t)(r_sh * 2), (cuuint64_t)(r_sn * 2)};
+      rc = encode_map(&a.tmap_res, p.residual, 4, dims, rstr, box);
+      if (rc) return rc;
+    }
+  }
   a.n_total = p.c_out;
   a.n_tiles = ceil_div(p.c_out, block_n);
   a.c_blocks = p.c_in / kBlockK;
-  a.out = p.y;
-  a.residual = reinterpret_cast<const __nv_bfloat16*>(p.residual);
   a.scale = p.scale;
   a.shift = p.shift;
   a.relu = p.relu;
-  a.out_fp32 = (p.y_dtype == RMV_DTYPE_F32);
-  const int total = a.tiles_w * a.tiles_h * a.tiles_n * a.n_tiles;
+  const int total = (int)(m_tiles * a.n_tiles);
   if (total == 0) return 0;
+  const bool has_res = p.residual != nullptr;
   switch (block_n) {
-    case 64: return launch<64>(a, total, stream);
-    case 128: return launch<128>(a, total, stream);
-    default: return launch<256>(a, total, stream);
+    case 64: return dispatch<64>(a, total, has_res, out_f32, stream);
+    case 128: return dispatch<128>(a, total, has_res, out_f32, stream);
+    default: return dispatch<256>(a, total, has_res, out_f32, stream);
   }
 }
 

@@ -88,7 +88,15 @@ def load():
     return lib
 
 
+# Number of successful kernel-launching C-ABI calls since import (bench.py's `gpu_launches`).
+STATS = {"launches": 0}
+
+
 def check(rc: int, what: str) -> None:
+    if rc == 0:
+        if what != "rmv_device_check":
+            STATS["launches"] += 1
+        return
     if rc != 0:
         msg = load().rmv_last_error()
         raise RotmvError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")

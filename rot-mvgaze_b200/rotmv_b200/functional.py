@@ -10,6 +10,23 @@ import torch
 from . import _lib as L
 
 
+# When set to a list, conv2d/linear append (engine, flops, start_event, end_event) per launch
+# (CUDA events on the launching stream) -- used by bench.py for the live roofline measurement.
+PROFILE = None
+
+
+def _call(what, meta, fn, *args):
+    """Launch through the C ABI; with PROFILE on, bracket the launch with CUDA events."""
+    if PROFILE is None:
+        L.check(fn(*args), what)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.check(fn(*args), what)
+    e1.record()
+    PROFILE.append((meta.get("engine", what), meta.get("flops", 0.0), e0, e1, what, meta))
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -56,7 +73,16 @@ def conv2d(x, w, *, stride=1, pad=0, scale=None, shift=None, residual=None, relu
         a.residual = residual.data_ptr()
         a.r_sn, a.r_sh, a.r_sw = residual.stride(0), residual.stride(1), residual.stride(2)
     a.relu = int(relu)
-    L.check(L.load().rmv_conv2d_fwd(C.byref(a), L.stream_ptr()), "rmv_conv2d_fwd")
+    meta = {}
+    if PROFILE is not None:
+        tc = x.dtype == torch.bfloat16 and engine != L.ENGINE_SIMT and c % 64 == 0
+        es, eo = x.element_size(), out.element_size()
+        meta = {"engine": "tcgen05" if tc else "ffma",
+                "flops": 2.0 * n * oh * ow * k * kh * kw * c,
+                "bytes": float(n * h * wd * c * es / (stride * stride if kh == 1 else 1)
+                               + w.numel() * es + n * oh * ow * k * eo * (2 if residual is not None else 1)),
+                "desc": f"conv {kh}x{kw}s{stride} [{n},{h},{wd},{c}]->{k}"}
+    _call("rmv_conv2d_fwd", meta, L.load().rmv_conv2d_fwd, C.byref(a), L.stream_ptr())
     return out
 
 
@@ -86,7 +112,7 @@ def conv2d_nchw_input(x_nchw, w, *, stride, pad, scale=None, shift=None, relu=Fa
     a.scale = L.ptr(scale)
     a.shift = L.ptr(shift)
     a.relu = int(relu)
-    L.check(L.load().rmv_conv2d_fwd(C.byref(a), L.stream_ptr()), "rmv_conv2d_fwd")
+    _call("rmv_conv2d_fwd", {"desc": "rmv_conv2d_fwd"}, L.load().rmv_conv2d_fwd, C.byref(a), L.stream_ptr())
     return out
 
 
@@ -113,9 +139,8 @@ def stem_im2col(x_nchw, k_pad=192, dtype=torch.bfloat16, kh=7, kw=7, stride=2, p
     oh = (h + 2 * pad - kh) // stride + 1
     ow = (w + 2 * pad - kw) // stride + 1
     a = torch.empty((n * oh * ow, k_pad), dtype=dtype, device=x_nchw.device)
-    L.check(L.load().rmv_stem_im2col(x_nchw.data_ptr(), a.data_ptr(), n, c, h, w, kh, kw, stride,
-                                     pad, oh, ow, k_pad, L.dtype_code(dtype), L.stream_ptr()),
-            "rmv_stem_im2col")
+    _call("rmv_stem_im2col", {"desc": "rmv_stem_im2col"}, L.load().rmv_stem_im2col, x_nchw.data_ptr(), a.data_ptr(), n, c, h, w, kh, kw, stride,
+                                     pad, oh, ow, k_pad, L.dtype_code(dtype), L.stream_ptr())
     return a, oh, ow
 
 
@@ -124,8 +149,8 @@ def nchw_to_nhwc(x_nchw, dtype):
     assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
     n, c, h, w = x_nchw.shape
     y = torch.empty((n, h, w, c), dtype=dtype, device=x_nchw.device)
-    L.check(L.load().rmv_nchw_to_nhwc(x_nchw.data_ptr(), y.data_ptr(), n, c, h, w,
-                                      L.dtype_code(dtype), L.stream_ptr()), "rmv_nchw_to_nhwc")
+    _call("rmv_nchw_to_nhwc", {"desc": "rmv_nchw_to_nhwc"}, L.load().rmv_nchw_to_nhwc, x_nchw.data_ptr(), y.data_ptr(), n, c, h, w,
+                                      L.dtype_code(dtype), L.stream_ptr())
     return y
 
 
@@ -135,9 +160,8 @@ def maxpool3x3s2(x):
     n, h, w, c = x.shape
     oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     y = torch.empty((n, oh, ow, c), dtype=x.dtype, device=x.device)
-    L.check(L.load().rmv_maxpool3x3s2_fwd(x.data_ptr(), y.data_ptr(), n, h, w, c,
-                                          L.dtype_code(x.dtype), L.stream_ptr()),
-            "rmv_maxpool3x3s2_fwd")
+    _call("rmv_maxpool3x3s2_fwd", {"desc": "rmv_maxpool3x3s2_fwd"}, L.load().rmv_maxpool3x3s2_fwd, x.data_ptr(), y.data_ptr(), n, h, w, c,
+                                          L.dtype_code(x.dtype), L.stream_ptr())
     return y
 
 
@@ -147,10 +171,9 @@ def avgpool(x, out0, out1=None):
     assert x.is_contiguous()
     n, h, w, c = x.shape
     assert out0.dtype == x.dtype and (out1 is None or out1.dtype == x.dtype)
-    L.check(L.load().rmv_avgpool_fwd(x.data_ptr(), n, h * w, c, L.dtype_code(x.dtype),
+    _call("rmv_avgpool_fwd", {"desc": "rmv_avgpool_fwd"}, L.load().rmv_avgpool_fwd, x.data_ptr(), n, h * w, c, L.dtype_code(x.dtype),
                                      out0.data_ptr(), out0.stride(0), L.ptr(out1),
-                                     0 if out1 is None else out1.stride(0), L.stream_ptr()),
-            "rmv_avgpool_fwd")
+                                     0 if out1 is None else out1.stride(0), L.stream_ptr())
 
 
 def rotate_gather(feat, rot, dst, batch, views, nvec=512, apply_rot=True):
@@ -160,10 +183,10 @@ def rotate_gather(feat, rot, dst, batch, views, nvec=512, apply_rot=True):
     assert feat.dtype == dst.dtype and feat.stride(1) == 1 and dst.stride(1) == 1
     assert rot.dtype == torch.float32 and rot.is_contiguous()
     assert tuple(rot.shape) == (batch, views, views, 3, 3)
-    L.check(L.load().rmv_rotate_gather_fwd(feat.data_ptr(), feat.stride(0), rot.data_ptr(),
+    _call("rmv_rotate_gather_fwd", {"desc": "rmv_rotate_gather_fwd"}, L.load().rmv_rotate_gather_fwd, feat.data_ptr(), feat.stride(0), rot.data_ptr(),
                                            dst.data_ptr(), dst.stride(0), batch, views, nvec,
                                            L.dtype_code(feat.dtype), int(apply_rot),
-                                           L.stream_ptr()), "rmv_rotate_gather_fwd")
+                                           L.stream_ptr())
 
 
 def head_loss(hidden, w2, b2, pred, gt=None, loss_scale=0.0, loss_out=None, views=1,
@@ -173,19 +196,19 @@ def head_loss(hidden, w2, b2, pred, gt=None, loss_scale=0.0, loss_out=None, view
     assert w2.dtype == torch.float32 and w2.is_contiguous() and tuple(w2.shape) == (2, hid)
     assert pred.dtype == torch.float32 and pred.is_contiguous()
     assert gt is None or (gt.dtype == torch.float32 and gt.is_contiguous())
-    L.check(L.load().rmv_head_loss_fwd(hidden.data_ptr(), hidden.stride(0),
+    _call("rmv_head_loss_fwd", {"desc": "rmv_head_loss_fwd"}, L.load().rmv_head_loss_fwd, hidden.data_ptr(), hidden.stride(0),
                                        L.dtype_code(hidden.dtype), w2.data_ptr(), b2.data_ptr(),
                                        rows, hid, pred.data_ptr(), L.ptr(gt), float(loss_scale),
                                        int(views), float(aux_decay), L.ptr(loss_out),
-                                       L.stream_ptr()), "rmv_head_loss_fwd")
+                                       L.stream_ptr())
 
 
 def angular_error_accum(pred, gt, err_sum):
     _need_cuda(pred, gt, err_sum)
     assert pred.dtype == gt.dtype == err_sum.dtype == torch.float32
-    L.check(L.load().rmv_angular_error_accum(pred.data_ptr(), pred.stride(0), gt.data_ptr(),
+    _call("rmv_angular_error_accum", {"desc": "rmv_angular_error_accum"}, L.load().rmv_angular_error_accum, pred.data_ptr(), pred.stride(0), gt.data_ptr(),
                                              gt.stride(0), pred.shape[0], err_sum.data_ptr(),
-                                             L.stream_ptr()), "rmv_angular_error_accum")
+                                             L.stream_ptr())
 
 
 def pose_to_rotations(head_pose):
@@ -194,8 +217,8 @@ def pose_to_rotations(head_pose):
     assert head_pose.dtype == torch.float32 and head_pose.is_contiguous()
     b, v, _ = head_pose.shape
     rot = torch.empty((b, v, v, 3, 3), dtype=torch.float32, device=head_pose.device)
-    L.check(L.load().rmv_pose_to_rotations(head_pose.data_ptr(), rot.data_ptr(), b, v,
-                                           L.stream_ptr()), "rmv_pose_to_rotations")
+    _call("rmv_pose_to_rotations", {"desc": "rmv_pose_to_rotations"}, L.load().rmv_pose_to_rotations, head_pose.data_ptr(), rot.data_ptr(), b, v,
+                                           L.stream_ptr())
     return rot
 
 
@@ -206,6 +229,5 @@ def relative_rotations(rot):
     rot = rot.float().contiguous()
     b, v = rot.shape[0], rot.shape[1]
     out = torch.empty((b, v, v, 3, 3), dtype=torch.float32, device=rot.device)
-    L.check(L.load().rmv_relative_rotations(rot.data_ptr(), out.data_ptr(), b, v, L.stream_ptr()),
-            "rmv_relative_rotations")
+    _call("rmv_relative_rotations", {"desc": "rmv_relative_rotations"}, L.load().rmv_relative_rotations, rot.data_ptr(), out.data_ptr(), b, v, L.stream_ptr())
     return out
