@@ -72,6 +72,16 @@ int rmv_stem_im2col(const float* x, void* a, int n_img, int c_in, int in_h, int 
                     int kw, int stride, int pad, int out_h, int out_w, int k_pad, int a_dtype,
                     void* stream);
 
+/* Fused stem on the tensor cores: fp32 NCHW image [n,3,in_h,in_w] -> Conv2d(3,64,k7,s2,p3) ->
+ * scale/shift (folded BatchNorm) -> ReLU -> bf16 NHWC [n,out_h,out_w,64]; the im2col rows are
+ * built in shared memory and never touch HBM (models/resnet.py:184-188,262-264).
+ * w_packed is produced once by rmv_stem_pack_weights from the fp32 [64,3,7,7] filters
+ * (bf16 [64,192], k = c*56 + kh*8 + kw). */
+int rmv_stem_pack_weights(const float* w_oihw, void* w_packed, void* stream);
+int rmv_stem_conv_fwd(const float* x_nchw, const void* w_packed, const float* scale,
+                      const float* shift, void* y_nhwc, int n_img, int in_h, int in_w,
+                      void* stream);
+
 /* fp32 NCHW -> NHWC (fp32 or bf16) layout change (the reference keeps NCHW, trainer.py:100-106). */
 int rmv_nchw_to_nhwc(const float* x, void* y, int n_img, int c, int h, int w, int y_dtype,
                      void* stream);

@@ -361,8 +361,10 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+}  // namespace
+
 int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
-               const cuuint64_t* strides_bytes, const cuuint32_t* box, bool f32 = false) {
+               const cuuint64_t* strides_bytes, const cuuint32_t* box, bool f32) {
   EncodeTiledFn fn = get_encode_fn();
   RMV_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -381,6 +383,8 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dim
                 rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
   return 0;
 }
+
+namespace {
 
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 

@@ -76,14 +76,10 @@ class InferenceEngine:
         dt = self.dtype
         # ---- trunk ----
         self.stem_scale, self.stem_shift = _bn_fold(trunk.bn1)
-        w7 = trunk.conv1.weight.detach().permute(0, 2, 3, 1).contiguous()  # [64,7,7,3]
         if precision == "bf16":
-            self.stem_kpad = 192
-            wk = torch.zeros((64, self.stem_kpad), device=dev, dtype=torch.float32)
-            wk[:, :147] = w7.reshape(64, 147)
-            self.stem_w = wk.to(dt)
+            self.stem_w = RF.stem_pack_weights(trunk.conv1.weight.detach().float())
         else:
-            self.stem_w = w7.float()
+            self.stem_w = trunk.conv1.weight.detach().permute(0, 2, 3, 1).contiguous().float()
         self.kind = trunk.kind
         self.blocks: List[Dict[str, Any]] = []
         for blk in trunk.blocks():
@@ -135,12 +131,9 @@ class InferenceEngine:
         (reference `_feat_extractor`, models/rot_mv.py:124-128,196-197)."""
         n = imgs.shape[0]
         if self.precision == "bf16":
-            a, oh, ow = RF.stem_im2col(imgs, k_pad=self.stem_kpad, dtype=self.dtype)
-            y = self._buf("stem", (n * oh * ow, 64))
-            RF.conv2d(a.view(1, 1, n * oh * ow, self.stem_kpad), self.stem_w.view(64, 1, 1, -1),
-                      scale=self.stem_scale, shift=self.stem_shift, relu=True,
-                      out=y.view(1, 1, n * oh * ow, 64))
-            y = y.view(n, oh, ow, 64)
+            oh, ow = (imgs.shape[2] - 1) // 2 + 1, (imgs.shape[3] - 1) // 2 + 1
+            y = RF.stem_conv(imgs, self.stem_w, self.stem_scale, self.stem_shift,
+                             out=self._buf("stem", (n, oh, ow, 64)))
         else:
             y = RF.conv2d_nchw_input(imgs, self.stem_w, stride=2, pad=3, scale=self.stem_scale,
                                      shift=self.stem_shift, relu=True)

@@ -144,6 +144,34 @@ def stem_im2col(x_nchw, k_pad=192, dtype=torch.bfloat16, kh=7, kw=7, stride=2, p
     return a, oh, ow
 
 
+def stem_pack_weights(w_oihw):
+    """fp32 [64,3,7,7] -> bf16 [64,192] in the k = c*56 + kh*8 + kw order of the fused stem."""
+    _need_cuda(w_oihw)
+    assert tuple(w_oihw.shape) == (64, 3, 7, 7) and w_oihw.dtype == torch.float32
+    w_oihw = w_oihw.contiguous()
+    packed = torch.empty((64, 192), dtype=torch.bfloat16, device=w_oihw.device)
+    _call("rmv_stem_pack_weights", {"desc": "rmv_stem_pack_weights"},
+          L.load().rmv_stem_pack_weights, w_oihw.data_ptr(), packed.data_ptr(), L.stream_ptr())
+    return packed
+
+
+def stem_conv(x_nchw, w_packed, scale, shift, out=None):
+    """Fused conv7x7/s2 + BN(eval) + ReLU, fp32 NCHW in -> bf16 NHWC out (tcgen05)."""
+    _need_cuda(x_nchw, w_packed, scale, shift, out)
+    assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and x_nchw.shape[1] == 3
+    n, _, h, w = x_nchw.shape
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    if out is None:
+        out = torch.empty((n, oh, ow, 64), dtype=torch.bfloat16, device=x_nchw.device)
+    assert out.is_contiguous() and tuple(out.shape) == (n, oh, ow, 64)
+    meta = {"desc": f"stem conv7x7s2+bn+relu [{n},3,{h},{w}]", "engine": "tcgen05-stem",
+            "flops": 2.0 * n * oh * ow * 64 * 147,
+            "bytes": float(x_nchw.numel() * 4 + out.numel() * 2)}
+    _call("rmv_stem_conv_fwd", meta, L.load().rmv_stem_conv_fwd, x_nchw.data_ptr(),
+          w_packed.data_ptr(), L.ptr(scale), L.ptr(shift), out.data_ptr(), n, h, w, L.stream_ptr())
+    return out
+
+
 def nchw_to_nhwc(x_nchw, dtype):
     _need_cuda(x_nchw)
     assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()

@@ -175,3 +175,21 @@ def test_stem_im2col_matches_conv():
     y32 = RF.conv2d_nchw_input(x, w.permute(0, 2, 3, 1).contiguous(), stride=2, pad=3)
     ref32 = F.conv2d(x, w, stride=2, padding=3).permute(0, 2, 3, 1)
     assert (y32 - ref32).abs().max().item() <= 2e-5 * ref32.abs().max().item()
+
+
+@pytest.mark.parametrize("n,h,w", [(3, 224, 224), (2, 96, 96), (1, 70, 106)])
+def test_fused_stem_matches_conv_bn_relu(n, h, w):
+    """rmv_stem_conv_fwd (in-smem im2col + tcgen05 + TMA store) vs conv7x7/s2 + affine + ReLU."""
+    from rotmv_b200 import functional as RF
+
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + h)
+    x = torch.randn((n, 3, h, w), device="cuda", generator=g)
+    wt = torch.randn((64, 3, 7, 7), device="cuda", generator=g) / 12
+    scale = torch.rand((64,), device="cuda", generator=g) + 0.5
+    shift = torch.randn((64,), device="cuda", generator=g)
+    y = RF.stem_conv(x, RF.stem_pack_weights(wt), scale, shift)
+    ref = F.conv2d(x.bfloat16().float(), wt.bfloat16().float(), stride=2, padding=3)
+    ref = torch.relu(ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    assert tuple(y.shape) == tuple(ref.shape)
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 1.2e-2 * ref.abs().max().item(), err
