@@ -79,7 +79,7 @@ int rmv_stem_im2col(const float* x, void* a, int n_img, int c_in, int in_h, int 
  * (bf16 [64,192], k = c*56 + kh*8 + kw). */
 int rmv_stem_pack_weights(const float* w_oihw, void* w_packed, void* stream);
 int rmv_stem_conv_fwd(const float* x_nchw, const void* w_packed, const float* scale,
-                      const float* shift, void* y_nhwc, int n_img, int in_h, int in_w,
+                      const float* shift, void* y_nhwc, int n_img, int in_h, int in_w, int relu,
                       void* stream);
 
 /* fp32 NCHW -> NHWC (fp32 or bf16) layout change (the reference keeps NCHW, trainer.py:100-106). */
@@ -98,7 +98,9 @@ int rmv_avgpool_fwd(const void* x, int n_img, int hw, int c, int dtype, void* y0
 /* Rotation-constrained cross-view gather (models/rot_mv.py:193-194,234,238; SURVEY D1 for V>2):
  *   dst[(b*V+v), r*nvec + k] = 1/(V-1) * sum_{u != v} sum_c rot[b,v,u,r,c] * feat[(b*V+u), c*nvec + k]
  * feat rows have stride ld_feat, dst rows ld_dst (both in elements); rot is fp32 [B,V,V,3,3] with
- * rot[b,i,j] = R_i R_j^T. With apply_rot == 0 the rotation is skipped (ignore_rotmat=True). */
+ * rot[b,i,j] = R_i R_j^T. apply_rot bit 0: apply the rotation (0 = ignore_rotmat=True, plain
+ * mean of the partner features); bit 1: BACKWARD of the gather -- dst row (b,v) receives
+ * 1/(V-1) * sum_{u != v} rot[b,u,v]^T applied to feat row (b,u) (feat = gradient w.r.t. dst). */
 int rmv_rotate_gather_fwd(const void* feat, long long ld_feat, const float* rot, void* dst,
                           long long ld_dst, int batch, int views, int nvec, int dtype,
                           int apply_rot, void* stream);
@@ -131,6 +133,75 @@ int rmv_pose_to_rotations(const float* head_pose, float* rotations, int batch, i
  * (models/rot_mv.py:193-194: rot_10 = rot_0 rot_1^T, rot_01 = rot_1 rot_0^T). */
 int rmv_relative_rotations(const float* rot, float* rotations, int batch, int views,
                            void* stream);
+
+/* ==============================================================================================
+ * Training step (trainer.py:119-123,141-143): batch-statistic BatchNorm, backward kernels, Adam.
+ * Image n of a [B*V, ...] activation belongs to view n % views; BatchNorm statistics are PER VIEW
+ * because the reference calls the trunk once per view (models/rot_mv.py:196-197).
+ * ============================================================================================ */
+
+/* acc[views][c][2] (fp64, zero on entry) += per-(view,channel) sum and sum of squares of z[n,pix,c]. */
+int rmv_bn_stats(const void* z, int dtype, int n_img, int pix, int c, int views, double* acc,
+                 void* stream);
+/* mean/invstd[views][c]; fused affine a = gamma*invstd, b = beta - mean*a; running_mean/var
+ * updated once per view in view order with momentum (unbiased variance), num_batches += views
+ * (nn.BatchNorm2d train semantics, models/resnet.py:187 etc.); resets acc to zero. */
+int rmv_bn_finalize(double* acc, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, long long* num_batches, float* mean, float* invstd,
+                    float* a, float* b, int c, int views, long long count_per_view, float eps,
+                    float momentum, void* stream);
+/* y = relu?(a[v,c]*z + b[v,c] + residual) */
+int rmv_bn_apply(const void* z, const float* a, const float* b, const void* residual, void* y,
+                 int dtype, int n_img, int pix, int c, int views, int relu, void* stream);
+/* acc[views][c][2] += { sum dyr, sum dyr*xhat }, dyr = dy * (y_mask > 0) (y_mask may be NULL). */
+int rmv_bn_bwd_reduce(const void* z, const void* dy, const void* y_mask, const float* mean,
+                      const float* invstd, int dtype, int n_img, int pix, int c, int views,
+                      double* acc, void* stream);
+/* dgamma/dbeta[c] and the per-(view,channel) coefficients of dz = k0*dyr + k1*z + k2; resets acc. */
+int rmv_bn_bwd_finalize(double* acc, const float* gamma, const float* mean, const float* invstd,
+                        float* dgamma, float* dbeta, float* k0, float* k1, float* k2, int c,
+                        int views, long long count_per_view, void* stream);
+/* dz = k0*dyr + k1*z + k2; optionally also writes dyr (the gradient of the residual branch). */
+int rmv_bn_bwd_apply(const void* z, const void* dy, const void* y_mask, const float* k0,
+                     const float* k1, const float* k2, void* dz, void* dyr_out, int dtype,
+                     int n_img, int pix, int c, int views, void* stream);
+/* dst = (mask > 0 ? src : 0) + add, 2-D row-strided (mask/add may be NULL): ReLU backward,
+ * gradient accumulation of the concat-free fusion buffers. */
+int rmv_relu_bwd(const void* src, long long ld_src, const void* mask, long long ld_mask,
+                 const void* add, long long ld_add, void* dst, long long ld_dst, int rows, int cols,
+                 int dtype, void* stream);
+/* out[col] += sum_rows x[row,col] (fp32): Linear bias gradients. */
+int rmv_colsum(const void* x, long long ld, int rows, int cols, int dtype, float* out,
+               void* stream);
+/* dst[i0,i1,i2,i3] (contiguous, fp32 or bf16) = src[i0*s0 + f1(i1)*s1 + f2(i2)*s2 + i3*s3] with
+ * optional flips of dims 1,2: filter layout changes (OIHW fp32 master -> KRSC, and the
+ * flipped/transposed filters of the data-gradient convolution). */
+int rmv_permute_cast(const float* src, void* dst, int d0, int d1, int d2, int d3, long long s0,
+                     long long s1, long long s2, long long s3, int flip1, int flip2, int dst_dtype,
+                     void* stream);
+/* dst[n,2h,2w,:] = src[n,h,w,:], zeros elsewhere (dst [n,2H,2W,c]): stride-2 data gradient. */
+int rmv_dilate2(const void* src, void* dst, int n_img, int h, int w, int c, int dtype,
+                void* stream);
+int rmv_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int n_img, int in_h, int in_w,
+                         int c, int dtype, void* stream);
+int rmv_avgpool_bwd(const void* dfeat, long long ld, void* dx, int n_img, int hw, int c, int dtype,
+                    void* stream);
+/* Analytic gradient of the weighted angular loss w.r.t. pred (zero where the cosine saturates,
+ * like F.hardtanh) + backward of the head's last Linear(512,2) and the ReLU before it:
+ * dhidden = (hidden>0) * dpred w2; dw2 += dpred^T hidden; db2 += colsum(dpred). */
+int rmv_head_loss_bwd(const float* pred, const float* gt, const void* hidden, long long ld_hidden,
+                      int hid_dtype, const float* w2, int rows, int hid, float loss_scale,
+                      int views, float aux_decay, void* dhidden, long long ld_dhidden,
+                      float* dpred, float* dw2, float* db2, void* stream);
+/* Filter gradient: dw[k,c,r,s] (fp32, OIHW like the PyTorch parameter) += sum over output pixels
+ * of dy[p,k] * x[p shifted by (r,s), c]; `args` describes the forward convolution (x, strides,
+ * shapes; args->y_s* are the strides of dy). */
+int rmv_conv2d_wgrad(const rmv_conv_args* args, const void* dy, float* dw, void* stream);
+/* Fused Adam over a flat fp32 buffer; hyper = double{lr, beta1, beta2, eps, weight_decay, step} in
+ * DEVICE memory (step is incremented by the call). decoupled=0: torch.optim.Adam(weight_decay),
+ * i.e. coupled L2 as trainer.py:54; decoupled=1: AdamW. grads are multiplied by grad_scale. */
+int rmv_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                  double* hyper, long long n, int decoupled, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

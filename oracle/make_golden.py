@@ -154,7 +154,7 @@ def main():
                       "_lifter._lifter.blocks.1.0.bias", "_img_fusers.2._fuser.blocks.1.0.bias",
                       "_gaze_estimators.2.blocks.1.0.weight", "_gaze_estimators.0.blocks.1.0.bias"]:
                 g = rg[k].grad
-                gold["grad0::" + k] = g.numpy() if g.numel() <= 70000 else g.flatten()[:4096].numpy()
+                gold["grad0::" + k] = (g if g.numel() <= 70000 else g.flatten()[:4096]).detach().clone().numpy()
             gold["grad0_norms"] = np.array([rg[k].grad.norm().item() if rg[k].grad is not None else -1.0
                                             for k in rg], dtype=np.float64)
         else:
@@ -163,11 +163,11 @@ def main():
     rsd, osd = ref.state_dict(), ora.state_dict()
     for k in rsd:
         assert_same(rsd[k], osd[k], f"after 2 steps {k}")
-    gold["after2_bn1_running_mean"] = rsd["_feat_extractor.0.bn1.running_mean"].numpy()
-    gold["after2_bn1_running_var"] = rsd["_feat_extractor.0.bn1.running_var"].numpy()
-    gold["after2_num_batches_tracked"] = rsd["_feat_extractor.0.bn1.num_batches_tracked"].numpy()
-    gold["after2_head2_w"] = rsd["_gaze_estimators.2.blocks.1.0.weight"].numpy()
-    gold["after2_bn1_weight"] = rsd["_feat_extractor.0.bn1.weight"].numpy()
+    gold["after2_bn1_running_mean"] = rsd["_feat_extractor.0.bn1.running_mean"].detach().clone().numpy()
+    gold["after2_bn1_running_var"] = rsd["_feat_extractor.0.bn1.running_var"].detach().clone().numpy()
+    gold["after2_num_batches_tracked"] = rsd["_feat_extractor.0.bn1.num_batches_tracked"].detach().clone().numpy()
+    gold["after2_head2_w"] = rsd["_gaze_estimators.2.blocks.1.0.weight"].detach().clone().numpy()
+    gold["after2_bn1_weight"] = rsd["_feat_extractor.0.bn1.weight"].detach().clone().numpy()
     gold["after2_delta_norms"] = np.array(
         [(rsd[k].double() - init_state[k].double()).norm().item() for k in rsd], dtype=np.float64)
     meta["after2_sha256"] = tensor_digest(rsd)

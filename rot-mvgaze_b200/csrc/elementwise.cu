@@ -179,7 +179,12 @@ __global__ void rotate_gather_kernel(const T* __restrict__ feat, long long ld_fe
 #pragma unroll
     for (int c = 0; c < 3; ++c) Vec8<T>::load(fp + (long long)c * nvec, f[c]);
     float R[9];
-    if (apply_rot) {
+    if (apply_rot & 2) {
+      // backward of the gather: this row (self = v) receives rot[b,u,v]^T applied to d/dA of row u
+      const float* rp = rot + ((b * views + u) * views + v) * 9;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + (i % 3) * 3 + i / 3);
+    } else if (apply_rot & 1) {
       const float* rp = rot + ((b * views + v) * views + u) * 9;
 #pragma unroll
       for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + i);

@@ -37,6 +37,7 @@ struct StemArgs {
   const float* scale;
   const float* shift;
   int n_img, in_h, in_w, out_h, out_w, tiles_w, tiles_h, total_tiles;
+  int relu;
 };
 
 __device__ __forceinline__ void stem_tma_store(const void* tmap, const void* src, int c0, int c1,
@@ -186,7 +187,8 @@ __global__ void __launch_bounds__(kThreads, 2) stem_kernel(const __grid_constant
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const int col = colhalf * 32 + q * 8 + t;
-        f[t] = fmaxf(fmaf(__uint_as_float(v[q * 8 + t]), s_scale[col], s_shift[col]), 0.f);
+        f[t] = fmaf(__uint_as_float(v[q * 8 + t]), s_scale[col], s_shift[col]);
+        if (a.relu) f[t] = fmaxf(f[t], 0.f);
       }
       uint4 o;
       o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
@@ -240,7 +242,7 @@ extern "C" int rmv_stem_pack_weights(const float* w_oihw, void* packed, void* st
 
 extern "C" int rmv_stem_conv_fwd(const float* x_nchw, const void* w_packed, const float* scale,
                                  const float* shift, void* y_nhwc, int n_img, int in_h, int in_w,
-                                 void* stream) {
+                                 int relu, void* stream) {
   RMV_CHECK_ARG(x_nchw && w_packed && y_nhwc, "stem_conv_fwd: null pointer");
   RMV_CHECK_ARG(in_h >= 7 && in_w >= 7, "stem_conv_fwd: input %dx%d too small", in_h, in_w);
   RMV_CHECK_ARG((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 &&
@@ -250,7 +252,7 @@ extern "C" int rmv_stem_conv_fwd(const float* x_nchw, const void* w_packed, cons
   StemArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x_nchw; a.scale = scale; a.shift = shift;
-  a.n_img = n_img; a.in_h = in_h; a.in_w = in_w;
+  a.n_img = n_img; a.in_h = in_h; a.in_w = in_w; a.relu = relu;
   a.out_h = (in_h + 6 - 7) / 2 + 1;
   a.out_w = (in_w + 6 - 7) / 2 + 1;
   a.tiles_w = ceil_div(a.out_w, kTW);

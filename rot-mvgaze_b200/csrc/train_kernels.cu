@@ -1,0 +1,843 @@
+// Training-side kernels of the Rot-MV path (all HBM-bound except the FFMA weight gradient):
+// batch-statistic BatchNorm forward/backward with PER-VIEW statistics (the reference runs the trunk
+// once per view, models/rot_mv.py:196-197), pooling backward, ReLU masks, bias/column
+// sums, the analytic angular-loss gradient, the gaze-head tail backward, weight layout transforms,
+// gradient dilation for stride-2 dgrad, the FFMA weight-gradient GEMM and the fused multi-tensor
+// Adam step (coupled L2 = torch.optim.Adam(weight_decay) as in trainer.py:54, or decoupled).
+#include "common.cuh"
+#include "ops.h"
+
+namespace rmv {
+namespace {
+
+constexpr float kRadToDeg = 57.29577951308232f;
+
+template <typename T> struct V8;
+template <> struct V8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 v = unpack_bf16x2(w[i]);
+      f[2 * i] = v.x; f[2 * i + 1] = v.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* f) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <> struct V8<float> {
+  static __device__ __forceinline__ void load(const float* p, float* f) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* f) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+
+inline unsigned nblk(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm (train): per-(view, channel) statistics. Image n belongs to view n % views.
+// Partial sums are fp32 inside a thread (<= rows_per_block terms), fp64 across threads/blocks.
+// ---------------------------------------------------------------------------------------------
+// grid = (slabs, n_img); block = 256 threads = (c/8 channel groups) x (256/(c/8)) row lanes when
+// c <= 2048; each thread strides over the rows of its slab.
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256)
+bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* __restrict__ y_mask,
+                 const float* __restrict__ mean, const float* __restrict__ invstd, int pix, int c,
+                 int views, double* __restrict__ acc /* [views][c][2] */) {
+  extern __shared__ float s_red[];  // [row_lanes][c][2]
+  const int cg = c / 8;
+  const int lanes = blockDim.x / cg;  // row lanes per block (>= 1)
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+  const int n = blockIdx.y, v = n % views;
+  const int slabs = gridDim.x;
+  const int rows_per = (pix + slabs - 1) / slabs;
+  const int r0 = blockIdx.x * rows_per, r1 = min(pix, r0 + rows_per);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  float mu[8], is[8];
+  if (BWD) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mu[i] = __ldg(mean + v * c + g * 8 + i);
+      is[i] = __ldg(invstd + v * c + g * 8 + i);
+    }
+  }
+  if (lane < lanes) {
+    for (int r = r0 + lane; r < r1; r += lanes) {
+      const long long off = ((long long)n * pix + r) * c + g * 8;
+      float f[8];
+      V8<T>::load(z + off, f);
+      if (!BWD) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1[i] += f[i]; s2[i] = fmaf(f[i], f[i], s2[i]); }
+      } else {
+        float d[8];
+        V8<T>::load(dy + off, d);
+        if (y_mask != nullptr) {
+          float m[8];
+          V8<T>::load(y_mask + off, m);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1[i] += d[i];
+          s2[i] = fmaf(d[i], (f[i] - mu[i]) * is[i], s2[i]);
+        }
+      }
+    }
+  }
+  // reduce over row lanes through shared memory, then one fp64 atomic per (channel, stat)
+  if (lane < lanes) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s_red[(lane * c + g * 8 + i) * 2] = s1[i];
+      s_red[(lane * c + g * 8 + i) * 2 + 1] = s2[i];
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < c * 2; j += blockDim.x) {
+    double s = 0.0;
+    for (int l = 0; l < lanes; ++l) s += (double)s_red[l * c * 2 + j];
+    atomicAdd(acc + (long long)v * c * 2 + j, s);
+  }
+}
+
+// mean / invstd, fused affine (a = gamma*invstd, b = beta - mean*a), running-stat update in VIEW
+// ORDER (rm <- (1-m) rm + m mean_v for v = 0..V-1; unbiased variance), accumulator reset.
+__global__ void bn_finalize_kernel(double* __restrict__ acc, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ nbt,
+                                   float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ a, float* __restrict__ b, int c, int views,
+                                   double count, float eps, float momentum) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch == 0 && nbt != nullptr) *nbt += views;
+  if (ch >= c) return;
+  float rm = running_mean ? running_mean[ch] : 0.f, rv = running_var ? running_var[ch] : 0.f;
+  for (int v = 0; v < views; ++v) {
+    double* p = acc + ((long long)v * c + ch) * 2;
+    const double m = p[0] / count;
+    double var = p[1] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    p[0] = 0.0; p[1] = 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    mean[v * c + ch] = (float)m;
+    invstd[v * c + ch] = is;
+    const float av = gamma[ch] * is;
+    a[v * c + ch] = av;
+    b[v * c + ch] = beta[ch] - (float)m * av;
+    const float unbiased = (float)(var * (count / (count - 1.0)));
+    rm = (1.f - momentum) * rm + momentum * (float)m;
+    rv = (1.f - momentum) * rv + momentum * unbiased;
+  }
+  if (running_mean) running_mean[ch] = rm;
+  if (running_var) running_var[ch] = rv;
+}
+
+// y = relu?(a[v,c] * z + b[v,c] + residual)
+template <typename T>
+__global__ void bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ a,
+                                const float* __restrict__ b, const T* __restrict__ residual,
+                                T* __restrict__ y, int pix, int c, int views, int relu,
+                                long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = c / 8;
+  const int g = (int)(idx % cg);
+  const long long row = idx / cg;
+  const int v = (int)((row / pix) % views);
+  float f[8], o[8];
+  V8<T>::load(z + row * c + g * 8, f);
+  const float* ap = a + v * c + g * 8;
+  const float* bp = b + v * c + g * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = fmaf(f[i], __ldg(ap + i), __ldg(bp + i));
+  if (residual != nullptr) {
+    float r[8];
+    V8<T>::load(residual + row * c + g * 8, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] += r[i];
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+  }
+  V8<T>::store(y + row * c + g * 8, o);
+}
+
+// finalize of the backward reduction: dgamma/dbeta (+=), per-(v,c) coefficients for the apply pass
+//   dz = k0 * dyr + k1 * z + k2  with  k0 = gamma*invstd, k1 = -k0*invstd*s2/cnt,
+//   k2 = -k0*s1/cnt - k1*mean   (from dz = gamma*invstd*(dyr - s1/cnt - xhat*s2/cnt))
+__global__ void bn_bwd_finalize_kernel(double* __restrict__ acc, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean,
+                                       const float* __restrict__ invstd,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ k0, float* __restrict__ k1,
+                                       float* __restrict__ k2, int c, int views, double count) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double dg = 0.0, db = 0.0;
+  for (int v = 0; v < views; ++v) {
+    double* p = acc + ((long long)v * c + ch) * 2;
+    const double s1 = p[0], s2 = p[1];
+    p[0] = 0.0; p[1] = 0.0;
+    dg += s2; db += s1;
+    const double is = invstd[v * c + ch], m = mean[v * c + ch];
+    const double c0 = (double)gamma[ch] * is;
+    const double c1 = -c0 * is * s2 / count;
+    k0[v * c + ch] = (float)c0;
+    k1[v * c + ch] = (float)c1;
+    k2[v * c + ch] = (float)(-c0 * s1 / count - c1 * m);
+  }
+  dgamma[ch] = (float)dg;
+  dbeta[ch] = (float)db;
+}
+
+// dz = k0*dyr + k1*z + k2, dyr = dy * (y_mask > 0); optionally also writes dyr (skip-path grad)
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ dy,
+                                    const T* __restrict__ y_mask, const float* __restrict__ k0,
+                                    const float* __restrict__ k1, const float* __restrict__ k2,
+                                    T* __restrict__ dz, T* __restrict__ dyr_out, int pix, int c,
+                                    int views, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = c / 8;
+  const int g = (int)(idx % cg);
+  const long long row = idx / cg;
+  const int v = (int)((row / pix) % views);
+  const long long off = row * c + g * 8;
+  float f[8], d[8], o[8];
+  V8<T>::load(z + off, f);
+  V8<T>::load(dy + off, d);
+  if (y_mask != nullptr) {
+    float m[8];
+    V8<T>::load(y_mask + off, m);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+  }
+  const int pc = v * c + g * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    o[i] = fmaf(__ldg(k0 + pc + i), d[i], fmaf(__ldg(k1 + pc + i), f[i], __ldg(k2 + pc + i)));
+  V8<T>::store(dz + off, o);
+  if (dyr_out != nullptr) V8<T>::store(dyr_out + off, d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Elementwise helpers
+// ---------------------------------------------------------------------------------------------
+// dst = (mask > 0 ? src : 0) [+ add]; 2-D with row strides (columns contiguous, multiple of 8)
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ src, long long ld_src,
+                                const T* __restrict__ mask, long long ld_mask,
+                                const T* __restrict__ add, long long ld_add, T* __restrict__ dst,
+                                long long ld_dst, int cols, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = cols / 8;
+  const int g = (int)(idx % cg);
+  const long long row = idx / cg;
+  float s[8];
+  V8<T>::load(src + row * ld_src + g * 8, s);
+  if (mask != nullptr) {
+    float m[8];
+    V8<T>::load(mask + row * ld_mask + g * 8, m);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = m[i] > 0.f ? s[i] : 0.f;
+  }
+  if (add != nullptr) {
+    float a[8];
+    V8<T>::load(add + row * ld_add + g * 8, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += a[i];
+  }
+  V8<T>::store(dst + row * ld_dst + g * 8, s);
+}
+
+// out[col] (+)= sum_rows x[row, col]  (fp32 output; bias gradients)
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out) {
+  __shared__ float s[8][32 + 1];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_r = threadIdx.x >> 5;  // 8 row lanes
+  const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  float acc = 0.f;
+  if (col < cols)
+    for (int r = r0 + lane_r; r < r1; r += 8) {
+      if constexpr (sizeof(T) == 2) acc += __bfloat162float(x[(long long)r * ld + col]);
+      else acc += x[(long long)r * ld + col];
+    }
+  s[lane_r][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (lane_r == 0 && col < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x & 31];
+    atomicAdd(out + col, t);
+  }
+}
+
+// Generic 4-D permute + cast (+ flips on output dims 1,2): weight layout transforms
+//   dst[i0,i1,i2,i3] (contiguous) = src[i0*s0 + f(i1)*s1 + f(i2)*s2 + i3*s3]
+template <typename TD>
+__global__ void permute_cast_kernel(const float* __restrict__ src, TD* __restrict__ dst, int d0,
+                                    int d1, int d2, int d3, long long s0, long long s1,
+                                    long long s2, long long s3, int flip1, int flip2,
+                                    long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int i3 = (int)(idx % d3);
+  long long t = idx / d3;
+  int i2 = (int)(t % d2); t /= d2;
+  int i1 = (int)(t % d1);
+  const int i0 = (int)(t / d1);
+  if (flip1) i1 = d1 - 1 - i1;
+  if (flip2) i2 = d2 - 1 - i2;
+  const float v = __ldg(src + i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3);
+  if constexpr (sizeof(TD) == 2) dst[idx] = __float2bfloat16_rn(v);
+  else dst[idx] = v;
+}
+
+// dst[n, 2h, 2w, :] = src[n, h, w, :], zeros elsewhere (dst is [n, 2H, 2W, c]) -- stride-2 dgrad
+template <typename T>
+__global__ void dilate2_kernel(const T* __restrict__ src, T* __restrict__ dst, int h, int w, int c,
+                               long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over dst / 8
+  if (idx >= total) return;
+  const int cg = c / 8;
+  const int g = (int)(idx % cg);
+  long long t = idx / cg;
+  const int ow = (int)(t % (2 * w)); t /= (2 * w);
+  const int oh = (int)(t % (2 * h));
+  const long long n = t / (2 * h);
+  float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (((ow | oh) & 1) == 0) V8<T>::load(src + ((n * h + oh / 2) * w + ow / 2) * c + g * 8, f);
+  V8<T>::store(dst + idx * 8, f);
+}
+
+// MaxPool 3x3 s2 p1 backward (NHWC): gather form -- each input pixel sums the gradients of the
+// (<= 4) windows whose maximum it is (first maximum in scan order wins, as in ATen).
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                   T* __restrict__ dx, int in_h, int in_w, int c, int out_h,
+                                   int out_w, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = c / 8;
+  const int g = (int)(idx % cg);
+  long long t = idx / cg;
+  const int iw = (int)(t % in_w); t /= in_w;
+  const int ih = (int)(t % in_h);
+  const long long n = t / in_h;
+  float xv[8], acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  V8<T>::load(x + idx * 8, xv);
+  for (int oh = max(0, (ih - 1 + 1) / 2); oh <= min(out_h - 1, (ih + 1) / 2); ++oh)
+    for (int ow = max(0, (iw - 1 + 1) / 2); ow <= min(out_w - 1, (iw + 1) / 2); ++ow) {
+      // window of (oh, ow): rows 2oh-1..2oh+1, cols 2ow-1..2ow+1; find its first argmax per channel
+      float best[8];
+      int arg[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { best[i] = -3.4e38f; arg[i] = -1; }
+      for (int r = 0; r < 3; ++r) {
+        const int hh = 2 * oh - 1 + r;
+        if (hh < 0 || hh >= in_h) continue;
+        for (int s = 0; s < 3; ++s) {
+          const int ww = 2 * ow - 1 + s;
+          if (ww < 0 || ww >= in_w) continue;
+          float f[8];
+          V8<T>::load(x + ((n * in_h + hh) * in_w + ww) * c + g * 8, f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (f[i] > best[i]) { best[i] = f[i]; arg[i] = hh * in_w + ww; }
+        }
+      }
+      float d[8];
+      V8<T>::load(dy + ((n * out_h + oh) * out_w + ow) * c + g * 8, d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (arg[i] == ih * in_w + iw) acc[i] += d[i];
+    }
+  V8<T>::store(dx + idx * 8, acc);
+}
+
+// dx[n, p, :] = dfeat[n, :] / hw
+template <typename T>
+__global__ void avgpool_bwd_kernel(const T* __restrict__ dfeat, long long ld, T* __restrict__ dx,
+                                   int hw, int c, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = c / 8;
+  const int g = (int)(idx % cg);
+  const long long n = idx / cg / hw;
+  float f[8];
+  V8<T>::load(dfeat + n * ld + g * 8, f);
+  const float inv = 1.f / (float)hw;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] *= inv;
+  V8<T>::store(dx + idx * 8, f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Angular-loss gradient + gaze-head tail backward
+//   dpred[m,:] = loss_scale * d_m * d(angular_deg(pred_m, gt_m))/dpred   (0 where the cosine clamps)
+//   dhidden[m,:] = (hidden > 0) * (dpred[m,0] w2[0,:] + dpred[m,1] w2[1,:])
+//   dw2 += dpred^T hidden,  db2 += colsum(dpred)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void loss_grad_row(float p, float y, float gp, float gy, float w,
+                                              float* dp, float* dyw) {
+  float sp, cp, sy, cy, sgp, cgp, sgy, cgy;
+  sincosf(p, &sp, &cp); sincosf(y, &sy, &cy);
+  sincosf(gp, &sgp, &cgp); sincosf(gy, &sgy, &cgy);
+  const float b[3] = {cp * sy, sp, cp * cy};
+  const float a[3] = {cgp * sgy, sgp, cgp * cgy};
+  const float na = fmaxf(sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), 1e-6f);
+  const float nb = fmaxf(sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]), 1e-6f);
+  const float an[3] = {a[0] / na, a[1] / na, a[2] / na};
+  const float bn[3] = {b[0] / nb, b[1] / nb, b[2] / nb};
+  const float sim = an[0] * bn[0] + an[1] * bn[1] + an[2] * bn[2];
+  if (!(sim > -1.f && sim < 1.f)) { *dp = 0.f; *dyw = 0.f; return; }  // hardtanh saturated
+  const float dth = -kRadToDeg * w * rsqrtf(1.f - sim * sim);  // d(deg)/d(sim) * weight
+  // d sim / d b = (an - sim * bn) / nb
+  const float g[3] = {(an[0] - sim * bn[0]) / nb, (an[1] - sim * bn[1]) / nb,
+                      (an[2] - sim * bn[2]) / nb};
+  *dp = dth * (g[0] * (-sp * sy) + g[1] * cp + g[2] * (-sp * cy));
+  *dyw = dth * (g[0] * (cp * cy) + g[2] * (-cp * sy));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                     const T* __restrict__ hidden, long long ld_h, const float* __restrict__ w2,
+                     int rows, int hid, float loss_scale, int views, float aux_decay,
+                     T* __restrict__ dhidden, long long ld_dh, float* __restrict__ dpred_out,
+                     float* __restrict__ dw2, float* __restrict__ db2) {
+  // one warp per row; block-level partial dw2/db2 reduced through shared memory + atomics
+  extern __shared__ float s_dw[];  // [2][hid] + [2]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 2 * hid + 2; i += blockDim.x) s_dw[i] = 0.f;
+  __syncthreads();
+  const int row = blockIdx.x * 8 + warp;
+  if (row < rows) {
+    float dp, dyw;
+    const float wgt = loss_scale * ((row % views) == 0 ? 1.f : aux_decay);
+    loss_grad_row(__ldg(pred + row * 2), __ldg(pred + row * 2 + 1), __ldg(gt + row * 2),
+                  __ldg(gt + row * 2 + 1), wgt, &dp, &dyw);
+    if (lane == 0) {
+      dpred_out[row * 2] = dp; dpred_out[row * 2 + 1] = dyw;
+      atomicAdd(&s_dw[2 * hid], dp); atomicAdd(&s_dw[2 * hid + 1], dyw);
+    }
+    for (int k = lane * 8; k < hid; k += 256) {
+      float h[8], a[8], b[8], o[8];
+      V8<T>::load(hidden + (long long)row * ld_h + k, h);
+      V8<float>::load(w2 + k, a);
+      V8<float>::load(w2 + hid + k, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[i] = h[i] > 0.f ? fmaf(dp, a[i], dyw * b[i]) : 0.f;
+        atomicAdd(&s_dw[k + i], dp * h[i]);
+        atomicAdd(&s_dw[hid + k + i], dyw * h[i]);
+      }
+      V8<T>::store(dhidden + (long long)row * ld_dh + k, o);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * hid; i += blockDim.x) atomicAdd(dw2 + i, s_dw[i]);
+  if (threadIdx.x < 2) atomicAdd(db2 + threadIdx.x, s_dw[2 * hid + threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// FFMA weight gradient: dW[k, c, r, s] (fp32, PyTorch OIHW layout, +=) =
+//     sum_p dY[p, k] * X[p shifted by (r,s), c]           (split over pixels, fp32 atomics)
+// ---------------------------------------------------------------------------------------------
+struct WgradArgs {
+  const void* x; const void* dy; float* dw;
+  long long x_sn, x_sh, x_sw, x_sc;
+  long long dy_sn, dy_sh, dy_sw;
+  int n_img, in_h, in_w, c_in, c_out, kh, kw, stride, pad, out_h, out_w;
+  long long p_total;
+  int k_cols;  // kh*kw*c_in
+  int p_per_split;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) simt_wgrad_kernel(const WgradArgs a) {
+  constexpr int TM = 64, TN = 64, TP = 16;
+  __shared__ float As[TP][TM + 4];  // dY tile  [pixel][k_out]
+  __shared__ float Bs[TP][TN + 4];  // X tile   [pixel][(r,s,c) column]
+  const T* __restrict__ x = reinterpret_cast<const T*>(a.x);
+  const T* __restrict__ dy = reinterpret_cast<const T*>(a.dy);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * TM;   // k_out tile
+  const int n0 = blockIdx.x * TN;   // (r,s,c) column tile
+  const long long p_begin = (long long)blockIdx.z * a.p_per_split;
+  const long long p_end = min(a.p_total, p_begin + a.p_per_split);
+  // loader assignment: thread -> (pixel lane 0..15, 4 consecutive columns)
+  const int l_p = tid >> 4, l_c0 = (tid & 15) * 4;
+  // decode this thread's 4 B columns once
+  int b_r[4], b_s[4], b_c[4];
+  bool b_ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int col = n0 + l_c0 + i;
+    b_ok[i] = col < a.k_cols;
+    const int tap = b_ok[i] ? col / a.c_in : 0;
+    b_c[i] = b_ok[i] ? col - tap * a.c_in : 0;
+    b_r[i] = tap / a.kw;
+    b_s[i] = tap - b_r[i] * a.kw;
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long p0 = p_begin; p0 < p_end; p0 += TP) {
+    const long long p = p0 + l_p;
+    const bool p_ok = p < p_end;
+    int ow = 0, oh = 0, n = 0;
+    if (p_ok) {
+      ow = (int)(p % a.out_w);
+      const long long t = p / a.out_w;
+      oh = (int)(t % a.out_h);
+      n = (int)(t / a.out_h);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float av = 0.f, bv = 0.f;
+      const int k = m0 + l_c0 + i;
+      if (p_ok && k < a.c_out) {
+        const T* q = dy + n * a.dy_sn + oh * a.dy_sh + ow * a.dy_sw + k;
+        if constexpr (sizeof(T) == 2) av = __bfloat162float(*q); else av = *q;
+      }
+      if (p_ok && b_ok[i]) {
+        const int ih = oh * a.stride - a.pad + b_r[i], iw = ow * a.stride - a.pad + b_s[i];
+        if (ih >= 0 && ih < a.in_h && iw >= 0 && iw < a.in_w) {
+          const T* q = x + n * a.x_sn + ih * a.x_sh + iw * a.x_sw + b_c[i] * a.x_sc;
+          if constexpr (sizeof(T) == 2) bv = __bfloat162float(*q); else bv = *q;
+        }
+      }
+      As[l_p][l_c0 + i] = av;
+      Bs[l_p][l_c0 + i] = bv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < TP; ++q) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[q][tx * 4]);
+      const float am[4] = {av.x, av.y, av.z, av.w};
+      const float bn[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(am[i], bn[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = m0 + ty * 4 + i;
+    if (k >= a.c_out) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= a.k_cols) continue;
+      const int tap = col / a.c_in, c = col - tap * a.c_in;
+      const int r = tap / a.kw, s = tap - r * a.kw;
+      atomicAdd(a.dw + (((long long)k * a.c_in + c) * a.kh + r) * a.kw + s, acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused Adam over one flat fp32 buffer. hyper = double{lr, beta1, beta2, eps, weight_decay, step} lives in
+// DEVICE memory (graph-capturable; the step counter is advanced by adam_tick_kernel).
+//   decoupled == 0: torch.optim.Adam(weight_decay): g += wd * p   (trainer.py:54)
+//   decoupled == 1: AdamW: p *= 1 - lr * wd
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_tick_kernel(double* hyper) { hyper[5] += 1.0; }
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                            float* __restrict__ m, float* __restrict__ v,
+                            const double* __restrict__ hyper, int decoupled, float grad_scale,
+                            long long n) {
+  // scalar prefactors in fp64, exactly as torch.optim.Adam computes them on the host
+  const double lr_d = hyper[0], b1_d = hyper[1], b2_d = hyper[2], step_d = hyper[5];
+  const float lr = (float)lr_d, b1 = (float)b1_d, b2 = (float)b2_d;
+  const float eps = (float)hyper[3], wd = (float)hyper[4];
+  const float bc2_sqrt = (float)sqrt(1.0 - pow(b2_d, step_d));
+  const float step_size = (float)(lr_d / (1.0 - pow(b1_d, step_d)));
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
+       i += (long long)gridDim.x * blockDim.x * 4) {
+    if (i + 3 < n) {
+      float4 pp = *reinterpret_cast<float4*>(p + i);
+      const float4 gg = *reinterpret_cast<const float4*>(g + i);
+      float4 mm = *reinterpret_cast<float4*>(m + i);
+      float4 vv = *reinterpret_cast<float4*>(v + i);
+      float* P = &pp.x; const float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float gr = G[j] * grad_scale;
+        if (decoupled) P[j] *= 1.f - lr * wd; else gr = fmaf(wd, P[j], gr);
+        M[j] = fmaf(b1, M[j], (1.f - b1) * gr);       // m.lerp_(g, 1-b1) up to rounding
+        V[j] = fmaf(b2, V[j], (1.f - b2) * gr * gr);
+        const float denom = sqrtf(V[j]) / bc2_sqrt + eps;
+        P[j] -= step_size * (M[j] / denom);
+      }
+      *reinterpret_cast<float4*>(p + i) = pp;
+      *reinterpret_cast<float4*>(m + i) = mm;
+      *reinterpret_cast<float4*>(v + i) = vv;
+    } else {
+      for (long long k = i; k < n; ++k) {
+        float gr = g[k] * grad_scale;
+        float pk = p[k];
+        if (decoupled) pk *= 1.f - lr * wd; else gr = fmaf(wd, pk, gr);
+        const float mk = fmaf(b1, m[k], (1.f - b1) * gr);
+        const float vk = fmaf(b2, v[k], (1.f - b2) * gr * gr);
+        m[k] = mk; v[k] = vk;
+        p[k] = pk - step_size * (mk / (sqrtf(vk) / bc2_sqrt + eps));
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace rmv
+
+using namespace rmv;
+
+#define DISPATCH_T(dtype, ...)                                   \
+  if ((dtype) == RMV_DTYPE_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+  else { using T = float; __VA_ARGS__; }
+
+static int bn_reduce_cfg(int pix, int c, int n_img, dim3* grid, int* smem) {
+  const int cg = c / 8;
+  RMV_CHECK_ARG(c % 8 == 0 && cg <= 256 && 256 % cg == 0,
+                "batchnorm: channels=%d must be 8*2^k with c <= 2048", c);
+  const int lanes = 256 / cg;
+  int slabs = (pix + lanes * 8 - 1) / (lanes * 8);  // ~8 rows per thread
+  if (slabs < 1) slabs = 1;
+  long want = 8L * num_sms() / (n_img > 0 ? n_img : 1);
+  if (want < 1) want = 1;
+  if (slabs > want) slabs = (int)want;
+  *grid = dim3((unsigned)slabs, (unsigned)n_img);
+  *smem = lanes * c * 2 * (int)sizeof(float);
+  return 0;
+}
+
+extern "C" int rmv_bn_stats(const void* z, int dtype, int n_img, int pix, int c, int views,
+                            double* acc, void* stream) {
+  RMV_CHECK_ARG(views >= 1 && n_img % views == 0, "bn_stats: n_img=%d not a multiple of views=%d", n_img, views);
+  if (n_img == 0) return 0;
+  dim3 grid; int smem;
+  if (int rc = bn_reduce_cfg(pix, c, n_img, &grid, &smem)) return rc;
+  DISPATCH_T(dtype, (bn_reduce_kernel<T, false><<<grid, 256, smem, (cudaStream_t)stream>>>(
+      (const T*)z, nullptr, nullptr, nullptr, nullptr, pix, c, views, acc)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_bn_finalize(double* acc, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, long long* num_batches,
+                               float* mean, float* invstd, float* a, float* b, int c, int views,
+                               long long count_per_view, float eps, float momentum, void* stream) {
+  RMV_CHECK_ARG(count_per_view > 1, "bn_finalize: need more than one value per channel");
+  bn_finalize_kernel<<<nblk(c, 128), 128, 0, (cudaStream_t)stream>>>(
+      acc, gamma, beta, running_mean, running_var, num_batches, mean, invstd, a, b, c, views,
+      (double)count_per_view, eps, momentum);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_bn_apply(const void* z, const float* a, const float* b, const void* residual,
+                            void* y, int dtype, int n_img, int pix, int c, int views, int relu,
+                            void* stream) {
+  RMV_CHECK_ARG(c % 8 == 0, "bn_apply: c must be a multiple of 8");
+  const long long total = (long long)n_img * pix * (c / 8);
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, (bn_apply_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)z, a, b, (const T*)residual, (T*)y, pix, c, views, relu, total)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_bn_bwd_reduce(const void* z, const void* dy, const void* y_mask,
+                                 const float* mean, const float* invstd, int dtype, int n_img,
+                                 int pix, int c, int views, double* acc, void* stream) {
+  RMV_CHECK_ARG(views >= 1 && n_img % views == 0, "bn_bwd_reduce: n_img not a multiple of views");
+  if (n_img == 0) return 0;
+  dim3 grid; int smem;
+  if (int rc = bn_reduce_cfg(pix, c, n_img, &grid, &smem)) return rc;
+  DISPATCH_T(dtype, (bn_reduce_kernel<T, true><<<grid, 256, smem, (cudaStream_t)stream>>>(
+      (const T*)z, (const T*)dy, (const T*)y_mask, mean, invstd, pix, c, views, acc)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_bn_bwd_finalize(double* acc, const float* gamma, const float* mean,
+                                   const float* invstd, float* dgamma, float* dbeta, float* k0,
+                                   float* k1, float* k2, int c, int views, long long count_per_view,
+                                   void* stream) {
+  bn_bwd_finalize_kernel<<<nblk(c, 128), 128, 0, (cudaStream_t)stream>>>(
+      acc, gamma, mean, invstd, dgamma, dbeta, k0, k1, k2, c, views, (double)count_per_view);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_bn_bwd_apply(const void* z, const void* dy, const void* y_mask, const float* k0,
+                                const float* k1, const float* k2, void* dz, void* dyr_out,
+                                int dtype, int n_img, int pix, int c, int views, void* stream) {
+  const long long total = (long long)n_img * pix * (c / 8);
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)z, (const T*)dy, (const T*)y_mask, k0, k1, k2, (T*)dz, (T*)dyr_out, pix, c, views,
+      total)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_relu_bwd(const void* src, long long ld_src, const void* mask, long long ld_mask,
+                            const void* add, long long ld_add, void* dst, long long ld_dst,
+                            int rows, int cols, int dtype, void* stream) {
+  RMV_CHECK_ARG(cols % 8 == 0 && ld_src % 8 == 0 && ld_dst % 8 == 0 && ld_mask % 8 == 0 && ld_add % 8 == 0,
+                "relu_bwd: cols/ld must be multiples of 8");
+  const long long total = (long long)rows * (cols / 8);
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, (relu_bwd_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)src, ld_src, (const T*)mask, ld_mask, (const T*)add, ld_add, (T*)dst, ld_dst, cols,
+      total)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_colsum(const void* x, long long ld, int rows, int cols, int dtype, float* out,
+                          void* stream) {
+  if (rows == 0 || cols == 0) return 0;
+  int ysplit = (rows + 255) / 256;
+  if (ysplit > 64) ysplit = 64;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)ysplit);
+  DISPATCH_T(dtype, (colsum_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, rows, cols, out)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_permute_cast(const float* src, void* dst, int d0, int d1, int d2, int d3,
+                                long long s0, long long s1, long long s2, long long s3, int flip1,
+                                int flip2, int dst_dtype, void* stream) {
+  const long long total = (long long)d0 * d1 * d2 * d3;
+  if (total == 0) return 0;
+  if (dst_dtype == RMV_DTYPE_BF16)
+    permute_cast_kernel<__nv_bfloat16><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        src, (__nv_bfloat16*)dst, d0, d1, d2, d3, s0, s1, s2, s3, flip1, flip2, total);
+  else
+    permute_cast_kernel<float><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        src, (float*)dst, d0, d1, d2, d3, s0, s1, s2, s3, flip1, flip2, total);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_dilate2(const void* src, void* dst, int n_img, int h, int w, int c, int dtype,
+                           void* stream) {
+  RMV_CHECK_ARG(c % 8 == 0, "dilate2: c must be a multiple of 8");
+  const long long total = (long long)n_img * 2 * h * 2 * w * (c / 8);
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, (dilate2_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)src, (T*)dst, h, w, c, total)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int n_img, int in_h,
+                                    int in_w, int c, int dtype, void* stream) {
+  RMV_CHECK_ARG(c % 8 == 0, "maxpool_bwd: c must be a multiple of 8");
+  const int out_h = (in_h - 1) / 2 + 1, out_w = (in_w - 1) / 2 + 1;
+  const long long total = (long long)n_img * in_h * in_w * (c / 8);
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, (maxpool_bwd_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)x, (const T*)dy, (T*)dx, in_h, in_w, c, out_h, out_w, total)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_avgpool_bwd(const void* dfeat, long long ld, void* dx, int n_img, int hw, int c,
+                               int dtype, void* stream) {
+  RMV_CHECK_ARG(c % 8 == 0 && ld % 8 == 0, "avgpool_bwd: c/ld must be multiples of 8");
+  const long long total = (long long)n_img * hw * (c / 8);
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, (avgpool_bwd_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)dfeat, ld, (T*)dx, hw, c, total)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_head_loss_bwd(const float* pred, const float* gt, const void* hidden,
+                                 long long ld_hidden, int hid_dtype, const float* w2, int rows,
+                                 int hid, float loss_scale, int views, float aux_decay,
+                                 void* dhidden, long long ld_dhidden, float* dpred, float* dw2,
+                                 float* db2, void* stream) {
+  RMV_CHECK_ARG(hid % 8 == 0 && ld_hidden % 8 == 0 && ld_dhidden % 8 == 0,
+                "head_loss_bwd: hid/ld must be multiples of 8");
+  if (rows == 0) return 0;
+  const int smem = (2 * hid + 2) * (int)sizeof(float);
+  DISPATCH_T(hid_dtype, (head_loss_bwd_kernel<T><<<(rows + 7) / 8, 256, smem, (cudaStream_t)stream>>>(
+      pred, gt, (const T*)hidden, ld_hidden, w2, rows, hid, loss_scale, views, aux_decay,
+      (T*)dhidden, ld_dhidden, dpred, dw2, db2)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_conv2d_wgrad(const rmv_conv_args* args, const void* dy, float* dw, void* stream) {
+  RMV_CHECK_ARG(args && dy && dw, "conv2d_wgrad: null pointer");
+  const rmv_conv_args& p = *args;
+  WgradArgs a;
+  a.x = p.x; a.dy = dy; a.dw = dw;
+  a.x_sn = p.x_sn; a.x_sh = p.x_sh; a.x_sw = p.x_sw; a.x_sc = p.x_sc ? p.x_sc : 1;
+  a.dy_sn = p.y_sn; a.dy_sh = p.y_sh; a.dy_sw = p.y_sw;
+  a.n_img = p.n_img; a.in_h = p.in_h; a.in_w = p.in_w; a.c_in = p.c_in; a.c_out = p.c_out;
+  a.kh = p.kh; a.kw = p.kw; a.stride = p.stride; a.pad = p.pad; a.out_h = p.out_h; a.out_w = p.out_w;
+  a.p_total = (long long)p.n_img * p.out_h * p.out_w;
+  a.k_cols = p.kh * p.kw * p.c_in;
+  if (a.p_total == 0) return 0;
+  const int gx = ceil_div(a.k_cols, 64), gy = ceil_div(p.c_out, 64);
+  long splits = (6L * num_sms() + (long)gx * gy - 1) / ((long)gx * gy);
+  const long max_splits = (a.p_total + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  a.p_per_split = (int)(((a.p_total + splits - 1) / splits + 15) / 16 * 16);
+  const int gz = ceil_div(a.p_total, a.p_per_split);
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz);
+  DISPATCH_T(p.x_dtype, (simt_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(a)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                             double* hyper, long long n, int decoupled, float grad_scale,
+                             void* stream) {
+  RMV_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && hyper, "adam_step: null pointer");
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  adam_tick_kernel<<<1, 1, 0, s>>>(hyper);
+  long blocks = (n / 4 + 255) / 256;
+  if (blocks > 16L * num_sms()) blocks = 16L * num_sms();
+  adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, hyper, decoupled,
+                                               grad_scale, n);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}

@@ -4,5 +4,7 @@ Host side mirrors the reference operator surface (models/rot_mv.py::FeatRotation
 in librotmv_sm100.so (hand-written CUDA: tcgen05/TMEM/TMA implicit GEMM + HBM-bound fusion kernels).
 """
 from . import _lib  # noqa: F401
+from . import functional  # noqa: F401
+from .module import FeatRotationSymm  # noqa: F401
 
-__all__ = ["_lib"]
+__all__ = ["FeatRotationSymm", "functional", "_lib"]

@@ -54,7 +54,7 @@ SIGNATURES = {
     "rmv_conv2d_fwd": (_i, [C.POINTER(ConvArgs), _vp]),
     "rmv_stem_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rmv_stem_pack_weights": (_i, [_vp, _vp, _vp]),
-    "rmv_stem_conv_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "rmv_stem_conv_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rmv_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rmv_maxpool3x3s2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rmv_avgpool_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp]),
@@ -63,6 +63,23 @@ SIGNATURES = {
     "rmv_angular_error_accum": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp]),
     "rmv_pose_to_rotations": (_i, [_vp, _vp, _i, _i, _vp]),
     "rmv_relative_rotations": (_i, [_vp, _vp, _i, _i, _vp]),
+    # training step
+    "rmv_bn_stats": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rmv_bn_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _f, _f, _vp]),
+    "rmv_bn_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "rmv_bn_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rmv_bn_bwd_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp]),
+    "rmv_bn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rmv_relu_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
+    "rmv_colsum": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp]),
+    "rmv_permute_cast": (_i, [_vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _vp]),
+    "rmv_dilate2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rmv_maxpool3x3s2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rmv_avgpool_bwd": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _vp]),
+    "rmv_head_loss_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _vp, _i, _i, _f, _i, _f, _vp, _ll, _vp, _vp,
+                               _vp, _vp]),
+    "rmv_conv2d_wgrad": (_i, [C.POINTER(ConvArgs), _vp, _vp, _vp]),
+    "rmv_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
 }
 
 

@@ -155,7 +155,7 @@ def stem_pack_weights(w_oihw):
     return packed
 
 
-def stem_conv(x_nchw, w_packed, scale, shift, out=None):
+def stem_conv(x_nchw, w_packed, scale, shift, out=None, relu=True):
     """Fused conv7x7/s2 + BN(eval) + ReLU, fp32 NCHW in -> bf16 NHWC out (tcgen05)."""
     _need_cuda(x_nchw, w_packed, scale, shift, out)
     assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and x_nchw.shape[1] == 3
@@ -168,7 +168,8 @@ def stem_conv(x_nchw, w_packed, scale, shift, out=None):
             "flops": 2.0 * n * oh * ow * 64 * 147,
             "bytes": float(x_nchw.numel() * 4 + out.numel() * 2)}
     _call("rmv_stem_conv_fwd", meta, L.load().rmv_stem_conv_fwd, x_nchw.data_ptr(),
-          w_packed.data_ptr(), L.ptr(scale), L.ptr(shift), out.data_ptr(), n, h, w, L.stream_ptr())
+          w_packed.data_ptr(), L.ptr(scale), L.ptr(shift), out.data_ptr(), n, h, w, int(relu),
+          L.stream_ptr())
     return out
 
 
@@ -204,7 +205,7 @@ def avgpool(x, out0, out1=None):
                                      0 if out1 is None else out1.stride(0), L.stream_ptr())
 
 
-def rotate_gather(feat, rot, dst, batch, views, nvec=512, apply_rot=True):
+def rotate_gather(feat, rot, dst, batch, views, nvec=512, apply_rot=True, transpose=False):
     """dst[b*V+v, r*nvec+k] = 1/(V-1) sum_{u!=v} sum_c rot[b,v,u,r,c] feat[b*V+u, c*nvec+k].
     feat/dst: [B*V, 3*nvec] row-strided views. Reference models/rot_mv.py:234,238."""
     _need_cuda(feat, rot, dst)
@@ -213,7 +214,7 @@ def rotate_gather(feat, rot, dst, batch, views, nvec=512, apply_rot=True):
     assert tuple(rot.shape) == (batch, views, views, 3, 3)
     _call("rmv_rotate_gather_fwd", {"desc": "rmv_rotate_gather_fwd"}, L.load().rmv_rotate_gather_fwd, feat.data_ptr(), feat.stride(0), rot.data_ptr(),
                                            dst.data_ptr(), dst.stride(0), batch, views, nvec,
-                                           L.dtype_code(feat.dtype), int(apply_rot),
+                                           L.dtype_code(feat.dtype), (3 if transpose else 1) if apply_rot else 0,
                                            L.stream_ptr())
 
 

@@ -1,0 +1,397 @@
+"""Training step of the Rot-MV path on the GPU: forward with batch-statistic BatchNorm (per-view
+statistics), fused angular loss, hand-written backward, fused Adam, optional data-parallel gradient
+all-reduce. Mirrors the step body of the reference trainer (trainer.py:119-123,141-143) with the
+optimizer of trainer.py:54 (`optim.Adam(lr, weight_decay=1e-6)` = COUPLED L2; `decoupled=True`
+gives AdamW as BASELINE config 4 words it).
+
+No autograd: the backward pass is an explicit sequence of librotmv_sm100 launches (dgrad through
+the same tcgen05/FFMA convolution kernels with flipped/transposed filters, FFMA weight gradients,
+BatchNorm backward reductions, ...). Parameters are re-pointed at one flat fp32 buffer (as are the
+gradients and the Adam moments) so the optimizer is one kernel and the DP all-reduce one NCCL call.
+
+precision "fp32": FFMA engine end to end (step parity with torch.optim.Adam on the CPU oracle).
+precision "bf16": bf16 activations/filters, tcgen05 forward + data gradients, fp32 master weights.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import functional as RF
+
+_DT = {"bf16": torch.bfloat16, "fp32": torch.float32}
+
+
+def _ck(name, *args):
+    RF._call(name, {"desc": name}, getattr(L.load(), name), *args, L.stream_ptr())
+
+
+class _BN:
+    """Per-layer BatchNorm state: parameter views + saved statistics of the last forward."""
+
+    def __init__(self, eng, bn, gamma_g, beta_g):
+        c = bn.num_features
+        self.c, self.eps, self.momentum = c, float(bn.eps), float(bn.momentum)
+        self.gamma, self.beta = bn.weight, bn.bias
+        self.rm, self.rv, self.nbt = bn.running_mean, bn.running_var, bn.num_batches_tracked
+        self.dgamma, self.dbeta = gamma_g, beta_g
+        v, dev = eng.max_views, eng.device
+        f = lambda: torch.empty((v, c), device=dev, dtype=torch.float32)  # noqa: E731
+        self.mean, self.invstd, self.a, self.b, self.k0, self.k1, self.k2 = (f() for _ in range(7))
+
+
+class TrainEngine:
+    def __init__(self, model, precision: str = "bf16", lr: float = 1e-6, betas=(0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 1e-6, decoupled: bool = False,
+                 process_group=None, max_views: int = 8):
+        if precision not in _DT:
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        L.load()
+        self.model, self.precision, self.dt = model, precision, _DT[precision]
+        self.dtc = L.dtype_code(self.dt)
+        trunk = model._feat_extractor[0]
+        if trunk.kind != "bottleneck":
+            raise NotImplementedError("TrainEngine covers backbone_depth=50 (the main.py config)")
+        self.device = trunk.conv1.weight.device
+        if self.device.type != "cuda":
+            raise L.RotmvError("TrainEngine needs the model on a CUDA device; there is no CPU path")
+        self.max_views = max_views
+        self.num_iter, self.fc_dim, self.nvec = model._num_iter, model._fc_dim, model._num_feat_vec
+        self.apply_rot = not model._ignore_rotmat
+        self.decoupled = bool(decoupled)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        # ---- flat parameter / gradient / moment buffers (fc.* never gets a gradient: SURVEY Q4) ----
+        named = [(n, p) for n, p in model.named_parameters() if not n.startswith("_feat_extractor.0.fc.")]
+        offs, total = [], 0
+        for _, p in named:
+            offs.append(total)
+            total += (p.numel() + 63) // 64 * 64
+        self.flat_p = torch.zeros(total, device=self.device, dtype=torch.float32)
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.flat_m = torch.zeros_like(self.flat_p)
+        self.flat_v = torch.zeros_like(self.flat_p)
+        self.grads: Dict[int, torch.Tensor] = {}
+        self.names: List[str] = []
+        for (n, p), o in zip(named, offs):
+            view = self.flat_p[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            self.grads[id(p)] = self.flat_g[o:o + p.numel()].view(p.shape)
+            self.names.append(n)
+        self.n_trained = sum(p.numel() for _, p in named)
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 0.0],
+                                  device=self.device, dtype=torch.float64)
+        # ---- layer table ----
+        g = self.grads
+        self.stem_bn = _BN(self, trunk.bn1, g[id(trunk.bn1.weight)], g[id(trunk.bn1.bias)])
+        self.stem_conv = trunk.conv1
+        self.blocks = []
+        for blk in trunk.blocks():
+            e = {"convs": [blk.conv1, blk.conv2, blk.conv3],
+                 "bns": [_BN(self, b, g[id(b.weight)], g[id(b.bias)]) for b in (blk.bn1, blk.bn2, blk.bn3)]}
+            if blk.downsample is not None:
+                e["ds_conv"] = blk.downsample[0]
+                d = blk.downsample[1]
+                e["ds_bn"] = _BN(self, d, g[id(d.weight)], g[id(d.bias)])
+            self.blocks.append(e)
+        lif = model._lifter._lifter.blocks
+        self.lift = [lif[0][0], lif[1][0]]
+        self.fusers = [[m._fuser.blocks[0][0], m._fuser.blocks[1][0]] for m in model._img_fusers]
+        self.heads = [[m.blocks[0][0], m.blocks[1][0]] for m in model._gaze_estimators]
+        self.acc = torch.zeros((max_views, 2048, 2), device=self.device, dtype=torch.float64)
+        self._bufs: Dict[Any, torch.Tensor] = {}
+        self.loss = torch.zeros((1,), device=self.device, dtype=torch.float32)
+        self.launches_last_step = 0
+
+    # ------------------------------------------------------------------------------------------
+    def set_lr(self, lr: float) -> None:
+        self.hyper[0:1].copy_(torch.tensor([lr], dtype=torch.float64), non_blocking=True)
+
+    def _buf(self, tag, shape, dtype=None):
+        key = (tag, tuple(shape), dtype or self.dt)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, device=self.device, dtype=dtype or self.dt)
+            self._bufs[key] = t
+        return t
+
+    # ---- filter layout transforms (fp32 OIHW master -> engine layouts) ------------------------
+    def _w_fwd(self, conv, tag):
+        k, c, r, s = conv.weight.shape
+        out = self._buf(("wf", tag), (k, r, s, c))
+        _ck("rmv_permute_cast", conv.weight.data_ptr(), out.data_ptr(), k, r, s, c, c * r * s, s, 1,
+            r * s, 0, 0, self.dtc)
+        return out
+
+    def _w_dgrad(self, conv, tag):
+        """Filters of the data-gradient convolution: wt[c][r'][s'][k] = w[k][c][R-1-r'][S-1-s']."""
+        k, c, r, s = conv.weight.shape
+        out = self._buf(("wd", tag), (c, r, s, k))
+        _ck("rmv_permute_cast", conv.weight.data_ptr(), out.data_ptr(), c, r, s, k, r * s, s, 1,
+            c * r * s, 1, 1, self.dtc)
+        return out
+
+    def _lin_fwd(self, lin, tag):
+        n, k = lin.weight.shape
+        out = self._buf(("lf", tag), (n, k))
+        _ck("rmv_permute_cast", lin.weight.data_ptr(), out.data_ptr(), 1, 1, n, k, 0, 0, k, 1, 0, 0, self.dtc)
+        return out
+
+    def _lin_t(self, lin, tag):
+        n, k = lin.weight.shape
+        out = self._buf(("lt", tag), (k, n))
+        _ck("rmv_permute_cast", lin.weight.data_ptr(), out.data_ptr(), 1, 1, k, n, 0, 0, 1, k, 0, 0, self.dtc)
+        return out
+
+    # ---- BatchNorm -----------------------------------------------------------------------------
+    def _bn_fwd(self, bn: _BN, z, residual, relu, tag):
+        n, h, w, c = z.shape
+        v = self.views
+        _ck("rmv_bn_stats", z.data_ptr(), self.dtc, n, h * w, c, v, self.acc.data_ptr())
+        _ck("rmv_bn_finalize", self.acc.data_ptr(), bn.gamma.data_ptr(), bn.beta.data_ptr(),
+            bn.rm.data_ptr(), bn.rv.data_ptr(), bn.nbt.data_ptr(), bn.mean.data_ptr(),
+            bn.invstd.data_ptr(), bn.a.data_ptr(), bn.b.data_ptr(), c, v, (n // v) * h * w, bn.eps,
+            bn.momentum)
+        y = self._buf(tag, z.shape)
+        _ck("rmv_bn_apply", z.data_ptr(), bn.a.data_ptr(), bn.b.data_ptr(), L.ptr(residual),
+            y.data_ptr(), self.dtc, n, h * w, c, v, int(relu))
+        return y
+
+    def _bn_bwd(self, bn: _BN, z, dy, mask, tag, want_dyr=False):
+        n, h, w, c = z.shape
+        v = self.views
+        _ck("rmv_bn_bwd_reduce", z.data_ptr(), dy.data_ptr(), L.ptr(mask), bn.mean.data_ptr(),
+            bn.invstd.data_ptr(), self.dtc, n, h * w, c, v, self.acc.data_ptr())
+        _ck("rmv_bn_bwd_finalize", self.acc.data_ptr(), bn.gamma.data_ptr(), bn.mean.data_ptr(),
+            bn.invstd.data_ptr(), bn.dgamma.data_ptr(), bn.dbeta.data_ptr(), bn.k0.data_ptr(),
+            bn.k1.data_ptr(), bn.k2.data_ptr(), c, v, (n // v) * h * w)
+        dz = self._buf(("dz", tag), z.shape)
+        dyr = self._buf(("dyr", tag), z.shape) if want_dyr else None
+        _ck("rmv_bn_bwd_apply", z.data_ptr(), dy.data_ptr(), L.ptr(mask), bn.k0.data_ptr(),
+            bn.k1.data_ptr(), bn.k2.data_ptr(), dz.data_ptr(), L.ptr(dyr), self.dtc, n, h * w, c, v)
+        return dz, dyr
+
+    # ---- convolution gradients -----------------------------------------------------------------
+    def _wgrad(self, x, dy, conv_or_lin, kh, kw, stride, pad, x_strides=None):
+        """dW (fp32, parameter layout) += sum_p dy[p,k] x[p+(r,s), c]."""
+        a = L.ConvArgs()
+        a.x_dtype = L.dtype_code(x.dtype)
+        a.x = x.data_ptr()
+        if x_strides is None:
+            a.x_sn, a.x_sh, a.x_sw, a.x_sc = x.stride(0), x.stride(1), x.stride(2), 1
+            n, h, w, c = x.shape
+        else:
+            (n, h, w, c), (a.x_sn, a.x_sh, a.x_sw, a.x_sc) = x_strides
+        a.n_img, a.in_h, a.in_w, a.c_in = n, h, w, c
+        a.c_out, a.kh, a.kw, a.stride, a.pad = dy.shape[3], kh, kw, stride, pad
+        a.y_sn, a.y_sh, a.y_sw = dy.stride(0), dy.stride(1), dy.stride(2)
+        a.out_h, a.out_w = dy.shape[1], dy.shape[2]
+        assert L.dtype_code(dy.dtype) == a.x_dtype
+        RF._call("rmv_conv2d_wgrad", {"desc": f"wgrad {kh}x{kw}s{stride} [{n},{h},{w},{c}]->{dy.shape[3]}",
+                                      "engine": "ffma-wgrad",
+                                      "flops": 2.0 * n * dy.shape[1] * dy.shape[2] * dy.shape[3] * kh * kw * c},
+                 L.load().rmv_conv2d_wgrad, C.byref(a), dy.data_ptr(),
+                 self.grads[id(conv_or_lin.weight)].data_ptr(), L.stream_ptr())
+
+    def _dgrad(self, dz, conv, tag, in_shape, residual=None):
+        """dx = conv_transpose(dz, w) (+ residual) via the forward kernel with flipped filters."""
+        wt = self._w_dgrad(conv, tag)
+        r = conv.kernel_size[0]
+        stride, pad = conv.stride[0], conv.padding[0]
+        src = dz
+        if stride == 2:
+            n, oh, ow, k = dz.shape
+            src = self._buf(("dil", tag), (n, 2 * oh, 2 * ow, k))
+            _ck("rmv_dilate2", dz.data_ptr(), src.data_ptr(), n, oh, ow, k, self.dtc)
+        elif stride != 1:
+            raise NotImplementedError("stride > 2")
+        out = self._buf(("dx", tag), in_shape)
+        assert src.shape[1] == in_shape[1] and src.shape[2] == in_shape[2], (src.shape, in_shape)
+        return RF.conv2d(src, wt, stride=1, pad=r - 1 - pad, residual=residual, out=out)
+
+    def _lin(self, x, w, bias, relu, out):
+        return RF.linear(x, w, bias, relu=relu, out=out)
+
+    def _lin_bwd(self, lin, tag, x, dy, dx_out, need_dx=True):
+        """bias grad, weight grad and (optionally) input grad of y = x W^T + b."""
+        m, n = dy.shape
+        _ck("rmv_colsum", dy.data_ptr(), dy.stride(0), m, n, self.dtc, self.grads[id(lin.bias)].data_ptr())
+        x4 = x.as_strided((1, 1, m, x.shape[1]), (0, 0, x.stride(0), 1), x.storage_offset())
+        d4 = dy.as_strided((1, 1, m, n), (0, 0, dy.stride(0), 1), dy.storage_offset())
+        self._wgrad(x4, d4, lin, 1, 1, 1, 0)
+        if need_dx:
+            RF.linear(dy, self._lin_t(lin, tag), None, out=dx_out)
+        return dx_out
+
+    def _add(self, src, dst, mask=None, add=None):
+        """dst = (mask > 0 ? src : 0) + add   (2-D, row-strided)."""
+        rows, cols = src.shape
+        _ck("rmv_relu_bwd", src.data_ptr(), src.stride(0), L.ptr(mask), 0 if mask is None else mask.stride(0),
+            L.ptr(add), 0 if add is None else add.stride(0), dst.data_ptr(), dst.stride(0), rows, cols,
+            self.dtc)
+
+    # ------------------------------------------------------------------------------------------
+    def step(self, images: torch.Tensor, rotations: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+        """One optimisation step; returns the (device) loss tensor of this step's forward pass."""
+        before = L.STATS["launches"]
+        self.forward_backward(images, rotations, gt)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.pg)
+        _ck("rmv_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
+            self.flat_v.data_ptr(), self.hyper.data_ptr(), self.flat_p.numel(), int(self.decoupled),
+            1.0 / self.world)
+        self.launches_last_step = L.STATS["launches"] - before
+        return self.loss
+
+    def forward_backward(self, images, rotations, gt) -> Dict[str, Any]:
+        if not images.is_cuda:
+            raise L.RotmvError("images must be CUDA tensors (there is no CPU path)")
+        b, v = images.shape[0], images.shape[1]
+        if v > self.max_views:
+            raise ValueError(f"views={v} exceeds max_views={self.max_views}")
+        m = b * v
+        self.views = v
+        dt, dtc = self.dt, self.dtc
+        cfg = self.model.loss_cfg
+        imgs = images.reshape(m, *images.shape[2:]).float().contiguous()
+        rot = rotations.float().contiguous()
+        gt_flat = gt.float().reshape(m, 2).contiguous()
+        self.flat_g.zero_()
+        self.loss.zero_()
+        trunk = self.model._feat_extractor[0]
+
+        # ================================ forward ================================
+        # stem (models/resnet.py:262-265)
+        if self.precision == "bf16":
+            wp = RF.stem_pack_weights(self.stem_conv.weight.detach())
+            z0 = RF.stem_conv(imgs, wp, None, None, out=self._buf("z_stem", (m, 112, 112, 64))
+                              if imgs.shape[2] == 224 and imgs.shape[3] == 224 else None, relu=False)
+            x_img = RF.nchw_to_nhwc(imgs, dt)  # bf16 NHWC copy of the images for the stem wgrad
+            stem_x, stem_xs = x_img, None
+        else:
+            w7 = self._w_fwd(self.stem_conv, "stem")
+            z0 = RF.conv2d_nchw_input(imgs, w7, stride=2, pad=3)
+            xv = imgs.permute(0, 2, 3, 1)
+            stem_x, stem_xs = imgs, (tuple(xv.shape), (xv.stride(0), xv.stride(1), xv.stride(2), xv.stride(3)))
+        y0 = self._bn_fwd(self.stem_bn, z0, None, True, "y_stem")
+        x = RF.maxpool3x3s2(y0)
+        pool_out = x
+        saved = []
+        for bi, e in enumerate(self.blocks):
+            c1, c2, c3 = e["convs"]
+            b1, b2, b3 = e["bns"]
+            x_in = x
+            z1 = RF.conv2d(x_in, self._w_fwd(c1, (bi, 1)), out=self._buf(("z1", bi), (*x_in.shape[:3], c1.out_channels)))
+            y1 = self._bn_fwd(b1, z1, None, True, ("y1", bi))
+            s2 = c2.stride[0]
+            oh = (y1.shape[1] + 2 - 3) // s2 + 1
+            z2 = RF.conv2d(y1, self._w_fwd(c2, (bi, 2)), stride=s2, pad=1,
+                           out=self._buf(("z2", bi), (m, oh, oh, c2.out_channels)))
+            y2 = self._bn_fwd(b2, z2, None, True, ("y2", bi))
+            z3 = RF.conv2d(y2, self._w_fwd(c3, (bi, 3)), out=self._buf(("z3", bi), (m, oh, oh, c3.out_channels)))
+            zd = None
+            if "ds_conv" in e:
+                dc = e["ds_conv"]
+                zd = RF.conv2d(x_in, self._w_fwd(dc, (bi, "d")), stride=dc.stride[0],
+                               out=self._buf(("zd", bi), (m, oh, oh, dc.out_channels)))
+                skip = self._bn_fwd(e["ds_bn"], zd, None, False, ("skip", bi))
+            else:
+                skip = x_in
+            x = self._bn_fwd(b3, z3, skip, True, ("out", bi))
+            saved.append((x_in, z1, y1, z2, y2, z3, zd, x))
+        wide = self.fc_dim + 3 * self.nvec
+        fd = self.fc_dim
+        xs = [self._buf(("X", i), (m, wide)) for i in range(self.num_iter)]
+        ys = [self._buf(("Y", i), (m, wide)) for i in range(self.num_iter)]
+        hs = [self._buf(("H", i), (m, wide)) for i in range(self.num_iter)]
+        gs = [self._buf(("G", i), (m, 512)) for i in range(self.num_iter)]
+        preds = [self._buf(("pred", i), (m, 2), torch.float32) for i in range(self.num_iter)]
+        y_init = self._buf("Yinit", (m, wide))
+        RF.avgpool(x, y_init, xs[0])
+        img = y_init[:, :fd]
+        for i in range(self.num_iter):
+            if i > 0:
+                self._add(img, xs[i][:, :fd])
+            self._add(img, ys[i][:, :fd])
+        l1 = self._buf("L1", (m, 3 * self.nvec))
+        self._lin(img, self._lin_fwd(self.lift[0], "l0"), self.lift[0].bias, True, l1)
+        self._lin(l1, self._lin_fwd(self.lift[1], "l1"), self.lift[1].bias, False, y_init[:, fd:])
+        scales = []
+        for i in range(self.num_iter):
+            f_prev = (y_init if i == 0 else ys[i - 1])[:, fd:]
+            RF.rotate_gather(f_prev, rot, xs[i][:, fd:], b, v, self.nvec, self.apply_rot)
+            f1, f2 = self.fusers[i]
+            self._lin(xs[i], self._lin_fwd(f1, ("f1", i)), f1.bias, True, hs[i])
+            self._lin(hs[i], self._lin_fwd(f2, ("f2", i)), f2.bias, False, ys[i][:, fd:])
+            h1, h2 = self.heads[i]
+            self._lin(ys[i], self._lin_fwd(h1, ("h1", i)), h1.bias, True, gs[i])
+            scale = (cfg["iter_decay"] ** (self.num_iter - 1 - i)) * cfg["rel_weight"] / b
+            scales.append(scale)
+            RF.head_loss(gs[i], h2.weight.detach(), h2.bias.detach(), preds[i], gt_flat, scale,
+                         self.loss, views=v, aux_decay=cfg["reference_decay"])
+
+        # ================================ backward ================================
+        dimg = self._buf("dimg", (m, fd))
+        dimg.zero_()
+        d_f_next = None
+        for i in reversed(range(self.num_iter)):
+            h1, h2 = self.heads[i]
+            f1, f2 = self.fusers[i]
+            dg = self._buf("dG", (m, 512))
+            dpred = self._buf("dpred", (m, 2), torch.float32)
+            _ck("rmv_head_loss_bwd", preds[i].data_ptr(), gt_flat.data_ptr(), gs[i].data_ptr(),
+                gs[i].stride(0), dtc, h2.weight.data_ptr(), m, 512, scales[i], v,
+                cfg["reference_decay"], dg.data_ptr(), dg.stride(0), dpred.data_ptr(),
+                self.grads[id(h2.weight)].data_ptr(), self.grads[id(h2.bias)].data_ptr())
+            d_y = self._lin_bwd(h1, ("h1", i), ys[i], dg, self._buf("dY", (m, wide)))
+            self._add(d_y[:, :fd], dimg, add=dimg)
+            d_f = self._buf("dF", (m, 3 * self.nvec))
+            self._add(d_y[:, fd:], d_f, add=d_f_next)
+            d_h = self._lin_bwd(f2, ("f2", i), hs[i], d_f, self._buf("dH", (m, wide)))
+            self._add(d_h, d_h, mask=hs[i])
+            d_x = self._lin_bwd(f1, ("f1", i), xs[i], d_h, self._buf("dX", (m, wide)))
+            self._add(d_x[:, :fd], dimg, add=dimg)
+            d_f_next = self._buf("dFn", (m, 3 * self.nvec))
+            RF.rotate_gather(d_x[:, fd:], rot, d_f_next, b, v, self.nvec, self.apply_rot, transpose=True)
+        d_l1 = self._lin_bwd(self.lift[1], "l1", l1, d_f_next, self._buf("dL1", (m, 3 * self.nvec)))
+        self._add(d_l1, d_l1, mask=l1)
+        d_img2 = self._lin_bwd(self.lift[0], "l0", img, d_l1, self._buf("dimg2", (m, fd)))
+        self._add(d_img2, dimg, add=dimg)
+        # trunk
+        last = saved[-1][7]
+        d_out = self._buf(("dx", "avg"), last.shape)
+        _ck("rmv_avgpool_bwd", dimg.data_ptr(), dimg.stride(0), d_out.data_ptr(), m,
+            last.shape[1] * last.shape[2], last.shape[3], dtc)
+        for bi in reversed(range(len(self.blocks))):
+            e = self.blocks[bi]
+            c1, c2, c3 = e["convs"]
+            b1, b2, b3 = e["bns"]
+            x_in, z1, y1, z2, y2, z3, zd, out = saved[bi]
+            dz3, dyr = self._bn_bwd(b3, z3, d_out, out, (bi, 3), want_dyr=True)
+            self._wgrad(y2, dz3, c3, 1, 1, 1, 0)
+            dy2 = self._dgrad(dz3, c3, (bi, 3), y2.shape)
+            dz2, _ = self._bn_bwd(b2, z2, dy2, y2, (bi, 2))
+            self._wgrad(y1, dz2, c2, 3, 3, c2.stride[0], 1)
+            dy1 = self._dgrad(dz2, c2, (bi, 2), y1.shape)
+            dz1, _ = self._bn_bwd(b1, z1, dy1, y1, (bi, 1))
+            self._wgrad(x_in, dz1, c1, 1, 1, 1, 0)
+            if zd is not None:
+                dc = e["ds_conv"]
+                dzd, _ = self._bn_bwd(e["ds_bn"], zd, dyr, None, (bi, "d"))
+                self._wgrad(x_in, dzd, dc, 1, 1, dc.stride[0], 0)
+                res = self._dgrad(dzd, dc, (bi, "d"), x_in.shape)
+            else:
+                res = dyr
+            d_out = self._dgrad(dz1, c1, (bi, 1), x_in.shape, residual=res)
+        d_y0 = self._buf("dy_stem", y0.shape)
+        _ck("rmv_maxpool3x3s2_bwd", y0.data_ptr(), d_out.data_ptr(), d_y0.data_ptr(), m, y0.shape[1],
+            y0.shape[2], y0.shape[3], dtc)
+        dz0, _ = self._bn_bwd(self.stem_bn, z0, d_y0, y0, "stem")
+        self._wgrad(stem_x, dz0, self.stem_conv, 7, 7, 2, 3, x_strides=stem_xs)
+        return {"loss": self.loss, "preds": preds, "pool_out": pool_out}
