@@ -197,6 +197,11 @@ int rmv_head_loss_bwd(const float* pred, const float* gt, const void* hidden, lo
  * of dy[p,k] * x[p shifted by (r,s), c]; `args` describes the forward convolution (x, strides,
  * shapes; args->y_s* are the strides of dy). */
 int rmv_conv2d_wgrad(const rmv_conv_args* args, const void* dy, float* dw, void* stream);
+/* Same gradient on the tensor cores (bf16 x and dy, c_in % 64 == 0): tcgen05.mma with MN-major
+ * operands straight from the NHWC tensors (TMA boxes, tap shift + zero padding by TMA), split over
+ * the pixel axis with TMA reduce-add. dw_krsc is fp32 [c_out][kh][kw][c_in] (+=, caller zeroes);
+ * rmv_permute_cast brings it to the parameter layout. */
+int rmv_conv2d_wgrad_tc(const rmv_conv_args* args, const void* dy, float* dw_krsc, void* stream);
 /* Fused Adam over a flat fp32 buffer; hyper = double{lr, beta1, beta2, eps, weight_decay, step} in
  * DEVICE memory (step is incremented by the call). decoupled=0: torch.optim.Adam(weight_decay),
  * i.e. coupled L2 as trainer.py:54; decoupled=1: AdamW. grads are multiplied by grad_scale. */

@@ -79,6 +79,7 @@ SIGNATURES = {
     "rmv_head_loss_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _vp, _i, _i, _f, _i, _f, _vp, _ll, _vp, _vp,
                                _vp, _vp]),
     "rmv_conv2d_wgrad": (_i, [C.POINTER(ConvArgs), _vp, _vp, _vp]),
+    "rmv_conv2d_wgrad_tc": (_i, [C.POINTER(ConvArgs), _vp, _vp, _vp]),
     "rmv_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
 }
 

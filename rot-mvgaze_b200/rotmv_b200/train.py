@@ -59,6 +59,7 @@ class TrainEngine:
         if self.device.type != "cuda":
             raise L.RotmvError("TrainEngine needs the model on a CUDA device; there is no CPU path")
         self.max_views = max_views
+        self.use_tc_wgrad = True  # bf16: weight gradients on tcgen05 (False -> FFMA kernel)
         self.num_iter, self.fc_dim, self.nvec = model._num_iter, model._fc_dim, model._num_feat_vec
         self.apply_rot = not model._ignore_rotmat
         self.decoupled = bool(decoupled)
@@ -193,6 +194,24 @@ class TrainEngine:
         a.y_sn, a.y_sh, a.y_sw = dy.stride(0), dy.stride(1), dy.stride(2)
         a.out_h, a.out_w = dy.shape[1], dy.shape[2]
         assert L.dtype_code(dy.dtype) == a.x_dtype
+        grad = self.grads[id(conv_or_lin.weight)]
+        if self.use_tc_wgrad and x.dtype == torch.bfloat16 and c % 64 == 0 and a.x_sc == 1:
+            # tcgen05 weight gradient into an fp32 [k][r][s][c] buffer; 1x1 / Linear: that IS the
+            # parameter layout, so accumulate straight into the (zeroed) flat gradient slice.
+            k = dy.shape[3]
+            meta = {"desc": f"wgrad-tc {kh}x{kw}s{stride} [{n},{h},{w},{c}]->{k}", "engine": "tcgen05-wgrad",
+                    "flops": 2.0 * n * dy.shape[1] * dy.shape[2] * k * kh * kw * c}
+            if kh * kw == 1:
+                RF._call("rmv_conv2d_wgrad_tc", meta, L.load().rmv_conv2d_wgrad_tc, C.byref(a),
+                         dy.data_ptr(), grad.data_ptr(), L.stream_ptr())
+            else:
+                scratch = self._buf(("wg", id(conv_or_lin)), (k, kh, kw, c), torch.float32)
+                scratch.zero_()
+                RF._call("rmv_conv2d_wgrad_tc", meta, L.load().rmv_conv2d_wgrad_tc, C.byref(a),
+                         dy.data_ptr(), scratch.data_ptr(), L.stream_ptr())
+                _ck("rmv_permute_cast", scratch.data_ptr(), grad.data_ptr(), k, c, kh, kw,
+                    kh * kw * c, 1, kw * c, c, 0, 0, L.F32)
+            return
         RF._call("rmv_conv2d_wgrad", {"desc": f"wgrad {kh}x{kw}s{stride} [{n},{h},{w},{c}]->{dy.shape[3]}",
                                       "engine": "ffma-wgrad",
                                       "flops": 2.0 * n * dy.shape[1] * dy.shape[2] * dy.shape[3] * kh * kw * c},

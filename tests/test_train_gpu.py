@@ -309,3 +309,44 @@ def test_head_loss_bwd_matches_autograd():
     assert torch.allclose(dg, g_in.grad * mask, rtol=1e-3, atol=1e-6 + 1e-3 * g_in.grad.abs().max().item())
     assert torch.allclose(dw2, w2.grad, rtol=1e-3, atol=1e-3 * w2.grad.abs().max().item())
     assert torch.allclose(db2, b2.grad, rtol=1e-3, atol=1e-5)
+
+
+WGRAD_TC_CASES = [
+    # n, h, c_in, c_out, k, stride, pad
+    (4, 56, 64, 64, 3, 1, 1), (4, 56, 64, 256, 1, 1, 0), (3, 28, 128, 128, 3, 1, 1),
+    (4, 56, 128, 128, 3, 2, 1), (5, 14, 256, 256, 3, 1, 1), (6, 28, 512, 1024, 1, 2, 0),
+    (7, 7, 512, 512, 3, 1, 1), (9, 7, 2048, 512, 1, 1, 0), (2, 14, 1024, 256, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_TC_CASES)
+def test_wgrad_tcgen05_matches_autograd(case):
+    """rmv_conv2d_wgrad_tc (MN-major tcgen05 + TMA reduce-add split over pixels) vs torch autograd
+    on the same bf16-rounded operands."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from rotmv_b200 import _lib as L
+
+    n, hh, ci, co, k, s, p = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn((n, hh, hh, ci), device="cuda", generator=g).bfloat16()
+    oh = (hh + 2 * p - k) // s + 1
+    dy = torch.randn((n, oh, oh, co), device="cuda", generator=g).bfloat16()
+    wt = torch.zeros((co, ci, k, k), device="cuda", requires_grad=True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, stride=s, padding=p)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    ref = wt.grad.permute(0, 2, 3, 1).contiguous()  # KRSC
+    dw = torch.zeros((co, k, k, ci), device="cuda")
+    a = L.ConvArgs()
+    a.x_dtype = 1; a.x = x.data_ptr()
+    a.x_sn, a.x_sh, a.x_sw, a.x_sc = x.stride(0), x.stride(1), x.stride(2), 1
+    a.n_img, a.in_h, a.in_w, a.c_in = n, hh, hh, ci
+    a.c_out, a.kh, a.kw, a.stride, a.pad = co, k, k, s, p
+    a.y_sn, a.y_sh, a.y_sw = dy.stride(0), dy.stride(1), dy.stride(2)
+    a.out_h, a.out_w = oh, oh
+    L.check(L.load().rmv_conv2d_wgrad_tc(C.byref(a), dy.data_ptr(), dw.data_ptr(), L.stream_ptr()), "wgrad_tc")
+    err = (dw - ref).abs().max().item()
+    assert err <= 2e-4 * ref.abs().max().item() + 1e-4, (case, err, ref.abs().max().item())
+    # accumulation semantics (+=)
+    L.check(L.load().rmv_conv2d_wgrad_tc(C.byref(a), dy.data_ptr(), dw.data_ptr(), L.stream_ptr()), "wgrad_tc")
+    assert (dw - 2 * ref).abs().max().item() <= 4e-4 * ref.abs().max().item() + 2e-4
