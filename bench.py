@@ -88,19 +88,30 @@ def run_reference(args):
 
     torch.set_num_threads(os.cpu_count())
     model = O.build_model(num_iter=3, depth=50, seed=0).eval()
-    images, pose, _ = O.synthetic_batch(sample, args.views, seed=1)
+    images, pose, gt = O.synthetic_batch(sample, args.views, seed=1)
     rot = O.pairwise_rotations(pose)
-    with torch.no_grad():
+    metric = METRIC
+    if args.mode == "train":
+        metric = "multi-view samples/sec (224^2, fwd+bwd+Adam)"
+        opt = O.make_adam(model, lr=1e-6)
         for _ in range(args.warmup):
-            model.forward_views(images, rot)
+            O.train_step(model, opt, images, rot, gt)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            model.forward_views(images, rot)
+            O.train_step(model, opt, images, rot, gt)
         dt = time.perf_counter() - t0
+    else:
+        with torch.no_grad():
+            for _ in range(args.warmup):
+                model.forward_views(images, rot)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                model.forward_views(images, rot)
+            dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     desc = (f"oracle port of the reference PyTorch CPU path; each step = {sample} of the "
-            f"{args.batch} samples of the workload batch ({args.views} views, fp32, eval)")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+            f"{args.batch} samples of the workload batch ({args.views} views, fp32, {args.mode})")
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -287,21 +298,146 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE config 4: Rot-MV 2-view training step (fwd + loss + bwd + Adam), data-parallel,
+    batch 128 per GPU; gradients all-reduced over NCCL when N > 1."""
+    import torch.distributed as dist
+
+    from rotmv_b200 import _lib as L
+    from rotmv_b200 import functional as RF
+    from rotmv_b200.module import FeatRotationSymm
+    from rotmv_b200.train import TrainEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    B, V = args.batch, args.views
+    torch.manual_seed(0)
+    model = FeatRotationSymm(50, 3, precision=args.precision).to(dev).train()
+    eng = TrainEngine(model, precision=args.precision, lr=1e-6, weight_decay=1e-6,
+                      decoupled=args.adamw)
+    g = torch.Generator().manual_seed(1 + rank)
+    images_host = torch.randn((B, V, 3, 224, 224), generator=g).pin_memory()
+    pose_host = (torch.rand((B, V, 2), generator=g) - 0.5).pin_memory()
+    gt_host = (torch.rand((B, V, 2), generator=g) - 0.5).pin_memory()
+    images = images_host.to(dev)
+    rot = RF.pose_to_rotations(pose_host.to(dev))
+    gt = gt_host.to(dev)
+    for _ in range(max(args.warmup, 3)):
+        eng.step(images, rot, gt)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record()
+    for _ in range(args.steps):
+        eng.step(images, rot, gt)
+        launches += eng.launches_last_step
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    value = world * B * args.steps / (ms_total * 1e-3)
+    loss = eng.loss.item()
+    if not (loss == loss):
+        raise SystemExit("bench.py: non-finite loss")
+    # end to end: host batch (images, head poses, labels) in, loss out, every step
+    img_d = torch.empty_like(images)
+    pose_d = torch.empty((B, V, 2), device=dev)
+    gt_d = torch.empty_like(gt)
+    loss_h = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+    def host_step():
+        img_d.copy_(images_host, non_blocking=True)
+        pose_d.copy_(pose_host, non_blocking=True)
+        gt_d.copy_(gt_host, non_blocking=True)
+        loss_dev = eng.step(img_d, RF.pose_to_rotations(pose_d), gt_d)
+        loss_h.copy_(loss_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    train_flops = 3 * V * FLOPS_PER_VIEW - V * 0.236e9   # SURVEY 8d
+    pk = peaks()
+    line = {"metric": "multi-view samples/sec (224^2, fwd+bwd+Adam)", "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "configs[3]: Rot-MV 2-view training step (fwd+bwd+Adam), "
+                                   "data-parallel, batch 128 per GPU" if (B, V) == (128, 2)
+                       else f"Rot-MV {V}-view training step, batch {B} per GPU",
+                       "batch_per_gpu": B, "views": V, "backbone": "resnet50", "num_iter": 3,
+                       "optimizer": "AdamW (decoupled)" if args.adamw else
+                       "Adam + coupled L2 (reference trainer.py:54)",
+                       "parallelism": f"dp{world}, one fp32 gradient all-reduce of "
+                                      f"{eng.flat_g.numel() * 4 / 1e6:.0f} MB per step" if world > 1
+                       else "dp1", "precision": args.precision,
+                       "l2": "inputs %.0f MB/step per GPU exceed the 126 MB L2" % (B * V * 602112 / 1e6)},
+            "clocks": clocks, "loss": loss,
+            "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": images_host.numel() * 4 + pose_host.numel() * 4 + gt_host.numel() * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "whole step (conv fwd/dgrad/wgrad on tcgen05 + HBM-bound BN/elementwise)",
+                         "bound": "tensor", "achieved": B * train_flops / (ms_total / args.steps * 1e-3) / 1e12,
+                         "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": B * train_flops / (ms_total / args.steps * 1e-3) / 1e12 / pk["tflops"],
+                         "traffic": None, "peak_source": pk["src"]}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="multi-view samples per GPU per step")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer = BASELINE configs[1] (headline); train = configs[3] (fwd+bwd+Adam)")
+    ap.add_argument("--batch", type=int, default=None, help="multi-view samples per GPU per step "
+                    "(default 256 for infer, 128 for train)")
     ap.add_argument("--views", type=int, default=2)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--chunk", type=int, default=int(os.environ.get("ROTMV_CHUNK", "64")),
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("ROTMV_CHUNK", "512")),
                     help="images per trunk micro-batch")
+    ap.add_argument("--adamw", action="store_true", help="train: decoupled weight decay")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 256 if args.mode == "infer" else 128
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "train":
+        run_train(args)
     else:
         run_ours(args)
 

@@ -1,0 +1,48 @@
+"""Data parallelism for the Rot-MV path: one process per GPU, the batch of multi-view
+samples is sharded across ranks (all V views of a sample stay on one GPU), weights / BatchNorm
+buffers / optimizer state are replicated. Inference needs no collective; training needs ONE
+gradient all-reduce of the flat fp32 gradient buffer per step (NCCL over NVLink on GPUs; the same
+code runs on `gloo` for the CPU tests). BatchNorm statistics stay per rank, as they would under DDP
+of the reference (it has no SyncBN).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) slice of samples owned by `rank`; sizes differ by at most one."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of size {world}")
+    base, extra = divmod(global_batch, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place average of a flat gradient buffer over the ranks (sum, then scale)."""
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size(group)
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            flat.mul_(1.0 / world)
+    return flat
+
+
+def max_over_ranks(value: float, device=None, group=None) -> float:
+    """Max of a host scalar over the ranks (multi-GPU timings are reported as the slowest rank)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
+
+
+def broadcast_buffers_(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Checkpoint-time helper: make rank `src`'s BatchNorm running statistics the saved ones."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for b in module.buffers():
+            dist.broadcast(b, src=src, group=group)
