@@ -28,7 +28,9 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kMaxTaps = 49;
-constexpr int kNumThreads = 224;  // warp0 TMA(A,B), warp1 MMA, warps2-5 epilogue, warp6 TMA(residual)
+constexpr int kEpiThreads = 256;  // 8 epilogue warps
+constexpr int kResWarp = 10;
+constexpr int kNumThreads = 352;  // warp0 TMA(A,B), warp1 MMA, warps2-9 epilogue, warp10 TMA(residual)
 constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kChunkBytes = kBlockM * 128;  // one staged output / residual chunk: 128 rows x 128 B
 
@@ -53,10 +55,14 @@ template <int BLOCK_N, bool HAS_RES>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? (HAS_RES ? 5 : 6) : 6);
+  // Layers with a residual (the expanding 1x1 convs) are HBM-bound with 1-8 k-blocks per tile: they
+  // trade A/B stages for a deeper residual ring (4 x 16 KiB) so the residual loads run well ahead.
+  static constexpr int kStages = HAS_RES ? (BLOCK_N == 256 ? 2 : (BLOCK_N == 128 ? 3 : 4))
+                                         : (BLOCK_N == 256 ? 3 : 6);
+  static constexpr int kResSlots = 4;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
   static constexpr int kOutBytes = 2 * kChunkBytes;
-  static constexpr int kResBytes = HAS_RES ? 2 * kChunkBytes : 0;
+  static constexpr int kResBytes = HAS_RES ? kResSlots * kChunkBytes : 0;
   static constexpr int kVecBytes = 2 * BLOCK_N * 4;  // scale + shift of the current N tile
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kOutBytes + kResBytes + kVecBytes + 256 /*barriers*/ + 1024 /*align*/;
@@ -82,7 +88,7 @@ __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void epi_bar_sync(int id) {
-  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+  asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory");
 }
 
 // OUT_F32: 32 fp32 columns per staged chunk; otherwise 64 bf16 columns (both 128 B per row).
@@ -93,8 +99,9 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   constexpr int kChunkCols = OUT_F32 ? 32 : 64;
   constexpr int kChunks = BLOCK_N / kChunkCols;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~uintptr_t(1023));
+  // 1024-byte alignment by OFFSET (not by an integer round trip of the pointer) so the compiler
+  // keeps the shared address space and emits LDS/STS instead of generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + C::kStages * kABytes;
   uint8_t* smem_out = smem_b + C::kStages * C::kBBytes;  // [2][128 rows][128 B], SW128
@@ -106,9 +113,9 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   uint64_t* empty_bar = bars + C::kStages;        // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * C::kStages;    // [2]        MMA -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;           // [2]        epilogue -> MMA
-  uint64_t* res_full = tmem_empty + 2;            // [2]        TMA(residual) -> epilogue
-  uint64_t* res_empty = res_full + 2;             // [2]        epilogue -> TMA(residual)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;            // [4]        TMA(residual) -> epilogue
+  uint64_t* res_empty = res_full + C::kResSlots;  // [4]        epilogue -> TMA(residual)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_empty + C::kResSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -123,9 +130,11 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], kEpiThreads);
+    }
+    for (int i = 0; i < C::kResSlots; ++i) {
       mbar_init(&res_full[i], 1);
-      mbar_init(&res_empty[i], 128);
+      mbar_init(&res_empty[i], kEpiThreads);
     }
     fence_mbar_init();
   }
@@ -197,7 +206,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == kResWarp) {
     // ------------------------------- TMA producer (residual) --------------------
     if (HAS_RES && lane == 0) {
       tma_prefetch_desc(&args.tmap_res);
@@ -215,16 +224,20 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
           tma_load_4d(smem_res + slot * kChunkBytes, &args.tmap_res, &res_full[slot],
                       n_tile * BLOCK_N + c * kChunkCols, tw * args.box_w, th * args.box_h,
                       tn * args.box_n);
-          if (++slot == 2) { slot = 0; phase ^= 1; }
+          if (++slot == C::kResSlots) { slot = 0; phase ^= 1; }
         }
       }
     }
   } else {
-    // ------------------------------- epilogue (warps 2..5) ----------------------
+    // ------------------------------- epilogue (warps 2..9) ----------------------
+    // Two warps per TMEM lane quarter (= two per SM sub-partition, so one can issue while the
+    // other waits on TMEM / shared memory); each owns half of the chunk's columns = 64 B per row.
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
-    const int tid_e = threadIdx.x - 64;  // 0..127
+    const int tid_e = threadIdx.x - 64;  // 0..255
     const uint32_t sw = (uint32_t)(row & 7);
+    constexpr int kWarpCols = kChunkCols / 2;  // 32 (bf16 out) or 16 (fp32 out)
     int local = 0;
     int cc = 0;  // running chunk counter: staging buffer = cc & 1
     int rslot = 0;
@@ -239,7 +252,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       const int tn = m_tile / (args.tiles_w * args.tiles_h);
       // per-channel scale/shift of this N tile -> smem (all readers of the previous tile's values
       // are behind the last epi_bar_sync(2) of that tile)
-      for (int i = tid_e; i < BLOCK_N; i += 128) {
+      for (int i = tid_e; i < BLOCK_N; i += kEpiThreads) {
         const int col = n_tile * BLOCK_N + i;
         const bool ok = col < args.n_total;
         s_scale[i] = (ok && args.scale != nullptr) ? __ldg(args.scale + col) : 1.f;
@@ -256,67 +269,63 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
         if (HAS_RES) mbar_wait(&res_full[rslot], rphase);
         const uint8_t* rbuf = smem_res + rslot * kChunkBytes;
         // (2) TMEM -> registers -> scale/shift(/residual)/ReLU -> swizzled smem
+        const int col_in_tile = c * kChunkCols + half * kWarpCols;
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + col_in_tile;
+        uint32_t v[32];
+        if (OUT_F32) tmem_ld_32x32b_x16(taddr, v); else tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        if (c == kChunks - 1) {
+          // accumulator fully read: hand the TMEM buffer back to the MMA warp early
+          tc_fence_before_sync();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        float f[32];
 #pragma unroll
-        for (int half = 0; half < (OUT_F32 ? 1 : 2); ++half) {
-          uint32_t v[32];
-          const int col_in_tile = c * kChunkCols + half * 32;
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N +
-                                 col_in_tile, v);
-          tmem_ld_wait();
-          if (c == kChunks - 1 && half == (OUT_F32 ? 0 : 1)) {
-            // accumulator fully read: hand the TMEM buffer back to the MMA warp early
-            tc_fence_before_sync();
-            mbar_arrive(&tmem_empty[acc]);
-          }
-          float f[32];
+        for (int q = 0; q < kWarpCols / 4; ++q) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + col_in_tile + q * 4);
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + col_in_tile + q * 4);
+          f[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]), sc.x, sh.x);
+          f[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]), sc.y, sh.y);
+          f[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]), sc.z, sh.z);
+          f[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]), sc.w, sh.w);
+        }
+        if (HAS_RES) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 sc = *reinterpret_cast<const float4*>(s_scale + col_in_tile + q * 4);
-            const float4 sh = *reinterpret_cast<const float4*>(s_shift + col_in_tile + q * 4);
-            f[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]), sc.x, sh.x);
-            f[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]), sc.y, sh.y);
-            f[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]), sc.z, sh.z);
-            f[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]), sc.w, sh.w);
-          }
-          if (HAS_RES) {
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t j = (uint32_t)(half * 4 + q);  // 16-byte unit within the 128-byte row
+            const uint4 r = *reinterpret_cast<const uint4*>(rbuf + row * 128 + ((j ^ sw) << 4));
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t j = (uint32_t)(half * 4 + q);  // 16-byte unit within the 128-byte row
-              const uint4 r = *reinterpret_cast<const uint4*>(rbuf + row * 128 + ((j ^ sw) << 4));
-              const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 p = unpack_bf16x2(w[t]);
-                f[q * 8 + t * 2] += p.x;
-                f[q * 8 + t * 2 + 1] += p.y;
-              }
-            }
-          }
-          if (args.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (OUT_F32) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(obuf + row * 128 + (((uint32_t)q ^ sw) << 4)) =
-                  make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-              o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-              o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-              o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-              const uint32_t j = (uint32_t)(half * 4 + q);
-              *reinterpret_cast<uint4*>(obuf + row * 128 + ((j ^ sw) << 4)) = o;
+            for (int t = 0; t < 4; ++t) {
+              const float2 p = unpack_bf16x2(w[t]);
+              f[q * 8 + t * 2] += p.x;
+              f[q * 8 + t * 2 + 1] += p.y;
             }
           }
         }
+        if (args.relu) {
+#pragma unroll
+          for (int j = 0; j < kWarpCols; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          if (OUT_F32) {
+            o = make_uint4(__float_as_uint(f[q * 4]), __float_as_uint(f[q * 4 + 1]),
+                           __float_as_uint(f[q * 4 + 2]), __float_as_uint(f[q * 4 + 3]));
+          } else {
+            o.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+            o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+            o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+            o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+          }
+          const uint32_t j = (uint32_t)(half * 4 + q);
+          *reinterpret_cast<uint4*>(obuf + row * 128 + ((j ^ sw) << 4)) = o;
+        }
         if (HAS_RES) {
           mbar_arrive(&res_empty[rslot]);
-          if (++rslot == 2) { rslot = 0; rphase ^= 1; }
+          if (++rslot == C::kResSlots) { rslot = 0; rphase ^= 1; }
         }
         // (3) make the generic-proxy smem writes visible to the TMA store, then (4) store
         fence_proxy_async_smem();

@@ -50,17 +50,18 @@ __device__ __forceinline__ void stem_tma_store(const void* tmap, const void* src
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-__device__ __forceinline__ void load_patch(const StemArgs& a, int tile, __nv_bfloat16* patch,
-                                           int tid) {
+constexpr int kPatchIters = (kPatchElems + kThreads - 1) / kThreads;  // 12
+
+// Issue the (coalesced, bounds-checked) global loads of a tile's input patch into registers...
+__device__ __forceinline__ void patch_issue(const StemArgs& a, int tile, int tid,
+                                            float (&v)[kPatchIters]) {
   const int tw = tile % a.tiles_w;
   const int th = (tile / a.tiles_w) % a.tiles_h;
   const int n = tile / (a.tiles_w * a.tiles_h);
   const int ih0 = 2 * th * kTH - 3, iw0 = 2 * tw * kTW - 3;
   const float* xn = a.x + (long long)n * 3 * a.in_h * a.in_w;
-  constexpr int kIters = (kPatchElems + kThreads - 1) / kThreads;  // 12
-  float v[kIters];
 #pragma unroll
-  for (int it = 0; it < kIters; ++it) {
+  for (int it = 0; it < kPatchIters; ++it) {
     const int i = tid + it * kThreads;
     float f = 0.f;
     if (i < kPatchElems) {
@@ -73,8 +74,12 @@ __device__ __forceinline__ void load_patch(const StemArgs& a, int tile, __nv_bfl
     }
     v[it] = f;
   }
+}
+// ... and, one pipeline phase later, convert to bf16 and park them in shared memory.
+__device__ __forceinline__ void patch_store(const float (&v)[kPatchIters], __nv_bfloat16* patch,
+                                            int tid) {
 #pragma unroll
-  for (int it = 0; it < kIters; ++it) {
+  for (int it = 0; it < kPatchIters; ++it) {
     const int i = tid + it * kThreads;
     if (i < kPatchElems) patch[i] = __float2bfloat16_rn(v[it]);
   }
@@ -82,8 +87,9 @@ __device__ __forceinline__ void load_patch(const StemArgs& a, int tile, __nv_bfl
 
 __global__ void __launch_bounds__(kThreads, 2) stem_kernel(const __grid_constant__ StemArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~uintptr_t(1023));
+  // 1024-byte alignment by OFFSET (not by an integer round trip of the pointer) so the compiler
+  // keeps the shared address space and emits LDS/STS instead of generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sB = smem;
   uint8_t* sA = sB + 3 * kBBytes;
   uint8_t* sOut = sA + 3 * kABytes;
@@ -126,8 +132,14 @@ __global__ void __launch_bounds__(kThreads, 2) stem_kernel(const __grid_constant
     for (int kb = 0; kb < 3; ++kb) tma_load_2d(sB + kb * kBBytes, &a.tmap_w, w_bar, kb * 64, 0);
   }
 
+  // software pipeline over tiles: patch(T) in smem, patch(T+1) in flight in registers
+  float pv[kPatchIters];
   int tile = blockIdx.x;
-  if (tile < a.total_tiles) load_patch(a, tile, sPatch, tid);
+  if (tile < a.total_tiles) {
+    patch_issue(a, tile, tid, pv);
+    patch_store(pv, sPatch, tid);
+    if (tile + (int)gridDim.x < a.total_tiles) patch_issue(a, tile + gridDim.x, tid, pv);
+  }
   __syncthreads();
 
   const int row = tid & 127, half = tid >> 7;
@@ -171,9 +183,11 @@ __global__ void __launch_bounds__(kThreads, 2) stem_kernel(const __grid_constant
       umma_commit(mma_bar);
     }
     first = false;
-    // ---- prefetch the next tile's patch while the MMA runs --------------------------------------
+    // ---- the patch buffer is free (everyone is past SYNC1): park the next tile's patch, whose
+    //      loads were issued a whole phase ago, and issue the loads of the tile after it ---------
     const int next = tile + gridDim.x;
-    if (next < a.total_tiles) load_patch(a, next, sPatch, tid);
+    if (next < a.total_tiles) patch_store(pv, sPatch, tid);
+    if (next + (int)gridDim.x < a.total_tiles) patch_issue(a, next + gridDim.x, tid, pv);
     // ---- epilogue: TMEM -> scale/shift/ReLU -> bf16 -> swizzled staging -> TMA store --------------
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;

@@ -148,34 +148,52 @@ __global__ void bn_finalize_kernel(double* __restrict__ acc, const float* __rest
 }
 
 // y = relu?(a[v,c] * z + b[v,c] + residual)
+// grid = (x, n_img): every thread owns ONE 8-channel group (its coefficients live in registers) and
+// walks the image's pixels with 4 independent 16-byte loads in flight per tensor.
+constexpr int kEwUnroll = 4;
+
 template <typename T>
-__global__ void bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ a,
-                                const float* __restrict__ b, const T* __restrict__ residual,
-                                T* __restrict__ y, int pix, int c, int views, int relu,
-                                long long total) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ a, const float* __restrict__ b,
+                const T* __restrict__ residual, T* __restrict__ y, int pix, int c, int views,
+                int relu) {
   const int cg = c / 8;
-  const int g = (int)(idx % cg);
-  const long long row = idx / cg;
-  const int v = (int)((row / pix) % views);
-  float f[8], o[8];
-  V8<T>::load(z + row * c + g * 8, f);
-  const float* ap = a + v * c + g * 8;
-  const float* bp = b + v * c + g * 8;
+  const int n = blockIdx.y, v = n % views;
+  const long long per_img = (long long)pix * cg;  // 8-channel vectors in this image
+  const long long stride = (long long)gridDim.x * blockDim.x;  // multiple of cg (cg | 256)
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = (int)(i0 % cg);
+  float ca[8], cb[8];
+  V8<float>::load(a + v * c + g * 8, ca);
+  V8<float>::load(b + v * c + g * 8, cb);
+  const T* zi = z + (long long)n * pix * c;
+  const T* ri = residual ? residual + (long long)n * pix * c : nullptr;
+  T* yi = y + (long long)n * pix * c;
+  for (long long i = i0; i < per_img; i += stride * kEwUnroll) {
+    float f[kEwUnroll][8], r[kEwUnroll][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = fmaf(f[i], __ldg(ap + i), __ldg(bp + i));
-  if (residual != nullptr) {
-    float r[8];
-    V8<T>::load(residual + row * c + g * 8, r);
+    for (int j = 0; j < kEwUnroll; ++j) {
+      const long long k = i + j * stride;
+      if (k < per_img) {
+        V8<T>::load(zi + k * 8, f[j]);
+        if (ri) V8<T>::load(ri + k * 8, r[j]);
+      }
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] += r[i];
+    for (int j = 0; j < kEwUnroll; ++j) {
+      const long long k = i + j * stride;
+      if (k < per_img) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o[e] = fmaf(f[j][e], ca[e], cb[e]);
+          if (ri) o[e] += r[j][e];
+          if (relu) o[e] = fmaxf(o[e], 0.f);
+        }
+        V8<T>::store(yi + k * 8, o);
+      }
+    }
   }
-  if (relu) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
-  }
-  V8<T>::store(y + row * c + g * 8, o);
 }
 
 // finalize of the backward reduction: dgamma/dbeta (+=), per-(v,c) coefficients for the apply pass
@@ -207,34 +225,51 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ acc, const float* __
 }
 
 // dz = k0*dyr + k1*z + k2, dyr = dy * (y_mask > 0); optionally also writes dyr (skip-path grad)
+constexpr int kBwdUnroll = 2;  // 3 input streams: 6 loads in flight per thread, <= 80 registers
+
 template <typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ dy,
-                                    const T* __restrict__ y_mask, const float* __restrict__ k0,
-                                    const float* __restrict__ k1, const float* __restrict__ k2,
-                                    T* __restrict__ dz, T* __restrict__ dyr_out, int pix, int c,
-                                    int views, long long total) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+__global__ void __launch_bounds__(256, 3)
+bn_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* __restrict__ y_mask,
+                    const float* __restrict__ k0, const float* __restrict__ k1,
+                    const float* __restrict__ k2, T* __restrict__ dz, T* __restrict__ dyr_out,
+                    int pix, int c, int views) {
   const int cg = c / 8;
-  const int g = (int)(idx % cg);
-  const long long row = idx / cg;
-  const int v = (int)((row / pix) % views);
-  const long long off = row * c + g * 8;
-  float f[8], d[8], o[8];
-  V8<T>::load(z + off, f);
-  V8<T>::load(dy + off, d);
-  if (y_mask != nullptr) {
-    float m[8];
-    V8<T>::load(y_mask + off, m);
+  const int n = blockIdx.y, v = n % views;
+  const long long per_img = (long long)pix * cg;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = (int)(i0 % cg);
+  float c0[8], c1[8], c2[8];
+  V8<float>::load(k0 + v * c + g * 8, c0);
+  V8<float>::load(k1 + v * c + g * 8, c1);
+  V8<float>::load(k2 + v * c + g * 8, c2);
+  const long long img = (long long)n * pix * c;
+  for (long long i = i0; i < per_img; i += stride * kBwdUnroll) {
+    float f[kBwdUnroll][8], d[kBwdUnroll][8], m[kBwdUnroll][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+    for (int j = 0; j < kBwdUnroll; ++j) {
+      const long long k = i + j * stride;
+      if (k < per_img) {
+        V8<T>::load(z + img + k * 8, f[j]);
+        V8<T>::load(dy + img + k * 8, d[j]);
+        if (y_mask) V8<T>::load(y_mask + img + k * 8, m[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kBwdUnroll; ++j) {
+      const long long k = i + j * stride;
+      if (k < per_img) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (y_mask) d[j][e] = m[j][e] > 0.f ? d[j][e] : 0.f;
+          o[e] = fmaf(c0[e], d[j][e], fmaf(c1[e], f[j][e], c2[e]));
+        }
+        V8<T>::store(dz + img + k * 8, o);
+        if (dyr_out) V8<T>::store(dyr_out + img + k * 8, d[j]);
+      }
+    }
   }
-  const int pc = v * c + g * 8;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    o[i] = fmaf(__ldg(k0 + pc + i), d[i], fmaf(__ldg(k1 + pc + i), f[i], __ldg(k2 + pc + i)));
-  V8<T>::store(dz + off, o);
-  if (dyr_out != nullptr) V8<T>::store(dyr_out + off, d);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -625,6 +660,15 @@ using namespace rmv;
   if ((dtype) == RMV_DTYPE_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
   else { using T = float; __VA_ARGS__; }
 
+// blocks along x for the per-image elementwise kernels: enough threads for kEwUnroll vectors each,
+// but at least ~4 waves of blocks over the whole launch
+static unsigned ew_blocks_x(int pix, int c, int n_img, int unroll = rmv::kEwUnroll) {
+  const long long per_img = (long long)pix * (c / 8);
+  long long bx = (per_img + 256LL * unroll - 1) / (256LL * unroll);
+  if (bx < 1) bx = 1;
+  return (unsigned)bx;
+}
+
 static int bn_reduce_cfg(int pix, int c, int n_img, dim3* grid, int* smem) {
   const int cg = c / 8;
   RMV_CHECK_ARG(c % 8 == 0 && cg <= 256 && 256 % cg == 0,
@@ -667,11 +711,11 @@ extern "C" int rmv_bn_finalize(double* acc, const float* gamma, const float* bet
 extern "C" int rmv_bn_apply(const void* z, const float* a, const float* b, const void* residual,
                             void* y, int dtype, int n_img, int pix, int c, int views, int relu,
                             void* stream) {
-  RMV_CHECK_ARG(c % 8 == 0, "bn_apply: c must be a multiple of 8");
-  const long long total = (long long)n_img * pix * (c / 8);
-  if (total == 0) return 0;
-  DISPATCH_T(dtype, (bn_apply_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const T*)z, a, b, (const T*)residual, (T*)y, pix, c, views, relu, total)));
+  RMV_CHECK_ARG(c % 8 == 0 && 256 % (c / 8) == 0, "bn_apply: c=%d must be 8*2^k, <= 2048", c);
+  if ((long long)n_img * pix == 0) return 0;
+  const dim3 grid(ew_blocks_x(pix, c, n_img), (unsigned)n_img);
+  DISPATCH_T(dtype, (bn_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const T*)z, a, b, (const T*)residual, (T*)y, pix, c, views, relu)));
   RMV_LAUNCH_CHECK();
   return 0;
 }
@@ -702,11 +746,11 @@ extern "C" int rmv_bn_bwd_finalize(double* acc, const float* gamma, const float*
 extern "C" int rmv_bn_bwd_apply(const void* z, const void* dy, const void* y_mask, const float* k0,
                                 const float* k1, const float* k2, void* dz, void* dyr_out,
                                 int dtype, int n_img, int pix, int c, int views, void* stream) {
-  const long long total = (long long)n_img * pix * (c / 8);
-  if (total == 0) return 0;
-  DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const T*)z, (const T*)dy, (const T*)y_mask, k0, k1, k2, (T*)dz, (T*)dyr_out, pix, c, views,
-      total)));
+  RMV_CHECK_ARG(c % 8 == 0 && 256 % (c / 8) == 0, "bn_bwd_apply: c=%d must be 8*2^k, <= 2048", c);
+  if ((long long)n_img * pix == 0) return 0;
+  const dim3 grid(ew_blocks_x(pix, c, n_img, rmv::kBwdUnroll), (unsigned)n_img);
+  DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const T*)z, (const T*)dy, (const T*)y_mask, k0, k1, k2, (T*)dz, (T*)dyr_out, pix, c, views)));
   RMV_LAUNCH_CHECK();
   return 0;
 }

@@ -54,8 +54,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   constexpr int kStageBytes = 2 * kBoxBytes + kNB * kBoxBytes;
   constexpr int kStages = (N_TILE == 128) ? 3 : 4;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~uintptr_t(1023));
+  // 1024-byte alignment by OFFSET (not by an integer round trip of the pointer) so the compiler
+  // keeps the shared address space and emits LDS/STS instead of generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint8_t* s_out = smem + kStages * kStageBytes;  // [128 rows][32 fp32], SW128
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + kBoxBytes);
