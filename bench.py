@@ -308,7 +308,7 @@ def run_train(args):
     from rotmv_b200 import _lib as L
     from rotmv_b200 import functional as RF
     from rotmv_b200.module import FeatRotationSymm
-    from rotmv_b200.train import TrainEngine
+    from rotmv_b200.train import GraphedTrainStep, TrainEngine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -344,16 +344,18 @@ def run_train(args):
     images = images_host.to(dev)
     rot = RF.pose_to_rotations(pose_host.to(dev))
     gt = gt_host.to(dev)
+    gstep = GraphedTrainStep(eng, B, V)   # forward+backward graph, [NCCL all-reduce], Adam graph
+    gstep.step(images, rot, gt)
     for _ in range(max(args.warmup, 3)):
-        eng.step(images, rot, gt)
+        gstep.step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     e0.record()
     for _ in range(args.steps):
-        eng.step(images, rot, gt)
-        launches += eng.launches_last_step
+        gstep.step()
+        launches += gstep.launches_per_step
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -363,17 +365,15 @@ def run_train(args):
     if not (loss == loss):
         raise SystemExit("bench.py: non-finite loss")
     # end to end: host batch (images, head poses, labels) in, loss out, every step
-    img_d = torch.empty_like(images)
     pose_d = torch.empty((B, V, 2), device=dev)
-    gt_d = torch.empty_like(gt)
     loss_h = torch.empty((1,), dtype=torch.float32).pin_memory()
 
     def host_step():
-        img_d.copy_(images_host, non_blocking=True)
+        gstep.images.copy_(images_host, non_blocking=True)
         pose_d.copy_(pose_host, non_blocking=True)
-        gt_d.copy_(gt_host, non_blocking=True)
-        loss_dev = eng.step(img_d, RF.pose_to_rotations(pose_d), gt_d)
-        loss_h.copy_(loss_dev, non_blocking=True)
+        gstep.gt.copy_(gt_host, non_blocking=True)
+        gstep.rotations.copy_(RF.pose_to_rotations(pose_d), non_blocking=True)
+        loss_h.copy_(gstep.step(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     for _ in range(2):

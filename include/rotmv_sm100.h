@@ -82,6 +82,12 @@ int rmv_stem_conv_fwd(const float* x_nchw, const void* w_packed, const float* sc
                       const float* shift, void* y_nhwc, int n_img, int in_h, int in_w, int relu,
                       void* stream);
 
+/* Stem weight gradient on the tensor cores (training): dw_oihw[64,3,7,7] (fp32, =) from the fp32
+ * NCHW images and dz (bf16 NHWC [n,out_h,out_w,64], gradient of the stem conv output); the im2col
+ * rows are rebuilt in shared memory exactly as in the forward. scratch: fp32 [192*64] workspace. */
+int rmv_stem_wgrad(const float* x_nchw, const void* dz_nhwc, float* scratch, float* dw_oihw,
+                   int n_img, int in_h, int in_w, void* stream);
+
 /* fp32 NCHW -> NHWC (fp32 or bf16) layout change (the reference keeps NCHW, trainer.py:100-106). */
 int rmv_nchw_to_nhwc(const float* x, void* y, int n_img, int c, int h, int w, int y_dtype,
                      void* stream);

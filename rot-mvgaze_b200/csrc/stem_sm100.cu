@@ -229,6 +229,154 @@ __global__ void __launch_bounds__(kThreads, 2) stem_kernel(const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stem weight gradient on the tensor cores: dW[col, k] = sum_pixels P[pixel, col] * dZ[pixel, k]
+// with P the same in-shared-memory im2col rows the forward builds (col = c*56 + kh*8 + kw) and dZ
+// the gradient of the stem conv output (bf16 NHWC, TMA-loaded 16x8-pixel boxes). Both operands are
+// MN-major (pixels along K); every CTA accumulates all its tiles in TMEM and adds its partial
+// [256 cols][64 k] result to an fp32 scratch with atomics once, at the end.
+// ---------------------------------------------------------------------------------------------
+struct StemWgArgs {
+  CUtensorMap tmap_dz;   // (64 ch, out_w, out_h, n), box (64, 16, 8, 1)
+  const float* x;
+  float* scratch;        // [192][64] fp32, +=
+  int n_img, in_h, in_w, out_h, out_w, tiles_w, tiles_h, total_tiles;
+};
+constexpr int kWgSmemBytes = 4 * kABytes + 2 * kABytes + 6144 + 64 + 1024;
+
+__global__ void __launch_bounds__(kThreads, 2) stem_wgrad_kernel(const __grid_constant__ StemWgArgs w) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                       // 4 column blocks of [128 px][64 cols] (block 3 = zeros)
+  uint8_t* sB = sA + 4 * kABytes;           // 2 x [128 px][64 ch] dZ tiles
+  __nv_bfloat16* sPatch = reinterpret_cast<__nv_bfloat16*>(sB + 2 * kABytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPatch) + 6144);  // [2]
+  uint64_t* mma_bar = full_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // StemArgs view for the shared patch helpers
+  StemArgs a;
+  a.x = w.x; a.in_h = w.in_h; a.in_w = w.in_w; a.tiles_w = w.tiles_w; a.tiles_h = w.tiles_h;
+  a.total_tiles = w.total_tiles;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&w.tmap_dz);
+    mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1); mbar_init(mma_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, 128); tmem_relinquish(); }
+  // zero block 3 and the K-padding units 5..7 of block 2 once
+  for (int i = tid; i < 128 * 8; i += kThreads)
+    *reinterpret_cast<uint4*>(sA + 3 * kABytes + i * 16) = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 128 * 3; i += kThreads) {
+    const int row = i / 3;
+    const uint32_t j = 5 + i % 3;
+    *reinterpret_cast<uint4*>(sA + 2 * kABytes + row * 128 + ((j ^ (uint32_t)(row & 7)) << 4)) =
+        make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_ptr;
+
+  auto issue_dz = [&](int tile, int buf) {
+    const int tw = tile % w.tiles_w;
+    const int th = (tile / w.tiles_w) % w.tiles_h;
+    const int n = tile / (w.tiles_w * w.tiles_h);
+    mbar_expect_tx(&full_bar[buf], kABytes);
+    tma_load_4d(sB + buf * kABytes, &w.tmap_dz, &full_bar[buf], 0, tw * kTW, th * kTH, n);
+  };
+
+  float pv[kPatchIters];
+  int tile = blockIdx.x;
+  const int step = gridDim.x;
+  if (tile < w.total_tiles) {
+    if (tid == 0) {
+      issue_dz(tile, 0);
+      if (tile + step < w.total_tiles) issue_dz(tile + step, 1);
+    }
+    patch_issue(a, tile, tid, pv);
+    patch_store(pv, sPatch, tid);
+    if (tile + step < w.total_tiles) patch_issue(a, tile + step, tid, pv);
+  }
+  __syncthreads();
+
+  const int row = tid & 127, half = tid >> 7;
+  const int dy = row >> 4, dx = row & 15;
+  const uint32_t sw = (uint32_t)(row & 7);
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+  int it = 0;
+  for (; tile < w.total_tiles; tile += step, ++it) {
+    // the previous tile's MMAs must be done before sA (and its dZ buffer) are overwritten
+    if (it > 0) {
+      mbar_wait(mma_bar, (uint32_t)((it - 1) & 1));
+      tc_fence_after_sync();
+      if (tid == 0 && tile + step < w.total_tiles) issue_dz(tile + step, (it + 1) & 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const int q = half * 12 + i;
+      if (q < 21) {
+        const int c = q / 7, kh = q - c * 7;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(
+            sPatch + (c * kPatchH + 2 * dy + kh) * kPatchPitch + 2 * dx);
+        const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
+        *reinterpret_cast<uint4*>(sA + (q >> 3) * kABytes + row * 128 +
+                                  ((((uint32_t)q & 7) ^ sw) << 4)) = v;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after_sync();
+      mbar_wait(&full_bar[it & 1], (uint32_t)((it >> 1) & 1));
+      const uint32_t sa = smem_u32(sA), sb = smem_u32(sB + (it & 1) * kABytes);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {   // 16 pixels per MMA
+        const uint64_t bdesc = umma_desc_sw128(sb + k * 2048, 16, 1024);
+        umma_f16(tmem, umma_desc_sw128(sa + k * 2048, kABytes, 1024), bdesc, idesc, (it | k) != 0);
+        umma_f16(tmem + 64, umma_desc_sw128(sa + 2 * kABytes + k * 2048, kABytes, 1024), bdesc,
+                 idesc, (it | k) != 0);
+      }
+      umma_commit(mma_bar);
+    }
+    const int next = tile + step;
+    if (next < w.total_tiles) patch_store(pv, sPatch, tid);
+    if (next + step < w.total_tiles) patch_issue(a, next + step, tid, pv);
+    __syncthreads();
+  }
+  if (it > 0) {
+    mbar_wait(mma_bar, (uint32_t)((it - 1) & 1));
+    tc_fence_after_sync();
+    const int quarter = warp & 3, colhalf = warp >> 2;
+    const int erow = quarter * 32 + lane;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem + ((uint32_t)(quarter * 32) << 16) + mt * 64 + colhalf * 32, v);
+      tmem_ld_wait();
+      const int col = mt * 128 + erow;
+      if (col < kKPad) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          atomicAdd(w.scratch + col * kCout + colhalf * 32 + j, __uint_as_float(v[j]));
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem, 128); }
+}
+
+// dw[k][c][kh][kw] (fp32 OIHW) = scratch[c*56 + kh*8 + kw][k]
+__global__ void stem_wgrad_unpack_kernel(const float* __restrict__ scratch, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 64*3*7*7
+  if (i >= kCout * 147) return;
+  const int kw = i % 7, kh = (i / 7) % 7, c = (i / 49) % 3, k = i / 147;
+  dw[i] = scratch[(c * 56 + kh * 8 + kw) * kCout + k];
+}
+
 __global__ void stem_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 64 * 192
   if (i >= kCout * kKPad) return;
@@ -296,6 +444,42 @@ extern "C" int rmv_stem_conv_fwd(const float* x_nchw, const void* w_packed, cons
   }
   const int grid = a.total_tiles < 2 * num_sms() ? a.total_tiles : 2 * num_sms();
   stem_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_stem_wgrad(const float* x_nchw, const void* dz_nhwc, float* scratch, float* dw_oihw,
+                              int n_img, int in_h, int in_w, void* stream) {
+  RMV_CHECK_ARG(x_nchw && dz_nhwc && scratch && dw_oihw, "stem_wgrad: null pointer");
+  RMV_CHECK_ARG((reinterpret_cast<uintptr_t>(dz_nhwc) & 15) == 0, "stem_wgrad: dz must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  RMV_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * kKPad * kCout, s));
+  if (n_img > 0) {
+    StemWgArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x_nchw; a.scratch = scratch;
+    a.n_img = n_img; a.in_h = in_h; a.in_w = in_w;
+    a.out_h = (in_h + 6 - 7) / 2 + 1;
+    a.out_w = (in_w + 6 - 7) / 2 + 1;
+    a.tiles_w = ceil_div(a.out_w, kTW);
+    a.tiles_h = ceil_div(a.out_h, kTH);
+    a.total_tiles = a.tiles_w * a.tiles_h * n_img;
+    cuuint64_t dims[4] = {(cuuint64_t)kCout, (cuuint64_t)a.out_w, (cuuint64_t)a.out_h, (cuuint64_t)n_img};
+    cuuint64_t strides[3] = {(cuuint64_t)(kCout * 2), (cuuint64_t)a.out_w * kCout * 2,
+                             (cuuint64_t)a.out_h * a.out_w * kCout * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kCout, (cuuint32_t)kTW, (cuuint32_t)kTH, 1};
+    if (int rc = encode_map(&a.tmap_dz, dz_nhwc, 4, dims, strides, box)) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+      RMV_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kWgSmemBytes));
+      attr_set = true;
+    }
+    const int grid = a.total_tiles < 2 * num_sms() ? a.total_tiles : 2 * num_sms();
+    stem_wgrad_kernel<<<grid, kThreads, kWgSmemBytes, s>>>(a);
+    RMV_LAUNCH_CHECK();
+  }
+  stem_wgrad_unpack_kernel<<<(kCout * 147 + 255) / 256, 256, 0, s>>>(scratch, dw_oihw);
   RMV_LAUNCH_CHECK();
   return 0;
 }

@@ -55,6 +55,7 @@ SIGNATURES = {
     "rmv_stem_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rmv_stem_pack_weights": (_i, [_vp, _vp, _vp]),
     "rmv_stem_conv_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "rmv_stem_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "rmv_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rmv_maxpool3x3s2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rmv_avgpool_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp]),

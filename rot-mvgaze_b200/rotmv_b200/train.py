@@ -291,8 +291,7 @@ class TrainEngine:
             wp = RF.stem_pack_weights(self.stem_conv.weight.detach())
             z0 = RF.stem_conv(imgs, wp, None, None, out=self._buf("z_stem", (m, 112, 112, 64))
                               if imgs.shape[2] == 224 and imgs.shape[3] == 224 else None, relu=False)
-            x_img = RF.nchw_to_nhwc(imgs, dt)  # bf16 NHWC copy of the images for the stem wgrad
-            stem_x, stem_xs = x_img, None
+            stem_x, stem_xs = None, None
         else:
             w7 = self._w_fwd(self.stem_conv, "stem")
             z0 = RF.conv2d_nchw_input(imgs, w7, stride=2, pad=3)
@@ -412,5 +411,71 @@ class TrainEngine:
         _ck("rmv_maxpool3x3s2_bwd", y0.data_ptr(), d_out.data_ptr(), d_y0.data_ptr(), m, y0.shape[1],
             y0.shape[2], y0.shape[3], dtc)
         dz0, _ = self._bn_bwd(self.stem_bn, z0, d_y0, y0, "stem")
-        self._wgrad(stem_x, dz0, self.stem_conv, 7, 7, 2, 3, x_strides=stem_xs)
+        if stem_x is None:   # bf16: tcgen05 stem weight gradient straight from the fp32 NCHW images
+            RF._call("rmv_stem_wgrad", {"desc": "stem wgrad (tcgen05)", "engine": "tcgen05-wgrad",
+                                        "flops": 2.0 * m * y0.shape[1] * y0.shape[2] * 64 * 147},
+                     L.load().rmv_stem_wgrad, imgs.data_ptr(), dz0.data_ptr(),
+                     self._buf("stem_wg", (192 * 64,), torch.float32).data_ptr(),
+                     self.grads[id(self.stem_conv.weight)].data_ptr(), m, imgs.shape[2], imgs.shape[3],
+                     L.stream_ptr())
+        else:
+            self._wgrad(stem_x, dz0, self.stem_conv, 7, 7, 2, 3, x_strides=stem_xs)
         return {"loss": self.loss, "preds": preds, "pool_out": pool_out}
+
+
+class GraphedTrainStep:
+    """CUDA-graph-captured training step (north_star: "trainer.py step loop (CUDA-graph captured)").
+
+    forward + loss + backward are one graph, the Adam update another; between them the flat fp32
+    gradient buffer is all-reduced over NCCL when the job is data-parallel. Per step the host
+    replays two graphs (and issues one collective); learning rate and step count live in device
+    memory (`TrainEngine.hyper`), so `set_lr` needs no re-capture. The per-step D2H of the reference
+    (trainer.py:128) is gone: `loss` stays on the device until the caller reads it.
+    """
+
+    def __init__(self, engine: TrainEngine, batch: int, views: int, size: int = 224):
+        self.engine = engine
+        dev = engine.device
+        self.images = torch.zeros((batch, views, 3, size, size), device=dev)
+        self.rotations = torch.eye(3, device=dev).expand(batch, views, views, 3, 3).contiguous()
+        self.gt = torch.zeros((batch, views, 2), device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        # warm-up on a side stream allocates every cached buffer; restore what it touched
+        saved_p = engine.flat_p.clone()
+        bufs = [b.clone() for b in engine.model.buffers()]
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                engine.forward_backward(self.images, self.rotations, self.gt)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        n0 = L.STATS["launches"]
+        self.fwd_bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.fwd_bwd):
+            engine.forward_backward(self.images, self.rotations, self.gt)
+        self.adam = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.adam, pool=self.fwd_bwd.pool()):
+            _ck("rmv_adam_step", engine.flat_p.data_ptr(), engine.flat_g.data_ptr(),
+                engine.flat_m.data_ptr(), engine.flat_v.data_ptr(), engine.hyper.data_ptr(),
+                engine.flat_p.numel(), int(engine.decoupled), 1.0 / engine.world)
+        self.launches_per_step = L.STATS["launches"] - n0
+        engine.flat_p.copy_(saved_p)
+        for b, s in zip(engine.model.buffers(), bufs):
+            b.copy_(s)
+        engine.flat_m.zero_(); engine.flat_v.zero_()
+        engine.hyper[5] = 0.0
+        torch.cuda.synchronize(dev)
+
+    def step(self, images=None, rotations=None, gt=None) -> torch.Tensor:
+        if images is not None:
+            self.images.copy_(images, non_blocking=True)
+        if rotations is not None:
+            self.rotations.copy_(rotations, non_blocking=True)
+        if gt is not None:
+            self.gt.copy_(gt, non_blocking=True)
+        self.fwd_bwd.replay()
+        eng = self.engine
+        if eng.world > 1:
+            torch.distributed.all_reduce(eng.flat_g, group=eng.pg)
+        self.adam.replay()
+        return eng.loss

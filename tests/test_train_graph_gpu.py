@@ -1,0 +1,70 @@
+"""The CUDA-graph-captured training step replays exactly what the eager step launches."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(precision):
+    from rotmv_b200.module import FeatRotationSymm
+    from rotmv_b200.train import TrainEngine
+
+    torch.manual_seed(0)
+    model = FeatRotationSymm(50, 2).cuda().train()
+    return model, TrainEngine(model, precision=precision, lr=1e-4)
+
+
+@pytest.mark.parametrize("precision", ["bf16"])
+def test_graphed_step_matches_eager(precision):
+    from rotmv_b200 import functional as RF
+    from rotmv_b200.train import GraphedTrainStep
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    images = torch.randn((4, 2, 3, 224, 224), device="cuda", generator=g)
+    rot = RF.pose_to_rotations(torch.rand((4, 2, 2), device="cuda", generator=g) - 0.5)
+    gt = torch.rand((4, 2, 2), device="cuda", generator=g) - 0.5
+
+    model_a, eng_a = _make(precision)
+    eager = [eng_a.step(images, rot, gt).item() for _ in range(3)]
+
+    model_b, eng_b = _make(precision)
+    graphed = GraphedTrainStep(eng_b, 4, 2)
+    assert graphed.launches_per_step > 400
+    got = [graphed.step(images, rot, gt).item() for _ in range(3)]
+    # fp32 atomics (weight-gradient split-K, loss sum) make runs non-bit-reproducible
+    for a, b in zip(eager, got):
+        assert abs(a - b) <= 5e-3 * abs(a), (eager, got)
+    assert eng_b.hyper[5].item() == 3.0
+    sa, sb = model_a.state_dict(), model_b.state_dict()
+    k = "_feat_extractor.0.bn1.num_batches_tracked"
+    assert int(sa[k]) == int(sb[k]) == 6
+    w = "_gaze_estimators.1.blocks.1.0.weight"
+    # Adam moves every element by ~lr per step whatever the gradient's size, so run-to-run noise in
+    # near-zero gradients can flip single updates: bound the difference by the distance moved
+    assert (sa[w] - sb[w]).abs().max().item() <= 2 * 3 * 1e-4
+    # learning-rate change without re-capture
+    eng_b.set_lr(0.0)
+    before = sb[w].clone()
+    graphed.step(images, rot, gt)
+    torch.cuda.synchronize()
+    assert torch.equal(model_b.state_dict()[w], before)
+
+
+def test_stem_wgrad_tcgen05_matches_autograd():
+    import torch.nn.functional as F
+    from rotmv_b200 import _lib as L
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for n, h, w in [(3, 224, 224), (2, 96, 64)]:
+        x = torch.randn((n, 3, h, w), device="cuda", generator=g)
+        oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        dz = torch.randn((n, oh, ow, 64), device="cuda", generator=g).bfloat16()
+        wt = torch.zeros((64, 3, 7, 7), device="cuda", requires_grad=True)
+        y = F.conv2d(x.bfloat16().float(), wt, stride=2, padding=3)
+        y.backward(dz.float().permute(0, 3, 1, 2))
+        dw = torch.empty((64, 3, 7, 7), device="cuda")
+        scratch = torch.empty((192 * 64,), device="cuda")
+        L.check(L.load().rmv_stem_wgrad(x.data_ptr(), dz.data_ptr(), scratch.data_ptr(), dw.data_ptr(),
+                                        n, h, w, L.stream_ptr()), "rmv_stem_wgrad")
+        err = (dw - wt.grad).abs().max().item()
+        assert err <= 2e-4 * wt.grad.abs().max().item() + 1e-3, (n, h, w, err, wt.grad.abs().max().item())
