@@ -185,11 +185,31 @@ int rmv_colsum(const void* x, long long ld, int rows, int cols, int dtype, float
 int rmv_permute_cast(const float* src, void* dst, int d0, int d1, int d2, int d3, long long s0,
                      long long s1, long long s2, long long s3, int flip1, int flip2, int dst_dtype,
                      void* stream);
+/* Batched rmv_permute_cast: `jobs_dev` is a DEVICE array of n_jobs jobs sorted by first_block;
+ * job i owns blocks [first_block_i, first_block_{i+1}) of 1024 elements each (total_blocks in all).
+ * One launch re-derives every engine-layout filter tensor of a training step. */
+typedef struct rmv_permute_job {
+  const float* src;
+  void* dst;
+  int d0, d1, d2, d3;
+  long long s0, s1, s2, s3;
+  int flip1, flip2, dst_dtype;
+  unsigned first_block;
+} rmv_permute_job;
+int rmv_permute_cast_batch(const rmv_permute_job* jobs_dev, int n_jobs, unsigned total_blocks,
+                           void* stream);
 /* dst[n,2h,2w,:] = src[n,h,w,:], zeros elsewhere (dst [n,2H,2W,c]): stride-2 data gradient. */
 int rmv_dilate2(const void* src, void* dst, int n_img, int h, int w, int c, int dtype,
                 void* stream);
 int rmv_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int n_img, int in_h, int in_w,
                          int c, int dtype, void* stream);
+/* Training variant of the max-pool: forward also records the winning window position (uint8,
+ * 0..8 = r*3+s, first maximum in scan order like ATen) per output element; the backward routes
+ * each gradient through that index. idx has the shape of y. */
+int rmv_maxpool3x3s2_fwd_idx(const void* x, void* y, void* idx, int n_img, int in_h, int in_w,
+                             int c, int dtype, void* stream);
+int rmv_maxpool3x3s2_bwd_idx(const void* idx, const void* dy, void* dx, int n_img, int in_h,
+                             int in_w, int c, int dtype, void* stream);
 int rmv_avgpool_bwd(const void* dfeat, long long ld, void* dx, int n_img, int hw, int c, int dtype,
                     void* stream);
 /* Analytic gradient of the weighted angular loss w.r.t. pred (zero where the cosine saturates,

@@ -349,6 +349,48 @@ __global__ void permute_cast_kernel(const float* __restrict__ src, TD* __restric
   else dst[idx] = v;
 }
 
+// Batched variant: one launch re-derives EVERY engine-layout filter tensor of a training step from
+// the fp32 masters (job table in device memory; block b belongs to the last job with
+// first_block <= b; 1024 elements per block).
+template <typename TD>
+__device__ __forceinline__ void permute_job_elems(const rmv_permute_job& j, long long base, int tid) {
+  const long long total = (long long)j.d0 * j.d1 * j.d2 * j.d3;
+  TD* dst = reinterpret_cast<TD*>(j.dst);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long idx = base + tid + u * 256;
+    if (idx >= total) return;
+    const int i3 = (int)(idx % j.d3);
+    long long t = idx / j.d3;
+    int i2 = (int)(t % j.d2); t /= j.d2;
+    int i1 = (int)(t % j.d1);
+    const int i0 = (int)(t / j.d1);
+    if (j.flip1) i1 = j.d1 - 1 - i1;
+    if (j.flip2) i2 = j.d2 - 1 - i2;
+    const float v = __ldg(j.src + i0 * j.s0 + i1 * j.s1 + i2 * j.s2 + i3 * j.s3);
+    if constexpr (sizeof(TD) == 2) dst[idx] = __float2bfloat16_rn(v);
+    else dst[idx] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+permute_cast_batch_kernel(const rmv_permute_job* __restrict__ jobs, int n_jobs) {
+  __shared__ int s_job;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].first_block <= blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    s_job = lo;
+  }
+  __syncthreads();
+  const rmv_permute_job j = jobs[s_job];
+  const long long base = (long long)(blockIdx.x - j.first_block) * 1024;
+  if (j.dst_dtype == RMV_DTYPE_BF16) permute_job_elems<__nv_bfloat16>(j, base, threadIdx.x);
+  else permute_job_elems<float>(j, base, threadIdx.x);
+}
+
 // dst[n, 2h, 2w, :] = src[n, h, w, :], zeros elsewhere (dst is [n, 2H, 2W, c]) -- stride-2 dgrad
 template <typename T>
 __global__ void dilate2_kernel(const T* __restrict__ src, T* __restrict__ dst, int h, int w, int c,
@@ -409,6 +451,76 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
         if (arg[i] == ih * in_w + iw) acc[i] += d[i];
     }
   V8<T>::store(dx + idx * 8, acc);
+}
+
+// MaxPool 3x3 s2 p1 forward that also records, per output element, WHICH of the 9 window positions
+// won (first maximum in scan order, as ATen): idx in 0..8 = r*3+s. The backward then needs 4 index
+// bytes + 4 gradient values per input element instead of re-scanning 4 windows x 9 inputs.
+template <typename T>
+__global__ void maxpool_fwd_idx_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                       uint8_t* __restrict__ idx, int in_h, int in_w, int c,
+                                       int out_h, int out_w, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cg = c / 8;
+  const int g = (int)(i % cg);
+  long long t = i / cg;
+  const int ow = (int)(t % out_w); t /= out_w;
+  const int oh = (int)(t % out_h);
+  const long long n = t / out_h;
+  float best[8];
+  uint32_t arg[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { best[e] = -3.4e38f; arg[e] = 0; }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int ih = 2 * oh - 1 + r;
+    if (ih < 0 || ih >= in_h) continue;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int iw = 2 * ow - 1 + q;
+      if (iw < 0 || iw >= in_w) continue;
+      float f[8];
+      V8<T>::load(x + ((n * in_h + ih) * in_w + iw) * c + g * 8, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (f[e] > best[e]) { best[e] = f[e]; arg[e] = r * 3 + q; }
+    }
+  }
+  V8<T>::store(y + i * 8, best);
+  uint2 packed;
+  packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+  packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+  *reinterpret_cast<uint2*>(idx + i * 8) = packed;
+}
+
+template <typename T>
+__global__ void maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const T* __restrict__ dy,
+                                       T* __restrict__ dx, int in_h, int in_w, int c, int out_h,
+                                       int out_w, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cg = c / 8;
+  const int g = (int)(i % cg);
+  long long t = i / cg;
+  const int iw = (int)(t % in_w); t /= in_w;
+  const int ih = (int)(t % in_h);
+  const long long n = t / in_h;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int oh = max(0, ih / 2); oh <= min(out_h - 1, (ih + 1) / 2); ++oh)
+    for (int ow = max(0, iw / 2); ow <= min(out_w - 1, (iw + 1) / 2); ++ow) {
+      const uint32_t code = (uint32_t)((ih - 2 * oh + 1) * 3 + (iw - 2 * ow + 1));
+      const long long o = ((n * out_h + oh) * out_w + ow) * c + g * 8;
+      const uint2 p = *reinterpret_cast<const uint2*>(idx + o);
+      float d[8];
+      V8<T>::load(dy + o, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t a = ((e < 4 ? p.x : p.y) >> (8 * (e & 3))) & 0xffu;
+        if (a == code) acc[e] += d[e];
+      }
+    }
+  V8<T>::store(dx + i * 8, acc);
 }
 
 // dx[n, p, :] = dfeat[n, :] / hw
@@ -882,6 +994,39 @@ extern "C" int rmv_adam_step(float* params, const float* grads, float* exp_avg, 
   if (blocks > 16L * num_sms()) blocks = 16L * num_sms();
   adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, hyper, decoupled,
                                                grad_scale, n);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_maxpool3x3s2_fwd_idx(const void* x, void* y, void* idx, int n_img, int in_h,
+                                        int in_w, int c, int dtype, void* stream) {
+  RMV_CHECK_ARG(c % 8 == 0, "maxpool_fwd_idx: c must be a multiple of 8");
+  const int out_h = (in_h - 1) / 2 + 1, out_w = (in_w - 1) / 2 + 1;
+  const long long total = (long long)n_img * out_h * out_w * (c / 8);
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, (maxpool_fwd_idx_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)x, (T*)y, (uint8_t*)idx, in_h, in_w, c, out_h, out_w, total)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_maxpool3x3s2_bwd_idx(const void* idx, const void* dy, void* dx, int n_img,
+                                        int in_h, int in_w, int c, int dtype, void* stream) {
+  RMV_CHECK_ARG(c % 8 == 0, "maxpool_bwd_idx: c must be a multiple of 8");
+  const int out_h = (in_h - 1) / 2 + 1, out_w = (in_w - 1) / 2 + 1;
+  const long long total = (long long)n_img * in_h * in_w * (c / 8);
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, (maxpool_bwd_idx_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint8_t*)idx, (const T*)dy, (T*)dx, in_h, in_w, c, out_h, out_w, total)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_permute_cast_batch(const rmv_permute_job* jobs_dev, int n_jobs,
+                                      unsigned total_blocks, void* stream) {
+  RMV_CHECK_ARG(jobs_dev != nullptr || n_jobs == 0, "permute_cast_batch: null job table");
+  if (n_jobs == 0 || total_blocks == 0) return 0;
+  permute_cast_batch_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, n_jobs);
   RMV_LAUNCH_CHECK();
   return 0;
 }

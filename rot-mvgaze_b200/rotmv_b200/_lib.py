@@ -44,6 +44,16 @@ class ConvArgs(C.Structure):
     ]
 
 
+class PermuteJob(C.Structure):
+    """Mirror of `struct rmv_permute_job`."""
+
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p),
+                ("d0", C.c_int), ("d1", C.c_int), ("d2", C.c_int), ("d3", C.c_int),
+                ("s0", C.c_longlong), ("s1", C.c_longlong), ("s2", C.c_longlong), ("s3", C.c_longlong),
+                ("flip1", C.c_int), ("flip2", C.c_int), ("dst_dtype", C.c_int),
+                ("first_block", C.c_uint)]
+
+
 # name -> (restype, argtypes); every symbol include/rotmv_sm100.h declares must be listed here
 # (tests/test_abi.py checks the header against this table and against the built library).
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
@@ -74,8 +84,11 @@ SIGNATURES = {
     "rmv_relu_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "rmv_colsum": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp]),
     "rmv_permute_cast": (_i, [_vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _vp]),
+    "rmv_permute_cast_batch": (_i, [_vp, _i, C.c_uint, _vp]),
     "rmv_dilate2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rmv_maxpool3x3s2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rmv_maxpool3x3s2_fwd_idx": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rmv_maxpool3x3s2_bwd_idx": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rmv_avgpool_bwd": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _vp]),
     "rmv_head_loss_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _vp, _i, _i, _f, _i, _f, _vp, _ll, _vp, _vp,
                                _vp, _vp]),

@@ -29,6 +29,11 @@ def _ck(name, *args):
     RF._call(name, {"desc": name}, getattr(L.load(), name), *args, L.stream_ptr())
 
 
+def dims4(dims):
+    """Pad a shape to four dims on the left (the permute kernels are 4-D)."""
+    return (1,) * (4 - len(dims)) + tuple(dims)
+
+
 class _BN:
     """Per-layer BatchNorm state: parameter views + saved statistics of the last forward."""
 
@@ -109,6 +114,7 @@ class TrainEngine:
         self._bufs: Dict[Any, torch.Tensor] = {}
         self.loss = torch.zeros((1,), device=self.device, dtype=torch.float32)
         self.launches_last_step = 0
+        self._wjobs, self._wjob_tags, self._wjobs_ready = [], set(), False
 
     # ------------------------------------------------------------------------------------------
     def set_lr(self, lr: float) -> None:
@@ -123,32 +129,59 @@ class TrainEngine:
         return t
 
     # ---- filter layout transforms (fp32 OIHW master -> engine layouts) ------------------------
+    # The first step launches one rmv_permute_cast per tensor and records the jobs; from the second
+    # step on, ONE batched launch at the top of the step re-derives all of them (the masters only
+    # change in the Adam kernel at the end of a step) and these helpers just return the buffers.
+    def _transform(self, src, tag, dims, strides, flip):
+        out = self._buf(tag, dims)
+        if self._wjobs_ready:
+            return out
+        job = (src.data_ptr(), out.data_ptr(), *[int(d) for d in dims4(dims)], *strides, flip, flip,
+               self.dtc)
+        if tag not in self._wjob_tags:
+            self._wjob_tags.add(tag)
+            self._wjobs.append(job)
+        d = dims4(dims)
+        _ck("rmv_permute_cast", src.data_ptr(), out.data_ptr(), d[0], d[1], d[2], d[3], *strides,
+            flip, flip, self.dtc)
+        return out
+
     def _w_fwd(self, conv, tag):
         k, c, r, s = conv.weight.shape
-        out = self._buf(("wf", tag), (k, r, s, c))
-        _ck("rmv_permute_cast", conv.weight.data_ptr(), out.data_ptr(), k, r, s, c, c * r * s, s, 1,
-            r * s, 0, 0, self.dtc)
-        return out
+        return self._transform(conv.weight, ("wf", tag), (k, r, s, c), (c * r * s, s, 1, r * s), 0)
 
     def _w_dgrad(self, conv, tag):
         """Filters of the data-gradient convolution: wt[c][r'][s'][k] = w[k][c][R-1-r'][S-1-s']."""
         k, c, r, s = conv.weight.shape
-        out = self._buf(("wd", tag), (c, r, s, k))
-        _ck("rmv_permute_cast", conv.weight.data_ptr(), out.data_ptr(), c, r, s, k, r * s, s, 1,
-            c * r * s, 1, 1, self.dtc)
-        return out
+        return self._transform(conv.weight, ("wd", tag), (c, r, s, k), (r * s, s, 1, c * r * s), 1)
 
     def _lin_fwd(self, lin, tag):
         n, k = lin.weight.shape
-        out = self._buf(("lf", tag), (n, k))
-        _ck("rmv_permute_cast", lin.weight.data_ptr(), out.data_ptr(), 1, 1, n, k, 0, 0, k, 1, 0, 0, self.dtc)
-        return out
+        return self._transform(lin.weight, ("lf", tag), (n, k), (0, 0, k, 1), 0)
 
     def _lin_t(self, lin, tag):
         n, k = lin.weight.shape
-        out = self._buf(("lt", tag), (k, n))
-        _ck("rmv_permute_cast", lin.weight.data_ptr(), out.data_ptr(), 1, 1, k, n, 0, 0, 1, k, 0, 0, self.dtc)
-        return out
+        return self._transform(lin.weight, ("lt", tag), (k, n), (0, 0, 1, k), 0)
+
+    def _finish_wjobs(self):
+        """Upload the recorded job table (once)."""
+        jobs = (L.PermuteJob * len(self._wjobs))()
+        block = 0
+        for i, (src, dst, d0, d1, d2, d3, s0, s1, s2, s3, f1, f2, dt) in enumerate(self._wjobs):
+            j = jobs[i]
+            j.src, j.dst, j.d0, j.d1, j.d2, j.d3 = src, dst, d0, d1, d2, d3
+            j.s0, j.s1, j.s2, j.s3, j.flip1, j.flip2, j.dst_dtype = s0, s1, s2, s3, f1, f2, dt
+            j.first_block = block
+            block += (d0 * d1 * d2 * d3 + 1023) // 1024
+        raw = bytes(jobs)
+        self._wjob_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+        self._wjob_count, self._wjob_blocks = len(self._wjobs), block
+        self._wjobs_ready = True
+
+    def _run_wjobs(self):
+        RF._call("rmv_permute_cast_batch", {"desc": "rmv_permute_cast_batch"},
+                 L.load().rmv_permute_cast_batch, self._wjob_table.data_ptr(), self._wjob_count,
+                 self._wjob_blocks, L.stream_ptr())
 
     # ---- BatchNorm -----------------------------------------------------------------------------
     def _bn_fwd(self, bn: _BN, z, residual, relu, tag):
@@ -283,7 +316,8 @@ class TrainEngine:
         gt_flat = gt.float().reshape(m, 2).contiguous()
         self.flat_g.zero_()
         self.loss.zero_()
-        trunk = self.model._feat_extractor[0]
+        if self._wjobs_ready:
+            self._run_wjobs()
 
         # ================================ forward ================================
         # stem (models/resnet.py:262-265)
@@ -298,7 +332,11 @@ class TrainEngine:
             xv = imgs.permute(0, 2, 3, 1)
             stem_x, stem_xs = imgs, (tuple(xv.shape), (xv.stride(0), xv.stride(1), xv.stride(2), xv.stride(3)))
         y0 = self._bn_fwd(self.stem_bn, z0, None, True, "y_stem")
-        x = RF.maxpool3x3s2(y0)
+        ph, pw = (y0.shape[1] - 1) // 2 + 1, (y0.shape[2] - 1) // 2 + 1
+        x = self._buf("pool", (m, ph, pw, 64))
+        pool_idx = self._buf("pool_idx", (m, ph, pw, 64), torch.uint8)
+        _ck("rmv_maxpool3x3s2_fwd_idx", y0.data_ptr(), x.data_ptr(), pool_idx.data_ptr(), m,
+            y0.shape[1], y0.shape[2], 64, dtc)
         pool_out = x
         saved = []
         for bi, e in enumerate(self.blocks):
@@ -408,8 +446,8 @@ class TrainEngine:
                 res = dyr
             d_out = self._dgrad(dz1, c1, (bi, 1), x_in.shape, residual=res)
         d_y0 = self._buf("dy_stem", y0.shape)
-        _ck("rmv_maxpool3x3s2_bwd", y0.data_ptr(), d_out.data_ptr(), d_y0.data_ptr(), m, y0.shape[1],
-            y0.shape[2], y0.shape[3], dtc)
+        _ck("rmv_maxpool3x3s2_bwd_idx", pool_idx.data_ptr(), d_out.data_ptr(), d_y0.data_ptr(), m,
+            y0.shape[1], y0.shape[2], y0.shape[3], dtc)
         dz0, _ = self._bn_bwd(self.stem_bn, z0, d_y0, y0, "stem")
         if stem_x is None:   # bf16: tcgen05 stem weight gradient straight from the fp32 NCHW images
             RF._call("rmv_stem_wgrad", {"desc": "stem wgrad (tcgen05)", "engine": "tcgen05-wgrad",
@@ -420,6 +458,8 @@ class TrainEngine:
                      L.stream_ptr())
         else:
             self._wgrad(stem_x, dz0, self.stem_conv, 7, 7, 2, 3, x_strides=stem_xs)
+        if not self._wjobs_ready:
+            self._finish_wjobs()
         return {"loss": self.loss, "preds": preds, "pool_out": pool_out}
 
 
