@@ -14,6 +14,18 @@ constexpr float kRadToDeg = 57.29577951308232f;
 
 template <typename T> struct V8;
 template <> struct V8<__nv_bfloat16> {
+  typedef uint4 Raw;  // packed form: keeps unrolled loads in 4 registers until they are consumed
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) {
+    return *reinterpret_cast<const uint4*>(p);
+  }
+  static __device__ __forceinline__ void unpack(const Raw& u, float* f) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 v = unpack_bf16x2(w[i]);
+      f[2 * i] = v.x; f[2 * i + 1] = v.y;
+    }
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
     const uint4 u = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -31,6 +43,17 @@ template <> struct V8<__nv_bfloat16> {
   }
 };
 template <> struct V8<float> {
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw load_raw(const float* p) {
+    Raw r;
+    r.a = *reinterpret_cast<const float4*>(p);
+    r.b = *(reinterpret_cast<const float4*>(p) + 1);
+    return r;
+  }
+  static __device__ __forceinline__ void unpack(const Raw& r, float* f) {
+    f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w;
+    f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+  }
   static __device__ __forceinline__ void load(const float* p, float* f) {
     const float4 a = *reinterpret_cast<const float4*>(p);
     const float4 b = *(reinterpret_cast<const float4*>(p) + 1);
@@ -54,15 +77,19 @@ template <typename T, bool BWD>
 __global__ void __launch_bounds__(256)
 bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* __restrict__ y_mask,
                  const float* __restrict__ mean, const float* __restrict__ invstd, int pix, int c,
-                 int views, double* __restrict__ acc /* [views][c][2] */) {
+                 int views, int imgs_per_view, double* __restrict__ acc /* [views][c][2] */) {
   extern __shared__ float s_red[];  // [row_lanes][c][2]
   const int cg = c / 8;
   const int lanes = blockDim.x / cg;  // row lanes per block (>= 1)
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
-  const int n = blockIdx.y, v = n % views;
+  // block (x, v): a slab of the rows (image-of-this-view, pixel) -- the number of fp64 atomics per
+  // launch depends on the grid only, not on the batch size
+  const int v = blockIdx.y;
   const int slabs = gridDim.x;
-  const int rows_per = (pix + slabs - 1) / slabs;
-  const int r0 = blockIdx.x * rows_per, r1 = min(pix, r0 + rows_per);
+  const long long rows_total = (long long)imgs_per_view * pix;
+  const long long rows_per = (rows_total + slabs - 1) / slabs;
+  const long long r0 = blockIdx.x * rows_per;
+  const long long r1 = r0 + rows_per < rows_total ? r0 + rows_per : rows_total;
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
@@ -75,26 +102,46 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* __r
     }
   }
   if (lane < lanes) {
-    for (int r = r0 + lane; r < r1; r += lanes) {
-      const long long off = ((long long)n * pix + r) * c + g * 8;
-      float f[8];
-      V8<T>::load(z + off, f);
-      if (!BWD) {
+    constexpr int U = 4;  // independent 16-byte loads in flight per tensor
+    for (long long r = r0 + lane; r < r1; r += lanes * U) {
+      typename V8<T>::Raw zr[U], dr[U], mr[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s1[i] += f[i]; s2[i] = fmaf(f[i], f[i], s2[i]); }
-      } else {
-        float d[8];
-        V8<T>::load(dy + off, d);
-        if (y_mask != nullptr) {
-          float m[8];
-          V8<T>::load(y_mask + off, m);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+      for (int j = 0; j < U; ++j) {
+        const long long rr = r + j * lanes;
+        if (rr < r1) {
+          const long long img = rr / pix;
+          const long long off = ((img * views + v) * pix + (rr - img * pix)) * c + g * 8;
+          zr[j] = V8<T>::load_raw(z + off);
+          if (BWD) {
+            dr[j] = V8<T>::load_raw(dy + off);
+            if (y_mask != nullptr) mr[j] = V8<T>::load_raw(y_mask + off);
+          }
         }
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s1[i] += d[i];
-          s2[i] = fmaf(d[i], (f[i] - mu[i]) * is[i], s2[i]);
+      for (int j = 0; j < U; ++j) {
+        const long long rr = r + j * lanes;
+        if (rr < r1) {
+          float f[8];
+          V8<T>::unpack(zr[j], f);
+          if (!BWD) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s1[i] += f[i]; s2[i] = fmaf(f[i], f[i], s2[i]); }
+          } else {
+            float d[8];
+            V8<T>::unpack(dr[j], d);
+            if (y_mask != nullptr) {
+              float m[8];
+              V8<T>::unpack(mr[j], m);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              s1[i] += d[i];
+              s2[i] = fmaf(d[i], (f[i] - mu[i]) * is[i], s2[i]);
+            }
+          }
         }
       }
     }
@@ -153,7 +200,7 @@ __global__ void bn_finalize_kernel(double* __restrict__ acc, const float* __rest
 constexpr int kEwUnroll = 4;
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ a, const float* __restrict__ b,
                 const T* __restrict__ residual, T* __restrict__ y, int pix, int c, int views,
                 int relu) {
@@ -170,24 +217,26 @@ bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ a, const floa
   const T* ri = residual ? residual + (long long)n * pix * c : nullptr;
   T* yi = y + (long long)n * pix * c;
   for (long long i = i0; i < per_img; i += stride * kEwUnroll) {
-    float f[kEwUnroll][8], r[kEwUnroll][8];
+    typename V8<T>::Raw zr[kEwUnroll], rr[kEwUnroll];
 #pragma unroll
     for (int j = 0; j < kEwUnroll; ++j) {
       const long long k = i + j * stride;
       if (k < per_img) {
-        V8<T>::load(zi + k * 8, f[j]);
-        if (ri) V8<T>::load(ri + k * 8, r[j]);
+        zr[j] = V8<T>::load_raw(zi + k * 8);
+        if (ri) rr[j] = V8<T>::load_raw(ri + k * 8);
       }
     }
 #pragma unroll
     for (int j = 0; j < kEwUnroll; ++j) {
       const long long k = i + j * stride;
       if (k < per_img) {
-        float o[8];
+        float f[8], r[8], o[8];
+        V8<T>::unpack(zr[j], f);
+        if (ri) V8<T>::unpack(rr[j], r);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          o[e] = fmaf(f[j][e], ca[e], cb[e]);
-          if (ri) o[e] += r[j][e];
+          o[e] = fmaf(f[e], ca[e], cb[e]);
+          if (ri) o[e] += r[e];
           if (relu) o[e] = fmaxf(o[e], 0.f);
         }
         V8<T>::store(yi + k * 8, o);
@@ -225,10 +274,10 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ acc, const float* __
 }
 
 // dz = k0*dyr + k1*z + k2, dyr = dy * (y_mask > 0); optionally also writes dyr (skip-path grad)
-constexpr int kBwdUnroll = 2;  // 3 input streams: 6 loads in flight per thread, <= 80 registers
+constexpr int kBwdUnroll = 4;  // 3 input streams x 4 packed 16-byte loads in flight per thread
 
 template <typename T>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* __restrict__ y_mask,
                     const float* __restrict__ k0, const float* __restrict__ k1,
                     const float* __restrict__ k2, T* __restrict__ dz, T* __restrict__ dyr_out,
@@ -245,28 +294,31 @@ bn_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* 
   V8<float>::load(k2 + v * c + g * 8, c2);
   const long long img = (long long)n * pix * c;
   for (long long i = i0; i < per_img; i += stride * kBwdUnroll) {
-    float f[kBwdUnroll][8], d[kBwdUnroll][8], m[kBwdUnroll][8];
+    typename V8<T>::Raw zr[kBwdUnroll], dr[kBwdUnroll], mr[kBwdUnroll];
 #pragma unroll
     for (int j = 0; j < kBwdUnroll; ++j) {
       const long long k = i + j * stride;
       if (k < per_img) {
-        V8<T>::load(z + img + k * 8, f[j]);
-        V8<T>::load(dy + img + k * 8, d[j]);
-        if (y_mask) V8<T>::load(y_mask + img + k * 8, m[j]);
+        zr[j] = V8<T>::load_raw(z + img + k * 8);
+        dr[j] = V8<T>::load_raw(dy + img + k * 8);
+        if (y_mask) mr[j] = V8<T>::load_raw(y_mask + img + k * 8);
       }
     }
 #pragma unroll
     for (int j = 0; j < kBwdUnroll; ++j) {
       const long long k = i + j * stride;
       if (k < per_img) {
-        float o[8];
+        float f[8], d[8], m[8], o[8];
+        V8<T>::unpack(zr[j], f);
+        V8<T>::unpack(dr[j], d);
+        if (y_mask) V8<T>::unpack(mr[j], m);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          if (y_mask) d[j][e] = m[j][e] > 0.f ? d[j][e] : 0.f;
-          o[e] = fmaf(c0[e], d[j][e], fmaf(c1[e], f[j][e], c2[e]));
+          if (y_mask) d[e] = m[e] > 0.f ? d[e] : 0.f;
+          o[e] = fmaf(c0[e], d[e], fmaf(c1[e], f[e], c2[e]));
         }
         V8<T>::store(dz + img + k * 8, o);
-        if (dyr_out) V8<T>::store(dyr_out + img + k * 8, d[j]);
+        if (dyr_out) V8<T>::store(dyr_out + img + k * 8, d);
       }
     }
   }
@@ -781,17 +833,18 @@ static unsigned ew_blocks_x(int pix, int c, int n_img, int unroll = rmv::kEwUnro
   return (unsigned)bx;
 }
 
-static int bn_reduce_cfg(int pix, int c, int n_img, dim3* grid, int* smem) {
+static int bn_reduce_cfg(int pix, int c, int n_img, int views, dim3* grid, int* smem) {
   const int cg = c / 8;
   RMV_CHECK_ARG(c % 8 == 0 && cg <= 256 && 256 % cg == 0,
                 "batchnorm: channels=%d must be 8*2^k with c <= 2048", c);
   const int lanes = 256 / cg;
-  int slabs = (pix + lanes * 8 - 1) / (lanes * 8);  // ~8 rows per thread
+  const long long rows_total = (long long)(n_img / views) * pix;
+  long long slabs = (rows_total + lanes * 16 - 1) / (lanes * 16);  // >= 16 rows per thread
   if (slabs < 1) slabs = 1;
-  long want = 8L * num_sms() / (n_img > 0 ? n_img : 1);
+  long want = 6L * num_sms() / views;
   if (want < 1) want = 1;
-  if (slabs > want) slabs = (int)want;
-  *grid = dim3((unsigned)slabs, (unsigned)n_img);
+  if (slabs > want) slabs = want;
+  *grid = dim3((unsigned)slabs, (unsigned)views);
   *smem = lanes * c * 2 * (int)sizeof(float);
   return 0;
 }
@@ -801,9 +854,9 @@ extern "C" int rmv_bn_stats(const void* z, int dtype, int n_img, int pix, int c,
   RMV_CHECK_ARG(views >= 1 && n_img % views == 0, "bn_stats: n_img=%d not a multiple of views=%d", n_img, views);
   if (n_img == 0) return 0;
   dim3 grid; int smem;
-  if (int rc = bn_reduce_cfg(pix, c, n_img, &grid, &smem)) return rc;
+  if (int rc = bn_reduce_cfg(pix, c, n_img, views, &grid, &smem)) return rc;
   DISPATCH_T(dtype, (bn_reduce_kernel<T, false><<<grid, 256, smem, (cudaStream_t)stream>>>(
-      (const T*)z, nullptr, nullptr, nullptr, nullptr, pix, c, views, acc)));
+      (const T*)z, nullptr, nullptr, nullptr, nullptr, pix, c, views, n_img / views, acc)));
   RMV_LAUNCH_CHECK();
   return 0;
 }
@@ -838,9 +891,9 @@ extern "C" int rmv_bn_bwd_reduce(const void* z, const void* dy, const void* y_ma
   RMV_CHECK_ARG(views >= 1 && n_img % views == 0, "bn_bwd_reduce: n_img not a multiple of views");
   if (n_img == 0) return 0;
   dim3 grid; int smem;
-  if (int rc = bn_reduce_cfg(pix, c, n_img, &grid, &smem)) return rc;
+  if (int rc = bn_reduce_cfg(pix, c, n_img, views, &grid, &smem)) return rc;
   DISPATCH_T(dtype, (bn_reduce_kernel<T, true><<<grid, 256, smem, (cudaStream_t)stream>>>(
-      (const T*)z, (const T*)dy, (const T*)y_mask, mean, invstd, pix, c, views, acc)));
+      (const T*)z, (const T*)dy, (const T*)y_mask, mean, invstd, pix, c, views, n_img / views, acc)));
   RMV_LAUNCH_CHECK();
   return 0;
 }
