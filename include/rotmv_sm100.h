@@ -65,6 +65,17 @@ typedef struct rmv_conv_args {
 
 int rmv_conv2d_fwd(const rmv_conv_args* args, void* stream);
 
+/* Data gradient of y = conv(x, w, stride, pad) on the tcgen05 engine (the backward of
+ * models/resnet.py:31-47 that autograd/cuDNN computes for trainer.py:142):
+ *     dx[n,ih,iw,c] (+ residual) = sum_{r,s,k} dy[n,oh,ow,k] * w[k,c,r,s],   ih = oh*stride - pad + r
+ * The argument struct is read "transposed": x/in_h/in_w/c_in describe dy (c_in = the forward
+ * c_out), y/out_h/out_w/c_out describe dx (c_out = the forward c_in), kh/kw/stride/pad are the
+ * FORWARD conv's, and w holds the reversed, transposed filters wt[c][kh-1-r][kw-1-s][k] = w[k][c][r][s]
+ * (bf16). scale/shift/relu must be unset; residual (bf16, dx geometry) is added. stride 2 runs as
+ * four parity-class convolutions over the undilated dy (1x1 filters: dx is zero-filled first and
+ * must be dense). */
+int rmv_conv2d_dgrad(const rmv_conv_args* args, void* stream);
+
 /* Stem im2col: x fp32 NCHW [n,3,224,224]-like -> A[n*out_h*out_w, k_pad] (bf16 or fp32), row =
  * (kh,kw,c)-ordered 7x7x3 patch (stride 2, pad 3) zero-padded to k_pad columns. Feeds the stem
  * conv (models/resnet.py:184-186,262) to the tensor-core GEMM. */
@@ -156,21 +167,38 @@ int rmv_bn_finalize(double* acc, const float* gamma, const float* beta, float* r
                     float* running_var, long long* num_batches, float* mean, float* invstd,
                     float* a, float* b, int c, int views, long long count_per_view, float eps,
                     float momentum, void* stream);
-/* y = relu?(a[v,c]*z + b[v,c] + residual) */
+/* rmv_bn_stats + rmv_bn_finalize in ONE launch: the last block to finish (ticket counter, zero on
+ * entry and on exit) turns the sums into the coefficients; count_per_view = n_img/views * pix. */
+int rmv_bn_stats_finalize(const void* z, int dtype, int n_img, int pix, int c, int views,
+                          double* acc, unsigned int* ticket, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, long long* num_batches,
+                          float* mean, float* invstd, float* a, float* b, float eps, float momentum,
+                          void* stream);
+/* y = relu?(a[v,c]*z + b[v,c] + residual). relu_bits (may be NULL): packed ReLU mask for the
+ * backward pass, [n_img*pix*c/8] bytes, bit e of byte i = element 8*i+e was > 0 (16x less
+ * backward traffic than re-reading y). */
 int rmv_bn_apply(const void* z, const float* a, const float* b, const void* residual, void* y,
-                 int dtype, int n_img, int pix, int c, int views, int relu, void* stream);
-/* acc[views][c][2] += { sum dyr, sum dyr*xhat }, dyr = dy * (y_mask > 0) (y_mask may be NULL). */
-int rmv_bn_bwd_reduce(const void* z, const void* dy, const void* y_mask, const float* mean,
-                      const float* invstd, int dtype, int n_img, int pix, int c, int views,
-                      double* acc, void* stream);
+                 unsigned char* relu_bits, int dtype, int n_img, int pix, int c, int views,
+                 int relu, void* stream);
+/* acc[views][c][2] += { sum dyr, sum dyr*xhat }, dyr = dy masked by the ReLU: y_mask is NULL (no
+ * ReLU), the ReLU output tensor (mask_is_bits = 0: y > 0) or rmv_bn_apply's relu_bits (= 1). */
+int rmv_bn_bwd_reduce(const void* z, const void* dy, const void* y_mask, int mask_is_bits,
+                      const float* mean, const float* invstd, int dtype, int n_img, int pix, int c,
+                      int views, double* acc, void* stream);
 /* dgamma/dbeta[c] and the per-(view,channel) coefficients of dz = k0*dyr + k1*z + k2; resets acc. */
 int rmv_bn_bwd_finalize(double* acc, const float* gamma, const float* mean, const float* invstd,
                         float* dgamma, float* dbeta, float* k0, float* k1, float* k2, int c,
                         int views, long long count_per_view, void* stream);
+/* rmv_bn_bwd_reduce + rmv_bn_bwd_finalize in ONE launch (same ticket protocol). */
+int rmv_bn_bwd_reduce_finalize(const void* z, const void* dy, const void* y_mask, int mask_is_bits,
+                               const float* mean, const float* invstd, int dtype, int n_img,
+                               int pix, int c, int views, double* acc, unsigned int* ticket,
+                               const float* gamma, float* dgamma, float* dbeta, float* k0,
+                               float* k1, float* k2, void* stream);
 /* dz = k0*dyr + k1*z + k2; optionally also writes dyr (the gradient of the residual branch). */
-int rmv_bn_bwd_apply(const void* z, const void* dy, const void* y_mask, const float* k0,
-                     const float* k1, const float* k2, void* dz, void* dyr_out, int dtype,
-                     int n_img, int pix, int c, int views, void* stream);
+int rmv_bn_bwd_apply(const void* z, const void* dy, const void* y_mask, int mask_is_bits,
+                     const float* k0, const float* k1, const float* k2, void* dz, void* dyr_out,
+                     int dtype, int n_img, int pix, int c, int views, void* stream);
 /* dst = (mask > 0 ? src : 0) + add, 2-D row-strided (mask/add may be NULL): ReLU backward,
  * gradient accumulation of the concat-free fusion buffers. */
 int rmv_relu_bwd(const void* src, long long ld_src, const void* mask, long long ld_mask,
@@ -186,8 +214,14 @@ int rmv_permute_cast(const float* src, void* dst, int d0, int d1, int d2, int d3
                      long long s1, long long s2, long long s3, int flip1, int flip2, int dst_dtype,
                      void* stream);
 /* Batched rmv_permute_cast: `jobs_dev` is a DEVICE array of n_jobs jobs sorted by first_block;
- * job i owns blocks [first_block_i, first_block_{i+1}) of 1024 elements each (total_blocks in all).
- * One launch re-derives every engine-layout filter tensor of a training step. */
+ * job i owns blocks [first_block_i, first_block_{i+1}) (total_blocks in all). One launch re-derives
+ * every engine-layout filter tensor of a training step. `kind` picks the access pattern (all give
+ * the result the generic form describes):
+ *   0 generic 4-D permute (rmv_permute_cast semantics), ceil(total/1024) blocks;
+ *   1 contiguous cast, ceil(total/1024) blocks;
+ *   2 dims (C,R,S,K): src [K][C][R*S] -> dst [C][R*S (reversed if flip1)][K], 64x64 tiles through
+ *     shared memory, ceil(C*R*S/64)*ceil(K/64) blocks;
+ *   3 dims (K,R,S,C): src [K][C][R*S] -> dst [K][R*S][C], one block per k. */
 typedef struct rmv_permute_job {
   const float* src;
   void* dst;
@@ -195,6 +229,7 @@ typedef struct rmv_permute_job {
   long long s0, s1, s2, s3;
   int flip1, flip2, dst_dtype;
   unsigned first_block;
+  int kind;
 } rmv_permute_job;
 int rmv_permute_cast_batch(const rmv_permute_job* jobs_dev, int n_jobs, unsigned total_blocks,
                            void* stream);

@@ -66,3 +66,21 @@ extern "C" int rmv_conv2d_fwd(const rmv_conv_args* args, void* stream) {
   if (p.engine == RMV_ENGINE_AUTO && tc_ok) return conv_fwd_tc(p, s);
   return conv_fwd_simt(p, s);
 }
+
+extern "C" int rmv_conv2d_dgrad(const rmv_conv_args* args, void* stream) {
+  RMV_CHECK_ARG(args != nullptr, "conv2d_dgrad: null args");
+  const ConvArgs& p = *args;
+  RMV_CHECK_ARG(p.x && p.w && p.y, "conv2d_dgrad: null tensor pointer");
+  RMV_CHECK_ARG(p.n_img >= 0 && p.in_h > 0 && p.in_w > 0 && p.c_in > 0 && p.c_out > 0,
+                "conv2d_dgrad: bad shape");
+  RMV_CHECK_ARG(p.in_h == (p.out_h + 2 * p.pad - p.kh) / p.stride + 1 &&
+                    p.in_w == (p.out_w + 2 * p.pad - p.kw) / p.stride + 1,
+                "conv2d_dgrad: dy %dx%d is not the output of a k%d s%d p%d conv over %dx%d", p.in_h,
+                p.in_w, p.kh, p.stride, p.pad, p.out_h, p.out_w);
+  RMV_CHECK_ARG(p.x_dtype == RMV_DTYPE_BF16 && p.c_in % 64 == 0 && p.c_out % 8 == 0 &&
+                    (p.x_sc == 0 || p.x_sc == 1),
+                "conv2d_dgrad: tcgen05 engine needs bf16, c(dy) %% 64 == 0, c(dx) %% 8 == 0");
+  RMV_CHECK_ARG(p.scale == nullptr && p.shift == nullptr && p.relu == 0,
+                "conv2d_dgrad: no scale/shift/relu epilogue");
+  return conv_dgrad_tc(p, (cudaStream_t)stream);
+}

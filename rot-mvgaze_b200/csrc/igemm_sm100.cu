@@ -46,6 +46,7 @@ struct IgemmArgs {
   signed char tap_map[kMaxTaps];
   signed char tap_dw[kMaxTaps];
   signed char tap_dh[kMaxTaps];
+  signed char tap_w[kMaxTaps];  // index of the tap inside the filter tensor (B operand K offset)
   const float* scale;
   const float* shift;
   int relu;
@@ -169,8 +170,8 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
           tma_load_4d(smem_a + stage * kABytes, &args.tmap_a[args.tap_map[tap]], &full_bar[stage],
                       cb * kBlockK, ow0 + args.tap_dw[tap], oh0 + args.tap_dh[tap], n0);
-          tma_load_2d(smem_b + stage * C::kBBytes, &args.tmap_b, &full_bar[stage], kb * kBlockK,
-                      n_tile * BLOCK_N);
+          tma_load_2d(smem_b + stage * C::kBBytes, &args.tmap_b, &full_bar[stage],
+                      (args.tap_w[tap] * args.c_blocks + cb) * kBlockK, n_tile * BLOCK_N);
           if (++cb == args.c_blocks) { cb = 0; ++tap; }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -421,13 +422,21 @@ int dispatch(const IgemmArgs& a, int total, bool has_res, bool out_f32, cudaStre
 
 }  // namespace
 
-int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) {
+int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) { return conv_taps_tc(p, nullptr, stream); }
+
+// `taps` == nullptr: the dense kh x kw filter of `p`. Otherwise (stride 1 only) an explicit list of
+// taps: A is the dy/x box shifted by (dh, dw), B the filter tap `widx` of a [c_out][w_taps][c_in]
+// tensor; p.kh/p.kw/p.pad are ignored (used by the stride-2 data gradient, see conv_dgrad_tc).
+int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
   const bool out_f32 = (p.y_dtype == RMV_DTYPE_F32);
   const int y_es = out_f32 ? 4 : 2;
   RMV_CHECK_ARG(p.c_in % kBlockK == 0, "tcgen05 conv: c_in=%d must be a multiple of 64", p.c_in);
   RMV_CHECK_ARG(p.c_out % 8 == 0, "tcgen05 conv: c_out=%d must be a multiple of 8", p.c_out);
   RMV_CHECK_ARG(p.stride == 1 || p.stride == 2, "tcgen05 conv: stride %d unsupported", p.stride);
   RMV_CHECK_ARG(p.kh * p.kw <= kMaxTaps, "tcgen05 conv: %dx%d filter too large", p.kh, p.kw);
+  RMV_CHECK_ARG(taps == nullptr || (p.stride == 1 && taps->n >= 1 && taps->n <= kMaxTaps &&
+                                    taps->w_taps >= 1),
+                "tcgen05 conv: explicit tap lists need stride 1 and 1..%d taps", kMaxTaps);
   RMV_CHECK_ARG(p.x_sw % 8 == 0 && p.x_sh % 8 == 0 && p.x_sn % 8 == 0,
                 "tcgen05 conv: input pixel strides must be multiples of 8 elements");
   RMV_CHECK_ARG((reinterpret_cast<uintptr_t>(p.x) & 15) == 0 &&
@@ -451,7 +460,7 @@ int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) {
   int in_w = p.in_w, in_h = p.in_h;
 
   // 1x1 stride-1 over a dense pixel grid is a plain GEMM: flatten (n, h, w) into one axis.
-  const bool pointwise = (p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0);
+  const bool pointwise = (taps == nullptr && p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0);
   const bool x_dense = (p.x_sh == p.x_sw * p.in_w) && (p.x_sn == p.x_sh * p.in_h);
   const bool y_dense = (p.y_sh == p.y_sw * p.out_w) && (p.y_sn == p.y_sh * p.out_h);
   const bool r_dense =
@@ -485,11 +494,14 @@ int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) {
   const int s = p.stride;
   int plane_id[2][2] = {{-1, -1}, {-1, -1}};
   int n_planes = 0;
-  a.num_taps = p.kh * p.kw;
-  for (int r = 0; r < p.kh; ++r)
-    for (int q = 0; q < p.kw; ++q) {
-      const int t = r * p.kw + q;
-      const int ph = ((r - p.pad) % s + s) % s, pw = ((q - p.pad) % s + s) % s;
+  a.num_taps = taps ? taps->n : p.kh * p.kw;
+  const int loop_h = taps ? 1 : p.kh, loop_w = taps ? taps->n : p.kw;
+  for (int r = 0; r < loop_h; ++r)
+    for (int q = 0; q < loop_w; ++q) {
+      const int t = r * loop_w + q;
+      // dense filter: tap (r,q) reads input pixel (oh*s - pad + r, ow*s - pad + q)
+      const int off_h = taps ? taps->dh[t] : r - p.pad, off_w = taps ? taps->dw[t] : q - p.pad;
+      const int ph = (off_h % s + s) % s, pw = (off_w % s + s) % s;
       if (plane_id[ph][pw] < 0) {
         const int pl_w = (in_w - pw + s - 1) / s, pl_h = (in_h - ph + s - 1) / s;
         RMV_CHECK_ARG(pl_w > 0 && pl_h > 0, "tcgen05 conv: empty parity plane");
@@ -506,8 +518,9 @@ int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) {
         plane_id[ph][pw] = n_planes++;
       }
       a.tap_map[t] = (signed char)plane_id[ph][pw];
-      a.tap_dh[t] = (signed char)floordiv(r - p.pad, s);
-      a.tap_dw[t] = (signed char)floordiv(q - p.pad, s);
+      a.tap_dh[t] = (signed char)floordiv(off_h, s);
+      a.tap_dw[t] = (signed char)floordiv(off_w, s);
+      a.tap_w[t] = (signed char)(taps ? taps->widx[t] : t);
     }
 
   const long m_tiles = (long)a.tiles_w * a.tiles_h * a.tiles_n;
@@ -517,7 +530,7 @@ int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) {
                       : 128;
   RMV_CHECK_ARG(block_n == 64 || block_n == 128 || block_n == 256, "bad block_n %d", block_n);
   {
-    const long long k_total = (long long)a.num_taps * p.c_in;
+    const long long k_total = (long long)(taps ? taps->w_taps : a.num_taps) * p.c_in;
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)p.c_out};
     cuuint64_t strides[1] = {(cuuint64_t)(k_total * 2)};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
@@ -554,6 +567,73 @@ int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream) {
     case 128: return dispatch<128>(a, total, has_res, out_f32, stream);
     default: return dispatch<256>(a, total, has_res, out_f32, stream);
   }
+}
+
+// Data gradient of y = conv(x, w, stride, pad) through the forward kernel (argument convention:
+// rmv_conv2d_dgrad in the header -- p.x = dy, p.w = reversed/transposed filters, p.y = dx).
+// stride 1: one conv with pad' = k-1-pad. stride 2: the four output parity classes (ih%2, iw%2)
+// are independent stride-1 convolutions over the UNDILATED dy with 1/2/2/4 of the 9 taps each,
+// written through TMA store maps with doubled pixel strides -- no zero-dilated copy of dy and a
+// quarter of the MMA work of the dilated formulation.
+int conv_dgrad_tc(const ConvArgs& p, cudaStream_t stream) {
+  RMV_CHECK_ARG(p.kh == p.kw, "dgrad: square filters only");
+  if (p.stride == 1) {
+    ConvArgs q = p;
+    q.pad = p.kh - 1 - p.pad;
+    RMV_CHECK_ARG(q.pad >= 0 && p.out_h == p.in_h + 2 * q.pad - p.kh + 1 &&
+                      p.out_w == p.in_w + 2 * q.pad - p.kw + 1,
+                  "dgrad: dx size %dx%d inconsistent with dy %dx%d k%d p%d", p.out_h, p.out_w,
+                  p.in_h, p.in_w, p.kh, p.pad);
+    return conv_fwd_tc(q, stream);
+  }
+  RMV_CHECK_ARG(p.stride == 2, "dgrad: stride %d unsupported", p.stride);
+  RMV_CHECK_ARG(p.kh * p.kw <= kMaxTaps, "dgrad: filter too large");
+  const int y_es = p.y_dtype == RMV_DTYPE_F32 ? 4 : 2;
+  TapList tl[2][2];
+  bool any_empty = false;
+  for (int pa = 0; pa < 2; ++pa)
+    for (int pb = 0; pb < 2; ++pb) {
+      TapList& t = tl[pa][pb];
+      t.n = 0;
+      t.w_taps = p.kh * p.kw;
+      // forward tap (r, s) contributes to dx row ih = 2*oh - pad + r: for ih = 2i + pa the dy row is
+      // oh = i + (pa + pad - r)/2 when that is an integer. The reversed filter tensor holds
+      // w[., ., r, s] at tap (kh-1-r, kw-1-s).
+      for (int r = 0; r < p.kh; ++r)
+        for (int q = 0; q < p.kw; ++q) {
+          if (((pa + p.pad - r) & 1) || ((pb + p.pad - q) & 1)) continue;
+          t.dh[t.n] = (signed char)floordiv(pa + p.pad - r, 2);
+          t.dw[t.n] = (signed char)floordiv(pb + p.pad - q, 2);
+          t.widx[t.n] = (signed char)((p.kh - 1 - r) * p.kw + (p.kw - 1 - q));
+          ++t.n;
+        }
+      const int sub_h = (p.out_h - pa + 1) / 2, sub_w = (p.out_w - pb + 1) / 2;
+      if (t.n == 0 && sub_h > 0 && sub_w > 0) any_empty = true;
+    }
+  if (any_empty) {
+    // some parity class receives no gradient (1x1 stride-2 filters): dx must read as zero there
+    RMV_CHECK_ARG(p.residual == nullptr, "dgrad: residual with an empty parity class");
+    const bool dense =
+        p.y_sw == p.c_out && p.y_sh == p.y_sw * p.out_w && p.y_sn == p.y_sh * p.out_h;
+    RMV_CHECK_ARG(dense, "dgrad: dx must be dense when a parity class is empty");
+    RMV_CUDA(cudaMemsetAsync(p.y, 0, (size_t)p.n_img * p.out_h * p.out_w * p.c_out * y_es, stream));
+  }
+  for (int pa = 0; pa < 2; ++pa)
+    for (int pb = 0; pb < 2; ++pb) {
+      const int sub_h = (p.out_h - pa + 1) / 2, sub_w = (p.out_w - pb + 1) / 2;
+      if (tl[pa][pb].n == 0 || sub_h <= 0 || sub_w <= 0) continue;
+      ConvArgs q = p;
+      q.stride = 1; q.pad = 0;
+      q.out_h = sub_h; q.out_w = sub_w;
+      q.y = (char*)p.y + ((long long)pa * p.y_sh + (long long)pb * p.y_sw) * y_es;
+      q.y_sh = 2 * p.y_sh; q.y_sw = 2 * p.y_sw;
+      if (p.residual) {
+        q.residual = (const char*)p.residual + ((long long)pa * p.r_sh + (long long)pb * p.r_sw) * 2;
+        q.r_sh = 2 * p.r_sh; q.r_sw = 2 * p.r_sw;
+      }
+      if (int rc = conv_taps_tc(q, &tl[pa][pb], stream)) return rc;
+    }
+  return 0;
 }
 
 }  // namespace rmv

@@ -10,8 +10,18 @@ namespace rmv {
 
 typedef rmv_conv_args ConvArgs;
 
+// Explicit tap list of an implicit GEMM: tap t reads the input box shifted by (dh, dw) pixels and
+// multiplies it with filter tap widx[t] of a [c_out][w_taps][c_in] tensor.
+struct TapList {
+  int n, w_taps;
+  signed char dh[49], dw[49], widx[49];
+};
+
 // tcgen05 / TMEM / TMA implicit GEMM (igemm_sm100.cu). bf16 in, bf16 or fp32 out.
 int conv_fwd_tc(const ConvArgs& p, cudaStream_t stream);
+int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream);
+// data gradient (stride 1 or 2) through the same kernel; see rmv_conv2d_dgrad
+int conv_dgrad_tc(const ConvArgs& p, cudaStream_t stream);
 // FFMA tiled implicit GEMM (simt_conv.cu). fp32 or bf16 storage, fp32 accumulation.
 int conv_fwd_simt(const ConvArgs& p, cudaStream_t stream);
 

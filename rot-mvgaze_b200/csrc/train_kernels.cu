@@ -71,25 +71,147 @@ inline unsigned nblk(long long total, int threads) { return (unsigned)((total + 
 // BatchNorm (train): per-(view, channel) statistics. Image n belongs to view n % views.
 // Partial sums are fp32 inside a thread (<= rows_per_block terms), fp64 across threads/blocks.
 // ---------------------------------------------------------------------------------------------
-// grid = (slabs, n_img); block = 256 threads = (c/8 channel groups) x (256/(c/8)) row lanes when
-// c <= 2048; each thread strides over the rows of its slab.
-template <typename T, bool BWD>
-__global__ void __launch_bounds__(256)
-bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* __restrict__ y_mask,
+// MASK: 0 = no ReLU mask, 1 = y_mask is the ReLU output tensor (mask = y > 0), 2 = y_mask is the
+// packed bit mask bn_apply wrote (one byte per 8-channel vector, bit e = channel e passed the ReLU).
+__device__ __forceinline__ void apply_bits(float* d, uint32_t bits) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = (bits >> i) & 1u ? d[i] : 0.f;
+}
+
+// Arguments of the finalize step the LAST block of a reduction launch runs (null ticket = none).
+struct BnFinalize {
+  unsigned int* ticket;  // zero on entry; the block that draws the last ticket finalizes + resets
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; long long* nbt;
+  float* mean; float* invstd; float* a; float* b;            // forward outputs
+  float* dgamma; float* dbeta; float* k0; float* k1; float* k2;  // backward outputs
+  double count; float eps, momentum;
+};
+
+// Finalize, written for a SINGLE block with plenty of memory-level parallelism (it is the serial
+// tail of the reduction launch): phase 1 is one item per (view, channel), four items in flight per
+// thread; phase 2 (running statistics in VIEW ORDER / dgamma, dbeta) is one item per channel.
+// Forward: mean / invstd, fused affine (a = gamma*invstd, b = beta - mean*a), running stats
+// (rm <- (1-m) rm + m mean_v for v = 0..V-1; unbiased variance), accumulator reset.
+__device__ __forceinline__ void bn_finalize_block(double* acc, const BnFinalize& f, int c, int views,
+                                                  int tid, int nthreads) {
+  const int items = views * c;
+  const double inv_count = 1.0 / f.count;
+  for (int i0 = tid; i0 < items; i0 += nthreads * 4) {
+    double s1[4], s2[4];
+    float ga[4], be[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * nthreads;
+      if (i < items) {
+        s1[j] = __ldcg(acc + 2 * (long long)i);
+        s2[j] = __ldcg(acc + 2 * (long long)i + 1);
+        ga[j] = __ldg(f.gamma + i % c);
+        be[j] = __ldg(f.beta + i % c);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * nthreads;
+      if (i < items) {
+        const double m = s1[j] * inv_count;
+        double var = s2[j] * inv_count - m * m;
+        if (var < 0.0) var = 0.0;
+        const float is = (float)(1.0 / sqrt(var + (double)f.eps));
+        f.mean[i] = (float)m;
+        f.invstd[i] = is;
+        const float av = ga[j] * is;
+        f.a[i] = av;
+        f.b[i] = be[j] - (float)m * av;
+        acc[2 * (long long)i] = m;       // parked for phase 2
+        acc[2 * (long long)i + 1] = var;
+      }
+    }
+  }
+  __syncthreads();
+  const double unb = f.count / (f.count - 1.0);
+  for (int ch = tid; ch < c; ch += nthreads) {
+    float rm = f.running_mean ? f.running_mean[ch] : 0.f, rv = f.running_var ? f.running_var[ch] : 0.f;
+    for (int v = 0; v < views; ++v) {
+      double* p = acc + ((long long)v * c + ch) * 2;
+      const float m = (float)p[0], unbiased = (float)(p[1] * unb);
+      p[0] = 0.0; p[1] = 0.0;
+      rm = (1.f - f.momentum) * rm + f.momentum * m;
+      rv = (1.f - f.momentum) * rv + f.momentum * unbiased;
+    }
+    if (f.running_mean) f.running_mean[ch] = rm;
+    if (f.running_var) f.running_var[ch] = rv;
+  }
+}
+
+// Backward: dgamma/dbeta (=), per-(v,c) coefficients for the apply pass
+//   dz = k0 * dyr + k1 * z + k2  with  k0 = gamma*invstd, k1 = -k0*invstd*s2/cnt,
+//   k2 = -k0*s1/cnt - k1*mean   (from dz = gamma*invstd*(dyr - s1/cnt - xhat*s2/cnt))
+__device__ __forceinline__ void bn_bwd_finalize_block(double* acc, const BnFinalize& f,
+                                                      const float* mean, const float* invstd, int c,
+                                                      int views, int tid, int nthreads) {
+  const int items = views * c;
+  const double inv_count = 1.0 / f.count;
+  for (int i0 = tid; i0 < items; i0 += nthreads * 4) {
+    double s1[4], s2[4];
+    float ga[4], is[4], mu[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * nthreads;
+      if (i < items) {
+        s1[j] = __ldcg(acc + 2 * (long long)i);
+        s2[j] = __ldcg(acc + 2 * (long long)i + 1);
+        ga[j] = __ldg(f.gamma + i % c);
+        is[j] = invstd[i];
+        mu[j] = mean[i];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * nthreads;
+      if (i < items) {
+        const double c0 = (double)ga[j] * (double)is[j];
+        const double c1 = -c0 * (double)is[j] * s2[j] * inv_count;
+        f.k0[i] = (float)c0;
+        f.k1[i] = (float)c1;
+        f.k2[i] = (float)(-c0 * s1[j] * inv_count - c1 * (double)mu[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int ch = tid; ch < c; ch += nthreads) {
+    double dg = 0.0, db = 0.0;
+    for (int v = 0; v < views; ++v) {
+      double* p = acc + ((long long)v * c + ch) * 2;
+      db += __ldcg(p); dg += __ldcg(p + 1);
+      p[0] = 0.0; p[1] = 0.0;
+    }
+    f.dgamma[ch] = (float)dg;
+    f.dbeta[ch] = (float)db;
+  }
+}
+
+// grid = (G, views) with G*views = the number of co-resident blocks (one balanced wave, no tail):
+// block (x, v) reduces a contiguous slab of the rows (image-of-view-v, pixel) of view v;
+// block = 256 threads = (c/8 channel groups) x (256/(c/8)) row lanes; each thread keeps U 16-byte
+// loads per stream in flight and tracks (image, pixel) incrementally -- no division in the loop.
+template <typename T, bool BWD, int MASK>
+__global__ void __launch_bounds__(256, BWD ? 2 : 3)
+bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const void* __restrict__ y_mask_v,
                  const float* __restrict__ mean, const float* __restrict__ invstd, int pix, int c,
-                 int views, int imgs_per_view, double* __restrict__ acc /* [views][c][2] */) {
+                 int views, int imgs_per_view, double* __restrict__ acc /* [views][c][2] */,
+                 const BnFinalize fin) {
   extern __shared__ float s_red[];  // [row_lanes][c][2]
+  __shared__ unsigned int s_ticket;
+  const T* y_mask = reinterpret_cast<const T*>(y_mask_v);
+  const uint8_t* y_bits = reinterpret_cast<const uint8_t*>(y_mask_v);
   const int cg = c / 8;
   const int lanes = blockDim.x / cg;  // row lanes per block (>= 1)
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
-  // block (x, v): a slab of the rows (image-of-this-view, pixel) -- the number of fp64 atomics per
-  // launch depends on the grid only, not on the batch size
   const int v = blockIdx.y;
-  const int slabs = gridDim.x;
   const long long rows_total = (long long)imgs_per_view * pix;
-  const long long rows_per = (rows_total + slabs - 1) / slabs;
-  const long long r0 = blockIdx.x * rows_per;
-  const long long r1 = r0 + rows_per < rows_total ? r0 + rows_per : rows_total;
+  const long long r0 = rows_total * blockIdx.x / gridDim.x;
+  const long long r1 = rows_total * (blockIdx.x + 1) / gridDim.x;
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
@@ -101,27 +223,36 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* __r
       is[i] = __ldg(invstd + v * c + g * 8 + i);
     }
   }
-  if (lane < lanes) {
-    constexpr int U = 4;  // independent 16-byte loads in flight per tensor
-    for (long long r = r0 + lane; r < r1; r += lanes * U) {
+  // independent 16-byte (bf16) / 32-byte (fp32) loads in flight per tensor
+  constexpr int U = sizeof(T) == 2 ? (BWD ? 4 : 8) : (BWD ? 2 : 4);
+  if (lane < lanes && r0 + lane < r1) {
+    // this thread's rows: r0 + lane + k*lanes; (img, p) of the current row, element offset `off`
+    long long img = (r0 + lane) / pix;
+    int p = (int)((r0 + lane) - img * pix);
+    long long off = ((img * views + v) * pix + p) * c + g * 8;
+    const long long row_step = (long long)lanes * c;                 // next row, same image
+    const long long wrap_step = (long long)(views - 1) * pix * c;    // extra when the image wraps
+    long long left = (r1 - (r0 + lane) + lanes - 1) / lanes;          // rows this thread owns
+    while (left > 0) {
       typename V8<T>::Raw zr[U], dr[U], mr[U];
+      uint32_t mb[U];
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        const long long rr = r + j * lanes;
-        if (rr < r1) {
-          const long long img = rr / pix;
-          const long long off = ((img * views + v) * pix + (rr - img * pix)) * c + g * 8;
+        if (j < left) {
           zr[j] = V8<T>::load_raw(z + off);
           if (BWD) {
             dr[j] = V8<T>::load_raw(dy + off);
-            if (y_mask != nullptr) mr[j] = V8<T>::load_raw(y_mask + off);
+            if (MASK == 1) mr[j] = V8<T>::load_raw(y_mask + off);
+            if (MASK == 2) mb[j] = y_bits[off >> 3];
           }
+          off += row_step;
+          p += lanes;
+          if (p >= pix) { p -= pix; off += wrap_step; }  // lanes <= 32 < pix: at most one wrap
         }
       }
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        const long long rr = r + j * lanes;
-        if (rr < r1) {
+        if (j < left) {
           float f[8];
           V8<T>::unpack(zr[j], f);
           if (!BWD) {
@@ -130,12 +261,13 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* __r
           } else {
             float d[8];
             V8<T>::unpack(dr[j], d);
-            if (y_mask != nullptr) {
+            if (MASK == 1) {
               float m[8];
               V8<T>::unpack(mr[j], m);
 #pragma unroll
               for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
             }
+            if (MASK == 2) apply_bits(d, mb[j]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               s1[i] += d[i];
@@ -144,6 +276,7 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* __r
           }
         }
       }
+      left -= U;
     }
   }
   // reduce over row lanes through shared memory, then one fp64 atomic per (channel, stat)
@@ -160,38 +293,32 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* __r
     for (int l = 0; l < lanes; ++l) s += (double)s_red[l * c * 2 + j];
     atomicAdd(acc + (long long)v * c * 2 + j, s);
   }
+  if (fin.ticket == nullptr) return;
+  // ---- the last block to finish turns the sums into the per-(view, channel) coefficients ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(fin.ticket, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x * gridDim.y - 1) return;
+  __threadfence();
+  if (BWD) bn_bwd_finalize_block(acc, fin, mean, invstd, c, views, threadIdx.x, blockDim.x);
+  else bn_finalize_block(acc, fin, c, views, threadIdx.x, blockDim.x);
+  if (threadIdx.x == 0) {
+    *fin.ticket = 0;
+    if (!BWD && fin.nbt != nullptr) *fin.nbt += views;
+  }
 }
 
-// mean / invstd, fused affine (a = gamma*invstd, b = beta - mean*a), running-stat update in VIEW
-// ORDER (rm <- (1-m) rm + m mean_v for v = 0..V-1; unbiased variance), accumulator reset.
-__global__ void bn_finalize_kernel(double* __restrict__ acc, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, long long* __restrict__ nbt,
-                                   float* __restrict__ mean, float* __restrict__ invstd,
-                                   float* __restrict__ a, float* __restrict__ b, int c, int views,
-                                   double count, float eps, float momentum) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch == 0 && nbt != nullptr) *nbt += views;
-  if (ch >= c) return;
-  float rm = running_mean ? running_mean[ch] : 0.f, rv = running_var ? running_var[ch] : 0.f;
-  for (int v = 0; v < views; ++v) {
-    double* p = acc + ((long long)v * c + ch) * 2;
-    const double m = p[0] / count;
-    double var = p[1] / count - m * m;
-    if (var < 0.0) var = 0.0;
-    p[0] = 0.0; p[1] = 0.0;
-    const float is = (float)(1.0 / sqrt(var + (double)eps));
-    mean[v * c + ch] = (float)m;
-    invstd[v * c + ch] = is;
-    const float av = gamma[ch] * is;
-    a[v * c + ch] = av;
-    b[v * c + ch] = beta[ch] - (float)m * av;
-    const float unbiased = (float)(var * (count / (count - 1.0)));
-    rm = (1.f - momentum) * rm + momentum * (float)m;
-    rv = (1.f - momentum) * rv + momentum * unbiased;
-  }
-  if (running_mean) running_mean[ch] = rm;
-  if (running_var) running_var[ch] = rv;
+// stand-alone finalize launches (one block)
+__global__ void __launch_bounds__(256) bn_finalize_kernel(double* __restrict__ acc, const BnFinalize fin, int c, int views) {
+  if (threadIdx.x == 0 && fin.nbt != nullptr) *fin.nbt += views;
+  bn_finalize_block(acc, fin, c, views, threadIdx.x, blockDim.x);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(double* __restrict__ acc, const BnFinalize fin,
+                                       const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, int c, int views) {
+  bn_bwd_finalize_block(acc, fin, mean, invstd, c, views, threadIdx.x, blockDim.x);
 }
 
 // y = relu?(a[v,c] * z + b[v,c] + residual)
@@ -202,8 +329,8 @@ constexpr int kEwUnroll = 4;
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
 bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ a, const float* __restrict__ b,
-                const T* __restrict__ residual, T* __restrict__ y, int pix, int c, int views,
-                int relu) {
+                const T* __restrict__ residual, T* __restrict__ y,
+                uint8_t* __restrict__ relu_bits, int pix, int c, int views, int relu) {
   const int cg = c / 8;
   const int n = blockIdx.y, v = n % views;
   const long long per_img = (long long)pix * cg;  // 8-channel vectors in this image
@@ -216,6 +343,7 @@ bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ a, const floa
   const T* zi = z + (long long)n * pix * c;
   const T* ri = residual ? residual + (long long)n * pix * c : nullptr;
   T* yi = y + (long long)n * pix * c;
+  uint8_t* bi = relu_bits ? relu_bits + (long long)n * per_img : nullptr;
   for (long long i = i0; i < per_img; i += stride * kEwUnroll) {
     typename V8<T>::Raw zr[kEwUnroll], rr[kEwUnroll];
 #pragma unroll
@@ -233,55 +361,32 @@ bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ a, const floa
         float f[8], r[8], o[8];
         V8<T>::unpack(zr[j], f);
         if (ri) V8<T>::unpack(rr[j], r);
+        uint32_t bits = 0;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           o[e] = fmaf(f[e], ca[e], cb[e]);
           if (ri) o[e] += r[e];
+          bits |= (o[e] > 0.f ? 1u : 0u) << e;
           if (relu) o[e] = fmaxf(o[e], 0.f);
         }
         V8<T>::store(yi + k * 8, o);
+        if (bi) bi[k] = (uint8_t)bits;
       }
     }
   }
 }
 
-// finalize of the backward reduction: dgamma/dbeta (+=), per-(v,c) coefficients for the apply pass
-//   dz = k0 * dyr + k1 * z + k2  with  k0 = gamma*invstd, k1 = -k0*invstd*s2/cnt,
-//   k2 = -k0*s1/cnt - k1*mean   (from dz = gamma*invstd*(dyr - s1/cnt - xhat*s2/cnt))
-__global__ void bn_bwd_finalize_kernel(double* __restrict__ acc, const float* __restrict__ gamma,
-                                       const float* __restrict__ mean,
-                                       const float* __restrict__ invstd,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ k0, float* __restrict__ k1,
-                                       float* __restrict__ k2, int c, int views, double count) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  double dg = 0.0, db = 0.0;
-  for (int v = 0; v < views; ++v) {
-    double* p = acc + ((long long)v * c + ch) * 2;
-    const double s1 = p[0], s2 = p[1];
-    p[0] = 0.0; p[1] = 0.0;
-    dg += s2; db += s1;
-    const double is = invstd[v * c + ch], m = mean[v * c + ch];
-    const double c0 = (double)gamma[ch] * is;
-    const double c1 = -c0 * is * s2 / count;
-    k0[v * c + ch] = (float)c0;
-    k1[v * c + ch] = (float)c1;
-    k2[v * c + ch] = (float)(-c0 * s1 / count - c1 * m);
-  }
-  dgamma[ch] = (float)dg;
-  dbeta[ch] = (float)db;
-}
-
 // dz = k0*dyr + k1*z + k2, dyr = dy * (y_mask > 0); optionally also writes dyr (skip-path grad)
 constexpr int kBwdUnroll = 4;  // 3 input streams x 4 packed 16-byte loads in flight per thread
 
-template <typename T>
+template <typename T, int MASK>
 __global__ void __launch_bounds__(256, 2)
-bn_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* __restrict__ y_mask,
+bn_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ dy, const void* __restrict__ y_mask_v,
                     const float* __restrict__ k0, const float* __restrict__ k1,
                     const float* __restrict__ k2, T* __restrict__ dz, T* __restrict__ dyr_out,
                     int pix, int c, int views) {
+  const T* y_mask = reinterpret_cast<const T*>(y_mask_v);
+  const uint8_t* y_bits = reinterpret_cast<const uint8_t*>(y_mask_v);
   const int cg = c / 8;
   const int n = blockIdx.y, v = n % views;
   const long long per_img = (long long)pix * cg;
@@ -295,13 +400,15 @@ bn_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* 
   const long long img = (long long)n * pix * c;
   for (long long i = i0; i < per_img; i += stride * kBwdUnroll) {
     typename V8<T>::Raw zr[kBwdUnroll], dr[kBwdUnroll], mr[kBwdUnroll];
+    uint32_t mb[kBwdUnroll];
 #pragma unroll
     for (int j = 0; j < kBwdUnroll; ++j) {
       const long long k = i + j * stride;
       if (k < per_img) {
         zr[j] = V8<T>::load_raw(z + img + k * 8);
         dr[j] = V8<T>::load_raw(dy + img + k * 8);
-        if (y_mask) mr[j] = V8<T>::load_raw(y_mask + img + k * 8);
+        if (MASK == 1) mr[j] = V8<T>::load_raw(y_mask + img + k * 8);
+        if (MASK == 2) mb[j] = y_bits[(img >> 3) + k];
       }
     }
 #pragma unroll
@@ -311,12 +418,14 @@ bn_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ dy, const T* 
         float f[8], d[8], m[8], o[8];
         V8<T>::unpack(zr[j], f);
         V8<T>::unpack(dr[j], d);
-        if (y_mask) V8<T>::unpack(mr[j], m);
+        if (MASK == 1) {
+          V8<T>::unpack(mr[j], m);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          if (y_mask) d[e] = m[e] > 0.f ? d[e] : 0.f;
-          o[e] = fmaf(c0[e], d[e], fmaf(c1[e], f[e], c2[e]));
+          for (int e = 0; e < 8; ++e) d[e] = m[e] > 0.f ? d[e] : 0.f;
         }
+        if (MASK == 2) apply_bits(d, mb[j]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(c0[e], d[e], fmaf(c1[e], f[e], c2[e]));
         V8<T>::store(dz + img + k * 8, o);
         if (dyr_out) V8<T>::store(dyr_out + img + k * 8, d);
       }
@@ -425,9 +534,82 @@ __device__ __forceinline__ void permute_job_elems(const rmv_permute_job& j, long
   }
 }
 
+// kind 1: dst = cast(src), both contiguous; 1024 elements per block.
+template <typename TD>
+__device__ __forceinline__ void permute_job_cast(const rmv_permute_job& j, long long blk, int tid) {
+  const long long total = (long long)j.d0 * j.d1 * j.d2 * j.d3;
+  TD* dst = reinterpret_cast<TD*>(j.dst);
+  const long long i = blk * 1024 + tid * 4;
+  if (i + 3 < total && ((reinterpret_cast<uintptr_t>(j.src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const float4 v = *reinterpret_cast<const float4*>(j.src + i);
+    if constexpr (sizeof(TD) == 2) {
+      uint2 o;
+      o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(dst + i) = o;
+    } else {
+      *reinterpret_cast<float4*>(dst + i) = v;
+    }
+  } else {
+    for (long long e = i; e < total && e < i + 4; ++e) {
+      if constexpr (sizeof(TD) == 2) dst[e] = __float2bfloat16_rn(j.src[e]);
+      else dst[e] = j.src[e];
+    }
+  }
+}
+
+// kind 2: src [K][J] (J = C*T contiguous) -> dst [J'][K], J' = c*T + (flip ? T-1-t : t): the
+// transposed (and tap-flipped) filters of the data-gradient convolutions / Linear dX GEMMs.
+// 64 x 64 tiles through shared memory, coalesced on both sides. (d0,d1,d2,d3) = (C,R,S,K).
+template <typename TD>
+__device__ __forceinline__ void permute_job_transpose(const rmv_permute_job& j, long long blk,
+                                                      int tid, float (*tile)[65]) {
+  const int K = j.d3, T = j.d1 * j.d2, J = j.d0 * T;
+  const int tiles_j = (J + 63) / 64;
+  const int j0 = (int)(blk % tiles_j) * 64, k0 = (int)(blk / tiles_j) * 64;
+  TD* dst = reinterpret_cast<TD*>(j.dst);
+  const int tx = tid & 63, ty = tid >> 6;  // 64 x 4
+#pragma unroll 4
+  for (int r = ty; r < 64; r += 4) {
+    const int k = k0 + r, jj = j0 + tx;
+    tile[r][tx] = (k < K && jj < J) ? __ldg(j.src + (long long)k * J + jj) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int r = ty; r < 64; r += 4) {
+    const int jj = j0 + r, k = k0 + tx;
+    if (jj < J && k < K) {
+      int c = jj / T, t = jj - c * T;
+      if (j.flip1) t = T - 1 - t;
+      const float v = tile[tx][r];
+      const long long o = ((long long)c * T + t) * K + k;
+      if constexpr (sizeof(TD) == 2) dst[o] = __float2bfloat16_rn(v);
+      else dst[o] = v;
+    }
+  }
+}
+
+// kind 3: src [K][C][T] -> dst [K][T][C] (forward KRSC filters of the 3x3 convs): one block per k.
+// (d0,d1,d2,d3) = (K,R,S,C)
+template <typename TD>
+__device__ __forceinline__ void permute_job_krsc(const rmv_permute_job& j, long long blk, int tid) {
+  const int T = j.d1 * j.d2, C = j.d3;
+  const long long per_k = (long long)C * T;
+  const float* src = j.src + blk * per_k;
+  TD* dst = reinterpret_cast<TD*>(j.dst) + blk * per_k;
+  // reads walk dst order (t, c): consecutive threads read stride-T floats (T odd: every 32-byte
+  // sector is fully used by the block within a few iterations, L1 keeps it); writes are coalesced
+  for (int o = tid; o < per_k; o += 256) {
+    const int t = o / C, c = o - t * C;
+    const float v = __ldg(src + (long long)c * T + t);
+    if constexpr (sizeof(TD) == 2) dst[o] = __float2bfloat16_rn(v);
+    else dst[o] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 permute_cast_batch_kernel(const rmv_permute_job* __restrict__ jobs, int n_jobs) {
   __shared__ int s_job;
+  __shared__ float s_tile[64][65];
   if (threadIdx.x == 0) {
     int lo = 0, hi = n_jobs - 1;
     while (lo < hi) {
@@ -438,9 +620,25 @@ permute_cast_batch_kernel(const rmv_permute_job* __restrict__ jobs, int n_jobs) 
   }
   __syncthreads();
   const rmv_permute_job j = jobs[s_job];
-  const long long base = (long long)(blockIdx.x - j.first_block) * 1024;
-  if (j.dst_dtype == RMV_DTYPE_BF16) permute_job_elems<__nv_bfloat16>(j, base, threadIdx.x);
-  else permute_job_elems<float>(j, base, threadIdx.x);
+  const long long blk = (long long)(blockIdx.x - j.first_block);
+  const bool bf = j.dst_dtype == RMV_DTYPE_BF16;
+  switch (j.kind) {
+    case 1:
+      if (bf) permute_job_cast<__nv_bfloat16>(j, blk, threadIdx.x);
+      else permute_job_cast<float>(j, blk, threadIdx.x);
+      break;
+    case 2:
+      if (bf) permute_job_transpose<__nv_bfloat16>(j, blk, threadIdx.x, s_tile);
+      else permute_job_transpose<float>(j, blk, threadIdx.x, s_tile);
+      break;
+    case 3:
+      if (bf) permute_job_krsc<__nv_bfloat16>(j, blk, threadIdx.x);
+      else permute_job_krsc<float>(j, blk, threadIdx.x);
+      break;
+    default:
+      if (bf) permute_job_elems<__nv_bfloat16>(j, blk * 1024, threadIdx.x);
+      else permute_job_elems<float>(j, blk * 1024, threadIdx.x);
+  }
 }
 
 // dst[n, 2h, 2w, :] = src[n, h, w, :], zeros elsewhere (dst is [n, 2H, 2W, c]) -- stride-2 dgrad
@@ -833,32 +1031,55 @@ static unsigned ew_blocks_x(int pix, int c, int n_img, int unroll = rmv::kEwUnro
   return (unsigned)bx;
 }
 
-static int bn_reduce_cfg(int pix, int c, int n_img, int views, dim3* grid, int* smem) {
+// grid (G, views): one wave of co-resident blocks (occ per SM), but no more blocks than there are
+// 16-row (per thread) slabs.
+static int bn_reduce_cfg(int pix, int c, int n_img, int views, int occ, dim3* grid, int* smem) {
   const int cg = c / 8;
   RMV_CHECK_ARG(c % 8 == 0 && cg <= 256 && 256 % cg == 0,
                 "batchnorm: channels=%d must be 8*2^k with c <= 2048", c);
+  RMV_CHECK_ARG(pix > 32 || 256 / cg <= pix, "batchnorm: %d pixels per image is too few", pix);
   const int lanes = 256 / cg;
   const long long rows_total = (long long)(n_img / views) * pix;
-  long long slabs = (rows_total + lanes * 16 - 1) / (lanes * 16);  // >= 16 rows per thread
-  if (slabs < 1) slabs = 1;
-  long want = 6L * num_sms() / views;
+  long long gx = (rows_total + lanes * 16 - 1) / (lanes * 16);
+  long long want = (long long)occ * num_sms() / views;
   if (want < 1) want = 1;
-  if (slabs > want) slabs = want;
-  *grid = dim3((unsigned)slabs, (unsigned)views);
+  if (gx > want) gx = want;
+  if (gx < 1) gx = 1;
+  *grid = dim3((unsigned)gx, (unsigned)views);
   *smem = lanes * c * 2 * (int)sizeof(float);
+  return 0;
+}
+
+static int bn_stats_launch(const void* z, int dtype, int n_img, int pix, int c, int views,
+                           double* acc, const BnFinalize& fin, cudaStream_t stream) {
+  RMV_CHECK_ARG(views >= 1 && n_img % views == 0, "bn_stats: n_img=%d not a multiple of views=%d", n_img, views);
+  if (n_img == 0 || pix == 0) return 0;
+  dim3 grid; int smem;
+  if (int rc = bn_reduce_cfg(pix, c, n_img, views, 3, &grid, &smem)) return rc;
+  DISPATCH_T(dtype, (bn_reduce_kernel<T, false, 0><<<grid, 256, smem, stream>>>(
+      (const T*)z, nullptr, nullptr, nullptr, nullptr, pix, c, views, n_img / views, acc, fin)));
+  RMV_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int rmv_bn_stats(const void* z, int dtype, int n_img, int pix, int c, int views,
                             double* acc, void* stream) {
-  RMV_CHECK_ARG(views >= 1 && n_img % views == 0, "bn_stats: n_img=%d not a multiple of views=%d", n_img, views);
-  if (n_img == 0) return 0;
-  dim3 grid; int smem;
-  if (int rc = bn_reduce_cfg(pix, c, n_img, views, &grid, &smem)) return rc;
-  DISPATCH_T(dtype, (bn_reduce_kernel<T, false><<<grid, 256, smem, (cudaStream_t)stream>>>(
-      (const T*)z, nullptr, nullptr, nullptr, nullptr, pix, c, views, n_img / views, acc)));
-  RMV_LAUNCH_CHECK();
-  return 0;
+  BnFinalize fin;
+  memset(&fin, 0, sizeof(fin));
+  return bn_stats_launch(z, dtype, n_img, pix, c, views, acc, fin, (cudaStream_t)stream);
+}
+
+static BnFinalize bn_fin_fwd(unsigned int* ticket, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, long long* num_batches,
+                             float* mean, float* invstd, float* a, float* b,
+                             long long count_per_view, float eps, float momentum) {
+  BnFinalize fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.ticket = ticket; fin.gamma = gamma; fin.beta = beta;
+  fin.running_mean = running_mean; fin.running_var = running_var; fin.nbt = num_batches;
+  fin.mean = mean; fin.invstd = invstd; fin.a = a; fin.b = b;
+  fin.count = (double)count_per_view; fin.eps = eps; fin.momentum = momentum;
+  return fin;
 }
 
 extern "C" int rmv_bn_finalize(double* acc, const float* gamma, const float* beta,
@@ -866,56 +1087,111 @@ extern "C" int rmv_bn_finalize(double* acc, const float* gamma, const float* bet
                                float* mean, float* invstd, float* a, float* b, int c, int views,
                                long long count_per_view, float eps, float momentum, void* stream) {
   RMV_CHECK_ARG(count_per_view > 1, "bn_finalize: need more than one value per channel");
-  bn_finalize_kernel<<<nblk(c, 128), 128, 0, (cudaStream_t)stream>>>(
-      acc, gamma, beta, running_mean, running_var, num_batches, mean, invstd, a, b, c, views,
-      (double)count_per_view, eps, momentum);
+  const BnFinalize fin = bn_fin_fwd(nullptr, gamma, beta, running_mean, running_var, num_batches,
+                                    mean, invstd, a, b, count_per_view, eps, momentum);
+  bn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(acc, fin, c, views);
   RMV_LAUNCH_CHECK();
   return 0;
 }
 
+extern "C" int rmv_bn_stats_finalize(const void* z, int dtype, int n_img, int pix, int c, int views,
+                                     double* acc, unsigned int* ticket, const float* gamma,
+                                     const float* beta, float* running_mean, float* running_var,
+                                     long long* num_batches, float* mean, float* invstd, float* a,
+                                     float* b, float eps, float momentum, void* stream) {
+  RMV_CHECK_ARG(ticket != nullptr, "bn_stats_finalize: null ticket");
+  RMV_CHECK_ARG(views >= 1 && n_img % views == 0 && (long long)(n_img / views) * pix > 1,
+                "bn_stats_finalize: need more than one value per (view, channel)");
+  const BnFinalize fin = bn_fin_fwd(ticket, gamma, beta, running_mean, running_var, num_batches,
+                                    mean, invstd, a, b, (long long)(n_img / views) * pix, eps,
+                                    momentum);
+  return bn_stats_launch(z, dtype, n_img, pix, c, views, acc, fin, (cudaStream_t)stream);
+}
+
 extern "C" int rmv_bn_apply(const void* z, const float* a, const float* b, const void* residual,
-                            void* y, int dtype, int n_img, int pix, int c, int views, int relu,
-                            void* stream) {
+                            void* y, unsigned char* relu_bits, int dtype, int n_img, int pix, int c,
+                            int views, int relu, void* stream) {
   RMV_CHECK_ARG(c % 8 == 0 && 256 % (c / 8) == 0, "bn_apply: c=%d must be 8*2^k, <= 2048", c);
   if ((long long)n_img * pix == 0) return 0;
   const dim3 grid(ew_blocks_x(pix, c, n_img), (unsigned)n_img);
   DISPATCH_T(dtype, (bn_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const T*)z, a, b, (const T*)residual, (T*)y, pix, c, views, relu)));
+      (const T*)z, a, b, (const T*)residual, (T*)y, relu_bits, pix, c, views, relu)));
   RMV_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int rmv_bn_bwd_reduce(const void* z, const void* dy, const void* y_mask,
-                                 const float* mean, const float* invstd, int dtype, int n_img,
-                                 int pix, int c, int views, double* acc, void* stream) {
+#define DISPATCH_MASK(y_mask, mask_is_bits, ...)                                  \
+  if ((y_mask) == nullptr) { constexpr int MASK = 0; __VA_ARGS__; }              \
+  else if (mask_is_bits) { constexpr int MASK = 2; __VA_ARGS__; }                \
+  else { constexpr int MASK = 1; __VA_ARGS__; }
+
+static int bn_bwd_reduce_launch(const void* z, const void* dy, const void* y_mask, int mask_is_bits,
+                                const float* mean, const float* invstd, int dtype, int n_img,
+                                int pix, int c, int views, double* acc, const BnFinalize& fin,
+                                cudaStream_t stream) {
   RMV_CHECK_ARG(views >= 1 && n_img % views == 0, "bn_bwd_reduce: n_img not a multiple of views");
-  if (n_img == 0) return 0;
+  if (n_img == 0 || pix == 0) return 0;
   dim3 grid; int smem;
-  if (int rc = bn_reduce_cfg(pix, c, n_img, views, &grid, &smem)) return rc;
-  DISPATCH_T(dtype, (bn_reduce_kernel<T, true><<<grid, 256, smem, (cudaStream_t)stream>>>(
-      (const T*)z, (const T*)dy, (const T*)y_mask, mean, invstd, pix, c, views, n_img / views, acc)));
+  if (int rc = bn_reduce_cfg(pix, c, n_img, views, 2, &grid, &smem)) return rc;
+  DISPATCH_T(dtype, DISPATCH_MASK(y_mask, mask_is_bits,
+      (bn_reduce_kernel<T, true, MASK><<<grid, 256, smem, stream>>>(
+          (const T*)z, (const T*)dy, y_mask, mean, invstd, pix, c, views, n_img / views, acc, fin))));
   RMV_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int rmv_bn_bwd_reduce(const void* z, const void* dy, const void* y_mask, int mask_is_bits,
+                                 const float* mean, const float* invstd, int dtype, int n_img,
+                                 int pix, int c, int views, double* acc, void* stream) {
+  BnFinalize fin;
+  memset(&fin, 0, sizeof(fin));
+  return bn_bwd_reduce_launch(z, dy, y_mask, mask_is_bits, mean, invstd, dtype, n_img, pix, c, views,
+                              acc, fin, (cudaStream_t)stream);
+}
+
+static BnFinalize bn_fin_bwd(unsigned int* ticket, const float* gamma, float* dgamma, float* dbeta,
+                             float* k0, float* k1, float* k2, long long count_per_view) {
+  BnFinalize fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.ticket = ticket; fin.gamma = gamma; fin.dgamma = dgamma; fin.dbeta = dbeta;
+  fin.k0 = k0; fin.k1 = k1; fin.k2 = k2; fin.count = (double)count_per_view;
+  return fin;
 }
 
 extern "C" int rmv_bn_bwd_finalize(double* acc, const float* gamma, const float* mean,
                                    const float* invstd, float* dgamma, float* dbeta, float* k0,
                                    float* k1, float* k2, int c, int views, long long count_per_view,
                                    void* stream) {
-  bn_bwd_finalize_kernel<<<nblk(c, 128), 128, 0, (cudaStream_t)stream>>>(
-      acc, gamma, mean, invstd, dgamma, dbeta, k0, k1, k2, c, views, (double)count_per_view);
+  const BnFinalize fin = bn_fin_bwd(nullptr, gamma, dgamma, dbeta, k0, k1, k2, count_per_view);
+  bn_bwd_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(acc, fin, mean, invstd, c, views);
   RMV_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int rmv_bn_bwd_apply(const void* z, const void* dy, const void* y_mask, const float* k0,
-                                const float* k1, const float* k2, void* dz, void* dyr_out,
+extern "C" int rmv_bn_bwd_reduce_finalize(const void* z, const void* dy, const void* y_mask,
+                                          int mask_is_bits, const float* mean, const float* invstd,
+                                          int dtype, int n_img, int pix, int c, int views,
+                                          double* acc, unsigned int* ticket, const float* gamma,
+                                          float* dgamma, float* dbeta, float* k0, float* k1,
+                                          float* k2, void* stream) {
+  RMV_CHECK_ARG(ticket != nullptr, "bn_bwd_reduce_finalize: null ticket");
+  RMV_CHECK_ARG(views >= 1 && n_img % views == 0, "bn_bwd_reduce_finalize: n_img not a multiple of views");
+  const BnFinalize fin =
+      bn_fin_bwd(ticket, gamma, dgamma, dbeta, k0, k1, k2, (long long)(n_img / views) * pix);
+  return bn_bwd_reduce_launch(z, dy, y_mask, mask_is_bits, mean, invstd, dtype, n_img, pix, c, views,
+                              acc, fin, (cudaStream_t)stream);
+}
+
+extern "C" int rmv_bn_bwd_apply(const void* z, const void* dy, const void* y_mask, int mask_is_bits,
+                                const float* k0, const float* k1, const float* k2, void* dz,
+                                void* dyr_out,
                                 int dtype, int n_img, int pix, int c, int views, void* stream) {
   RMV_CHECK_ARG(c % 8 == 0 && 256 % (c / 8) == 0, "bn_bwd_apply: c=%d must be 8*2^k, <= 2048", c);
   if ((long long)n_img * pix == 0) return 0;
   const dim3 grid(ew_blocks_x(pix, c, n_img, rmv::kBwdUnroll), (unsigned)n_img);
-  DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const T*)z, (const T*)dy, (const T*)y_mask, k0, k1, k2, (T*)dz, (T*)dyr_out, pix, c, views)));
+  DISPATCH_T(dtype, DISPATCH_MASK(y_mask, mask_is_bits,
+      (bn_bwd_apply_kernel<T, MASK><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          (const T*)z, (const T*)dy, y_mask, k0, k1, k2, (T*)dz, (T*)dyr_out, pix, c, views))));
   RMV_LAUNCH_CHECK();
   return 0;
 }

@@ -51,7 +51,7 @@ class PermuteJob(C.Structure):
                 ("d0", C.c_int), ("d1", C.c_int), ("d2", C.c_int), ("d3", C.c_int),
                 ("s0", C.c_longlong), ("s1", C.c_longlong), ("s2", C.c_longlong), ("s3", C.c_longlong),
                 ("flip1", C.c_int), ("flip2", C.c_int), ("dst_dtype", C.c_int),
-                ("first_block", C.c_uint)]
+                ("first_block", C.c_uint), ("kind", C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/rotmv_sm100.h declares must be listed here
@@ -61,6 +61,7 @@ SIGNATURES = {
     "rmv_version": (_i, []),
     "rmv_last_error": (C.c_char_p, []),
     "rmv_device_check": (_i, [_i]),
+    "rmv_conv2d_dgrad": (_i, [C.POINTER(ConvArgs), _vp]),
     "rmv_conv2d_fwd": (_i, [C.POINTER(ConvArgs), _vp]),
     "rmv_stem_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rmv_stem_pack_weights": (_i, [_vp, _vp, _vp]),
@@ -77,10 +78,14 @@ SIGNATURES = {
     # training step
     "rmv_bn_stats": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rmv_bn_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _f, _f, _vp]),
-    "rmv_bn_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "rmv_bn_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rmv_bn_stats_finalize": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _f, _f, _vp]),
+    "rmv_bn_bwd_reduce_finalize": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp,
+                                        _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rmv_bn_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "rmv_bn_bwd_reduce": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rmv_bn_bwd_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp]),
-    "rmv_bn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rmv_bn_bwd_apply": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rmv_relu_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "rmv_colsum": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp]),
     "rmv_permute_cast": (_i, [_vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _vp]),

@@ -86,6 +86,45 @@ def conv2d(x, w, *, stride=1, pad=0, scale=None, shift=None, residual=None, relu
     return out
 
 
+def conv2d_dgrad(dy, wt, *, stride, pad, in_hw, residual=None, out=None):
+    """dx (+ residual) of y = conv(x, w, stride, pad) on the tcgen05 engine.
+
+    dy: [N, OH, OW, K] bf16; wt: [C, kh, kw, K] = w reversed and transposed
+    (wt[c, kh-1-r, kw-1-s, k] = w[k, c, r, s]); in_hw = (H, W) of x; out/residual: [N, H, W, C].
+    stride 2 needs no zero-dilated copy of dy (four parity-class convolutions inside the library).
+    The backward of reference models/resnet.py:31-47 (autograd/cuDNN at trainer.py:142)."""
+    _need_cuda(dy, wt, residual, out)
+    n, oh, ow, k = dy.shape
+    c, kh, kw, k2 = wt.shape
+    h, w = in_hw
+    assert k == k2 and wt.is_contiguous() and wt.dtype == dy.dtype and dy.stride(3) == 1
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=dy.dtype, device=dy.device)
+    assert tuple(out.shape) == (n, h, w, c) and out.stride(3) == 1
+    a = L.ConvArgs()
+    a.x_dtype = a.y_dtype = L.dtype_code(dy.dtype)
+    a.engine = L.ENGINE_TC
+    a.x = dy.data_ptr()
+    a.x_sn, a.x_sh, a.x_sw, a.x_sc = dy.stride(0), dy.stride(1), dy.stride(2), 1
+    a.n_img, a.in_h, a.in_w, a.c_in = n, oh, ow, k
+    a.w = wt.data_ptr()
+    a.c_out, a.kh, a.kw, a.stride, a.pad = c, kh, kw, stride, pad
+    a.y = out.data_ptr()
+    a.y_sn, a.y_sh, a.y_sw = out.stride(0), out.stride(1), out.stride(2)
+    a.out_h, a.out_w = h, w
+    if residual is not None:
+        assert tuple(residual.shape) == tuple(out.shape) and residual.dtype == out.dtype
+        a.residual = residual.data_ptr()
+        a.r_sn, a.r_sh, a.r_sw = residual.stride(0), residual.stride(1), residual.stride(2)
+    meta = {}
+    if PROFILE is not None:
+        meta = {"engine": "tcgen05", "flops": 2.0 * n * oh * ow * k * kh * kw * c,
+                "bytes": float((dy.numel() + wt.numel() + out.numel() * (2 if residual is not None else 1)) * 2),
+                "desc": f"dgrad {kh}x{kw}s{stride} [{n},{oh},{ow},{k}]->{c}"}
+    _call("rmv_conv2d_dgrad", meta, L.load().rmv_conv2d_dgrad, C.byref(a), L.stream_ptr())
+    return out
+
+
 def conv2d_nchw_input(x_nchw, w, *, stride, pad, scale=None, shift=None, relu=False,
                       out_dtype=None):
     """FFMA conv that consumes the caller's NCHW fp32 tensor directly through strides

@@ -25,8 +25,8 @@ from . import functional as RF
 _DT = {"bf16": torch.bfloat16, "fp32": torch.float32}
 
 
-def _ck(name, *args):
-    RF._call(name, {"desc": name}, getattr(L.load(), name), *args, L.stream_ptr())
+def _ck(name, *args, desc=None):
+    RF._call(name, {"desc": desc or name}, getattr(L.load(), name), *args, L.stream_ptr())
 
 
 def dims4(dims):
@@ -111,7 +111,9 @@ class TrainEngine:
         self.fusers = [[m._fuser.blocks[0][0], m._fuser.blocks[1][0]] for m in model._img_fusers]
         self.heads = [[m.blocks[0][0], m.blocks[1][0]] for m in model._gaze_estimators]
         self.acc = torch.zeros((max_views, 2048, 2), device=self.device, dtype=torch.float64)
+        self.ticket = torch.zeros((1,), device=self.device, dtype=torch.int32)
         self._bufs: Dict[Any, torch.Tensor] = {}
+        self._bits: Dict[int, Optional[torch.Tensor]] = {}   # id(ReLU output) -> packed mask
         self.loss = torch.zeros((1,), device=self.device, dtype=torch.float32)
         self.launches_last_step = 0
         self._wjobs, self._wjob_tags, self._wjobs_ready = [], set(), False
@@ -132,12 +134,14 @@ class TrainEngine:
     # The first step launches one rmv_permute_cast per tensor and records the jobs; from the second
     # step on, ONE batched launch at the top of the step re-derives all of them (the masters only
     # change in the Adam kernel at the end of a step) and these helpers just return the buffers.
-    def _transform(self, src, tag, dims, strides, flip):
+    def _transform(self, src, tag, dims, strides, flip, kind=0):
+        """`kind` (rmv_permute_job.kind) names the access pattern the batched kernel uses for this
+        job; the first step runs the generic kernel, so both are exercised against each other."""
         out = self._buf(tag, dims)
         if self._wjobs_ready:
             return out
         job = (src.data_ptr(), out.data_ptr(), *[int(d) for d in dims4(dims)], *strides, flip, flip,
-               self.dtc)
+               self.dtc, kind)
         if tag not in self._wjob_tags:
             self._wjob_tags.add(tag)
             self._wjobs.append(job)
@@ -148,31 +152,39 @@ class TrainEngine:
 
     def _w_fwd(self, conv, tag):
         k, c, r, s = conv.weight.shape
-        return self._transform(conv.weight, ("wf", tag), (k, r, s, c), (c * r * s, s, 1, r * s), 0)
+        return self._transform(conv.weight, ("wf", tag), (k, r, s, c), (c * r * s, s, 1, r * s), 0,
+                               kind=1 if r * s == 1 else 3)
 
     def _w_dgrad(self, conv, tag):
         """Filters of the data-gradient convolution: wt[c][r'][s'][k] = w[k][c][R-1-r'][S-1-s']."""
         k, c, r, s = conv.weight.shape
-        return self._transform(conv.weight, ("wd", tag), (c, r, s, k), (r * s, s, 1, c * r * s), 1)
+        return self._transform(conv.weight, ("wd", tag), (c, r, s, k), (r * s, s, 1, c * r * s), 1, kind=2)
 
     def _lin_fwd(self, lin, tag):
         n, k = lin.weight.shape
-        return self._transform(lin.weight, ("lf", tag), (n, k), (0, 0, k, 1), 0)
+        return self._transform(lin.weight, ("lf", tag), (n, k), (0, 0, k, 1), 0, kind=1)
 
     def _lin_t(self, lin, tag):
         n, k = lin.weight.shape
-        return self._transform(lin.weight, ("lt", tag), (k, n), (0, 0, 1, k), 0)
+        # as a (C,R,S,K) = (k,1,1,n) transpose job; the buffer is the [k, n] matrix
+        out = self._transform(lin.weight, ("lt", tag), (k, 1, 1, n), (1, 0, 0, k), 0, kind=2)
+        return out.view(k, n)
 
     def _finish_wjobs(self):
         """Upload the recorded job table (once)."""
         jobs = (L.PermuteJob * len(self._wjobs))()
         block = 0
-        for i, (src, dst, d0, d1, d2, d3, s0, s1, s2, s3, f1, f2, dt) in enumerate(self._wjobs):
+        for i, (src, dst, d0, d1, d2, d3, s0, s1, s2, s3, f1, f2, dt, kind) in enumerate(self._wjobs):
             j = jobs[i]
             j.src, j.dst, j.d0, j.d1, j.d2, j.d3 = src, dst, d0, d1, d2, d3
             j.s0, j.s1, j.s2, j.s3, j.flip1, j.flip2, j.dst_dtype = s0, s1, s2, s3, f1, f2, dt
-            j.first_block = block
-            block += (d0 * d1 * d2 * d3 + 1023) // 1024
+            j.first_block, j.kind = block, kind
+            if kind == 2:      # (C,R,S,K): 64x64 tiles of the [K][C*R*S] matrix
+                block += ((d0 * d1 * d2 + 63) // 64) * ((d3 + 63) // 64)
+            elif kind == 3:    # (K,R,S,C): one block per k
+                block += d0
+            else:
+                block += (d0 * d1 * d2 * d3 + 1023) // 1024
         raw = bytes(jobs)
         self._wjob_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
         self._wjob_count, self._wjob_blocks = len(self._wjobs), block
@@ -187,28 +199,36 @@ class TrainEngine:
     def _bn_fwd(self, bn: _BN, z, residual, relu, tag):
         n, h, w, c = z.shape
         v = self.views
-        _ck("rmv_bn_stats", z.data_ptr(), self.dtc, n, h * w, c, v, self.acc.data_ptr())
-        _ck("rmv_bn_finalize", self.acc.data_ptr(), bn.gamma.data_ptr(), bn.beta.data_ptr(),
-            bn.rm.data_ptr(), bn.rv.data_ptr(), bn.nbt.data_ptr(), bn.mean.data_ptr(),
-            bn.invstd.data_ptr(), bn.a.data_ptr(), bn.b.data_ptr(), c, v, (n // v) * h * w, bn.eps,
-            bn.momentum)
+        shp = f" [{n},{h},{w},{c}]" if RF.PROFILE is not None else ""
+        _ck("rmv_bn_stats_finalize", z.data_ptr(), self.dtc, n, h * w, c, v, self.acc.data_ptr(),
+            self.ticket.data_ptr(), bn.gamma.data_ptr(), bn.beta.data_ptr(), bn.rm.data_ptr(),
+            bn.rv.data_ptr(), bn.nbt.data_ptr(), bn.mean.data_ptr(), bn.invstd.data_ptr(),
+            bn.a.data_ptr(), bn.b.data_ptr(), bn.eps, bn.momentum, desc="rmv_bn_stats_finalize" + shp)
         y = self._buf(tag, z.shape)
+        # packed ReLU mask (1 bit/element) for the backward pass instead of re-reading y there
+        bits = self._buf(("bits", tag), (n * h * w * c // 8,), torch.uint8) if relu else None
         _ck("rmv_bn_apply", z.data_ptr(), bn.a.data_ptr(), bn.b.data_ptr(), L.ptr(residual),
-            y.data_ptr(), self.dtc, n, h * w, c, v, int(relu))
+            y.data_ptr(), L.ptr(bits), self.dtc, n, h * w, c, v, int(relu), desc="rmv_bn_apply" + shp)
+        self._bits[id(y)] = bits
         return y
 
     def _bn_bwd(self, bn: _BN, z, dy, mask, tag, want_dyr=False):
+        """`mask` is the ReLU output tensor `_bn_fwd` returned (its packed bit mask is used) or None."""
         n, h, w, c = z.shape
         v = self.views
-        _ck("rmv_bn_bwd_reduce", z.data_ptr(), dy.data_ptr(), L.ptr(mask), bn.mean.data_ptr(),
-            bn.invstd.data_ptr(), self.dtc, n, h * w, c, v, self.acc.data_ptr())
-        _ck("rmv_bn_bwd_finalize", self.acc.data_ptr(), bn.gamma.data_ptr(), bn.mean.data_ptr(),
-            bn.invstd.data_ptr(), bn.dgamma.data_ptr(), bn.dbeta.data_ptr(), bn.k0.data_ptr(),
-            bn.k1.data_ptr(), bn.k2.data_ptr(), c, v, (n // v) * h * w)
+        is_bits = 0
+        if mask is not None and self._bits.get(id(mask)) is not None:
+            mask, is_bits = self._bits[id(mask)], 1
+        shp = f" [{n},{h},{w},{c}]" if RF.PROFILE is not None else ""
+        _ck("rmv_bn_bwd_reduce_finalize", z.data_ptr(), dy.data_ptr(), L.ptr(mask), is_bits,
+            bn.mean.data_ptr(), bn.invstd.data_ptr(), self.dtc, n, h * w, c, v, self.acc.data_ptr(),
+            self.ticket.data_ptr(), bn.gamma.data_ptr(), bn.dgamma.data_ptr(), bn.dbeta.data_ptr(),
+            bn.k0.data_ptr(), bn.k1.data_ptr(), bn.k2.data_ptr(), desc="rmv_bn_bwd_reduce_finalize" + shp)
         dz = self._buf(("dz", tag), z.shape)
         dyr = self._buf(("dyr", tag), z.shape) if want_dyr else None
-        _ck("rmv_bn_bwd_apply", z.data_ptr(), dy.data_ptr(), L.ptr(mask), bn.k0.data_ptr(),
-            bn.k1.data_ptr(), bn.k2.data_ptr(), dz.data_ptr(), L.ptr(dyr), self.dtc, n, h * w, c, v)
+        _ck("rmv_bn_bwd_apply", z.data_ptr(), dy.data_ptr(), L.ptr(mask), is_bits, bn.k0.data_ptr(),
+            bn.k1.data_ptr(), bn.k2.data_ptr(), dz.data_ptr(), L.ptr(dyr), self.dtc, n, h * w, c, v,
+            desc="rmv_bn_bwd_apply" + shp)
         return dz, dyr
 
     # ---- convolution gradients -----------------------------------------------------------------
@@ -256,6 +276,9 @@ class TrainEngine:
         wt = self._w_dgrad(conv, tag)
         r = conv.kernel_size[0]
         stride, pad = conv.stride[0], conv.padding[0]
+        if self.precision == "bf16":
+            return RF.conv2d_dgrad(dz, wt, stride=stride, pad=pad, in_hw=in_shape[1:3],
+                                   residual=residual, out=self._buf(("dx", tag), in_shape))
         src = dz
         if stride == 2:
             n, oh, ow, k = dz.shape

@@ -31,7 +31,8 @@ agg = {}; tot = 0
 for eng_name, flops, a, b, what, meta in recs:
     t = a.elapsed_time(b); tot += t
     key = what if what != "rmv_conv2d_fwd" else "rmv_conv2d_fwd[" + eng_name + "]"
+    if os.environ.get("DETAIL"): key = meta.get("desc", key)
     x = agg.setdefault(key, [0, 0.0, 0.0]); x[0] += 1; x[1] += t; x[2] += flops
 print(f"sum of launch times {tot:.2f} ms over {len(recs)} launches")
 for k, (c, t, f) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"{k:40s} {c:4d} {t:9.3f} ms {100 * t / tot:5.1f}%  {f / t / 1e9 if t else 0:8.1f} TF/s")
+    print(f"{k:56s} {c:4d} {t:9.3f} ms {100 * t / tot:5.1f}%  {f / t / 1e9 if t else 0:8.1f} TF/s")

@@ -213,7 +213,12 @@ def test_bn_train_kernels_match_torch():
     _ck("rmv_bn_finalize", acc.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
         nbt.data_ptr(), mean.data_ptr(), invstd.data_ptr(), a.data_ptr(), b.data_ptr(), c, views,
         (n // views) * h * w, 1e-5, 0.1)
-    _ck("rmv_bn_apply", z.data_ptr(), a.data_ptr(), b.data_ptr(), None, y.data_ptr(), 0, n, h * w, c, views, 1)
+    bits = torch.zeros((n * h * w * c // 8,), device="cuda", dtype=torch.uint8)
+    _ck("rmv_bn_apply", z.data_ptr(), a.data_ptr(), b.data_ptr(), None, y.data_ptr(), bits.data_ptr(), 0,
+        n, h * w, c, views, 1)
+    # packed ReLU mask: bit e of byte i <=> element 8*i+e passed the ReLU
+    want_bits = ((y.reshape(-1, 8) > 0).to(torch.int32) << torch.arange(8, device="cuda", dtype=torch.int32)).sum(1)
+    assert torch.equal(bits.to(torch.int32), want_bits)
     # reference: one nn.BatchNorm2d called once per view, in view order
     bn = torch.nn.BatchNorm2d(c).cuda().train()
     bn.weight.data.copy_(gamma); bn.bias.data.copy_(beta)
@@ -228,21 +233,44 @@ def test_bn_train_kernels_match_torch():
     assert torch.allclose(rm, bn.running_mean, rtol=1e-5, atol=1e-6)
     assert torch.allclose(rv, bn.running_var, rtol=1e-5, atol=1e-6)
     assert int(nbt) == views and acc.abs().max().item() == 0.0
+    # one-launch variant (the last block finalizes): same coefficients, running stats, counters
+    rm2 = torch.zeros(c, device="cuda"); rv2 = torch.ones(c, device="cuda")
+    nbt2 = torch.zeros((), device="cuda", dtype=torch.long)
+    ticket = torch.zeros((1,), device="cuda", dtype=torch.int32)
+    mean2, invstd2, a2, b2, k02, k12, k22 = (torch.empty((views, c), device="cuda") for _ in range(7))
+    for _ in range(2):   # twice: the accumulator/ticket reset must leave a clean state
+        rm2.zero_(); rv2.fill_(1.0); nbt2.zero_()
+        _ck("rmv_bn_stats_finalize", z.data_ptr(), 0, n, h * w, c, views, acc.data_ptr(), ticket.data_ptr(),
+            gamma.data_ptr(), beta.data_ptr(), rm2.data_ptr(), rv2.data_ptr(), nbt2.data_ptr(),
+            mean2.data_ptr(), invstd2.data_ptr(), a2.data_ptr(), b2.data_ptr(), 1e-5, 0.1)
+        for got, want in ((mean2, mean), (invstd2, invstd), (a2, a), (b2, b), (rm2, rm), (rv2, rv)):
+            assert torch.allclose(got, want, rtol=1e-6, atol=1e-7)
+        assert int(nbt2) == views and int(ticket) == 0 and acc.abs().max().item() == 0.0
     dy = torch.randn_like(z)
     loss = sum((outs[v] * dy[v::views]).sum() for v in range(views))
     loss.backward()
-    dgamma = torch.empty(c, device="cuda"); dbeta = torch.empty(c, device="cuda")
-    dz = torch.empty_like(z)
-    _ck("rmv_bn_bwd_reduce", z.data_ptr(), dy.data_ptr(), y.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
-        0, n, h * w, c, views, acc.data_ptr())
-    _ck("rmv_bn_bwd_finalize", acc.data_ptr(), gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
-        dgamma.data_ptr(), dbeta.data_ptr(), k0.data_ptr(), k1.data_ptr(), k2.data_ptr(), c, views,
-        (n // views) * h * w)
-    _ck("rmv_bn_bwd_apply", z.data_ptr(), dy.data_ptr(), y.data_ptr(), k0.data_ptr(), k1.data_ptr(),
-        k2.data_ptr(), dz.data_ptr(), None, 0, n, h * w, c, views)
-    assert torch.allclose(dz, zz.grad, rtol=1e-3, atol=1e-5), (dz - zz.grad).abs().max()
-    assert torch.allclose(dgamma, bn.weight.grad, rtol=1e-4, atol=1e-4)
-    assert torch.allclose(dbeta, bn.bias.grad, rtol=1e-4, atol=1e-4)
+    for mask, is_bits in ((y, 0), (bits, 1)):   # ReLU mask from the output tensor / from the packed bits
+        dgamma = torch.empty(c, device="cuda"); dbeta = torch.empty(c, device="cuda")
+        dz = torch.empty_like(z)
+        dyr = torch.empty_like(z)
+        _ck("rmv_bn_bwd_reduce", z.data_ptr(), dy.data_ptr(), mask.data_ptr(), is_bits, mean.data_ptr(),
+            invstd.data_ptr(), 0, n, h * w, c, views, acc.data_ptr())
+        _ck("rmv_bn_bwd_finalize", acc.data_ptr(), gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+            dgamma.data_ptr(), dbeta.data_ptr(), k0.data_ptr(), k1.data_ptr(), k2.data_ptr(), c, views,
+            (n // views) * h * w)
+        _ck("rmv_bn_bwd_apply", z.data_ptr(), dy.data_ptr(), mask.data_ptr(), is_bits, k0.data_ptr(),
+            k1.data_ptr(), k2.data_ptr(), dz.data_ptr(), dyr.data_ptr(), 0, n, h * w, c, views)
+        assert torch.allclose(dz, zz.grad, rtol=1e-3, atol=1e-5), (dz - zz.grad).abs().max()
+        assert torch.equal(dyr, dy * (y > 0))
+        assert torch.allclose(dgamma, bn.weight.grad, rtol=1e-4, atol=1e-4)
+        assert torch.allclose(dbeta, bn.bias.grad, rtol=1e-4, atol=1e-4)
+        dg2 = torch.empty(c, device="cuda"); db2 = torch.empty(c, device="cuda")
+        _ck("rmv_bn_bwd_reduce_finalize", z.data_ptr(), dy.data_ptr(), mask.data_ptr(), is_bits,
+            mean.data_ptr(), invstd.data_ptr(), 0, n, h * w, c, views, acc.data_ptr(), ticket.data_ptr(),
+            gamma.data_ptr(), dg2.data_ptr(), db2.data_ptr(), k02.data_ptr(), k12.data_ptr(), k22.data_ptr())
+        for got, want in ((dg2, dgamma), (db2, dbeta), (k02, k0), (k12, k1), (k22, k2)):
+            assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+        assert int(ticket) == 0 and acc.abs().max().item() == 0.0
 
 
 def test_wgrad_dgrad_pool_bwd_match_torch():
@@ -359,3 +387,77 @@ def test_wgrad_tcgen05_matches_autograd(case):
     # accumulation semantics (+=)
     L.check(L.load().rmv_conv2d_wgrad_tc(C.byref(a), dy.data_ptr(), dw.data_ptr(), L.stream_ptr()), "wgrad_tc")
     assert (dw - 2 * ref).abs().max().item() <= 4e-4 * ref.abs().max().item() + 2e-4
+
+
+def test_permute_batch_kinds_match_generic():
+    """rmv_permute_cast_batch: the tiled access patterns (kind 1/2/3) give exactly what the generic
+    4-D permute (kind 0 = rmv_permute_cast) gives, for bf16 and fp32 destinations."""
+    import ctypes as C
+    from rotmv_b200 import _lib as L
+    from rotmv_b200.train import _ck
+
+    torch.manual_seed(3)
+    cases = []  # (weight, dims, strides, flip, kind)
+    for (k, c, r) in ((64, 64, 3), (128, 64, 1), (72, 200, 3), (40, 24, 1)):
+        w = torch.randn((k, c, r, r), device="cuda")
+        cases.append((w, (k, r, r, c), (c * r * r, r, 1, r * r), 0, 1 if r == 1 else 3))   # forward KRSC
+        cases.append((w, (c, r, r, k), (r * r, r, 1, c * r * r), 1, 2))                    # dgrad layout
+    lw = torch.randn((136, 520), device="cuda")
+    cases.append((lw, (1, 1, 136, 520), (0, 0, 520, 1), 0, 1))
+    cases.append((lw, (520, 1, 1, 136), (1, 0, 0, 520), 0, 2))
+    for dt_code, dt in ((L.BF16, torch.bfloat16), (L.F32, torch.float32)):
+        jobs = (L.PermuteJob * len(cases))()
+        outs, refs, block = [], [], 0
+        for i, (w, dims, strides, flip, kind) in enumerate(cases):
+            out = torch.zeros(dims, device="cuda", dtype=dt)
+            ref = torch.zeros(dims, device="cuda", dtype=dt)
+            _ck("rmv_permute_cast", w.data_ptr(), ref.data_ptr(), *dims, *strides, flip, flip, dt_code)
+            j = jobs[i]
+            j.src, j.dst = w.data_ptr(), out.data_ptr()
+            j.d0, j.d1, j.d2, j.d3 = dims
+            j.s0, j.s1, j.s2, j.s3 = strides
+            j.flip1, j.flip2, j.dst_dtype, j.first_block, j.kind = flip, flip, dt_code, block, kind
+            if kind == 2:
+                block += ((dims[0] * dims[1] * dims[2] + 63) // 64) * ((dims[3] + 63) // 64)
+            elif kind == 3:
+                block += dims[0]
+            else:
+                block += (out.numel() + 1023) // 1024
+            outs.append(out); refs.append(ref)
+        table = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).cuda()
+        L.check(L.load().rmv_permute_cast_batch(table.data_ptr(), len(cases), block, L.stream_ptr()),
+                "rmv_permute_cast_batch")
+        torch.cuda.synchronize()
+        for (w, dims, strides, flip, kind), out, ref in zip(cases, outs, refs):
+            assert torch.equal(out, ref), (dims, kind, dt)
+    # and the generic kernel itself against torch on one case
+    w = cases[1][0]
+    assert torch.equal(refs[1], w.permute(1, 2, 3, 0).flip(1, 2).contiguous())
+
+
+def test_conv2d_dgrad_tc_matches_torch():
+    """rmv_conv2d_dgrad (tcgen05): stride 1 and the parity-class stride-2 path (no dilated copy),
+    3x3 and 1x1, odd and even input sizes, with and without a residual, against autograd on the
+    bf16-rounded operands (fp32 accumulation: only the bf16 rounding of dx remains)."""
+    import torch.nn.functional as F
+    from rotmv_b200 import functional as RF
+
+    torch.manual_seed(5)
+    cases = [(3, 14, 64, 128, 3, 1, 1, True), (2, 28, 64, 64, 3, 2, 1, False), (2, 28, 128, 64, 3, 2, 1, True),
+             (2, 14, 128, 256, 1, 2, 0, False), (3, 15, 64, 64, 3, 2, 1, True), (2, 9, 64, 128, 1, 2, 0, False),
+             (4, 56, 64, 64, 1, 1, 0, True)]
+    for (n, hh, ci, co, k, s, p, with_res) in cases:
+        x = torch.randn((n, ci, hh, hh), device="cuda", requires_grad=True)
+        w = (torch.randn((co, ci, k, k), device="cuda") / (k * k * co) ** 0.5).bfloat16().float().requires_grad_(True)
+        y = F.conv2d(x, w, stride=s, padding=p)
+        dy = torch.randn_like(y).bfloat16().float()
+        y.backward(dy)
+        ref = x.grad.permute(0, 2, 3, 1)
+        res = torch.randn((n, hh, hh, ci), device="cuda").bfloat16() if with_res else None
+        if with_res:
+            ref = ref + res.float()
+        wt = w.detach().permute(1, 2, 3, 0).flip(1, 2).contiguous().bfloat16()   # [C, kh, kw, K], taps reversed
+        dx = RF.conv2d_dgrad(dy.permute(0, 2, 3, 1).contiguous().bfloat16(), wt, stride=s, pad=p,
+                             in_hw=(hh, hh), residual=res)
+        err = (dx.float() - ref).abs().max().item()
+        assert err <= 1e-2 * ref.abs().max().item() + 1e-3, (n, hh, ci, co, k, s, p, err)
