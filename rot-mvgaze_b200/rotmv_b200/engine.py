@@ -310,6 +310,7 @@ class GraphedForward:
         self._copy_stream = torch.cuda.Stream(device=dev)
         self._copied = [torch.cuda.Event() for _ in self.slices]
         self._done = torch.cuda.Event()
+        self._pipe = None  # staging buffers of the asynchronous host path, allocated on first submit
 
     def __call__(self, images: Optional[torch.Tensor] = None,
                  rotations: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -341,3 +342,61 @@ class GraphedForward:
         self._pred_host.copy_(self.pred, non_blocking=True)
         main.synchronize()
         return self._pred_host
+
+    # ---- asynchronous host path: a two-deep pipeline across calls --------------------------------
+    def submit(self, images_host: torch.Tensor, rotations_host: torch.Tensor) -> int:
+        """Enqueue one forward from pinned host buffers and return a ticket for `result`.
+
+        The host->HBM copy of call k+1 runs on the copy stream into a staging buffer while the
+        kernels of call k execute; the compute stream then moves the staged batch into the graph's
+        input buffer with one device-to-device copy (0.1 ms at B=256) and replays the full-batch
+        graphs, and the prediction is copied back to pinned host memory. At most two calls may be
+        outstanding (`result` of call k-2 must have been taken before submit k)."""
+        dev = self.engine.device
+        if self._pipe is None:
+            self._pipe = {
+                "img": [torch.empty_like(self.images) for _ in range(2)],
+                "rot": [torch.empty_like(self.rotations) for _ in range(2)],
+                "pred": [torch.empty(self.pred.shape, dtype=torch.float32).pin_memory() for _ in range(2)],
+                "copied": [torch.cuda.Event() for _ in range(2)],
+                "free": [torch.cuda.Event() for _ in range(2)],
+                "done": [torch.cuda.Event() for _ in range(2)],
+                "count": 0, "taken": [True, True]}
+            for ev in self._pipe["free"]:
+                ev.record(torch.cuda.current_stream(dev))
+        p = self._pipe
+        k = p["count"]
+        slot = k & 1
+        if not p["taken"][slot]:
+            raise RuntimeError("GraphedForward.submit: two calls are already outstanding; take "
+                               "result() of the older one first")
+        main = torch.cuda.current_stream(dev)
+        cs = self._copy_stream
+        cs.wait_event(p["free"][slot])
+        with torch.cuda.stream(cs):
+            p["img"][slot].copy_(images_host, non_blocking=True)
+            p["rot"][slot].copy_(rotations_host, non_blocking=True)
+            p["copied"][slot].record(cs)
+        main.wait_event(p["copied"][slot])
+        self.images.copy_(p["img"][slot], non_blocking=True)
+        self.rotations.copy_(p["rot"][slot], non_blocking=True)
+        p["free"][slot].record(main)
+        self.full_trunk_graph.replay()
+        self.fusion_graph.replay()
+        p["pred"][slot].copy_(self.pred, non_blocking=True)
+        p["done"][slot].record(main)
+        self._done.record(main)
+        p["taken"][slot] = False
+        p["count"] = k + 1
+        return k
+
+    def result(self, ticket: int) -> torch.Tensor:
+        """Block until call `ticket` has finished; returns its prediction (pinned host tensor, valid
+        until the second-next submit)."""
+        p = self._pipe
+        if p is None or not (p["count"] - 2 <= ticket < p["count"]):
+            raise RuntimeError(f"GraphedForward.result: ticket {ticket} is not outstanding")
+        slot = ticket & 1
+        p["done"][slot].synchronize()
+        p["taken"][slot] = True
+        return p["pred"][slot]

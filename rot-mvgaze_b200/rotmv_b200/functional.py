@@ -279,12 +279,13 @@ def angular_error_accum(pred, gt, err_sum):
                                              L.stream_ptr())
 
 
-def pose_to_rotations(head_pose):
+def pose_to_rotations(head_pose, out=None):
     """[B, V, 2] (pitch, yaw) -> [B, V, V, 3, 3]; reference utils/math.py:188-219 + rot_mv.py:193-194."""
-    _need_cuda(head_pose)
+    _need_cuda(head_pose, out)
     assert head_pose.dtype == torch.float32 and head_pose.is_contiguous()
     b, v, _ = head_pose.shape
-    rot = torch.empty((b, v, v, 3, 3), dtype=torch.float32, device=head_pose.device)
+    rot = out if out is not None else torch.empty((b, v, v, 3, 3), dtype=torch.float32, device=head_pose.device)
+    assert tuple(rot.shape) == (b, v, v, 3, 3) and rot.dtype == torch.float32 and rot.is_contiguous()
     _call("rmv_pose_to_rotations", {"desc": "rmv_pose_to_rotations"}, L.load().rmv_pose_to_rotations, head_pose.data_ptr(), rot.data_ptr(), b, v,
                                            L.stream_ptr())
     return rot

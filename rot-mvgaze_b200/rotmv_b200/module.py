@@ -94,7 +94,7 @@ class FeatRotationSymm(nn.Module):
     def __init__(self, backbone_depth: int = 50, num_iter: Optional[int] = None,
                  share_weights: bool = False, encode_rotmat: bool = False,
                  share_feature: bool = False, ignore_rotmat: bool = False, *,
-                 precision: str = "bf16", trunk_chunk: int = 32):
+                 precision: str = "bf16", trunk_chunk: int = 512):
         super().__init__()
         self._num_iter = num_iter
         self._output_index = num_iter - 1  # TypeError when num_iter is None, as in the reference

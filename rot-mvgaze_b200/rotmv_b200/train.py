@@ -528,6 +528,8 @@ class GraphedTrainStep:
         engine.flat_m.zero_(); engine.flat_v.zero_()
         engine.hyper[5] = 0.0
         torch.cuda.synchronize(dev)
+        self._pipe = None
+        self._copy_stream = torch.cuda.Stream(device=dev)
 
     def step(self, images=None, rotations=None, gt=None) -> torch.Tensor:
         if images is not None:
@@ -542,3 +544,57 @@ class GraphedTrainStep:
             torch.distributed.all_reduce(eng.flat_g, group=eng.pg)
         self.adam.replay()
         return eng.loss
+
+    # ---- host-buffer entry, two steps in flight -------------------------------------------------
+    def submit(self, images_host, head_pose_host, gt_host) -> int:
+        """One optimisation step from pinned HOST buffers (images [B,V,3,H,W] fp32, head poses
+        [B,V,2], labels [B,V,2] -- what trainer.py:99-123 hands to the model); returns a ticket for
+        `result`. The host->HBM copies of step k+1 run on a copy stream into staging buffers while
+        step k computes; the loss of each step is copied back to pinned host memory."""
+        dev = self.engine.device
+        if self._pipe is None:
+            b, v = self.gt.shape[0], self.gt.shape[1]
+            self._pipe = {
+                "img": [torch.empty_like(self.images) for _ in range(2)],
+                "pose": [torch.empty((b, v, 2), device=dev) for _ in range(2)],
+                "gt": [torch.empty_like(self.gt) for _ in range(2)],
+                "loss": [torch.empty((1,), dtype=torch.float32).pin_memory() for _ in range(2)],
+                "copied": [torch.cuda.Event() for _ in range(2)],
+                "free": [torch.cuda.Event() for _ in range(2)],
+                "done": [torch.cuda.Event() for _ in range(2)],
+                "count": 0, "taken": [True, True]}
+            for ev in self._pipe["free"]:
+                ev.record(torch.cuda.current_stream(dev))
+        p = self._pipe
+        k = p["count"]
+        slot = k & 1
+        if not p["taken"][slot]:
+            raise RuntimeError("GraphedTrainStep.submit: two steps are already outstanding")
+        main = torch.cuda.current_stream(dev)
+        cs = self._copy_stream
+        cs.wait_event(p["free"][slot])
+        with torch.cuda.stream(cs):
+            p["img"][slot].copy_(images_host, non_blocking=True)
+            p["pose"][slot].copy_(head_pose_host, non_blocking=True)
+            p["gt"][slot].copy_(gt_host, non_blocking=True)
+            p["copied"][slot].record(cs)
+        main.wait_event(p["copied"][slot])
+        self.images.copy_(p["img"][slot], non_blocking=True)
+        self.gt.copy_(p["gt"][slot], non_blocking=True)
+        RF.pose_to_rotations(p["pose"][slot], out=self.rotations)
+        p["free"][slot].record(main)
+        loss = self.step()
+        p["loss"][slot].copy_(loss, non_blocking=True)
+        p["done"][slot].record(main)
+        p["taken"][slot] = False
+        p["count"] = k + 1
+        return k
+
+    def result(self, ticket: int) -> torch.Tensor:
+        p = self._pipe
+        if p is None or not (p["count"] - 2 <= ticket < p["count"]):
+            raise RuntimeError(f"GraphedTrainStep.result: ticket {ticket} is not outstanding")
+        slot = ticket & 1
+        p["done"][slot].synchronize()
+        p["taken"][slot] = True
+        return p["loss"][slot]
