@@ -4,6 +4,7 @@
 #include "ops.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace rmv {
 
@@ -28,6 +29,15 @@ int num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+int pdl_level() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("RMV_PDL");
+    cached = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  return cached;
 }
 
 }  // namespace rmv

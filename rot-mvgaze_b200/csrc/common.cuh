@@ -46,6 +46,41 @@ const char* last_error();
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 int num_sms();
+int pdl_level();  // RMV_PDL: 0 = plain stream order, 1 = PDL for the tcgen05 kernels, 2 = all kernels
+
+#ifdef __CUDACC__
+// Launch with programmatic stream serialization (PDL): the kernel may be scheduled while the
+// previous kernel of the stream is still draining, so its prologue (barrier init, TMEM allocation,
+// descriptor prefetch, launch latency) overlaps that kernel's tail. ONLY for kernels that execute
+// griddep_wait() before their first access to global memory another kernel may have written.
+// Captured into CUDA graphs as programmatic dependency edges.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_lvl(int level, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                                  size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_level() >= level ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// level 2: the HBM-bound elementwise / reduction kernels; level 1 (launch_pdl_tc): tcgen05 kernels
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  return launch_pdl_lvl(2, kernel, grid, block, smem, stream, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_tc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args&&... args) {
+  return launch_pdl_lvl(1, kernel, grid, block, smem, stream, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Device PTX wrappers
@@ -64,6 +99,14 @@ __device__ __forceinline__ bool elect_one() {
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(pred));
   return pred != 0;
+}
+
+// ---- programmatic dependent launch ----
+// wait: everything the previous kernel(s) of the stream wrote is complete and visible (no-op when
+// the kernel was launched without the PDL attribute). launch: let the next kernel be scheduled.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // ---- mbarrier ----
@@ -203,9 +246,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
 //   start address >>4 in [0,14); LBO>>4 in [16,30); SBO>>4 in [32,46); version=1 at [46,48);
 //   layout type at [61,64) (2 = SWIZZLE_128B).
+//   base offset at [49,52): (start address >> 7) & 7 when the start is not 1024-byte aligned.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                    uint32_t sbo_bytes) {
+                                                    uint32_t sbo_bytes, uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= (uint64_t)(base_offset & 7) << 49;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;

@@ -98,6 +98,9 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__
 template <typename T>
 __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int in_h, int in_w,
                                int c, int out_h, int out_w, long long total) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cv = c / 8;
@@ -132,6 +135,9 @@ __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int i
 template <typename T>
 __global__ void avgpool_kernel(const T* __restrict__ x, int hw, int c, T* __restrict__ y0,
                                long long ld0, T* __restrict__ y1, long long ld1, long long total) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cv = c / 8;
@@ -160,6 +166,9 @@ __global__ void rotate_gather_kernel(const T* __restrict__ feat, long long ld_fe
                                      const float* __restrict__ rot, T* __restrict__ dst,
                                      long long ld_dst, int views, int nvec, int apply_rot,
                                      long long total) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int kv = nvec / 8;
@@ -241,6 +250,9 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
                  const float* __restrict__ b2, int rows, int hid, float* __restrict__ pred,
                  const float* __restrict__ gt, float loss_scale, int views, float aux_decay,
                  float* __restrict__ loss_out) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   __shared__ float s_part[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -408,10 +420,10 @@ extern "C" int rmv_maxpool3x3s2_fwd(const void* x, void* y, int n_img, int in_h,
   if (total == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == RMV_DTYPE_BF16)
-    maxpool_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, s>>>(
+    rmv::launch_pdl(maxpool_kernel<__nv_bfloat16>, dim3(blocks_for(total, 256)), dim3(256), 0, s, 
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, in_h, in_w, c, out_h, out_w, total);
   else
-    maxpool_kernel<float><<<blocks_for(total, 256), 256, 0, s>>>((const float*)x, (float*)y, in_h, in_w, c, out_h, out_w, total);
+    rmv::launch_pdl(maxpool_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, s, (const float*)x, (float*)y, in_h, in_w, c, out_h, out_w, total);
   RMV_LAUNCH_CHECK();
   return 0;
 }
@@ -423,10 +435,10 @@ extern "C" int rmv_avgpool_fwd(const void* x, int n_img, int hw, int c, int dtyp
   if (total == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == RMV_DTYPE_BF16)
-    avgpool_kernel<__nv_bfloat16><<<blocks_for(total, 128), 128, 0, s>>>(
+    rmv::launch_pdl(avgpool_kernel<__nv_bfloat16>, dim3(blocks_for(total, 128)), dim3(128), 0, s, 
         (const __nv_bfloat16*)x, hw, c, (__nv_bfloat16*)y0, ld0, (__nv_bfloat16*)y1, ld1, total);
   else
-    avgpool_kernel<float><<<blocks_for(total, 128), 128, 0, s>>>((const float*)x, hw, c, (float*)y0, ld0, (float*)y1, ld1, total);
+    rmv::launch_pdl(avgpool_kernel<float>, dim3(blocks_for(total, 128)), dim3(128), 0, s, (const float*)x, hw, c, (float*)y0, ld0, (float*)y1, ld1, total);
   RMV_LAUNCH_CHECK();
   return 0;
 }
@@ -441,10 +453,10 @@ extern "C" int rmv_rotate_gather_fwd(const void* feat, long long ld_feat, const 
   if (total == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == RMV_DTYPE_BF16)
-    rotate_gather_kernel<__nv_bfloat16><<<blocks_for(total, 128), 128, 0, s>>>(
+    rmv::launch_pdl(rotate_gather_kernel<__nv_bfloat16>, dim3(blocks_for(total, 128)), dim3(128), 0, s, 
         (const __nv_bfloat16*)feat, ld_feat, rot, (__nv_bfloat16*)dst, ld_dst, views, nvec, apply_rot, total);
   else
-    rotate_gather_kernel<float><<<blocks_for(total, 128), 128, 0, s>>>(
+    rmv::launch_pdl(rotate_gather_kernel<float>, dim3(blocks_for(total, 128)), dim3(128), 0, s, 
         (const float*)feat, ld_feat, rot, (float*)dst, ld_dst, views, nvec, apply_rot, total);
   RMV_LAUNCH_CHECK();
   return 0;
@@ -461,9 +473,9 @@ extern "C" int rmv_head_loss_fwd(const void* hidden, long long ld_hidden, int hi
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (hid_dtype == RMV_DTYPE_BF16)
-    head_loss_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)hidden, ld_hidden, w2, b2, rows, hid, pred, gt, loss_scale, views, aux_decay, loss_out);
+    rmv::launch_pdl(head_loss_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, (const __nv_bfloat16*)hidden, ld_hidden, w2, b2, rows, hid, pred, gt, loss_scale, views, aux_decay, loss_out);
   else
-    head_loss_kernel<float><<<grid, 256, 0, s>>>((const float*)hidden, ld_hidden, w2, b2, rows, hid, pred, gt, loss_scale, views, aux_decay, loss_out);
+    rmv::launch_pdl(head_loss_kernel<float>, dim3(grid), dim3(256), 0, s, (const float*)hidden, ld_hidden, w2, b2, rows, hid, pred, gt, loss_scale, views, aux_decay, loss_out);
   RMV_LAUNCH_CHECK();
   return 0;
 }

@@ -19,6 +19,7 @@
 #include "ops.h"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace rmv {
 
@@ -50,23 +51,39 @@ struct IgemmArgs {
   const float* scale;
   const float* shift;
   int relu;
+  int halo_base_mode;  // HALO kernels: 1 = set the descriptor base offset for row-shifted starts
 };
 
-template <int BLOCK_N, bool HAS_RES>
+// HALO variant (3x3, stride 1, pad 1, 64 -> 64 channels; BLOCK_N = 64): the producer loads ONE
+// (16 wide x 18 high) input patch per 8x16-pixel output tile -- 16-pixel rows so that every image
+// row starts 2048 B (a whole number of 1024-byte swizzle atoms) after the previous one -- and the
+// nine taps are nine UMMA descriptors into that patch (start shifted by (r*16+s) pixels = rows of
+// 128 B, stride 2048 B between the 8-row groups), instead of nine separate TMA boxes: 6x less
+// L2->SM traffic for A. The 72 KiB of filters stay resident in shared memory for the whole kernel.
+constexpr int kHaloW = 16, kHaloH = 18;
+constexpr int kHaloABytes = kHaloW * kHaloH * 128;  // 36864
+constexpr int kHaloTaps = 9;
+constexpr int kHaloStages = 3;
+
+template <int BLOCK_N, bool HAS_RES, bool HALO = false>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageA = HALO ? kHaloABytes : kABytes;             // A bytes per stage
+  static constexpr int kStageB = HALO ? 0 : kBBytes;                        // B bytes per stage
+  static constexpr int kResidentB = HALO ? kHaloTaps * kBBytes : 0;         // filters kept in smem
+  static constexpr int kStageBytes = kStageA + kStageB;
   // Layers with a residual (the expanding 1x1 convs) are HBM-bound with 1-8 k-blocks per tile: they
   // trade A/B stages for a deeper residual ring (4 x 16 KiB) so the residual loads run well ahead.
-  static constexpr int kStages = HAS_RES ? (BLOCK_N == 256 ? 2 : (BLOCK_N == 128 ? 3 : 4))
-                                         : (BLOCK_N == 256 ? 3 : 6);
+  static constexpr int kStages = HALO ? kHaloStages
+                                 : HAS_RES ? (BLOCK_N == 256 ? 2 : (BLOCK_N == 128 ? 3 : 4))
+                                           : (BLOCK_N == 256 ? 3 : 6);
   static constexpr int kResSlots = 4;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
   static constexpr int kOutBytes = 2 * kChunkBytes;
   static constexpr int kResBytes = HAS_RES ? kResSlots * kChunkBytes : 0;
   static constexpr int kVecBytes = 2 * BLOCK_N * 4;  // scale + shift of the current N tile
-  static constexpr int kSmemBytes =
-      kStages * kStageBytes + kOutBytes + kResBytes + kVecBytes + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kResidentB + kOutBytes + kResBytes +
+                                    kVecBytes + 256 /*barriers*/ + 1024 /*align*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 };
 
@@ -93,10 +110,10 @@ __device__ __forceinline__ void epi_bar_sync(int id) {
 }
 
 // OUT_F32: 32 fp32 columns per staged chunk; otherwise 64 bf16 columns (both 128 B per row).
-template <int BLOCK_N, bool HAS_RES, bool OUT_F32>
+template <int BLOCK_N, bool HAS_RES, bool OUT_F32, bool HALO = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmArgs args) {
-  using C = Cfg<BLOCK_N, HAS_RES>;
+  using C = Cfg<BLOCK_N, HAS_RES, HALO>;
   constexpr int kChunkCols = OUT_F32 ? 32 : 64;
   constexpr int kChunks = BLOCK_N / kChunkCols;
   extern __shared__ uint8_t smem_raw[];
@@ -104,8 +121,8 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   // keeps the shared address space and emits LDS/STS instead of generic LD/ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + C::kStages * kABytes;
-  uint8_t* smem_out = smem_b + C::kStages * C::kBBytes;  // [2][128 rows][128 B], SW128
+  uint8_t* smem_b = smem_a + C::kStages * C::kStageA;
+  uint8_t* smem_out = smem_b + C::kStages * C::kStageB + C::kResidentB;  // [2][128 rows][128 B], SW128
   uint8_t* smem_res = smem_out + C::kOutBytes;           // [2][128 rows][128 B], SW128
   float* s_scale = reinterpret_cast<float*>(smem_res + C::kResBytes);
   float* s_shift = s_scale + BLOCK_N;
@@ -116,7 +133,8 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   uint64_t* tmem_empty = tmem_full + 2;           // [2]        epilogue -> MMA
   uint64_t* res_full = tmem_empty + 2;            // [4]        TMA(residual) -> epilogue
   uint64_t* res_empty = res_full + C::kResSlots;  // [4]        epilogue -> TMA(residual)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_empty + C::kResSlots);
+  uint64_t* b_bar = res_empty + C::kResSlots;     // [1]        HALO: resident filters landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -137,6 +155,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       mbar_init(&res_full[i], 1);
       mbar_init(&res_empty[i], kEpiThreads);
     }
+    mbar_init(b_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -147,6 +166,10 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail
+  // of the previous kernel; global memory is only touched from here on.
+  griddep_wait();
+  griddep_launch();
 
   const int m_tiles = args.tiles_w * args.tiles_h * args.tiles_n;
   const int total_tiles = m_tiles * args.n_tiles;
@@ -154,7 +177,24 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
 
   if (warp == 0) {
     // ------------------------------- TMA producer (A, B) ------------------------
-    if (lane == 0) {
+    if (HALO && lane == 0) {
+      // resident filters: tap t = rows [t*64, t*64+64) of the K axis, [64 c_out][64 c_in] each
+      mbar_expect_tx(b_bar, C::kResidentB);
+      for (int t = 0; t < kHaloTaps; ++t)
+        tma_load_2d(smem_b + t * C::kBBytes, &args.tmap_b, b_bar, t * kBlockK, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tw = tile % args.tiles_w;
+        const int th = (tile / args.tiles_w) % args.tiles_h;
+        const int tn = tile / (args.tiles_w * args.tiles_h);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], kHaloABytes);
+        tma_load_4d(smem_a + stage * kHaloABytes, &args.tmap_a[0], &full_bar[stage], 0,
+                    tw * args.box_w - 1, th * args.box_h - 1, tn);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -189,6 +229,31 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after_sync();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      if (HALO) {
+        if (local == 0) mbar_wait(b_bar, 0);
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        if (lane == 0) {
+          const uint32_t a0 = smem_u32(smem_a + stage * kHaloABytes);
+          const uint32_t b0 = smem_u32(smem_b);
+#pragma unroll
+          for (int tap = 0; tap < kHaloTaps; ++tap) {
+            // tap (r, s): the patch shifted by r rows of 16 pixels and s pixels (128 B each)
+            const uint32_t aaddr = a0 + ((tap / 3) * kHaloW + (tap % 3)) * 128;
+            const uint64_t adesc = umma_desc_sw128(
+                aaddr, 16, kHaloW * 128, args.halo_base_mode ? (aaddr >> 7) & 7 : 0);
+            const uint64_t bdesc = umma_desc_sw128(b0 + tap * C::kBBytes, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (tap | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        continue;
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
@@ -398,19 +463,33 @@ namespace {
 
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-template <int BLOCK_N, bool HAS_RES, bool OUT_F32>
+template <int BLOCK_N, bool HAS_RES, bool OUT_F32, bool HALO = false>
 int launch(const IgemmArgs& a, int total_tiles, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, HAS_RES>;
+  using C = Cfg<BLOCK_N, HAS_RES, HALO>;
   static bool attr_set = false;
   if (!attr_set) {
-    RMV_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, HAS_RES, OUT_F32>,
+    RMV_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, HAS_RES, OUT_F32, HALO>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  igemm_kernel<BLOCK_N, HAS_RES, OUT_F32><<<grid, kNumThreads, C::kSmemBytes, stream>>>(a);
-  RMV_LAUNCH_CHECK();
+  RMV_CUDA(launch_pdl_tc(igemm_kernel<BLOCK_N, HAS_RES, OUT_F32, HALO>, dim3(grid),
+                         dim3(kNumThreads), C::kSmemBytes, stream, a));
   return 0;
+}
+
+// RMV_HALO: 0 = never use the halo-patch 3x3 kernel; 1 (default) = use it. The row-shifted
+// descriptors keep base offset 0: measured on B200, tcgen05 applies the 128-byte swizzle to the
+// absolute shared-memory address (the same function TMA wrote the patch with), so a start address
+// that is a multiple of 128 B but not of 1024 B needs no base offset. 2 = set the base offset to
+// (addr >> 7) & 7 anyway (diagnostic: gives wrong results, kept to document the finding).
+int halo_mode() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("RMV_HALO");
+    cached = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  return cached;
 }
 
 template <int BLOCK_N>
@@ -474,6 +553,11 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
     r_sh = r_sw * out_w; r_sn = r_sh;
   }
 
+  // 3x3 / stride 1 / pad 1 / 64 -> 64 channels (layer1 conv2 and its data gradient): halo-patch
+  // kernel, 8 wide x 16 high tiles of one image, filters resident in shared memory.
+  const bool halo = taps == nullptr && halo_mode() != 0 && p.kh == 3 && p.kw == 3 && p.stride == 1 &&
+                    p.pad == 1 && p.c_in == 64 && p.c_out == 64 && !out_f32 &&
+                    p.residual == nullptr && p.block_n == 0 && out_w >= 8 && out_h >= 16;
   // Pick the (box_w, box_h, box_n) factorisation of the 128-row M tile with the least padding.
   int best_w = 128, best_h = 1, best_n = 1;
   double best_eff = -1;
@@ -485,6 +569,7 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
                           ceil_div(n_img, bn) * bn);
       if (eff > best_eff + 1e-9) { best_eff = eff; best_w = bw; best_h = bh; best_n = bn; }
     }
+  if (halo) { best_w = 8; best_h = 16; best_n = 1; }
   a.box_w = best_w; a.box_h = best_h; a.box_n = best_n;
   a.tiles_w = ceil_div(out_w, a.box_w);
   a.tiles_h = ceil_div(out_h, a.box_h);
@@ -511,6 +596,7 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
                                  (cuuint64_t)(x_sn * 2)};
         cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)a.box_w, (cuuint32_t)a.box_h,
                              (cuuint32_t)a.box_n};
+        if (halo) { box[1] = kHaloW; box[2] = kHaloH; box[3] = 1; }  // one patch per tile
         const __nv_bfloat16* base =
             reinterpret_cast<const __nv_bfloat16*>(p.x) + ph * x_sh + pw * x_sw;
         int rc = encode_map(&a.tmap_a[n_planes], base, 4, dims, strides, box);
@@ -561,6 +647,10 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
   a.relu = p.relu;
   const int total = (int)(m_tiles * a.n_tiles);
   if (total == 0) return 0;
+  if (halo) {
+    a.halo_base_mode = halo_mode() == 2;
+    return launch<64, false, false, true>(a, total, stream);
+  }
   const bool has_res = p.residual != nullptr;
   switch (block_n) {
     case 64: return dispatch<64>(a, total, has_res, out_f32, stream);

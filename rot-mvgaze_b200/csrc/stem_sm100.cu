@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(kThreads, 2) stem_kernel(const __grid_constant
     tmem_alloc(tmem_ptr, 64);
     tmem_relinquish();
   }
+  griddep_wait();    // PDL: global memory is touched from here on
+  griddep_launch();
   if (tid < kCout) {
     s_scale[tid] = a.scale ? __ldg(a.scale + tid) : 1.f;
     s_shift[tid] = a.shift ? __ldg(a.shift + tid) : 0.f;
@@ -443,8 +445,7 @@ extern "C" int rmv_stem_conv_fwd(const float* x_nchw, const void* w_packed, cons
     attr_set = true;
   }
   const int grid = a.total_tiles < 2 * num_sms() ? a.total_tiles : 2 * num_sms();
-  stem_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a);
-  RMV_LAUNCH_CHECK();
+  RMV_CUDA(launch_pdl_tc(stem_kernel, dim3(grid), dim3(kThreads), kSmemBytes, (cudaStream_t)stream, a));
   return 0;
 }
 

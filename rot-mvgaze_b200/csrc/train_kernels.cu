@@ -201,6 +201,9 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const void* 
                  const float* __restrict__ mean, const float* __restrict__ invstd, int pix, int c,
                  int views, int imgs_per_view, double* __restrict__ acc /* [views][c][2] */,
                  const BnFinalize fin) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   extern __shared__ float s_red[];  // [row_lanes][c][2]
   __shared__ unsigned int s_ticket;
   const T* y_mask = reinterpret_cast<const T*>(y_mask_v);
@@ -331,6 +334,9 @@ __global__ void __launch_bounds__(256, 3)
 bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ a, const float* __restrict__ b,
                 const T* __restrict__ residual, T* __restrict__ y,
                 uint8_t* __restrict__ relu_bits, int pix, int c, int views, int relu) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   const int cg = c / 8;
   const int n = blockIdx.y, v = n % views;
   const long long per_img = (long long)pix * cg;  // 8-channel vectors in this image
@@ -385,6 +391,9 @@ bn_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ dy, const voi
                     const float* __restrict__ k0, const float* __restrict__ k1,
                     const float* __restrict__ k2, T* __restrict__ dz, T* __restrict__ dyr_out,
                     int pix, int c, int views) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   const T* y_mask = reinterpret_cast<const T*>(y_mask_v);
   const uint8_t* y_bits = reinterpret_cast<const uint8_t*>(y_mask_v);
   const int cg = c / 8;
@@ -442,6 +451,9 @@ __global__ void relu_bwd_kernel(const T* __restrict__ src, long long ld_src,
                                 const T* __restrict__ mask, long long ld_mask,
                                 const T* __restrict__ add, long long ld_add, T* __restrict__ dst,
                                 long long ld_dst, int cols, long long total) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cg = cols / 8;
@@ -468,6 +480,9 @@ __global__ void relu_bwd_kernel(const T* __restrict__ src, long long ld_src,
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   __shared__ float s[8][32 + 1];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int lane_r = threadIdx.x >> 5;  // 8 row lanes
@@ -608,6 +623,9 @@ __device__ __forceinline__ void permute_job_krsc(const rmv_permute_job& j, long 
 
 __global__ void __launch_bounds__(256)
 permute_cast_batch_kernel(const rmv_permute_job* __restrict__ jobs, int n_jobs) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   __shared__ int s_job;
   __shared__ float s_tile[64][65];
   if (threadIdx.x == 0) {
@@ -710,6 +728,9 @@ template <typename T>
 __global__ void maxpool_fwd_idx_kernel(const T* __restrict__ x, T* __restrict__ y,
                                        uint8_t* __restrict__ idx, int in_h, int in_w, int c,
                                        int out_h, int out_w, long long total) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int cg = c / 8;
@@ -748,6 +769,9 @@ template <typename T>
 __global__ void maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const T* __restrict__ dy,
                                        T* __restrict__ dx, int in_h, int in_w, int c, int out_h,
                                        int out_w, long long total) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int cg = c / 8;
@@ -777,6 +801,9 @@ __global__ void maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const T*
 template <typename T>
 __global__ void avgpool_bwd_kernel(const T* __restrict__ dfeat, long long ld, T* __restrict__ dx,
                                    int hw, int c, long long total) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cg = c / 8;
@@ -824,6 +851,9 @@ head_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ g
                      int rows, int hid, float loss_scale, int views, float aux_decay,
                      T* __restrict__ dhidden, long long ld_dh, float* __restrict__ dpred_out,
                      float* __restrict__ dw2, float* __restrict__ db2) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   // one warp per row; block-level partial dw2/db2 reduced through shared memory + atomics
   extern __shared__ float s_dw[];  // [2][hid] + [2]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -973,6 +1003,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                             float* __restrict__ m, float* __restrict__ v,
                             const double* __restrict__ hyper, int decoupled, float grad_scale,
                             long long n) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
   // scalar prefactors in fp64, exactly as torch.optim.Adam computes them on the host
   const double lr_d = hyper[0], b1_d = hyper[1], b2_d = hyper[2], step_d = hyper[5];
   const float lr = (float)lr_d, b1 = (float)b1_d, b2 = (float)b2_d;
@@ -1056,7 +1089,7 @@ static int bn_stats_launch(const void* z, int dtype, int n_img, int pix, int c, 
   if (n_img == 0 || pix == 0) return 0;
   dim3 grid; int smem;
   if (int rc = bn_reduce_cfg(pix, c, n_img, views, 3, &grid, &smem)) return rc;
-  DISPATCH_T(dtype, (bn_reduce_kernel<T, false, 0><<<grid, 256, smem, stream>>>(
+  DISPATCH_T(dtype, (rmv::launch_pdl(bn_reduce_kernel<T, false, 0>, dim3(grid), dim3(256), smem, stream, 
       (const T*)z, nullptr, nullptr, nullptr, nullptr, pix, c, views, n_img / views, acc, fin)));
   RMV_LAUNCH_CHECK();
   return 0;
@@ -1114,7 +1147,7 @@ extern "C" int rmv_bn_apply(const void* z, const float* a, const float* b, const
   RMV_CHECK_ARG(c % 8 == 0 && 256 % (c / 8) == 0, "bn_apply: c=%d must be 8*2^k, <= 2048", c);
   if ((long long)n_img * pix == 0) return 0;
   const dim3 grid(ew_blocks_x(pix, c, n_img), (unsigned)n_img);
-  DISPATCH_T(dtype, (bn_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, (rmv::launch_pdl(bn_apply_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
       (const T*)z, a, b, (const T*)residual, (T*)y, relu_bits, pix, c, views, relu)));
   RMV_LAUNCH_CHECK();
   return 0;
@@ -1134,7 +1167,7 @@ static int bn_bwd_reduce_launch(const void* z, const void* dy, const void* y_mas
   dim3 grid; int smem;
   if (int rc = bn_reduce_cfg(pix, c, n_img, views, 2, &grid, &smem)) return rc;
   DISPATCH_T(dtype, DISPATCH_MASK(y_mask, mask_is_bits,
-      (bn_reduce_kernel<T, true, MASK><<<grid, 256, smem, stream>>>(
+      (rmv::launch_pdl(bn_reduce_kernel<T, true, MASK>, dim3(grid), dim3(256), smem, stream, 
           (const T*)z, (const T*)dy, y_mask, mean, invstd, pix, c, views, n_img / views, acc, fin))));
   RMV_LAUNCH_CHECK();
   return 0;
@@ -1190,7 +1223,7 @@ extern "C" int rmv_bn_bwd_apply(const void* z, const void* dy, const void* y_mas
   if ((long long)n_img * pix == 0) return 0;
   const dim3 grid(ew_blocks_x(pix, c, n_img, rmv::kBwdUnroll), (unsigned)n_img);
   DISPATCH_T(dtype, DISPATCH_MASK(y_mask, mask_is_bits,
-      (bn_bwd_apply_kernel<T, MASK><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (rmv::launch_pdl(bn_bwd_apply_kernel<T, MASK>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
           (const T*)z, (const T*)dy, y_mask, k0, k1, k2, (T*)dz, (T*)dyr_out, pix, c, views))));
   RMV_LAUNCH_CHECK();
   return 0;
@@ -1203,7 +1236,7 @@ extern "C" int rmv_relu_bwd(const void* src, long long ld_src, const void* mask,
                 "relu_bwd: cols/ld must be multiples of 8");
   const long long total = (long long)rows * (cols / 8);
   if (total == 0) return 0;
-  DISPATCH_T(dtype, (relu_bwd_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, (rmv::launch_pdl(relu_bwd_kernel<T>, dim3(nblk(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const T*)src, ld_src, (const T*)mask, ld_mask, (const T*)add, ld_add, (T*)dst, ld_dst, cols,
       total)));
   RMV_LAUNCH_CHECK();
@@ -1216,7 +1249,7 @@ extern "C" int rmv_colsum(const void* x, long long ld, int rows, int cols, int d
   int ysplit = (rows + 255) / 256;
   if (ysplit > 64) ysplit = 64;
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)ysplit);
-  DISPATCH_T(dtype, (colsum_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, rows, cols, out)));
+  DISPATCH_T(dtype, (rmv::launch_pdl(colsum_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)x, ld, rows, cols, out)));
   RMV_LAUNCH_CHECK();
   return 0;
 }
@@ -1264,7 +1297,7 @@ extern "C" int rmv_avgpool_bwd(const void* dfeat, long long ld, void* dx, int n_
   RMV_CHECK_ARG(c % 8 == 0 && ld % 8 == 0, "avgpool_bwd: c/ld must be multiples of 8");
   const long long total = (long long)n_img * hw * (c / 8);
   if (total == 0) return 0;
-  DISPATCH_T(dtype, (avgpool_bwd_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, (rmv::launch_pdl(avgpool_bwd_kernel<T>, dim3(nblk(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const T*)dfeat, ld, (T*)dx, hw, c, total)));
   RMV_LAUNCH_CHECK();
   return 0;
@@ -1279,7 +1312,7 @@ extern "C" int rmv_head_loss_bwd(const float* pred, const float* gt, const void*
                 "head_loss_bwd: hid/ld must be multiples of 8");
   if (rows == 0) return 0;
   const int smem = (2 * hid + 2) * (int)sizeof(float);
-  DISPATCH_T(hid_dtype, (head_loss_bwd_kernel<T><<<(rows + 7) / 8, 256, smem, (cudaStream_t)stream>>>(
+  DISPATCH_T(hid_dtype, (rmv::launch_pdl(head_loss_bwd_kernel<T>, dim3((rows + 7) / 8), dim3(256), smem, (cudaStream_t)stream, 
       pred, gt, (const T*)hidden, ld_hidden, w2, rows, hid, loss_scale, views, aux_decay,
       (T*)dhidden, ld_dhidden, dpred, dw2, db2)));
   RMV_LAUNCH_CHECK();
@@ -1321,7 +1354,7 @@ extern "C" int rmv_adam_step(float* params, const float* grads, float* exp_avg, 
   adam_tick_kernel<<<1, 1, 0, s>>>(hyper);
   long blocks = (n / 4 + 255) / 256;
   if (blocks > 16L * num_sms()) blocks = 16L * num_sms();
-  adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, hyper, decoupled,
+  rmv::launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, hyper, decoupled,
                                                grad_scale, n);
   RMV_LAUNCH_CHECK();
   return 0;
@@ -1333,7 +1366,7 @@ extern "C" int rmv_maxpool3x3s2_fwd_idx(const void* x, void* y, void* idx, int n
   const int out_h = (in_h - 1) / 2 + 1, out_w = (in_w - 1) / 2 + 1;
   const long long total = (long long)n_img * out_h * out_w * (c / 8);
   if (total == 0) return 0;
-  DISPATCH_T(dtype, (maxpool_fwd_idx_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, (rmv::launch_pdl(maxpool_fwd_idx_kernel<T>, dim3(nblk(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const T*)x, (T*)y, (uint8_t*)idx, in_h, in_w, c, out_h, out_w, total)));
   RMV_LAUNCH_CHECK();
   return 0;
@@ -1345,7 +1378,7 @@ extern "C" int rmv_maxpool3x3s2_bwd_idx(const void* idx, const void* dy, void* d
   const int out_h = (in_h - 1) / 2 + 1, out_w = (in_w - 1) / 2 + 1;
   const long long total = (long long)n_img * in_h * in_w * (c / 8);
   if (total == 0) return 0;
-  DISPATCH_T(dtype, (maxpool_bwd_idx_kernel<T><<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, (rmv::launch_pdl(maxpool_bwd_idx_kernel<T>, dim3(nblk(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const uint8_t*)idx, (const T*)dy, (T*)dx, in_h, in_w, c, out_h, out_w, total)));
   RMV_LAUNCH_CHECK();
   return 0;
@@ -1355,7 +1388,7 @@ extern "C" int rmv_permute_cast_batch(const rmv_permute_job* jobs_dev, int n_job
                                       unsigned total_blocks, void* stream) {
   RMV_CHECK_ARG(jobs_dev != nullptr || n_jobs == 0, "permute_cast_batch: null job table");
   if (n_jobs == 0 || total_blocks == 0) return 0;
-  permute_cast_batch_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, n_jobs);
+  rmv::launch_pdl(permute_cast_batch_kernel, dim3(total_blocks), dim3(256), 0, (cudaStream_t)stream, jobs_dev, n_jobs);
   RMV_LAUNCH_CHECK();
   return 0;
 }

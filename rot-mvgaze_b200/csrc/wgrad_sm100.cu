@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_ptr;
+  griddep_wait();    // PDL: the prologue above overlapped the previous kernel's tail
+  griddep_launch();
 
   // work item: tap fastest so the CTAs sharing a pixel range run together (L2 reuse of dY and X)
   int w = blockIdx.x;
@@ -178,8 +180,7 @@ int launch_wg(const WgArgs& a, int grid, cudaStream_t stream) {
     RMV_CUDA(cudaFuncSetAttribute(wgrad_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  wgrad_kernel<N_TILE><<<grid, kThreads, smem, stream>>>(a);
-  RMV_LAUNCH_CHECK();
+  RMV_CUDA(launch_pdl_tc(wgrad_kernel<N_TILE>, dim3(grid), dim3(kThreads), smem, stream, a));
   return 0;
 }
 

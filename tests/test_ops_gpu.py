@@ -193,3 +193,25 @@ def test_fused_stem_matches_conv_bn_relu(n, h, w):
     assert tuple(y.shape) == tuple(ref.shape)
     err = (y.float() - ref).abs().max().item()
     assert err <= 1.2e-2 * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("n,h,w", [(3, 56, 56), (2, 20, 23), (5, 16, 8), (1, 33, 40)])
+def test_conv3x3_halo_kernel(n, h, w):
+    """3x3/s1/p1 64->64 runs on the halo-patch kernel (one 16x18 input patch per 8x16 output tile,
+    nine row-shifted UMMA descriptors, resident filters): full tiles, ragged right/bottom edges,
+    several images; fp32 output isolates the accumulation, bf16 output is the production path."""
+    from rotmv_b200 import functional as RF, _lib as L
+
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + h * 10 + w)
+    x = torch.randn((n, h, w, 64), device="cuda", generator=g).bfloat16()
+    wt = (torch.randn((64, 3, 3, 64), device="cuda", generator=g) / 24).bfloat16()
+    scale = torch.rand((64,), device="cuda", generator=g) + 0.5
+    shift = torch.randn((64,), device="cuda", generator=g)
+    y = RF.conv2d(x, wt, stride=1, pad=1, scale=scale, shift=shift, relu=True, engine=L.ENGINE_TC)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), padding=1)
+    ref = torch.relu(ref.permute(0, 2, 3, 1) * scale + shift)
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 1.2e-2 * ref.abs().max().item(), (err, ref.abs().max().item())
+    # the generic tap-by-tap kernel (block_n given explicitly) must agree to bf16 rounding
+    y2 = RF.conv2d(x, wt, stride=1, pad=1, scale=scale, shift=shift, relu=True, engine=L.ENGINE_TC, block_n=64)
+    assert (y.float() - y2.float()).abs().max().item() <= 4e-2 * ref.abs().max().item() / 8
