@@ -38,6 +38,7 @@ struct StemArgs {
   const float* shift;
   int n_img, in_h, in_w, out_h, out_w, tiles_w, tiles_h, total_tiles;
   int relu;
+  int vec_ok;  // forward loader may use aligned 16-byte loads (in_w % 4 == 0, 16-byte aligned x)
 };
 
 __device__ __forceinline__ void stem_tma_store(const void* tmap, const void* src, int c0, int c1,
@@ -53,16 +54,17 @@ __device__ __forceinline__ void stem_tma_store(const void* tmap, const void* src
 constexpr int kPatchIters = (kPatchElems + kThreads - 1) / kThreads;  // 12
 
 // Issue the (coalesced, bounds-checked) global loads of a tile's input patch into registers...
+template <int NT>
 __device__ __forceinline__ void patch_issue(const StemArgs& a, int tile, int tid,
-                                            float (&v)[kPatchIters]) {
+                                            float (&v)[(kPatchElems + NT - 1) / NT]) {
   const int tw = tile % a.tiles_w;
   const int th = (tile / a.tiles_w) % a.tiles_h;
   const int n = tile / (a.tiles_w * a.tiles_h);
   const int ih0 = 2 * th * kTH - 3, iw0 = 2 * tw * kTW - 3;
   const float* xn = a.x + (long long)n * 3 * a.in_h * a.in_w;
 #pragma unroll
-  for (int it = 0; it < kPatchIters; ++it) {
-    const int i = tid + it * kThreads;
+  for (int it = 0; it < (kPatchElems + NT - 1) / NT; ++it) {
+    const int i = tid + it * NT;
     float f = 0.f;
     if (i < kPatchElems) {
       const int col = i % kPatchPitch;
@@ -76,158 +78,296 @@ __device__ __forceinline__ void patch_issue(const StemArgs& a, int tile, int tid
   }
 }
 // ... and, one pipeline phase later, convert to bf16 and park them in shared memory.
-__device__ __forceinline__ void patch_store(const float (&v)[kPatchIters], __nv_bfloat16* patch,
-                                            int tid) {
+template <int NT>
+__device__ __forceinline__ void patch_store(const float (&v)[(kPatchElems + NT - 1) / NT],
+                                            __nv_bfloat16* patch, int tid) {
 #pragma unroll
-  for (int it = 0; it < kPatchIters; ++it) {
-    const int i = tid + it * kThreads;
+  for (int it = 0; it < (kPatchElems + NT - 1) / NT; ++it) {
+    const int i = tid + it * NT;
     if (i < kPatchElems) patch[i] = __float2bfloat16_rn(v[it]);
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) stem_kernel(const __grid_constant__ StemArgs a) {
+// Warp-specialised forward kernel, one CTA per SM:
+//   warps 0-3   loader:   fp32 NCHW patch -> registers (two tiles in flight) -> bf16 patch ring
+//   warps 4-7   builder:  patch -> im2col rows in the swizzled UMMA layout (double-buffered)
+//   warp  8     MMA:      12 tcgen05.mma per tile into one of two TMEM accumulators
+//   warps 9-12  epilogue: TMEM -> scale/shift/ReLU -> bf16 -> swizzled staging -> TMA store
+// every hand-over is an mbarrier, so the four stages of consecutive tiles overlap.
+constexpr int kFwdThreads = 416;
+constexpr int kPatchSlots = 3;
+constexpr int kPatchBytes = 6144;
+constexpr int kLdIters = (kPatchElems + 127) / 128;  // 24
+constexpr int kFwdSmemBytes = 3 * kBBytes + 2 * 3 * kABytes + 2 * kABytes /*out staging*/ +
+                              kPatchSlots * kPatchBytes + 512 /*scale,shift*/ + 256 /*barriers*/ +
+                              1024 /*align*/;
+
+__global__ void __launch_bounds__(kFwdThreads, 1) stem_kernel(const __grid_constant__ StemArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by OFFSET (not by an integer round trip of the pointer) so the compiler
   // keeps the shared address space and emits LDS/STS instead of generic LD/ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sB = smem;
-  uint8_t* sA = sB + 3 * kBBytes;
-  uint8_t* sOut = sA + 3 * kABytes;
-  __nv_bfloat16* sPatch = reinterpret_cast<__nv_bfloat16*>(sOut + kABytes);
-  float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sPatch) + 6144);
+  uint8_t* sA = sB + 3 * kBBytes;        // [2][3 k-blocks][128 rows][128 B]
+  uint8_t* sOut = sA + 2 * 3 * kABytes;  // [2][128 rows][128 B]
+  uint8_t* sPatchBase = sOut + 2 * kABytes;
+  float* s_scale = reinterpret_cast<float*>(sPatchBase + kPatchSlots * kPatchBytes);
   float* s_shift = s_scale + kCout;
-  uint64_t* w_bar = reinterpret_cast<uint64_t*>(s_shift + kCout);
-  uint64_t* mma_bar = w_bar + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + kCout);
+  uint64_t* w_bar = bars;
+  uint64_t* patch_full = bars + 1;                 // [3] loader  -> builder
+  uint64_t* patch_empty = patch_full + kPatchSlots;  // [3] builder -> loader
+  uint64_t* a_full = patch_empty + kPatchSlots;    // [2] builder -> MMA
+  uint64_t* a_empty = a_full + 2;                  // [2] MMA     -> builder
+  uint64_t* tmem_full = a_empty + 2;               // [2] MMA     -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;            // [2] epilogue -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     tma_prefetch_desc(&a.tmap_w);
     tma_prefetch_desc(&a.tmap_out);
     mbar_init(w_bar, 1);
-    mbar_init(mma_bar, 1);
+    for (int i = 0; i < kPatchSlots; ++i) { mbar_init(&patch_full[i], 128); mbar_init(&patch_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1);
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_ptr, 64);
+  if (warp == 8) {
+    tmem_alloc(tmem_ptr, 128);
     tmem_relinquish();
   }
-  griddep_wait();    // PDL: global memory is touched from here on
-  griddep_launch();
-  if (tid < kCout) {
-    s_scale[tid] = a.scale ? __ldg(a.scale + tid) : 1.f;
-    s_shift[tid] = a.shift ? __ldg(a.shift + tid) : 0.f;
-  }
-  // zero K-padding columns 168..191 (16-byte units 5,6,7 of k-block 2) never change
-  for (int i = tid; i < 128 * 3; i += kThreads) {
-    const int row = i / 3;
+  // zero K-padding columns 168..191 (16-byte units 5,6,7 of k-block 2) of both A buffers: never change
+  for (int i = tid; i < 2 * 128 * 3; i += kFwdThreads) {
+    const int buf = i / (128 * 3), row = (i / 3) % 128;
     const uint32_t j = 5 + i % 3;
-    *reinterpret_cast<uint4*>(sA + 2 * kABytes + row * 128 + ((j ^ (uint32_t)(row & 7)) << 4)) =
-        make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sA + buf * 3 * kABytes + 2 * kABytes + row * 128 +
+                              ((j ^ (uint32_t)(row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
   }
+  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_ptr;
-  if (tid == 0) {
-    mbar_expect_tx(w_bar, 3 * kBBytes);
-    for (int kb = 0; kb < 3; ++kb) tma_load_2d(sB + kb * kBBytes, &a.tmap_w, w_bar, kb * 64, 0);
-  }
+  griddep_wait();    // PDL: global memory is touched from here on
+  griddep_launch();
+  const int step = gridDim.x;
 
-  // software pipeline over tiles: patch(T) in smem, patch(T+1) in flight in registers
-  float pv[kPatchIters];
-  int tile = blockIdx.x;
-  if (tile < a.total_tiles) {
-    patch_issue(a, tile, tid, pv);
-    patch_store(pv, sPatch, tid);
-    if (tile + (int)gridDim.x < a.total_tiles) patch_issue(a, tile + gridDim.x, tid, pv);
-  }
-  __syncthreads();
-
-  const int row = tid & 127, half = tid >> 7;
-  const int dy = row >> 4, dx = row & 15;
-  const uint32_t sw = (uint32_t)(row & 7);
-  const int quarter = warp & 3, colhalf = warp >> 2;
-  const int erow = quarter * 32 + lane;
-  const uint32_t esw = (uint32_t)(erow & 7);
-  constexpr uint32_t idesc = umma_idesc_bf16(128, kCout, 0, 0);
-  uint32_t mma_phase = 0;
-  bool first = true;
-
-  for (; tile < a.total_tiles; tile += gridDim.x) {
-    // ---- im2col rows straight into the swizzled UMMA layout: 16-byte unit q = (c, kh) ----------
+  if (warp < 4) {
+    // ------------------------------- loader ---------------------------------------------------
+    // A single warp issues only ~0.5 instructions per clock, so the per-element work must be tiny:
+    // the patch is fetched as ALIGNED 16-byte chunks (11 per row: global columns 32*tw-4 ...
+    // 32*tw+39, one to the left of the patch origin 32*tw-3), whose (row, chunk) -> offset tables
+    // do not depend on the tile and live in registers. Needs in_w % 4 == 0 and a 16-byte aligned
+    // image base (the 224x224 case); otherwise the element-wise path below is used.
+    if (a.vec_ok) {
+      constexpr int kChunksRow = 11, kChunks = 3 * kPatchH * kChunksRow;  // 693
+      constexpr int kIt = (kChunks + 127) / 128;                          // 6
+      int goff[kIt], poff[kIt], rr[kIt], jj[kIt];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      const int q = half * 12 + i;
-      if (q < 21) {
+      for (int it = 0; it < kIt; ++it) {
+        const int k = tid + it * 128;
+        const int row = k / kChunksRow, j = k - row * kChunksRow;  // row = c*21 + r
+        const int c = row / kPatchH, r = row - c * kPatchH;
+        rr[it] = (k < kChunks) ? r : -100000;                      // invalid chunk: never in range
+        jj[it] = 4 * j - 4;                                        // column relative to 32*tw
+        goff[it] = (c * a.in_h + r) * a.in_w + 4 * j - 4;
+        poff[it] = row * kPatchPitch + 4 * j - 1;                  // patch column of element 0
+      }
+      float4 q0[kIt], q1[kIt];
+      auto issue = [&](int tile, float4 (&q)[kIt]) {
+        const int tw = tile % a.tiles_w;
+        const int th = (tile / a.tiles_w) % a.tiles_h;
+        const int n = tile / (a.tiles_w * a.tiles_h);
+        const int ih0 = 2 * th * kTH - 3, gw0 = 2 * tw * kTW;
+        const float* org = a.x + ((long long)n * 3 * a.in_h + ih0) * a.in_w + gw0;
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          const int ih = ih0 + rr[it], gw = gw0 + jj[it];
+          q[it] = (ih >= 0 && ih < a.in_h && gw >= 0 && gw < a.in_w)
+                      ? __ldg(reinterpret_cast<const float4*>(org + goff[it]))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto park = [&](const float4 (&q)[kIt], __nv_bfloat16* patch) {
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          if (rr[it] >= 0) {
+            __nv_bfloat16* d = patch + poff[it];
+            if (jj[it] >= 0) d[0] = __float2bfloat16_rn(q[it].x);  // chunk 0 starts left of the patch
+            d[1] = __float2bfloat16_rn(q[it].y);
+            d[2] = __float2bfloat16_rn(q[it].z);
+            d[3] = __float2bfloat16_rn(q[it].w);
+          }
+        }
+      };
+      int tile = blockIdx.x;
+      if (tile < a.total_tiles) issue(tile, q0);
+      if (tile + step < a.total_tiles) issue(tile + step, q1);
+      for (int i = 0; tile < a.total_tiles; i += 2) {
+        {
+          const int slot = i % kPatchSlots;
+          mbar_wait(&patch_empty[slot], ((i / kPatchSlots) & 1) ^ 1);
+          park(q0, reinterpret_cast<__nv_bfloat16*>(sPatchBase + slot * kPatchBytes));
+          mbar_arrive(&patch_full[slot]);
+          if (tile + 2 * step < a.total_tiles) issue(tile + 2 * step, q0);
+          tile += step;
+        }
+        if (tile < a.total_tiles) {
+          const int slot = (i + 1) % kPatchSlots;
+          mbar_wait(&patch_empty[slot], (((i + 1) / kPatchSlots) & 1) ^ 1);
+          park(q1, reinterpret_cast<__nv_bfloat16*>(sPatchBase + slot * kPatchBytes));
+          mbar_arrive(&patch_full[slot]);
+          if (tile + 2 * step < a.total_tiles) issue(tile + 2 * step, q1);
+          tile += step;
+        }
+      }
+    } else {
+      float p0[kLdIters], p1[kLdIters];
+      int tile = blockIdx.x;
+      if (tile < a.total_tiles) patch_issue<128>(a, tile, tid, p0);
+      if (tile + step < a.total_tiles) patch_issue<128>(a, tile + step, tid, p1);
+      for (int i = 0; tile < a.total_tiles; i += 2) {
+        {
+          const int slot = i % kPatchSlots;
+          mbar_wait(&patch_empty[slot], ((i / kPatchSlots) & 1) ^ 1);
+          patch_store<128>(p0, reinterpret_cast<__nv_bfloat16*>(sPatchBase + slot * kPatchBytes), tid);
+          mbar_arrive(&patch_full[slot]);
+          if (tile + 2 * step < a.total_tiles) patch_issue<128>(a, tile + 2 * step, tid, p0);
+          tile += step;
+        }
+        if (tile < a.total_tiles) {
+          const int slot = (i + 1) % kPatchSlots;
+          mbar_wait(&patch_empty[slot], (((i + 1) / kPatchSlots) & 1) ^ 1);
+          patch_store<128>(p1, reinterpret_cast<__nv_bfloat16*>(sPatchBase + slot * kPatchBytes), tid);
+          mbar_arrive(&patch_full[slot]);
+          if (tile + 2 * step < a.total_tiles) patch_issue<128>(a, tile + 2 * step, tid, p1);
+          tile += step;
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------- im2col builder -------------------------------------------
+    const int row = tid - 128;
+    const int dy = row >> 4, dx = row & 15;
+    const uint32_t sw = (uint32_t)(row & 7);
+    int i = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += step, ++i) {
+      const int slot = i % kPatchSlots, ab = i & 1;
+      const __nv_bfloat16* sPatch =
+          reinterpret_cast<const __nv_bfloat16*>(sPatchBase + slot * kPatchBytes);
+      uint8_t* dst = sA + ab * 3 * kABytes;
+      mbar_wait(&patch_full[slot], (i / kPatchSlots) & 1);
+      mbar_wait(&a_empty[ab], ((i >> 1) & 1) ^ 1);
+      // 16-byte unit q = (c, kh): 8 consecutive kw taps of input row 2*dy+kh, channel c
+#pragma unroll
+      for (int q = 0; q < 21; ++q) {
         const int c = q / 7, kh = q - c * 7;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(
             sPatch + (c * kPatchH + 2 * dy + kh) * kPatchPitch + 2 * dx);
         const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
-        *reinterpret_cast<uint4*>(sA + (q >> 3) * kABytes + row * 128 +
+        *reinterpret_cast<uint4*>(dst + (q >> 3) * kABytes + row * 128 +
                                   ((((uint32_t)q & 7) ^ sw) << 4)) = v;
       }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[ab]);
+      mbar_arrive(&patch_empty[slot]);
     }
-    fence_proxy_async_smem();
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging free
-    tc_fence_before_sync();
-    __syncthreads();  // SYNC1
-    if (tid == 0) {
+  } else if (warp == 8) {
+    // ------------------------------- MMA issuer -----------------------------------------------
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, 3 * kBBytes);
+      for (int kb = 0; kb < 3; ++kb) tma_load_2d(sB + kb * kBBytes, &a.tmap_w, w_bar, kb * 64, 0);
+    }
+    constexpr uint32_t idesc = umma_idesc_bf16(128, kCout, 0, 0);
+    mbar_wait(w_bar, 0);
+    int i = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += step, ++i) {
+      const int ab = i & 1;
+      const uint32_t par = (i >> 1) & 1;
+      mbar_wait(&a_full[ab], par);
+      mbar_wait(&tmem_empty[ab], par ^ 1);
       tc_fence_after_sync();
-      if (first) mbar_wait(w_bar, 0);
+      if (lane == 0) {
 #pragma unroll
-      for (int kb = 0; kb < 3; ++kb) {
-        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + kb * kABytes), 16, 1024);
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + kb * kBBytes), 16, 1024);
+        for (int kb = 0; kb < 3; ++kb) {
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + (ab * 3 + kb) * kABytes), 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + kb * kBBytes), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem + ab * kCout, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(&a_empty[ab]);
+        umma_commit(&tmem_full[ab]);
       }
-      umma_commit(mma_bar);
+      __syncwarp();
     }
-    first = false;
-    // ---- the patch buffer is free (everyone is past SYNC1): park the next tile's patch, whose
-    //      loads were issued a whole phase ago, and issue the loads of the tile after it ---------
-    const int next = tile + gridDim.x;
-    if (next < a.total_tiles) patch_store(pv, sPatch, tid);
-    if (next + (int)gridDim.x < a.total_tiles) patch_issue(a, next + gridDim.x, tid, pv);
-    // ---- epilogue: TMEM -> scale/shift/ReLU -> bf16 -> swizzled staging -> TMA store --------------
-    mbar_wait(mma_bar, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after_sync();
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(tmem + ((uint32_t)(quarter * 32) << 16) + colhalf * 32, v);
-    tmem_ld_wait();
+  } else {
+    // ------------------------------- epilogue (warps 9..12) -----------------------------------
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int erow = quarter * 32 + lane;
+    const uint32_t esw = (uint32_t)(erow & 7);
+    const int tid_e = tid - 9 * 32;
+    if (tid_e < kCout) {
+      s_scale[tid_e] = a.scale ? __ldg(a.scale + tid_e) : 1.f;
+      s_shift[tid_e] = a.shift ? __ldg(a.shift + tid_e) : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    int i = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += step, ++i) {
+      const int tb = i & 1;
+      uint8_t* obuf = sOut + tb * kABytes;
+      mbar_wait(&tmem_full[tb], (i >> 1) & 1);
+      tc_fence_after_sync();
+      uint32_t v[64];
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + tb * kCout;
+      tmem_ld_32x32b_x32(taddr, v);
+      tmem_ld_32x32b_x32(taddr + 32, v + 32);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&tmem_empty[tb]);
+      // staging buffer tb was handed to the TMA store two tiles ago: make sure it has been read
+      if (tid_e == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float f[8];
+      for (int q = 0; q < 8; ++q) {
+        float f[8];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int col = colhalf * 32 + q * 8 + t;
-        f[t] = fmaf(__uint_as_float(v[q * 8 + t]), s_scale[col], s_shift[col]);
-        if (a.relu) f[t] = fmaxf(f[t], 0.f);
+        for (int h = 0; h < 2; ++h) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + q * 8 + h * 4);
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + q * 8 + h * 4);
+          f[h * 4 + 0] = fmaf(__uint_as_float(v[q * 8 + h * 4 + 0]), sc.x, sh.x);
+          f[h * 4 + 1] = fmaf(__uint_as_float(v[q * 8 + h * 4 + 1]), sc.y, sh.y);
+          f[h * 4 + 2] = fmaf(__uint_as_float(v[q * 8 + h * 4 + 2]), sc.z, sh.z);
+          f[h * 4 + 3] = fmaf(__uint_as_float(v[q * 8 + h * 4 + 3]), sc.w, sh.w);
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) f[t] = fmaxf(f[t], 0.f);
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(obuf + erow * 128 + (((uint32_t)q ^ esw) << 4)) = o;
       }
-      uint4 o;
-      o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-      o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-      const uint32_t j = (uint32_t)(colhalf * 4 + q);
-      *reinterpret_cast<uint4*>(sOut + erow * 128 + ((j ^ esw) << 4)) = o;
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (tid_e == 0) {
+        const int tw = tile % a.tiles_w;
+        const int th = (tile / a.tiles_w) % a.tiles_h;
+        const int n = tile / (a.tiles_w * a.tiles_h);
+        stem_tma_store(&a.tmap_out, obuf, 0, tw * kTW, th * kTH, n);
+      }
     }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();  // SYNC2: staging + next patch visible, TMEM drained, sA reusable
-    if (tid == 0) {
-      const int tw = tile % a.tiles_w;
-      const int th = (tile / a.tiles_w) % a.tiles_h;
-      const int n = tile / (a.tiles_w * a.tiles_h);
-      stem_tma_store(&a.tmap_out, sOut, 0, tw * kTW, th * kTH, n);
-    }
+    if (tid_e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 8) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem, 64);
+    tmem_dealloc(tmem, 128);
   }
 }
 
@@ -297,9 +437,9 @@ __global__ void __launch_bounds__(kThreads, 2) stem_wgrad_kernel(const __grid_co
       issue_dz(tile, 0);
       if (tile + step < w.total_tiles) issue_dz(tile + step, 1);
     }
-    patch_issue(a, tile, tid, pv);
-    patch_store(pv, sPatch, tid);
-    if (tile + step < w.total_tiles) patch_issue(a, tile + step, tid, pv);
+    patch_issue<kThreads>(a, tile, tid, pv);
+    patch_store<kThreads>(pv, sPatch, tid);
+    if (tile + step < w.total_tiles) patch_issue<kThreads>(a, tile + step, tid, pv);
   }
   __syncthreads();
 
@@ -344,8 +484,8 @@ __global__ void __launch_bounds__(kThreads, 2) stem_wgrad_kernel(const __grid_co
       umma_commit(mma_bar);
     }
     const int next = tile + step;
-    if (next < w.total_tiles) patch_store(pv, sPatch, tid);
-    if (next + step < w.total_tiles) patch_issue(a, next + step, tid, pv);
+    if (next < w.total_tiles) patch_store<kThreads>(pv, sPatch, tid);
+    if (next + step < w.total_tiles) patch_issue<kThreads>(a, next + step, tid, pv);
     __syncthreads();
   }
   if (it > 0) {
@@ -417,6 +557,7 @@ extern "C" int rmv_stem_conv_fwd(const float* x_nchw, const void* w_packed, cons
   memset(&a, 0, sizeof(a));
   a.x = x_nchw; a.scale = scale; a.shift = shift;
   a.n_img = n_img; a.in_h = in_h; a.in_w = in_w; a.relu = relu;
+  a.vec_ok = (in_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0);
   a.out_h = (in_h + 6 - 7) / 2 + 1;
   a.out_w = (in_w + 6 - 7) / 2 + 1;
   a.tiles_w = ceil_div(a.out_w, kTW);
@@ -441,11 +582,12 @@ extern "C" int rmv_stem_conv_fwd(const float* x_nchw, const void* w_packed, cons
   static bool attr_set = false;
   if (!attr_set) {
     RMV_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmemBytes));
+                                  kFwdSmemBytes));
     attr_set = true;
   }
-  const int grid = a.total_tiles < 2 * num_sms() ? a.total_tiles : 2 * num_sms();
-  RMV_CUDA(launch_pdl_tc(stem_kernel, dim3(grid), dim3(kThreads), kSmemBytes, (cudaStream_t)stream, a));
+  const int grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
+  RMV_CUDA(launch_pdl_tc(stem_kernel, dim3(grid), dim3(kFwdThreads), kFwdSmemBytes,
+                         (cudaStream_t)stream, a));
   return 0;
 }
 
