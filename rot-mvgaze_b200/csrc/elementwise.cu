@@ -129,6 +129,52 @@ __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int i
   Vec8<T>::store(y + ((n * out_h + oh) * out_w + ow) * c + cc, m);
 }
 
+// bf16 fast path: each thread produces TWO horizontally adjacent outputs (8 channels each) from a
+// 3 x 5 input window (15 instead of 18 16-byte loads), all loads issued before the first use, and
+// the maximum taken on packed bf16 pairs (max of bf16 values is exact, no fp32 round trip).
+__global__ void __launch_bounds__(256)
+maxpool_bf16x2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int in_h,
+                      int in_w, int c, int out_h, int out_w2 /* ceil(out_w/2) */, int out_w,
+                      long long total) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = c / 8;
+  const int cc = (int)(idx % cv) * 8;
+  long long t = idx / cv;
+  const int owp = (int)(t % out_w2); t /= out_w2;
+  const int oh = (int)(t % out_h);
+  const long long n = t / out_h;
+  const int ow = owp * 2;
+  const uint32_t ninf = 0xFF80FF80u;  // (-inf, -inf)
+  uint4 v[3][5];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int ih = oh * 2 - 1 + r;
+    const bool rok = ih >= 0 && ih < in_h;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const int iw = ow * 2 - 1 + q;
+      v[r][q] = (rok && iw >= 0 && iw < in_w)
+                    ? *reinterpret_cast<const uint4*>(x + ((n * in_h + ih) * in_w + iw) * c + cc)
+                    : make_uint4(ninf, ninf, ninf, ninf);
+    }
+  }
+  auto mx = [](uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  };
+  auto mx4 = [&](uint4 a, uint4 b) { return make_uint4(mx(a.x, b.x), mx(a.y, b.y), mx(a.z, b.z), mx(a.w, b.w)); };
+  uint4 col[5];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) col[q] = mx4(mx4(v[0][q], v[1][q]), v[2][q]);
+  const uint4 o0 = mx4(mx4(col[0], col[1]), col[2]);
+  __nv_bfloat16* yo = y + ((n * out_h + oh) * out_w + ow) * c + cc;
+  *reinterpret_cast<uint4*>(yo) = o0;
+  if (ow + 1 < out_w) *reinterpret_cast<uint4*>(yo + c) = mx4(mx4(col[2], col[3]), col[4]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Global average pool, NHWC [n, hw, c] -> [n, c] (one or two destinations, row strides ld0/ld1)
 // ---------------------------------------------------------------------------------------------
@@ -419,10 +465,13 @@ extern "C" int rmv_maxpool3x3s2_fwd(const void* x, void* y, int n_img, int in_h,
   const long long total = (long long)n_img * out_h * out_w * (c / 8);
   if (total == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == RMV_DTYPE_BF16)
-    rmv::launch_pdl(maxpool_kernel<__nv_bfloat16>, dim3(blocks_for(total, 256)), dim3(256), 0, s, 
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, in_h, in_w, c, out_h, out_w, total);
-  else
+  if (dtype == RMV_DTYPE_BF16) {
+    const int out_w2 = (out_w + 1) / 2;
+    const long long total2 = (long long)n_img * out_h * out_w2 * (c / 8);
+    rmv::launch_pdl(maxpool_bf16x2_kernel, dim3(blocks_for(total2, 256)), dim3(256), 0, s,
+                    (const __nv_bfloat16*)x, (__nv_bfloat16*)y, in_h, in_w, c, out_h, out_w2, out_w,
+                    total2);
+  } else
     rmv::launch_pdl(maxpool_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, s, (const float*)x, (float*)y, in_h, in_w, c, out_h, out_w, total);
   RMV_LAUNCH_CHECK();
   return 0;
