@@ -177,11 +177,41 @@ class _ImageRotmatFeatFuser(nn.Module):
             torch.cat([img_feat, rot_feat.flatten(-2, -1), rot.flatten(-2, -1)], dim=-1))
 
 
-class RotMVOracle(nn.Module):
-    """models/rot_mv.py:102-269 (`FeatRotationSymm`) with the same state_dict keys.
+class _IntensityBatchNorm(nn.Module):
+    """models/rot_mv.py:13-32: x / (running_std + eps); the running STD of the per-vector norm lives
+    in a buffer called `running_mean` (initialised to 1); eps is used twice (clamp and divide)."""
 
-    `share_feature=True` (RotFeatFuser + IntensityBatchNorm, :13-32,70-85) is outside the first
-    bar and raises NotImplementedError.
+    def __init__(self, n_channels: int, momentum: float = 0.05, eps: float = 1e-4):
+        super().__init__()
+        self.register_buffer("running_mean", torch.ones(1, 1, n_channels))
+        self._momentum, self._eps = momentum, eps
+
+    def forward(self, x):
+        intensity = torch.norm(x, dim=-2, keepdim=True).detach()
+        var = torch.var(intensity, unbiased=False, dim=0, keepdim=True)
+        std = torch.sqrt(var.clamp_min(self._eps))
+        if self.training:
+            self.running_mean = self.running_mean * (1 - self._momentum) + std * self._momentum
+        return x / (self.running_mean + self._eps)
+
+
+class _RotFeatFuser(nn.Module):
+    """models/rot_mv.py:70-85 (share_feature=True)."""
+
+    def __init__(self):
+        super().__init__()
+        c = 6 * NUM_FEAT_VEC
+        self._fuser = MlpOracle(c, [c, c, 3 * NUM_FEAT_VEC])
+        self._batchnorm = _IntensityBatchNorm(NUM_FEAT_VEC)
+
+    def forward(self, feat_0, feat_1):
+        x = torch.cat([self._batchnorm(feat_0), self._batchnorm(feat_1)], dim=-1).flatten(-2, -1)
+        return self._fuser(x).reshape(-1, 3, NUM_FEAT_VEC)
+
+
+class RotMVOracle(nn.Module):
+    """models/rot_mv.py:102-269 (`FeatRotationSymm`) with the same state_dict keys, all
+    constructor flags included (share_feature / encode_rotmat: two views only, like the reference).
     """
 
     def __init__(self, backbone_depth: int = 50, num_iter: Optional[int] = None,
@@ -195,14 +225,17 @@ class RotMVOracle(nn.Module):
         self._fc_dim = trunk.out_dim
         self._lifter = _Lifter(self._fc_dim)
         assert not (ignore_rotmat and encode_rotmat)
-        if share_feature:
-            raise NotImplementedError("share_feature=True is not covered by the oracle")
         self._ignore_rotmat, self._encode_rotmat = ignore_rotmat, encode_rotmat
+        self._share_feature = share_feature
         fuser_cls = _ImageRotmatFeatFuser if (encode_rotmat and not ignore_rotmat) else _ImageFeatFuser
         head_in = 3 * NUM_FEAT_VEC + self._fc_dim
         if share_weights:  # one module aliased num_iter times (:150-158)
             self._img_fusers = nn.ModuleList([fuser_cls(self._fc_dim)] * num_iter)
             self._gaze_estimators = nn.ModuleList([MlpOracle(head_in, [512, 2])] * num_iter)
+        elif share_feature:  # :160-171
+            self._img_fusers = nn.ModuleList([_RotFeatFuser() for _ in range(num_iter)])
+            self._gaze_estimators = nn.ModuleList(
+                [MlpOracle(6 * NUM_FEAT_VEC, [512, 2]) for _ in range(num_iter)])
         else:
             self._img_fusers = nn.ModuleList([fuser_cls(self._fc_dim) for _ in range(num_iter)])
             self._gaze_estimators = nn.ModuleList(
@@ -215,6 +248,10 @@ class RotMVOracle(nn.Module):
         # one trunk call PER VIEW: BatchNorm batch statistics are per view (:196-197)
         img_feat = [self._feat_extractor(images[:, v]) for v in range(n_views)]
         rot_feat = [self._lifter(f) for f in img_feat]
+        if self._share_feature or self._encode_rotmat:
+            assert n_views == 2, "share_feature / encode_rotmat are two-view configurations"
+        if self._share_feature:   # :201-203: the lifted feature replaces the image feature
+            img_feat = rot_feat
         out: Dict = {"num_iter": self._num_iter}
         for v in range(n_views):
             out[f"img_feat_{v}"] = img_feat[v]
@@ -230,17 +267,24 @@ class RotMVOracle(nn.Module):
                     f = fuser(img_feat[v], agg)
                 else:
                     rot = [rotations[:, v, u] for u in partners]
-                    if len(partners) == 1:
-                        agg = rot[0] @ old[partners[0]]
+                    if self._encode_rotmat:
+                        # :225-231: the partner feature is NOT rotated, the matrix is an input
+                        f = fuser(img_feat[v], old[partners[0]], rot[0])
                     else:
-                        agg = sum(r @ old[u] for r, u in zip(rot, partners)) / len(partners)
-                    f = fuser(img_feat[v], agg, rot[0]) if self._encode_rotmat else fuser(img_feat[v], agg)
+                        if len(partners) == 1:
+                            agg = rot[0] @ old[partners[0]]
+                        else:
+                            agg = sum(r @ old[u] for r, u in zip(rot, partners)) / len(partners)
+                        f = fuser(img_feat[v], agg)
                 new.append(f.reshape(-1, 3, NUM_FEAT_VEC))
             rot_feat = new
             it = {}
             for v in range(n_views):
                 it[f"feat_{v}"] = rot_feat[v]
-                it[f"pred_gaze_{v}"] = head(torch.cat([img_feat[v], rot_feat[v].flatten(1, -1)], dim=-1))
+                if self._share_feature:   # :243-248
+                    it[f"pred_gaze_{v}"] = head(torch.cat([img_feat[v], rot_feat[v]], dim=-1).flatten(1, -1))
+                else:
+                    it[f"pred_gaze_{v}"] = head(torch.cat([img_feat[v], rot_feat[v].flatten(1, -1)], dim=-1))
             out[f"iter_{i}"] = it
         out["pred_gaze"] = out[f"iter_{self._output_index}"]["pred_gaze_0"]  # :265
         return out

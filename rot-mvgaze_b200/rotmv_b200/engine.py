@@ -44,12 +44,29 @@ class _ConvSpec:
         self.stride, self.pad = conv.stride[0], conv.padding[0]
 
 
+def _up64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
 class _LinSpec:
+    """Prepared Linear weights; `pad_k` / `pad_n` zero-pad the reduction / output width (the
+    tcgen05 GEMM wants K % 64 == 0: encode_rotmat's 3593-wide layers run as 3648-wide ones whose
+    extra inputs, weights, biases and therefore outputs are exactly zero)."""
     __slots__ = ("w", "b")
 
-    def __init__(self, lin, dtype):
-        self.w = lin.weight.detach().to(dtype).contiguous()
-        self.b = lin.bias.detach().float().contiguous()
+    def __init__(self, lin, dtype, pad_k=None, pad_n=None):
+        w = lin.weight.detach()
+        b = lin.bias.detach().float()
+        n, k = w.shape
+        pk, pn = pad_k or k, pad_n or n
+        if (pk, pn) != (k, n):
+            wp = torch.zeros((pn, pk), device=w.device, dtype=w.dtype)
+            wp[:n, :k] = w
+            bp = torch.zeros((pn,), device=w.device, dtype=torch.float32)
+            bp[:n] = b
+            w, b = wp, bp
+        self.w = w.to(dtype).contiguous()
+        self.b = b.contiguous()
 
 
 class InferenceEngine:
@@ -64,6 +81,12 @@ class InferenceEngine:
         self.fc_dim = model._fc_dim
         self.nvec = model._num_feat_vec
         self.apply_rot = not model._ignore_rotmat
+        # constructor variants: encode_rotmat feeds the 9 entries of R_self<-partner
+        # to a 3-layer fuser instead of rotating the partner feature (models/rot_mv.py:53-67,
+        # 225-231); share_feature replaces the image feature by the lifted feature and fuses
+        # through RotFeatFuser + IntensityBatchNorm (:13-32,70-85,201-203,243-248)
+        self.encode_rot = bool(model._encode_rotmat) and not model._ignore_rotmat
+        self.share_feat = bool(model._share_feature)
         self.chunk = max(1, int(model.trunk_chunk))
         trunk = model._feat_extractor[0]
         dev = trunk.conv1.weight.device
@@ -92,11 +115,23 @@ class InferenceEngine:
         # ---- fusion stage ----
         lif = model._lifter._lifter.blocks
         self.lift = [_LinSpec(lif[0][0], dt), _LinSpec(lif[1][0], dt)]
-        self.fusers, self.heads = [], []
+        self.fusers, self.heads, self.int_bn = [], [], []
+        self.fuse_pad = None
         for i in range(self.num_iter):
             fb = model._img_fusers[i]._fuser.blocks
-            self.fusers.append([_LinSpec(fb[0][0], dt), _LinSpec(fb[1][0], dt)])
-            hb = model._gaze_estimators[i].blocks
+            if self.encode_rot:
+                wide = self.fc_dim + 3 * self.nvec + 9
+                self.fuse_pad = p = _up64(wide)
+                self.fusers.append([_LinSpec(fb[0][0], dt, pad_k=p, pad_n=p),
+                                    _LinSpec(fb[1][0], dt, pad_k=p, pad_n=p),
+                                    _LinSpec(fb[2][0], dt, pad_k=p)])
+            else:
+                self.fusers.append([_LinSpec(blk[0], dt) for blk in fb])
+            if self.share_feat:
+                bn = model._img_fusers[i]._batchnorm
+                # eval-mode IntensityBatchNorm is a per-vector scale 1 / (running_std + eps)
+                self.int_bn.append((1.0 / (bn.running_mean.detach().float().reshape(-1) + bn.eps)).contiguous())
+            hb = model._gaze_estimators[i].blocks   # Mlp(fc+1536 | 3072, [512, 2])
             self.heads.append((_LinSpec(hb[0][0], dt),
                                hb[1][0].weight.detach().float().contiguous(),
                                hb[1][0].bias.detach().float().contiguous()))
@@ -186,6 +221,11 @@ class InferenceEngine:
                    gt: Optional[torch.Tensor] = None) -> Dict[str, Any]:
         """Lifter + rotation-constrained fusion iterations + heads on the X/Y rows the trunk wrote."""
         m = b * v
+        if self.encode_rot or self.share_feat:
+            if v != 2:
+                raise NotImplementedError("encode_rotmat / share_feature are two-view configurations "
+                                          "(the reference defines nothing else)")
+            return self._run_fusion_variant(b, rot, want_all=want_all, gt=gt)
         wide = self.fc_dim + 3 * self.nvec
         x_buf, y_buf = self._xy(m)
         feat_y = y_buf[:, self.fc_dim:]
@@ -235,6 +275,95 @@ class InferenceEngine:
                     for k, t in enumerate(per_view(feat_y, (3, self.nvec))):
                         it[f"feat_{k}"] = t
                 out[f"iter_{i}"] = it
+        out["pred_gaze"] = out[f"iter_{self.num_iter - 1}"]["pred_gaze_0"]
+        return out
+
+
+    # ------------------------------------------------------------------------------------------
+    def _run_fusion_variant(self, b: int, rot: torch.Tensor, *, want_all: bool, gt) -> Dict[str, Any]:
+        """encode_rotmat / share_feature (two views). The GEMMs, the rotation gather
+        and the head/loss are the same sm_100a kernels as the default configuration; the few
+        re-layout copies these variants need (9 rotation entries per row, the [3][2][512]
+        interleave of RotFeatFuser's input) are plain tensor copies -- they are not on the path
+        main.py builds."""
+        v, m = 2, 2 * b
+        fc, nv = self.fc_dim, self.nvec
+        x_buf, y_buf = self._xy(m)            # [m, fc + 3*nv]; avgpool wrote the image feature
+        img = x_buf[:, :fc]
+        l1 = self._buf("L1", (m, 3 * nv))
+        f_init = self._buf("Finit", (m, 3 * nv))
+        RF.linear(img, self.lift[0].w, self.lift[0].b, relu=True, out=l1)
+        RF.linear(l1, self.lift[1].w, self.lift[1].b, out=f_init)
+        out: Dict[str, Any] = {"num_iter": self.num_iter}
+
+        def per_view(t2d, tail):
+            t = t2d.float().reshape(b, v, *tail)
+            return [t[:, k].contiguous() for k in range(v)]
+
+        if want_all:
+            src = f_init if self.share_feat else img   # share_feature: img_feat := lifted feature (:201-203)
+            for k, t in enumerate(per_view(src, (3, nv) if self.share_feat else (fc,))):
+                out[f"img_feat_{k}"] = t
+            for k, t in enumerate(per_view(f_init, (3, nv))):
+                out[f"initial_rot_feat_{k}"] = t
+        g = self._buf("G", (m, 512))
+        gt_flat = loss = None
+        if gt is not None:
+            gt_flat = gt.float().reshape(m, 2).contiguous()
+            loss = torch.zeros((1,), device=self.device, dtype=torch.float32)
+            out["loss"] = loss
+        cfg = self.model.loss_cfg
+        f_old = f_init
+        if self.encode_rot:
+            p = self.fuse_pad
+            xin = self._buf("Xenc", (m, p))
+            xin.zero_()
+            xin[:, :fc].copy_(img)
+            # row (b, view) gets R_{view <- partner}: rot[b,0,1] = rot_10, rot[b,1,0] = rot_01 (:193-194)
+            pair = torch.stack([rot[:, 0, 1], rot[:, 1, 0]], dim=1).reshape(m, 9)
+            xin[:, fc + 3 * nv: fc + 3 * nv + 9].copy_(pair)
+            h1, h2 = self._buf("Henc1", (m, p)), self._buf("Henc2", (m, p))
+        else:
+            xin = self._buf("Xsh", (m, 6 * nv))
+            yin = self._buf("Ysh", (m, 6 * nv))
+            h1, h2 = self._buf("Hsh1", (m, 6 * nv)), self._buf("Hsh2", (m, 6 * nv))
+            rotf = self._buf("rotF", (m, 3 * nv))
+            yin.view(m, 3, 2, nv)[:, :, 0].copy_(f_init.view(m, 3, nv))   # head input: cat(img_feat, F, -1)
+        for i in range(self.num_iter):
+            f_new = self._buf(("Fnew", i & 1), (m, 3 * nv))
+            f1, f2, f3 = self.fusers[i]
+            if self.encode_rot:
+                # partner feature, NOT rotated (the matrix itself is an input) -> xin[:, fc:fc+3nv]
+                RF.rotate_gather(f_old, rot, xin[:, fc:fc + 3 * nv], b, v, nv, False)
+            else:
+                s = self.int_bn[i].to(self.dtype)
+                RF.rotate_gather(f_old, rot, rotf, b, v, nv, True)          # R_{self<-partner} F_partner
+                xv = xin.view(m, 3, 2, nv)
+                xv[:, :, 0] = f_init.view(m, 3, nv) * s                      # IntensityBatchNorm(feat_0)
+                xv[:, :, 1] = rotf.view(m, 3, nv) * s                        # IntensityBatchNorm(rotated)
+            RF.linear(xin, f1.w, f1.b, relu=True, out=h1)
+            RF.linear(h1, f2.w, f2.b, relu=True, out=h2)
+            RF.linear(h2, f3.w, f3.b, out=f_new)
+            h_lin, w2, b2 = self.heads[i]
+            if self.encode_rot:
+                y_buf[:, fc:].copy_(f_new)
+                RF.linear(y_buf, h_lin.w, h_lin.b, relu=True, out=g)
+            else:
+                yin.view(m, 3, 2, nv)[:, :, 1].copy_(f_new.view(m, 3, nv))
+                RF.linear(yin, h_lin.w, h_lin.b, relu=True, out=g)
+            pred = torch.empty((m, 2), device=self.device, dtype=torch.float32)
+            scale = (cfg["iter_decay"] ** (self.num_iter - 1 - i)) * cfg["rel_weight"] / b
+            RF.head_loss(g, w2, b2, pred, gt_flat, scale, loss, views=v, aux_decay=cfg["reference_decay"])
+            if want_all or i == self.num_iter - 1:
+                it: Dict[str, Any] = {}
+                pv = pred.view(b, v, 2)
+                for k in range(v):
+                    it[f"pred_gaze_{k}"] = pv[:, k].contiguous()
+                if want_all:
+                    for k, t in enumerate(per_view(f_new, (3, nv))):
+                        it[f"feat_{k}"] = t
+                out[f"iter_{i}"] = it
+            f_old = f_new
         out["pred_gaze"] = out[f"iter_{self.num_iter - 1}"]["pred_gaze_0"]
         return out
 

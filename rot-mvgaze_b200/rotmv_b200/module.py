@@ -108,21 +108,30 @@ class FeatRotationSymm(nn.Module):
         assert not (ignore_rotmat and encode_rotmat)
         self._ignore_rotmat, self._encode_rotmat = ignore_rotmat, encode_rotmat
         self._share_feature, self._share_weights = share_feature, share_weights
-        if share_feature:
-            raise NotImplementedError(
-                "share_feature=True (RotFeatFuser + IntensityBatchNorm, models/rot_mv.py:13-32,"
-                "70-85) is not built yet; it is not reachable from the reference main.py")
-        if encode_rotmat:
-            raise NotImplementedError(
-                "encode_rotmat=True (ImageRotmatFeatFuser, models/rot_mv.py:53-67) is not built "
-                "yet; it is not reachable from the reference main.py")
+        if share_feature and share_weights:
+            # the reference builds ImageFeatFuser(fc_dim) here (:150-158 wins over :160) and then
+            # crashes in torch.cat on the [B,3,512] "image feature" of :201-203
+            raise ValueError("share_feature=True with share_weights=True is not a runnable "
+                             "configuration of the reference (models/rot_mv.py:150-158,201-203)")
         fuse_in = self._fc_dim + 3 * NUM_FEAT_VEC
+        head_in = fuse_in
+        if share_feature and not share_weights:   # RotFeatFuser + IntensityBatchNorm (:70-85,13-32)
+            fuse_in = head_in = 6 * NUM_FEAT_VEC
 
         def fuser():
+            if share_feature:
+                f = _wrap("_fuser", _mlp_params(fuse_in, [fuse_in, fuse_in, 3 * NUM_FEAT_VEC]))
+                bn = nn.Module()   # IntensityBatchNorm: running STD kept in a buffer named running_mean
+                bn.register_buffer("running_mean", torch.ones(1, 1, NUM_FEAT_VEC))
+                bn.momentum, bn.eps = 0.05, 1e-4
+                f._batchnorm = bn
+                return f
+            if encode_rotmat and not ignore_rotmat:   # ImageRotmatFeatFuser (:53-67): + 9 rotation entries
+                return _wrap("_fuser", _mlp_params(fuse_in + 9, [fuse_in + 9, fuse_in + 9, 3 * NUM_FEAT_VEC]))
             return _wrap("_fuser", _mlp_params(fuse_in, [fuse_in, 3 * NUM_FEAT_VEC]))
 
         def head():
-            return _mlp_params(fuse_in, [512, 2])
+            return _mlp_params(head_in, [512, 2])
 
         if share_weights:  # one module aliased num_iter times (:150-158, Q10)
             self._img_fusers = nn.ModuleList([fuser()] * num_iter)
