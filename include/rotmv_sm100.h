@@ -61,6 +61,12 @@ typedef struct rmv_conv_args {
   const void* residual;   /* same dtype as y, or NULL */
   long long r_sn, r_sh, r_sw;
   int relu;
+  /* Training (tcgen05 engine, bf16 output, no residual): fuse the BatchNorm batch statistics of y
+   * into the epilogue -- stat_acc[stat_views][c_out][2] (fp64, caller-zeroed or accumulating) +=
+   * per-(view, channel) sum and sum of squares of the bf16 values written to y; image n belongs
+   * to view n % stat_views. NULL = off. Only stat_views == 2 is implemented. */
+  double* stat_acc;
+  int stat_views;
 } rmv_conv_args;
 
 int rmv_conv2d_fwd(const rmv_conv_args* args, void* stream);

@@ -52,6 +52,14 @@ struct IgemmArgs {
   const float* shift;
   int relu;
   int halo_base_mode;  // HALO kernels: 1 = set the descriptor base offset for row-shifted starts
+  // STATS kernels (training): per-(view, channel) sum and sum of squares of the bf16 output, added
+  // into stat_acc[2][n_total][2] (fp64). Image n belongs to view n & 1.
+  double* stat_acc;
+  int stat_pix;        // > 0: flattened pointwise GEMM, image of output row P is P / stat_pix
+  long long stat_rows; //      ... and P < stat_rows are the rows of the tensor
+  int stat_ppi_shift;  // boxed tiles: image of tile row r is tn*box_n + (r >> stat_ppi_shift),
+  int stat_bw_shift;   //   its pixel (th*box_h + ((r >> stat_bw_shift) & (box_h-1)), tw*box_w + (r & (box_w-1)))
+  int stat_w, stat_h, stat_n;  // output extent
 };
 
 // HALO variant (3x3, stride 1, pad 1, 64 -> 64 channels; BLOCK_N = 64): the producer loads ONE
@@ -65,7 +73,7 @@ constexpr int kHaloABytes = kHaloW * kHaloH * 128;  // 36864
 constexpr int kHaloTaps = 9;
 constexpr int kHaloStages = 3;
 
-template <int BLOCK_N, bool HAS_RES, bool HALO = false>
+template <int BLOCK_N, bool HAS_RES, bool HALO = false, bool STATS = false>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageA = HALO ? kHaloABytes : kABytes;             // A bytes per stage
@@ -76,7 +84,7 @@ struct Cfg {
   // trade A/B stages for a deeper residual ring (4 x 16 KiB) so the residual loads run well ahead.
   static constexpr int kStages = HALO ? kHaloStages
                                  : HAS_RES ? (BLOCK_N == 256 ? 2 : (BLOCK_N == 128 ? 3 : 4))
-                                           : (BLOCK_N == 256 ? 3 : 6);
+                                           : (BLOCK_N == 256 ? 3 : (STATS && BLOCK_N == 128 ? 4 : 6));
   static constexpr int kResSlots = 4;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
   static constexpr int kOutBytes = 2 * kChunkBytes;
@@ -110,10 +118,11 @@ __device__ __forceinline__ void epi_bar_sync(int id) {
 }
 
 // OUT_F32: 32 fp32 columns per staged chunk; otherwise 64 bf16 columns (both 128 B per row).
-template <int BLOCK_N, bool HAS_RES, bool OUT_F32, bool HALO = false>
+template <int BLOCK_N, bool HAS_RES, bool OUT_F32, bool HALO = false, bool STATS = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmArgs args) {
-  using C = Cfg<BLOCK_N, HAS_RES, HALO>;
+  using C = Cfg<BLOCK_N, HAS_RES, HALO, STATS>;
+  static_assert(!STATS || (!HAS_RES && !OUT_F32), "STATS: bf16 output, no residual");
   constexpr int kChunkCols = OUT_F32 ? 32 : 64;
   constexpr int kChunks = BLOCK_N / kChunkCols;
   extern __shared__ uint8_t smem_raw[];
@@ -135,6 +144,9 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   uint64_t* res_empty = res_full + C::kResSlots;  // [4]        epilogue -> TMA(residual)
   uint64_t* b_bar = res_empty + C::kResSlots;     // [1]        HALO: resident filters landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_bar + 1);
+  // STATS: [2 views][n_total][2] fp32 partial sums of this CTA, after the fixed-size regions
+  float* s_slot = reinterpret_cast<float*>(smem + C::kSmemBytes - 1024);  // [8][4][64] fp32
+  float* s_stat = s_slot + 8 * 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -308,6 +320,12 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
     int cc = 0;  // running chunk counter: staging buffer = cc & 1
     int rslot = 0;
     uint32_t rphase = 0;
+    // STATS: thread = (column pair cp, 16-row group rg) of a staged chunk
+    const int st_cp = tid_e & 31, st_rg = tid_e >> 5;
+    if (STATS) {
+      for (int i = tid_e; i < 4 * args.n_total; i += kEpiThreads) s_stat[i] = 0.f;
+      epi_bar_sync(1);
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -316,6 +334,35 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       const int tw = m_tile % args.tiles_w;
       const int th = (m_tile / args.tiles_w) % args.tiles_h;
       const int tn = m_tile / (args.tiles_w * args.tiles_h);
+      // STATS: bit i of st_m0 / st_m1 = row st_rg*16 + i of this tile is a pixel of the tensor and
+      // belongs to view 0 / view 1 (image & 1). Rows outside the tensor must not be counted: a 3x3
+      // conv gives them non-zero values when their receptive field reaches into the image.
+      uint32_t st_m0 = 0, st_m1 = 0;
+      if (STATS) {
+        if (args.stat_pix > 0) {   // flattened: rows are consecutive pixels of consecutive images
+          const long long p0 = (long long)tw * args.box_w + st_rg * 16;
+          const int img0 = (int)(p0 / args.stat_pix);
+          const int rem = (int)(p0 - (long long)img0 * args.stat_pix);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t ok = (p0 + i < args.stat_rows) ? 1u : 0u;
+            const uint32_t v = (uint32_t)((img0 + ((rem + i) / args.stat_pix)) & 1);
+            st_m0 |= (ok & (v ^ 1u)) << i;
+            st_m1 |= (ok & v) << i;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = st_rg * 16 + i;
+            const int ow = tw * args.box_w + (r & (args.box_w - 1));
+            const int oh = th * args.box_h + ((r >> args.stat_bw_shift) & (args.box_h - 1));
+            const int n = tn * args.box_n + (r >> args.stat_ppi_shift);
+            const uint32_t ok = (ow < args.stat_w && oh < args.stat_h && n < args.stat_n) ? 1u : 0u;
+            st_m0 |= (ok & (uint32_t)((n & 1) ^ 1)) << i;
+            st_m1 |= (ok & (uint32_t)(n & 1)) << i;
+          }
+        }
+      }
       // per-channel scale/shift of this N tile -> smem (all readers of the previous tile's values
       // are behind the last epi_bar_sync(2) of that tile)
       for (int i = tid_e; i < BLOCK_N; i += kEpiThreads) {
@@ -401,9 +448,70 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
                        th * args.box_h, tn * args.box_n);
           tma_store_commit();
         }
+        if (STATS) {
+          // BatchNorm batch statistics of the chunk just staged (the bf16 values that go to HBM;
+          // rows outside the tensor are exact zeros). Thread = (column pair, 16-row group):
+          // conflict-free LDS.32 (a warp reads one whole 128-byte row per step). The eight row
+          // groups are combined through a slot array and ONE owner thread per (view, stat, column)
+          // adds into the CTA-resident sums -- no shared-memory atomics (fp32 atomicAdd on shared
+          // memory is a CAS loop and tripled the time of the HBM-bound layers).
+          float a1x = 0.f, a1y = 0.f, a2x = 0.f, a2y = 0.f;  // view 0: sum, sum of squares
+          float b1x = 0.f, b1y = 0.f, b2x = 0.f, b2y = 0.f;  // view 1
+          const uint8_t* src = obuf + st_rg * 16 * 128 + (st_cp & 3) * 4;
+          const uint32_t unit = (uint32_t)st_cp >> 2;
+          if ((st_m0 ^ st_m1) == 0xFFFFu && (st_m0 == 0u || st_m1 == 0u)) {
+            // warp-uniform fast path: all 16 rows are valid pixels of one view
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 z = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
+                  src + i * 128 + ((unit ^ (uint32_t)(i & 7)) << 4)));
+              a1x += z.x; a1y += z.y;
+              a2x = fmaf(z.x, z.x, a2x); a2y = fmaf(z.y, z.y, a2y);
+            }
+            if (st_m1 != 0u) {
+              b1x = a1x; b1y = a1y; b2x = a2x; b2y = a2y;
+              a1x = a1y = a2x = a2y = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 z = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
+                  src + i * 128 + ((unit ^ (uint32_t)(i & 7)) << 4)));
+              const float m0 = (float)((st_m0 >> i) & 1u), m1 = (float)((st_m1 >> i) & 1u);
+              a1x = fmaf(m0, z.x, a1x); a1y = fmaf(m0, z.y, a1y);
+              a2x = fmaf(m0 * z.x, z.x, a2x); a2y = fmaf(m0 * z.y, z.y, a2y);
+              b1x = fmaf(m1, z.x, b1x); b1y = fmaf(m1, z.y, b1y);
+              b2x = fmaf(m1 * z.x, z.x, b2x); b2y = fmaf(m1 * z.y, z.y, b2y);
+            }
+          }
+          // slot[rg][q][64 columns], q = view*2 + stat
+          float* slot = s_slot + st_rg * 256 + 2 * st_cp;
+          *reinterpret_cast<float2*>(slot + 0) = make_float2(a1x, a1y);
+          *reinterpret_cast<float2*>(slot + 64) = make_float2(a2x, a2y);
+          *reinterpret_cast<float2*>(slot + 128) = make_float2(b1x, b1y);
+          *reinterpret_cast<float2*>(slot + 192) = make_float2(b2x, b2y);
+          epi_bar_sync(3);
+          {
+            const int q = tid_e >> 6, cl = tid_e & 63;   // owner of (view q>>1, stat q&1, column cl)
+            float sum = 0.f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) sum += s_slot[g * 256 + q * 64 + cl];
+            const int col = n_tile * BLOCK_N + c * kChunkCols + cl;
+            if (col < args.n_total)
+              s_stat[((size_t)(q >> 1) * args.n_total + col) * 2 + (q & 1)] += sum;
+          }
+          // the slots are rewritten only after the next chunk's epi_bar_sync(1)/(2): ordered
+        }
       }
     }
     if (tid_e == 0) tma_store_wait_all();
+    if (STATS) {
+      epi_bar_sync(1);  // every thread's shared-memory atomics are done
+      for (int i = tid_e; i < 4 * args.n_total; i += kEpiThreads) {
+        const float v = s_stat[i];
+        if (v != 0.f) atomicAdd(args.stat_acc + i, (double)v);
+      }
+    }
   }
 
   tc_fence_before_sync();
@@ -463,18 +571,24 @@ namespace {
 
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-template <int BLOCK_N, bool HAS_RES, bool OUT_F32, bool HALO = false>
+template <int BLOCK_N, bool HAS_RES, bool OUT_F32, bool HALO = false, bool STATS = false>
 int launch(const IgemmArgs& a, int total_tiles, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, HAS_RES, HALO>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RMV_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, HAS_RES, OUT_F32, HALO>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
+  using C = Cfg<BLOCK_N, HAS_RES, HALO, STATS>;
+  // STATS: [2][n_total][2] floats behind the fixed regions (they replace the 1 KiB alignment slack
+  // at the end of kSmemBytes, which the 1024-byte aligned base may consume: keep it as well)
+  const int stat_bytes = STATS ? (4 * a.n_total + 8 * 256) * (int)sizeof(float) + 1024 : 0;
+  const int smem = C::kSmemBytes + stat_bytes;
+  RMV_CHECK_ARG(smem <= 232448, "tcgen05 conv: %d bytes of shared memory needed (c_out=%d)", smem,
+                a.n_total);
+  static int attr_bytes = 0;
+  if (smem > attr_bytes) {
+    RMV_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, HAS_RES, OUT_F32, HALO, STATS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_bytes = smem;
   }
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  RMV_CUDA(launch_pdl_tc(igemm_kernel<BLOCK_N, HAS_RES, OUT_F32, HALO>, dim3(grid),
-                         dim3(kNumThreads), C::kSmemBytes, stream, a));
+  RMV_CUDA(launch_pdl_tc(igemm_kernel<BLOCK_N, HAS_RES, OUT_F32, HALO, STATS>, dim3(grid),
+                         dim3(kNumThreads), smem, stream, a));
   return 0;
 }
 
@@ -494,6 +608,7 @@ int halo_mode() {
 
 template <int BLOCK_N>
 int dispatch(const IgemmArgs& a, int total, bool has_res, bool out_f32, cudaStream_t stream) {
+  if (a.stat_acc != nullptr) return launch<BLOCK_N, false, false, false, true>(a, total, stream);
   if (out_f32) return launch<BLOCK_N, false, true>(a, total, stream);
   if (has_res) return launch<BLOCK_N, true, false>(a, total, stream);
   return launch<BLOCK_N, false, false>(a, total, stream);
@@ -647,8 +762,24 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
   a.relu = p.relu;
   const int total = (int)(m_tiles * a.n_tiles);
   if (total == 0) return 0;
+  if (p.stat_acc != nullptr) {
+    RMV_CHECK_ARG(!out_f32 && p.residual == nullptr && p.stat_views == 2,
+                  "tcgen05 conv: fused BatchNorm statistics need bf16 output, no residual, 2 views");
+    a.stat_acc = p.stat_acc;
+    const bool flattened = (out_h == 1 && n_img == 1 && (p.out_h != 1 || p.n_img != 1));
+    a.stat_pix = flattened ? p.out_h * p.out_w : 0;
+    a.stat_rows = (long long)p.n_img * p.out_h * p.out_w;
+    int sh = 0;
+    while ((1 << sh) < a.box_w * a.box_h) ++sh;
+    a.stat_ppi_shift = sh;
+    sh = 0;
+    while ((1 << sh) < a.box_w) ++sh;
+    a.stat_bw_shift = sh;
+    a.stat_w = out_w; a.stat_h = out_h; a.stat_n = n_img;
+  }
   if (halo) {
     a.halo_base_mode = halo_mode() == 2;
+    if (a.stat_acc != nullptr) return launch<64, false, false, true, true>(a, total, stream);
     return launch<64, false, false, true>(a, total, stream);
   }
   const bool has_res = p.residual != nullptr;

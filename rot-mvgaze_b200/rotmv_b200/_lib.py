@@ -41,6 +41,7 @@ class ConvArgs(C.Structure):
         ("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
         ("r_sn", C.c_longlong), ("r_sh", C.c_longlong), ("r_sw", C.c_longlong),
         ("relu", C.c_int),
+        ("stat_acc", C.c_void_p), ("stat_views", C.c_int),
     ]
 
 

@@ -34,7 +34,7 @@ def _need_cuda(*ts):
 
 
 def conv2d(x, w, *, stride=1, pad=0, scale=None, shift=None, residual=None, relu=False,
-           out=None, out_dtype=None, engine=L.ENGINE_AUTO, block_n=0):
+           out=None, out_dtype=None, engine=L.ENGINE_AUTO, block_n=0, stat_acc=None, stat_views=0):
     """y = act(scale * conv(x, w) + shift + residual).
 
     x: [N, H, W, C] (any pixel strides, channel stride 1); w: [K, kh, kw, C] contiguous, same
@@ -73,6 +73,11 @@ def conv2d(x, w, *, stride=1, pad=0, scale=None, shift=None, residual=None, relu
         a.residual = residual.data_ptr()
         a.r_sn, a.r_sh, a.r_sw = residual.stride(0), residual.stride(1), residual.stride(2)
     a.relu = int(relu)
+    if stat_acc is not None:
+        # training: per-(view, channel) sum / sum of squares of `out` fused into the conv epilogue
+        assert stat_acc.dtype == torch.float64 and stat_acc.is_contiguous() and stat_acc.numel() >= stat_views * k * 2
+        a.stat_acc = stat_acc.data_ptr()
+        a.stat_views = stat_views
     meta = {}
     if PROFILE is not None:
         tc = x.dtype == torch.bfloat16 and engine != L.ENGINE_SIMT and c % 64 == 0

@@ -15,6 +15,7 @@ precision "bf16": bf16 activations/filters, tcgen05 forward + data gradients, fp
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Dict, List, Optional
 
 import torch
@@ -65,6 +66,8 @@ class TrainEngine:
             raise L.RotmvError("TrainEngine needs the model on a CUDA device; there is no CPU path")
         self.max_views = max_views
         self.use_tc_wgrad = True  # bf16: weight gradients on tcgen05 (False -> FFMA kernel)
+        # bf16, V == 2: BatchNorm statistics in the conv epilogue (RMV_FUSE_BN_STATS=0: separate pass)
+        self.fuse_bn_stats = os.environ.get("RMV_FUSE_BN_STATS", "1") != "0"
         self.num_iter, self.fc_dim, self.nvec = model._num_iter, model._fc_dim, model._num_feat_vec
         self.apply_rot = not model._ignore_rotmat
         self.decoupled = bool(decoupled)
@@ -196,14 +199,33 @@ class TrainEngine:
                  self._wjob_blocks, L.stream_ptr())
 
     # ---- BatchNorm -----------------------------------------------------------------------------
-    def _bn_fwd(self, bn: _BN, z, residual, relu, tag):
+    def _conv_stats(self, x, w, *, stride=1, pad=0, out=None):
+        """Forward conv of the training step. bf16 / two views: the BatchNorm batch statistics of
+        the output are accumulated by the conv epilogue itself (returns stats_done=True)."""
+        fused = self.fuse_bn_stats and self.precision == "bf16" and self.views == 2
+        # measured (B=128, V=2): free for the tensor-bound 3x3 and the reducing 1x1 convs, but the
+        # expanding 1x1 convs are HBM-bound with the epilogue on the critical path (+70 % with the
+        # statistics in it) -- those keep the separate one-wave reduction
+        if w.shape[1] == 1 and w.shape[0] > w.shape[3]:
+            fused = False
+        z = RF.conv2d(x, w, stride=stride, pad=pad, out=out,
+                      stat_acc=self.acc if fused else None, stat_views=2 if fused else 0)
+        return z, fused
+
+    def _bn_fwd(self, bn: _BN, z, residual, relu, tag, stats_done=False):
         n, h, w, c = z.shape
         v = self.views
         shp = f" [{n},{h},{w},{c}]" if RF.PROFILE is not None else ""
-        _ck("rmv_bn_stats_finalize", z.data_ptr(), self.dtc, n, h * w, c, v, self.acc.data_ptr(),
-            self.ticket.data_ptr(), bn.gamma.data_ptr(), bn.beta.data_ptr(), bn.rm.data_ptr(),
-            bn.rv.data_ptr(), bn.nbt.data_ptr(), bn.mean.data_ptr(), bn.invstd.data_ptr(),
-            bn.a.data_ptr(), bn.b.data_ptr(), bn.eps, bn.momentum, desc="rmv_bn_stats_finalize" + shp)
+        if stats_done:   # sums already in self.acc (fused conv epilogue): coefficients only
+            _ck("rmv_bn_finalize", self.acc.data_ptr(), bn.gamma.data_ptr(), bn.beta.data_ptr(),
+                bn.rm.data_ptr(), bn.rv.data_ptr(), bn.nbt.data_ptr(), bn.mean.data_ptr(),
+                bn.invstd.data_ptr(), bn.a.data_ptr(), bn.b.data_ptr(), c, v, (n // v) * h * w, bn.eps,
+                bn.momentum)
+        else:
+            _ck("rmv_bn_stats_finalize", z.data_ptr(), self.dtc, n, h * w, c, v, self.acc.data_ptr(),
+                self.ticket.data_ptr(), bn.gamma.data_ptr(), bn.beta.data_ptr(), bn.rm.data_ptr(),
+                bn.rv.data_ptr(), bn.nbt.data_ptr(), bn.mean.data_ptr(), bn.invstd.data_ptr(),
+                bn.a.data_ptr(), bn.b.data_ptr(), bn.eps, bn.momentum, desc="rmv_bn_stats_finalize" + shp)
         y = self._buf(tag, z.shape)
         # packed ReLU mask (1 bit/element) for the backward pass instead of re-reading y there
         bits = self._buf(("bits", tag), (n * h * w * c // 8,), torch.uint8) if relu else None
@@ -366,23 +388,27 @@ class TrainEngine:
             c1, c2, c3 = e["convs"]
             b1, b2, b3 = e["bns"]
             x_in = x
-            z1 = RF.conv2d(x_in, self._w_fwd(c1, (bi, 1)), out=self._buf(("z1", bi), (*x_in.shape[:3], c1.out_channels)))
-            y1 = self._bn_fwd(b1, z1, None, True, ("y1", bi))
+            # conv -> (statistics in the epilogue) -> finalize -> apply, strictly in this order: the
+            # fp64 accumulator `self.acc` is shared and reset by every finalize
+            z1, sd = self._conv_stats(x_in, self._w_fwd(c1, (bi, 1)),
+                                      out=self._buf(("z1", bi), (*x_in.shape[:3], c1.out_channels)))
+            y1 = self._bn_fwd(b1, z1, None, True, ("y1", bi), stats_done=sd)
             s2 = c2.stride[0]
             oh = (y1.shape[1] + 2 - 3) // s2 + 1
-            z2 = RF.conv2d(y1, self._w_fwd(c2, (bi, 2)), stride=s2, pad=1,
-                           out=self._buf(("z2", bi), (m, oh, oh, c2.out_channels)))
-            y2 = self._bn_fwd(b2, z2, None, True, ("y2", bi))
-            z3 = RF.conv2d(y2, self._w_fwd(c3, (bi, 3)), out=self._buf(("z3", bi), (m, oh, oh, c3.out_channels)))
+            z2, sd = self._conv_stats(y1, self._w_fwd(c2, (bi, 2)), stride=s2, pad=1,
+                                      out=self._buf(("z2", bi), (m, oh, oh, c2.out_channels)))
+            y2 = self._bn_fwd(b2, z2, None, True, ("y2", bi), stats_done=sd)
             zd = None
             if "ds_conv" in e:
                 dc = e["ds_conv"]
-                zd = RF.conv2d(x_in, self._w_fwd(dc, (bi, "d")), stride=dc.stride[0],
-                               out=self._buf(("zd", bi), (m, oh, oh, dc.out_channels)))
-                skip = self._bn_fwd(e["ds_bn"], zd, None, False, ("skip", bi))
+                zd, sd = self._conv_stats(x_in, self._w_fwd(dc, (bi, "d")), stride=dc.stride[0],
+                                          out=self._buf(("zd", bi), (m, oh, oh, dc.out_channels)))
+                skip = self._bn_fwd(e["ds_bn"], zd, None, False, ("skip", bi), stats_done=sd)
             else:
                 skip = x_in
-            x = self._bn_fwd(b3, z3, skip, True, ("out", bi))
+            z3, sd = self._conv_stats(y2, self._w_fwd(c3, (bi, 3)),
+                                      out=self._buf(("z3", bi), (m, oh, oh, c3.out_channels)))
+            x = self._bn_fwd(b3, z3, skip, True, ("out", bi), stats_done=sd)
             saved.append((x_in, z1, y1, z2, y2, z3, zd, x))
         wide = self.fc_dim + 3 * self.nvec
         fd = self.fc_dim

@@ -461,3 +461,40 @@ def test_conv2d_dgrad_tc_matches_torch():
                              in_hw=(hh, hh), residual=res)
         err = (dx.float() - ref).abs().max().item()
         assert err <= 1e-2 * ref.abs().max().item() + 1e-3, (n, hh, ci, co, k, s, p, err)
+
+
+@pytest.mark.parametrize("case", [
+    # n, h, w, ci, co, k, stride, pad
+    (6, 56, 56, 64, 256, 1, 1, 0),    # flattened pointwise, image boundaries warp aligned
+    (6, 28, 28, 128, 512, 1, 1, 0),   # flattened, 784 px per image (16-row aligned)
+    (10, 14, 14, 256, 1024, 1, 1, 0), # flattened, 196 px per image: views change inside 16-row groups
+    (14, 7, 7, 512, 2048, 1, 1, 0),   # flattened, 49 px per image
+    (4, 56, 56, 64, 64, 3, 1, 1),     # halo-patch kernel
+    (6, 28, 28, 128, 128, 3, 1, 1),   # boxed 4x4x8 tiles
+    (10, 14, 14, 256, 256, 3, 1, 1),  # boxed 2x2x32 tiles
+    (6, 7, 7, 512, 512, 3, 1, 1),     # boxed 1x1x128 tiles
+    (4, 56, 56, 128, 128, 3, 2, 1),   # stride 2 (parity planes)
+    (6, 28, 28, 256, 512, 1, 2, 0),   # stride-2 1x1 (downsample)
+    (4, 23, 19, 64, 64, 3, 1, 1),     # ragged tiles
+    (2, 30, 30, 64, 128, 1, 1, 0),    # ragged flattened tail
+])
+def test_conv_epilogue_bn_statistics(case):
+    """rmv_conv_args.stat_acc: the per-(view, channel) sum / sum of squares the tcgen05 conv
+    epilogue accumulates equal those of the bf16 tensor it wrote (fp64 reference), for every tile
+    geometry; the output itself is unchanged by the option."""
+    from rotmv_b200 import functional as RF, _lib as L
+
+    n, h, w, ci, co, k, stride, pad = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn((n, h, w, ci), device="cuda", generator=g).bfloat16()
+    wt = (torch.randn((co, k, k, ci), device="cuda", generator=g) / (k * k * ci) ** 0.5).bfloat16()
+    acc = torch.zeros((2, co, 2), device="cuda", dtype=torch.float64)
+    y = RF.conv2d(x, wt, stride=stride, pad=pad, engine=L.ENGINE_TC, stat_acc=acc, stat_views=2)
+    y0 = RF.conv2d(x, wt, stride=stride, pad=pad, engine=L.ENGINE_TC)
+    assert torch.equal(y, y0)
+    yd = y.double()
+    for v in range(2):
+        s1 = yd[v::2].sum(dim=(0, 1, 2))
+        s2 = (yd[v::2] ** 2).sum(dim=(0, 1, 2))
+        assert torch.allclose(acc[v, :, 0], s1, rtol=1e-5, atol=1e-4 * s2.sqrt().max().item()), (case, v)
+        assert torch.allclose(acc[v, :, 1], s2, rtol=1e-5, atol=1e-6 * s2.max().item()), (case, v)
