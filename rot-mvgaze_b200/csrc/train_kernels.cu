@@ -196,7 +196,7 @@ __device__ __forceinline__ void bn_bwd_finalize_block(double* acc, const BnFinal
 // block = 256 threads = (c/8 channel groups) x (256/(c/8)) row lanes; each thread keeps U 16-byte
 // loads per stream in flight and tracks (image, pixel) incrementally -- no division in the loop.
 template <typename T, bool BWD, int MASK>
-__global__ void __launch_bounds__(256, BWD ? 2 : 3)
+__global__ void __launch_bounds__(256, 3)
 bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const void* __restrict__ y_mask_v,
                  const float* __restrict__ mean, const float* __restrict__ invstd, int pix, int c,
                  int views, int imgs_per_view, double* __restrict__ acc /* [views][c][2] */,
@@ -218,14 +218,9 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const void* 
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-  float mu[8], is[8];
-  if (BWD) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      mu[i] = __ldg(mean + v * c + g * 8 + i);
-      is[i] = __ldg(invstd + v * c + g * 8 + i);
-    }
-  }
+  // BWD accumulates the raw sums S1 = sum d and S2' = sum d*z; sum d*xhat = invstd*(S2' - mean*S1)
+  // is formed in fp64 when the block's partial sums are combined (keeps mean/invstd out of the
+  // streaming loop: 16 fewer live registers, one FMA per element instead of three operations).
   // independent 16-byte (bf16) / 32-byte (fp32) loads in flight per tensor
   constexpr int U = sizeof(T) == 2 ? (BWD ? 4 : 8) : (BWD ? 2 : 4);
   if (lane < lanes && r0 + lane < r1) {
@@ -274,7 +269,7 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const void* 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               s1[i] += d[i];
-              s2[i] = fmaf(d[i], (f[i] - mu[i]) * is[i], s2[i]);
+              s2[i] = fmaf(d[i], f[i], s2[i]);
             }
           }
         }
@@ -294,6 +289,12 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const void* 
   for (int j = threadIdx.x; j < c * 2; j += blockDim.x) {
     double s = 0.0;
     for (int l = 0; l < lanes; ++l) s += (double)s_red[l * c * 2 + j];
+    if (BWD && (j & 1)) {
+      double sd = 0.0;
+      for (int l = 0; l < lanes; ++l) sd += (double)s_red[l * c * 2 + j - 1];
+      const int ch = j >> 1;
+      s = (double)__ldg(invstd + v * c + ch) * (s - (double)__ldg(mean + v * c + ch) * sd);
+    }
     atomicAdd(acc + (long long)v * c * 2 + j, s);
   }
   if (fin.ticket == nullptr) return;
@@ -765,10 +766,15 @@ __global__ void maxpool_fwd_idx_kernel(const T* __restrict__ x, T* __restrict__ 
   *reinterpret_cast<uint2*>(idx + i * 8) = packed;
 }
 
+// Thread = a 2x2 block of input pixels (8 channels): rows 2k, 2k+1 and columns 2j, 2j+1 are
+// covered by exactly the four windows (k..k+1, j..j+1) -- the even row/column only by window k/j
+// (its centre), the odd one by k (bottom/right edge) and k+1 (top/left edge). Four (index, dy)
+// loads give four outputs; every (pixel, window) pair has a compile-time index code.
 template <typename T>
-__global__ void maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const T* __restrict__ dy,
-                                       T* __restrict__ dx, int in_h, int in_w, int c, int out_h,
-                                       int out_w, long long total) {
+__global__ void __launch_bounds__(256)
+maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const T* __restrict__ dy,
+                       T* __restrict__ dx, int in_h, int in_w, int c, int out_h, int out_w,
+                       int blk_h, int blk_w, long long total) {
   griddep_wait();    // PDL: predecessors complete + visible
   griddep_launch();  // let the next kernel of the stream get scheduled
 
@@ -777,24 +783,48 @@ __global__ void maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const T*
   const int cg = c / 8;
   const int g = (int)(i % cg);
   long long t = i / cg;
-  const int iw = (int)(t % in_w); t /= in_w;
-  const int ih = (int)(t % in_h);
-  const long long n = t / in_h;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int oh = max(0, ih / 2); oh <= min(out_h - 1, (ih + 1) / 2); ++oh)
-    for (int ow = max(0, iw / 2); ow <= min(out_w - 1, (iw + 1) / 2); ++ow) {
-      const uint32_t code = (uint32_t)((ih - 2 * oh + 1) * 3 + (iw - 2 * ow + 1));
-      const long long o = ((n * out_h + oh) * out_w + ow) * c + g * 8;
-      const uint2 p = *reinterpret_cast<const uint2*>(idx + o);
-      float d[8];
-      V8<T>::load(dy + o, d);
+  const int j = (int)(t % blk_w); t /= blk_w;
+  const int k = (int)(t % blk_h);
+  const long long n = t / blk_h;
+  uint2 code[2][2];
+  float d[2][2][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const uint32_t a = ((e < 4 ? p.x : p.y) >> (8 * (e & 3))) & 0xffu;
-        if (a == code) acc[e] += d[e];
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int oh = k + a, ow = j + b;
+      if (oh < out_h && ow < out_w) {
+        const long long o = ((n * out_h + oh) * out_w + ow) * c + g * 8;
+        code[a][b] = *reinterpret_cast<const uint2*>(idx + o);
+        V8<T>::load(dy + o, d[a][b]);
+      } else {
+        code[a][b] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);  // matches no position
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[a][b][e] = 0.f;
       }
     }
-  V8<T>::store(dx + i * 8, acc);
+  // input pixel (2k+p, 2j+q): windows a <= p, b <= q; position inside window (k+a, j+b) is
+  // (p - 2a + 1, q - 2b + 1), stored as r*3 + s
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int ih = 2 * k + p, iw = 2 * j + q;
+      if (ih >= in_h || iw >= in_w) continue;
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int a = 0; a <= p; ++a)
+#pragma unroll
+        for (int b = 0; b <= q; ++b) {
+          const uint32_t want = (uint32_t)((p - 2 * a + 1) * 3 + (q - 2 * b + 1));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t got = ((e < 4 ? code[a][b].x : code[a][b].y) >> (8 * (e & 3))) & 0xffu;
+            if (got == want) acc[e] += d[a][b][e];
+          }
+        }
+      V8<T>::store(dx + (((n * in_h + ih) * in_w + iw) * c + g * 8), acc);
+    }
 }
 
 // dx[n, p, :] = dfeat[n, :] / hw
@@ -1165,7 +1195,7 @@ static int bn_bwd_reduce_launch(const void* z, const void* dy, const void* y_mas
   RMV_CHECK_ARG(views >= 1 && n_img % views == 0, "bn_bwd_reduce: n_img not a multiple of views");
   if (n_img == 0 || pix == 0) return 0;
   dim3 grid; int smem;
-  if (int rc = bn_reduce_cfg(pix, c, n_img, views, 2, &grid, &smem)) return rc;
+  if (int rc = bn_reduce_cfg(pix, c, n_img, views, 3, &grid, &smem)) return rc;
   DISPATCH_T(dtype, DISPATCH_MASK(y_mask, mask_is_bits,
       (rmv::launch_pdl(bn_reduce_kernel<T, true, MASK>, dim3(grid), dim3(256), smem, stream, 
           (const T*)z, (const T*)dy, y_mask, mean, invstd, pix, c, views, n_img / views, acc, fin))));
@@ -1376,10 +1406,12 @@ extern "C" int rmv_maxpool3x3s2_bwd_idx(const void* idx, const void* dy, void* d
                                         int in_h, int in_w, int c, int dtype, void* stream) {
   RMV_CHECK_ARG(c % 8 == 0, "maxpool_bwd_idx: c must be a multiple of 8");
   const int out_h = (in_h - 1) / 2 + 1, out_w = (in_w - 1) / 2 + 1;
-  const long long total = (long long)n_img * in_h * in_w * (c / 8);
+  const int blk_h = (in_h + 1) / 2, blk_w = (in_w + 1) / 2;
+  const long long total = (long long)n_img * blk_h * blk_w * (c / 8);
   if (total == 0) return 0;
-  DISPATCH_T(dtype, (rmv::launch_pdl(maxpool_bwd_idx_kernel<T>, dim3(nblk(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
-      (const uint8_t*)idx, (const T*)dy, (T*)dx, in_h, in_w, c, out_h, out_w, total)));
+  DISPATCH_T(dtype, (rmv::launch_pdl(maxpool_bwd_idx_kernel<T>, dim3(nblk(total, 256)), dim3(256), 0,
+                                     (cudaStream_t)stream, (const uint8_t*)idx, (const T*)dy, (T*)dx,
+                                     in_h, in_w, c, out_h, out_w, blk_h, blk_w, total)));
   RMV_LAUNCH_CHECK();
   return 0;
 }

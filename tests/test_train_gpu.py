@@ -498,3 +498,33 @@ def test_conv_epilogue_bn_statistics(case):
         s2 = (yd[v::2] ** 2).sum(dim=(0, 1, 2))
         assert torch.allclose(acc[v, :, 0], s1, rtol=1e-5, atol=1e-4 * s2.sqrt().max().item()), (case, v)
         assert torch.allclose(acc[v, :, 1], s2, rtol=1e-5, atol=1e-6 * s2.max().item()), (case, v)
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 12, 12), (3, 13, 11), (1, 112, 112), (2, 7, 9)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_maxpool_index_forward_backward(n, h, w, dt):
+    """Training max-pool: the forward records the winning window position, the backward (one thread
+    per 2x2 input block) routes every gradient through it. Against autograd, with ties (ReLU zeros):
+    the first maximum in scan order wins, as in ATen."""
+    import torch.nn.functional as F
+    from rotmv_b200 import _lib as L
+    from rotmv_b200.train import _ck
+
+    torch.manual_seed(n * 100 + h + w)
+    x = torch.relu(torch.randn((n, 64, h, w), device="cuda")).to(dt).float().requires_grad_(True)
+    y = F.max_pool2d(x, 3, 2, 1)
+    dy = torch.randn_like(y).to(dt).float()
+    y.backward(dy)
+    xn = x.detach().permute(0, 2, 3, 1).contiguous().to(dt)
+    dn = dy.permute(0, 2, 3, 1).contiguous().to(dt)
+    oh, ow = y.shape[2], y.shape[3]
+    yn = torch.empty((n, oh, ow, 64), device="cuda", dtype=dt)
+    idx = torch.empty((n, oh, ow, 64), device="cuda", dtype=torch.uint8)
+    dx = torch.full((n, h, w, 64), 7.0, device="cuda", dtype=dt)
+    code = L.dtype_code(dt)
+    _ck("rmv_maxpool3x3s2_fwd_idx", xn.data_ptr(), yn.data_ptr(), idx.data_ptr(), n, h, w, 64, code)
+    _ck("rmv_maxpool3x3s2_bwd_idx", idx.data_ptr(), dn.data_ptr(), dx.data_ptr(), n, h, w, 64, code)
+    assert torch.equal(yn.float(), y.detach().permute(0, 2, 3, 1))
+    ref = x.grad.permute(0, 2, 3, 1)
+    tol = 0.0 if dt == torch.float32 else 2e-2 * ref.abs().max().item()   # bf16: sums of up to 4 terms rounded
+    assert (dx.float() - ref).abs().max().item() <= tol + 1e-6
