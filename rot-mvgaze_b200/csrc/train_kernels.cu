@@ -208,7 +208,11 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const void* 
   __shared__ unsigned int s_ticket;
   const T* y_mask = reinterpret_cast<const T*>(y_mask_v);
   const uint8_t* y_bits = reinterpret_cast<const uint8_t*>(y_mask_v);
-  const int cg = c / 8;
+  // blockIdx.z = channel slice of cs = c / gridDim.z channels (<= 256): wide layers are split
+  // along the channels instead of the rows, so that the number of fp64 atomics per launch
+  // (blocks x slice channels x 2) does not grow with c
+  const int cs = c / gridDim.z, c0 = blockIdx.z * cs;
+  const int cg = cs / 8;
   const int lanes = blockDim.x / cg;  // row lanes per block (>= 1)
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
   const int v = blockIdx.y;
@@ -227,7 +231,7 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const void* 
     // this thread's rows: r0 + lane + k*lanes; (img, p) of the current row, element offset `off`
     long long img = (r0 + lane) / pix;
     int p = (int)((r0 + lane) - img * pix);
-    long long off = ((img * views + v) * pix + p) * c + g * 8;
+    long long off = ((img * views + v) * pix + p) * c + c0 + g * 8;
     const long long row_step = (long long)lanes * c;                 // next row, same image
     const long long wrap_step = (long long)(views - 1) * pix * c;    // extra when the image wraps
     long long left = (r1 - (r0 + lane) + lanes - 1) / lanes;          // rows this thread owns
@@ -281,21 +285,21 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const void* 
   if (lane < lanes) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      s_red[(lane * c + g * 8 + i) * 2] = s1[i];
-      s_red[(lane * c + g * 8 + i) * 2 + 1] = s2[i];
+      s_red[(lane * cs + g * 8 + i) * 2] = s1[i];
+      s_red[(lane * cs + g * 8 + i) * 2 + 1] = s2[i];
     }
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < c * 2; j += blockDim.x) {
+  for (int j = threadIdx.x; j < cs * 2; j += blockDim.x) {
     double s = 0.0;
-    for (int l = 0; l < lanes; ++l) s += (double)s_red[l * c * 2 + j];
+    for (int l = 0; l < lanes; ++l) s += (double)s_red[l * cs * 2 + j];
+    const int ch = c0 + (j >> 1);
     if (BWD && (j & 1)) {
       double sd = 0.0;
-      for (int l = 0; l < lanes; ++l) sd += (double)s_red[l * c * 2 + j - 1];
-      const int ch = j >> 1;
+      for (int l = 0; l < lanes; ++l) sd += (double)s_red[l * cs * 2 + j - 1];
       s = (double)__ldg(invstd + v * c + ch) * (s - (double)__ldg(mean + v * c + ch) * sd);
     }
-    atomicAdd(acc + (long long)v * c * 2 + j, s);
+    atomicAdd(acc + ((long long)v * c + ch) * 2 + (j & 1), s);
   }
   if (fin.ticket == nullptr) return;
   // ---- the last block to finish turns the sums into the per-(view, channel) coefficients ----
@@ -303,7 +307,7 @@ bn_reduce_kernel(const T* __restrict__ z, const T* __restrict__ dy, const void* 
   __syncthreads();
   if (threadIdx.x == 0) s_ticket = atomicAdd(fin.ticket, 1u);
   __syncthreads();
-  if (s_ticket != gridDim.x * gridDim.y - 1) return;
+  if (s_ticket != gridDim.x * gridDim.y * gridDim.z - 1) return;
   __threadfence();
   if (BWD) bn_bwd_finalize_block(acc, fin, mean, invstd, c, views, threadIdx.x, blockDim.x);
   else bn_finalize_block(acc, fin, c, views, threadIdx.x, blockDim.x);
@@ -1094,22 +1098,23 @@ static unsigned ew_blocks_x(int pix, int c, int n_img, int unroll = rmv::kEwUnro
   return (unsigned)bx;
 }
 
-// grid (G, views): one wave of co-resident blocks (occ per SM), but no more blocks than there are
-// 16-row (per thread) slabs.
+// grid (G, views, channel slices): one wave of co-resident blocks (occ per SM), but no more row
+// slabs than there are 16-row (per thread) pieces; channels in slices of at most 256.
 static int bn_reduce_cfg(int pix, int c, int n_img, int views, int occ, dim3* grid, int* smem) {
-  const int cg = c / 8;
-  RMV_CHECK_ARG(c % 8 == 0 && cg <= 256 && 256 % cg == 0,
+  RMV_CHECK_ARG(c % 8 == 0 && (c / 8) <= 256 && 256 % (c / 8) == 0,
                 "batchnorm: channels=%d must be 8*2^k with c <= 2048", c);
+  const int cs = c > 256 ? 256 : c, slices = c / cs;
+  const int cg = cs / 8;
   RMV_CHECK_ARG(pix > 32 || 256 / cg <= pix, "batchnorm: %d pixels per image is too few", pix);
   const int lanes = 256 / cg;
   const long long rows_total = (long long)(n_img / views) * pix;
   long long gx = (rows_total + lanes * 16 - 1) / (lanes * 16);
-  long long want = (long long)occ * num_sms() / views;
+  long long want = (long long)occ * num_sms() / (views * slices);
   if (want < 1) want = 1;
   if (gx > want) gx = want;
   if (gx < 1) gx = 1;
-  *grid = dim3((unsigned)gx, (unsigned)views);
-  *smem = lanes * c * 2 * (int)sizeof(float);
+  *grid = dim3((unsigned)gx, (unsigned)views, (unsigned)slices);
+  *smem = lanes * cs * 2 * (int)sizeof(float);
   return 0;
 }
 
