@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include "ops.h"
 
+#include <stdlib.h>
+
 namespace rmv {
 namespace {
 
@@ -167,6 +169,142 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem, N_TILE < 32 ? 32 : N_TILE); }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 / 64 -> 64 channels (layer1 conv2: the largest pixel count, the smallest
+// GEMM): tap-by-tap the kernel above re-reads dY and X nine times and issues N = 64 MMAs. Here one
+// CTA owns a TAP ROW r: per 8x16-pixel tile it loads dY once (16 KB) and ONE (16 wide x 16 high) box
+// of X starting at (ow0-1, oh0+r-1), and the three taps (r, 0..2) are the three 64-channel N-blocks
+// of a single N = 192 MN-major B operand whose blocks lie 128 B (one pixel) apart -- LBO = 128,
+// SBO = 2048 (one 16-pixel patch row per 8-pixel group). 3x fewer, 3x wider MMAs, 9x -> 3x dY
+// traffic, 9x -> 6x smaller X traffic. The upper 64 rows of the M = 128 accumulator are fed from a
+// shared-memory block of zeros (c_out = 64).
+// ---------------------------------------------------------------------------------------------
+struct WgRowsArgs {
+  CUtensorMap tmap_x;    // (64 ch, in_w, in_h, n), box (64, 16, 16, 1)
+  CUtensorMap tmap_dy;   // (64 ch, out_w, out_h, n), box (64, 8, 16, 1)
+  CUtensorMap tmap_dw;   // fp32 scratch [64][9*64], box (32 cols, 128 rows)
+  int tiles_w, tiles_h, m_blocks, blocks_per_split;
+};
+constexpr int kRowsStages = 3;
+constexpr int kRowsStageBytes = 2 * kBoxBytes /*dY + zeros*/ + 2 * kBoxBytes /*X patch 16x16*/;
+constexpr int kRowsSmem = kRowsStages * kRowsStageBytes + kBoxBytes + 256 + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_rows_kernel(const __grid_constant__ WgRowsArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_out = smem + kRowsStages * kRowsStageBytes;  // [128 rows][32 fp32], SW128
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + kBoxBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kRowsStages;
+  uint64_t* done_bar = bars + 2 * kRowsStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.tmap_dy);
+    tma_prefetch_desc(&a.tmap_x);
+    tma_prefetch_desc(&a.tmap_dw);
+    for (int s = 0; s < kRowsStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
+  // the zero half of every stage's A operand (channels 64..127 of dY do not exist)
+  for (int i = threadIdx.x; i < kRowsStages * (kBoxBytes / 16); i += kThreads) {
+    const int st = i / (kBoxBytes / 16), j = i % (kBoxBytes / 16);
+    *reinterpret_cast<uint4*>(smem + st * kRowsStageBytes + kBoxBytes + j * 16) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_ptr;
+  griddep_wait();
+  griddep_launch();
+
+  const int r = blockIdx.x % 3, split = blockIdx.x / 3;
+  const int pb0 = split * a.blocks_per_split;
+  const int pb1 = min(a.m_blocks, pb0 + a.blocks_per_split);
+  const int n_blocks = pb1 - pb0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int pb = pb0; pb < pb1; ++pb) {
+        const int tw = pb % a.tiles_w;
+        const int th = (pb / a.tiles_w) % a.tiles_h;
+        const int n = pb / (a.tiles_w * a.tiles_h);
+        uint8_t* sa = smem + stage * kRowsStageBytes;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], 3 * kBoxBytes);
+        tma_load_4d(sa, &a.tmap_dy, &full_bar[stage], 0, tw * 8, th * 16, n);
+        tma_load_4d(sa + 2 * kBoxBytes, &a.tmap_x, &full_bar[stage], 0, tw * 8 - 1, th * 16 + r - 1, n);
+        if (++stage == kRowsStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 192, 1, 1);  // both operands MN-major
+    int stage = 0; uint32_t phase = 0;
+    for (int i = 0; i < n_blocks; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after_sync();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * kRowsStageBytes);
+        const uint32_t sb = sa + 2 * kBoxBytes;
+#pragma unroll
+        for (int k = 0; k < kPix / 16; ++k) {
+          // A: 16 pixels = two 8-pixel atoms of the 8-wide dY box (2048 B), channel block 1 = zeros
+          const uint64_t adesc = umma_desc_sw128(sa + k * 2048, kBoxBytes, 1024);
+          // B: 16 pixels = two patch rows (2 x 2048 B); N-block j = tap (r, j) = one pixel further
+          const uint64_t bdesc = umma_desc_sw128(sb + k * 4096, 128, 2048);
+          umma_f16(tmem, adesc, bdesc, idesc, (i | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (i == n_blocks - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+      if (++stage == kRowsStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (n_blocks > 0) {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const int tid_e = threadIdx.x - 64;
+    mbar_wait(done_bar, 0);
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int c = 0; c < 192 / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem + ((uint32_t)(quarter * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      if (tid_e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(s_out + row * 128 + (((uint32_t)q ^ sw) << 4)) =
+            make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      // columns of the scratch: tap (r, s) * 64 + c_in = r*192 + accumulator column
+      if (tid_e == 0) tma_reduce_add_2d(&a.tmap_dw, s_out, r * 192 + c * 32, 0);
+    }
+    if (tid_e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem, 256); }
+}
+
+int wgrad_rows_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("RMV_WGRAD_ROWS");
+    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return cached;
+}
+
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 template <int N_TILE>
@@ -195,6 +333,44 @@ int conv_wgrad_tc(const ConvArgs& p, const void* dy, float* dw_scratch, cudaStre
   RMV_CHECK_ARG(p.x_sw % 8 == 0 && p.x_sh % 8 == 0 && p.x_sn % 8 == 0 && p.y_sw % 8 == 0 &&
                     p.y_sh % 8 == 0 && p.y_sn % 8 == 0,
                 "tcgen05 wgrad: pixel strides must be multiples of 8 elements");
+  if (wgrad_rows_enabled() && p.kh == 3 && p.kw == 3 && p.stride == 1 && p.pad == 1 && p.c_in == 64 &&
+      p.c_out == 64 && p.out_w >= 8 && p.out_h >= 16) {
+    WgRowsArgs r;
+    memset(&r, 0, sizeof(r));
+    r.tiles_w = ceil_div(p.out_w, 8);
+    r.tiles_h = ceil_div(p.out_h, 16);
+    r.m_blocks = r.tiles_w * r.tiles_h * p.n_img;
+    if (r.m_blocks == 0) return 0;
+    {
+      cuuint64_t dims[4] = {64, (cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.n_img};
+      cuuint64_t strides[3] = {(cuuint64_t)(p.x_sw * 2), (cuuint64_t)(p.x_sh * 2), (cuuint64_t)(p.x_sn * 2)};
+      cuuint32_t box[4] = {64, 16, 16, 1};
+      if (int rc = encode_map(&r.tmap_x, p.x, 4, dims, strides, box)) return rc;
+    }
+    {
+      cuuint64_t dims[4] = {64, (cuuint64_t)p.out_w, (cuuint64_t)p.out_h, (cuuint64_t)p.n_img};
+      cuuint64_t strides[3] = {(cuuint64_t)(p.y_sw * 2), (cuuint64_t)(p.y_sh * 2), (cuuint64_t)(p.y_sn * 2)};
+      cuuint32_t box[4] = {64, 8, 16, 1};
+      if (int rc = encode_map(&r.tmap_dy, dy, 4, dims, strides, box)) return rc;
+    }
+    {
+      cuuint64_t dims[2] = {9 * 64, 64};
+      cuuint64_t strides[1] = {9 * 64 * 4};
+      cuuint32_t obox[2] = {32, 128};
+      if (int rc = encode_map(&r.tmap_dw, dw_scratch, 2, dims, strides, obox, true)) return rc;
+    }
+    long splits = (num_sms() + 2) / 3;   // one wave: 3 tap rows x splits CTAs
+    if (splits > r.m_blocks) splits = r.m_blocks;
+    r.blocks_per_split = ceil_div(r.m_blocks, splits);
+    splits = ceil_div(r.m_blocks, r.blocks_per_split);
+    static bool attr_set = false;
+    if (!attr_set) {
+      RMV_CUDA(cudaFuncSetAttribute(wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowsSmem));
+      attr_set = true;
+    }
+    RMV_CUDA(launch_pdl_tc(wgrad_rows_kernel, dim3((unsigned)(3 * splits)), dim3(kThreads), kRowsSmem, stream, r));
+    return 0;
+  }
   WgArgs a;
   memset(&a, 0, sizeof(a));
   int out_w = p.out_w, out_h = p.out_h, n_img = p.n_img, in_w = p.in_w, in_h = p.in_h;

@@ -32,6 +32,31 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
+class OverlappedAllReduce:
+    """Sum-all-reduce of a flat gradient buffer in the order its slices become final, each slice as
+    an asynchronous collective (NCCL runs it on its own stream, ordered after the work already
+    queued on the caller's stream), so that communication of the early slices overlaps the compute
+    that is still producing the late ones. `finish()` makes the caller's stream wait for all of
+    them (the host does not block on NCCL). With no process group (single process) it is a no-op.
+
+    The Rot-MV step uses two slices: [grad_split:] (lifter/fuser/head gradients, complete before the
+    trunk backward starts) and [:grad_split] (trunk gradients)."""
+
+    def __init__(self, flat: torch.Tensor, group=None):
+        self.flat, self.group, self.works = flat, group, []
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def start(self, begin: int, end: int) -> None:
+        if self.active and end > begin:
+            self.works.append(dist.all_reduce(self.flat[begin:end], op=dist.ReduceOp.SUM,
+                                              group=self.group, async_op=True))
+
+    def finish(self) -> None:
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+
 def max_over_ranks(value: float, device=None, group=None) -> float:
     """Max of a host scalar over the ranks (multi-GPU timings are reported as the slowest rank)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:

@@ -21,12 +21,16 @@ def val(r, name):
 lines = ["# ncu --set full --clock-control none, igemm_kernel launches of one warm configs[1] forward (B=256, V=2, bf16)",
          "# us = gpu__time_duration.sum (cold-cache, serialised); tensor% = sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed;",
          "# dram% = dram__throughput.avg.pct_of_peak_sustained_elapsed; lts% = lts__throughput.avg.pct_of_peak_sustained_elapsed",
-         f"{'id':>3s} {'BLOCK_N,RES,F32':>16s} {'grid':>5s} {'us':>8s} {'rd MB':>8s} {'wr MB':>8s} {'GB/s':>7s} {'tensor%':>8s} {'dram%':>6s} {'lts%':>6s}"]
+         f"{'id':>3s} {'kernel / <N,RES,F32,HALO,STATS>':>16s} {'grid':>5s} {'us':>8s} {'rd MB':>8s} {'wr MB':>8s} {'GB/s':>7s} {'tensor%':>8s} {'dram%':>6s} {'lts%':>6s}"]
 tot_t = tot_b = 0.0
 for r in data:
     name = r[ix["Kernel Name"]]
-    m = re.search(r"igemm_kernel<(\d+), (\w+), (\w+)>", name)
-    cfg = ",".join(m.groups()) if m else name[:16]
+    m = re.search(r"igemm_kernel<([^>]*)>", name)
+    if m:
+        cfg = m.group(1).replace("(int)", "").replace("(bool)", "").replace(" ", "")
+    else:
+        m2 = re.search(r"(\w+_kernel)", name)
+        cfg = (m2.group(1) if m2 else name)[:16]
     t = val(r, "gpu__time_duration.sum")
     rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")
     tp = val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")

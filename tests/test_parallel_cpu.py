@@ -40,12 +40,27 @@ def _worker(rank, world, port, out_dir):
     loss.backward()
     params = [p for p in model.parameters() if p.grad is not None]
     flat = torch.cat([p.grad.flatten() for p in params])
+    # two-slice overlapped all-reduce (the order the training step produces the gradients in): the
+    # tail slice is reduced first, the head is still being written while that collective runs
+    flat2 = flat.clone()
+    split = flat2.numel() // 3
+    ar = P.OverlappedAllReduce(flat2)
+    assert ar.active
+    ar.start(split, flat2.numel())
+    flat2[:split] += 1.0            # "trunk backward" finishing the head slice
+    ar.start(0, split)
+    ar.finish()
+    flat2.mul_(1.0 / world)
+    flat_head_bias = flat.clone(); flat_head_bias[:split] += 1.0
+    P.allreduce_mean_(flat_head_bias)
+    overlap_ok = torch.allclose(flat2, flat_head_bias, rtol=1e-6, atol=1e-7)
     P.allreduce_mean_(flat)
     t = P.max_over_ranks(1.0 + rank)
     bn = next(m for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d))
     bn.running_mean.fill_(float(rank + 1))
     P.broadcast_buffers_(model, src=0)
-    torch.save({"flat": flat, "range": (b, e), "tmax": t, "rm": bn.running_mean.clone()},
+    torch.save({"flat": flat, "range": (b, e), "tmax": t, "rm": bn.running_mean.clone(),
+                "overlap_ok": overlap_ok},
                os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -79,6 +94,7 @@ def test_gloo_two_ranks_gradient_average_equals_global_batch(tmp_path):
     assert r0["range"] == (0, 3) and r1["range"] == (3, 5)
     assert torch.equal(r0["flat"], r1["flat"])          # every rank holds the same averaged gradient
     assert r0["tmax"] == r1["tmax"] == 2.0              # slowest rank wins
+    assert r0["overlap_ok"] and r1["overlap_ok"]        # two-slice overlapped all-reduce == one all-reduce
     assert torch.equal(r0["rm"], r1["rm"]) and float(r1["rm"][0]) == 1.0   # rank 0's buffers
     # single-process gradient on the global batch
     model = O.build_model(num_iter=2, depth=18, seed=0).eval()

@@ -353,6 +353,7 @@ WGRAD_TC_CASES = [
     (4, 56, 64, 64, 3, 1, 1), (4, 56, 64, 256, 1, 1, 0), (3, 28, 128, 128, 3, 1, 1),
     (4, 56, 128, 128, 3, 2, 1), (5, 14, 256, 256, 3, 1, 1), (6, 28, 512, 1024, 1, 2, 0),
     (7, 7, 512, 512, 3, 1, 1), (9, 7, 2048, 512, 1, 1, 0), (2, 14, 1024, 256, 1, 1, 0),
+    (3, 23, 64, 64, 3, 1, 1), (2, 40, 64, 64, 3, 1, 1),   # tap-row kernel, ragged tiles
 ]
 
 
