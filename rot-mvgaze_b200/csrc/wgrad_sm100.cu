@@ -359,7 +359,8 @@ int conv_wgrad_tc(const ConvArgs& p, const void* dy, float* dw_scratch, cudaStre
       cuuint32_t obox[2] = {32, 128};
       if (int rc = encode_map(&r.tmap_dw, dw_scratch, 2, dims, strides, obox, true)) return rc;
     }
-    long splits = (num_sms() + 2) / 3;   // one wave: 3 tap rows x splits CTAs
+    long splits = num_sms() / 3;   // one wave: 3 tap rows x splits CTAs <= SMs (1 CTA per SM)
+    if (splits < 1) splits = 1;
     if (splits > r.m_blocks) splits = r.m_blocks;
     r.blocks_per_split = ceil_div(r.m_blocks, splits);
     splits = ceil_div(r.m_blocks, r.blocks_per_split);

@@ -69,6 +69,9 @@ class TrainEngine:
         self.use_tc_wgrad = True  # bf16: weight gradients on tcgen05 (False -> FFMA kernel)
         # bf16, V == 2: BatchNorm statistics in the conv epilogue (RMV_FUSE_BN_STATS=0: separate pass)
         self.fuse_bn_stats = os.environ.get("RMV_FUSE_BN_STATS", "1") != "0"
+        # data parallel: all-reduce the fusion-stage gradients while the trunk backward runs
+        # (RMV_DP_OVERLAP=0: one all-reduce of the whole buffer after the backward pass)
+        self.dp_overlap = os.environ.get("RMV_DP_OVERLAP", "1") != "0"
         self.num_iter, self.fc_dim, self.nvec = model._num_iter, model._fc_dim, model._num_feat_vec
         self.apply_rot = not model._ignore_rotmat
         self.decoupled = bool(decoupled)
@@ -345,9 +348,10 @@ class TrainEngine:
         before = L.STATS["launches"]
         ar = P.OverlappedAllReduce(self.flat_g, self.pg)
         n = self.flat_g.numel()
+        split = self.grad_split if self.dp_overlap else n
         self.forward_backward(images, rotations, gt,
-                              hook=(lambda: ar.start(self.grad_split, n)) if ar.active else None)
-        ar.start(0, self.grad_split)
+                              hook=(lambda: ar.start(split, n)) if ar.active else None)
+        ar.start(0, split)
         ar.finish()   # the current stream waits for NCCL's stream; the host does not block
         _ck("rmv_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
             self.flat_v.data_ptr(), self.hyper.data_ptr(), self.flat_p.numel(), int(self.decoupled),
@@ -597,9 +601,10 @@ class GraphedTrainStep:
         eng = self.engine
         self.fwd_bwd.replay()
         ar = P.OverlappedAllReduce(eng.flat_g, eng.pg)
-        ar.start(eng.grad_split, eng.flat_g.numel())   # overlaps the trunk-backward graph
+        split = eng.grad_split if eng.dp_overlap else eng.flat_g.numel()
+        ar.start(split, eng.flat_g.numel())   # overlaps the trunk-backward graph
         self.trunk_bwd.replay()
-        ar.start(0, eng.grad_split)
+        ar.start(0, split)
         ar.finish()
         self.adam.replay()
         return eng.loss
