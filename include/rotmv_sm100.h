@@ -99,6 +99,13 @@ int rmv_stem_conv_fwd(const float* x_nchw, const void* w_packed, const float* sc
                       const float* shift, void* y_nhwc, int n_img, int in_h, int in_w, int relu,
                       void* stream);
 
+/* Same, from uint8 HWC images [n,in_h,in_w,3] (what an image decoder delivers): the loader applies
+ * ToTensor + Normalize(mean3, std3) (main.py:38-56; HOST pointers to three floats each) on the
+ * fly, so the host->HBM copy and the HBM read shrink 4x. Needs 3*in_w % 16 == 0. */
+int rmv_stem_conv_fwd_u8(const unsigned char* x_nhwc_u8, const float* mean3, const float* std3,
+                         const void* w_packed, const float* scale, const float* shift, void* y_nhwc,
+                         int n_img, int in_h, int in_w, int relu, void* stream);
+
 /* Stem weight gradient on the tensor cores (training): dw_oihw[64,3,7,7] (fp32, =) from the fp32
  * NCHW images and dz (bf16 NHWC [n,out_h,out_w,64], gradient of the stem conv output); the im2col
  * rows are rebuilt in shared memory exactly as in the forward. scratch: fp32 [192*64] workspace. */

@@ -39,6 +39,11 @@ struct StemArgs {
   int n_img, in_h, in_w, out_h, out_w, tiles_w, tiles_h, total_tiles;
   int relu;
   int vec_ok;  // forward loader may use aligned 16-byte loads (in_w % 4 == 0, 16-byte aligned x)
+  // uint8 input (x_u8 != nullptr): [n, in_h, in_w, 3] bytes (HWC, as image decoders deliver them);
+  // the loader applies ToTensor + Normalize (main.py:38-56): v = byte * u8_scale[c] + u8_offset[c]
+  // with u8_scale = 1 / (255 std), u8_offset = -mean / std. Needs 3*in_w % 16 == 0, aligned base.
+  const unsigned char* x_u8;
+  float u8_scale[3], u8_offset[3];
 };
 
 __device__ __forceinline__ void stem_tma_store(const void* tmap, const void* src, int c0, int c1,
@@ -162,7 +167,76 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stem_kernel(const __grid_const
     // 32*tw+39, one to the left of the patch origin 32*tw-3), whose (row, chunk) -> offset tables
     // do not depend on the tile and live in registers. Needs in_w % 4 == 0 and a 16-byte aligned
     // image base (the 224x224 case); otherwise the element-wise path below is used.
-    if (a.vec_ok) {
+    if (a.x_u8 != nullptr) {
+      // uint8 HWC: one image row holds all three channels of the 38 patch pixels in 114 contiguous
+      // bytes starting at byte 96*tw - 9 of the row; fetched as 8 aligned 16-byte chunks from byte
+      // 96*tw - 16, normalised, converted to bf16 and scattered into the planar patch.
+      constexpr int kChunksRow = 8, kChunks = kPatchH * kChunksRow;  // 168
+      constexpr int kIt = (kChunks + 127) / 128;                     // 2
+      const int row_bytes = 3 * a.in_w;
+      uint4 q0[kIt], q1[kIt];
+      auto issue = [&](int tile, uint4 (&q)[kIt]) {
+        const int tw = tile % a.tiles_w;
+        const int th = (tile / a.tiles_w) % a.tiles_h;
+        const int n = tile / (a.tiles_w * a.tiles_h);
+        const int ih0 = 2 * th * kTH - 3;
+        const unsigned char* img = a.x_u8 + (long long)n * a.in_h * row_bytes;
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          const int k = tid + it * 128;
+          const int r = k / kChunksRow, j = k - r * kChunksRow;
+          const int ih = ih0 + r, b0 = 96 * tw - 16 + 16 * j;   // first byte of the chunk in its row
+          q[it] = (k < kChunks && ih >= 0 && ih < a.in_h && b0 >= 0 && b0 < row_bytes)
+                      ? __ldg(reinterpret_cast<const uint4*>(img + (long long)ih * row_bytes + b0))
+                      : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        }
+      };
+      auto park = [&](int tile, const uint4 (&q)[kIt], __nv_bfloat16* patch) {
+        const int tw = tile % a.tiles_w;
+        const int th = (tile / a.tiles_w) % a.tiles_h;
+        const int ih0 = 2 * th * kTH - 3;
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          const int k = tid + it * 128;
+          if (k >= kChunks) continue;
+          const int r = k / kChunksRow, j = k - r * kChunksRow;
+          const int ih = ih0 + r, b0 = 96 * tw - 16 + 16 * j;
+          const bool in = ih >= 0 && ih < a.in_h && b0 >= 0 && b0 < row_bytes;  // else: conv zero padding
+          const uint32_t w4[4] = {q[it].x, q[it].y, q[it].z, q[it].w};
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            // byte position relative to the first byte of patch column 0 (= byte 96*tw - 9)
+            const int pos = 16 * j - 7 + e;
+            if (pos < 0 || pos >= 3 * kPatchWUsed) continue;
+            const int col = pos / 3, c = pos - 3 * col;
+            const float byte = (float)((w4[e >> 2] >> (8 * (e & 3))) & 0xFFu);
+            const float v = in ? fmaf(byte, a.u8_scale[c], a.u8_offset[c]) : 0.f;
+            patch[(c * kPatchH + r) * kPatchPitch + col] = __float2bfloat16_rn(v);
+          }
+        }
+      };
+      int tile = blockIdx.x;
+      if (tile < a.total_tiles) issue(tile, q0);
+      if (tile + step < a.total_tiles) issue(tile + step, q1);
+      for (int i = 0; tile < a.total_tiles; i += 2) {
+        {
+          const int slot = i % kPatchSlots;
+          mbar_wait(&patch_empty[slot], ((i / kPatchSlots) & 1) ^ 1);
+          park(tile, q0, reinterpret_cast<__nv_bfloat16*>(sPatchBase + slot * kPatchBytes));
+          mbar_arrive(&patch_full[slot]);
+          if (tile + 2 * step < a.total_tiles) issue(tile + 2 * step, q0);
+          tile += step;
+        }
+        if (tile < a.total_tiles) {
+          const int slot = (i + 1) % kPatchSlots;
+          mbar_wait(&patch_empty[slot], (((i + 1) / kPatchSlots) & 1) ^ 1);
+          park(tile, q1, reinterpret_cast<__nv_bfloat16*>(sPatchBase + slot * kPatchBytes));
+          mbar_arrive(&patch_full[slot]);
+          if (tile + 2 * step < a.total_tiles) issue(tile + 2 * step, q1);
+          tile += step;
+        }
+      }
+    } else if (a.vec_ok) {
       constexpr int kChunksRow = 11, kChunks = 3 * kPatchH * kChunksRow;  // 693
       constexpr int kIt = (kChunks + 127) / 128;                          // 6
       int goff[kIt], poff[kIt], rr[kIt], jj[kIt];
@@ -544,10 +618,37 @@ extern "C" int rmv_stem_pack_weights(const float* w_oihw, void* packed, void* st
   return 0;
 }
 
+static int stem_fwd_launch(const float* x_nchw, const unsigned char* x_u8, const float* mean,
+                           const float* stdv, const void* w_packed, const float* scale,
+                           const float* shift, void* y_nhwc, int n_img, int in_h, int in_w,
+                           int relu, void* stream);
+
 extern "C" int rmv_stem_conv_fwd(const float* x_nchw, const void* w_packed, const float* scale,
                                  const float* shift, void* y_nhwc, int n_img, int in_h, int in_w,
                                  int relu, void* stream) {
-  RMV_CHECK_ARG(x_nchw && w_packed && y_nhwc, "stem_conv_fwd: null pointer");
+  RMV_CHECK_ARG(x_nchw != nullptr, "stem_conv_fwd: null pointer");
+  return stem_fwd_launch(x_nchw, nullptr, nullptr, nullptr, w_packed, scale, shift, y_nhwc, n_img,
+                         in_h, in_w, relu, stream);
+}
+
+extern "C" int rmv_stem_conv_fwd_u8(const unsigned char* x_nhwc_u8, const float* mean3,
+                                    const float* std3, const void* w_packed, const float* scale,
+                                    const float* shift, void* y_nhwc, int n_img, int in_h, int in_w,
+                                    int relu, void* stream) {
+  RMV_CHECK_ARG(x_nhwc_u8 && mean3 && std3, "stem_conv_fwd_u8: null pointer");
+  RMV_CHECK_ARG((3 * in_w) % 16 == 0 && (reinterpret_cast<uintptr_t>(x_nhwc_u8) & 15) == 0,
+                "stem_conv_fwd_u8: 3*in_w must be a multiple of 16 bytes and x 16-byte aligned");
+  for (int c = 0; c < 3; ++c)
+    RMV_CHECK_ARG(std3[c] > 0.f, "stem_conv_fwd_u8: std must be positive");
+  return stem_fwd_launch(nullptr, x_nhwc_u8, mean3, std3, w_packed, scale, shift, y_nhwc, n_img,
+                         in_h, in_w, relu, stream);
+}
+
+static int stem_fwd_launch(const float* x_nchw, const unsigned char* x_u8, const float* mean,
+                           const float* stdv, const void* w_packed, const float* scale,
+                           const float* shift, void* y_nhwc, int n_img, int in_h, int in_w,
+                           int relu, void* stream) {
+  RMV_CHECK_ARG((x_nchw || x_u8) && w_packed && y_nhwc, "stem_conv_fwd: null pointer");
   RMV_CHECK_ARG(in_h >= 7 && in_w >= 7, "stem_conv_fwd: input %dx%d too small", in_h, in_w);
   RMV_CHECK_ARG((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(y_nhwc) & 15) == 0,
@@ -558,6 +659,13 @@ extern "C" int rmv_stem_conv_fwd(const float* x_nchw, const void* w_packed, cons
   a.x = x_nchw; a.scale = scale; a.shift = shift;
   a.n_img = n_img; a.in_h = in_h; a.in_w = in_w; a.relu = relu;
   a.vec_ok = (in_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0);
+  a.x_u8 = x_u8;
+  if (x_u8 != nullptr) {
+    for (int c = 0; c < 3; ++c) {
+      a.u8_scale[c] = 1.f / (255.f * stdv[c]);
+      a.u8_offset[c] = -mean[c] / stdv[c];
+    }
+  }
   a.out_h = (in_h + 6 - 7) / 2 + 1;
   a.out_w = (in_w + 6 - 7) / 2 + 1;
   a.tiles_w = ceil_div(a.out_w, kTW);

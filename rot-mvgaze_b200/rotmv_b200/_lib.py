@@ -66,6 +66,7 @@ SIGNATURES = {
     "rmv_conv2d_fwd": (_i, [C.POINTER(ConvArgs), _vp]),
     "rmv_stem_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rmv_stem_pack_weights": (_i, [_vp, _vp, _vp]),
+    "rmv_stem_conv_fwd_u8": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rmv_stem_conv_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rmv_stem_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "rmv_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -165,7 +165,14 @@ class InferenceEngine:
         """imgs [n,3,H,W] fp32 NCHW -> global-average-pooled features into feat0[:, :C], feat1[:, :C]
         (reference `_feat_extractor`, models/rot_mv.py:124-128,196-197)."""
         n = imgs.shape[0]
-        if self.precision == "bf16":
+        if imgs.dtype == torch.uint8:
+            # raw uint8 HWC images: ToTensor + Normalize folded into the stem loader (SURVEY 8f n1)
+            if self.precision != "bf16":
+                raise NotImplementedError("uint8 input runs on the bf16 (tcgen05) engine only")
+            oh, ow = (imgs.shape[1] - 1) // 2 + 1, (imgs.shape[2] - 1) // 2 + 1
+            y = RF.stem_conv_u8(imgs, self.model.input_mean, self.model.input_std, self.stem_w,
+                                self.stem_scale, self.stem_shift, out=self._buf("stem", (n, oh, ow, 64)))
+        elif self.precision == "bf16":
             oh, ow = (imgs.shape[2] - 1) // 2 + 1, (imgs.shape[3] - 1) // 2 + 1
             y = RF.stem_conv(imgs, self.stem_w, self.stem_scale, self.stem_shift,
                              out=self._buf("stem", (n, oh, ow, 64)))
@@ -204,7 +211,11 @@ class InferenceEngine:
         if tuple(rotations.shape) != (b, v, v, 3, 3):
             raise ValueError(f"rotations must be [B,V,V,3,3] = {(b, v, v, 3, 3)}, got {tuple(rotations.shape)}")
         imgs = images.reshape(b * v, *images.shape[2:])
-        if imgs.dtype != torch.float32 or not imgs.is_contiguous():
+        if imgs.dtype == torch.uint8:          # [B*V, H, W, 3] raw bytes
+            if imgs.shape[-1] != 3:
+                raise ValueError("uint8 images must be HWC: [B, V, H, W, 3]")
+            imgs = imgs.contiguous()
+        elif imgs.dtype != torch.float32 or not imgs.is_contiguous():
             imgs = imgs.float().contiguous()
         return imgs, rotations.float().contiguous(), b, v
 
@@ -379,15 +390,19 @@ class GraphedForward:
     """
 
     def __init__(self, model, batch: int, views: int, precision: Optional[str] = None,
-                 size: int = 224, copy_chunks: int = 1, slice_fracs=None):
+                 size: int = 224, copy_chunks: int = 1, slice_fracs=None, input_dtype=torch.float32):
         eng = model.engine(precision)
         self.engine = eng
         dev = eng.device
         self.batch, self.views = batch, views
         m = batch * views
-        self.images = torch.zeros((batch, views, 3, size, size), device=dev, dtype=torch.float32)
+        if input_dtype == torch.uint8:   # raw HWC bytes, normalised inside the stem kernel
+            self.images = torch.zeros((batch, views, size, size, 3), device=dev, dtype=torch.uint8)
+            imgs = self.images.view(m, size, size, 3)
+        else:
+            self.images = torch.zeros((batch, views, 3, size, size), device=dev, dtype=torch.float32)
+            imgs = self.images.view(m, 3, size, size)
         self.rotations = torch.eye(3, device=dev).expand(batch, views, views, 3, 3).contiguous()
-        imgs = self.images.view(m, 3, size, size)
         # batch slices of the host path; uneven by default (a small first slice starts the trunk
         # early, larger later slices keep the kernels efficient): cumulative fractions of the batch
         if slice_fracs is None:

@@ -217,6 +217,26 @@ def stem_conv(x_nchw, w_packed, scale, shift, out=None, relu=True):
     return out
 
 
+def stem_conv_u8(x_nhwc_u8, mean, std, w_packed, scale, shift, out=None, relu=True):
+    """Fused ToTensor + Normalize + conv7x7/s2 + BN(eval) + ReLU from uint8 HWC images
+    [n, H, W, 3] (main.py:38-56 + models/resnet.py:184-188,262-264) -> bf16 NHWC (tcgen05)."""
+    _need_cuda(x_nhwc_u8, w_packed, scale, shift, out)
+    assert x_nhwc_u8.dtype == torch.uint8 and x_nhwc_u8.is_contiguous() and x_nhwc_u8.shape[3] == 3
+    n, h, w, _ = x_nhwc_u8.shape
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    if out is None:
+        out = torch.empty((n, oh, ow, 64), dtype=torch.bfloat16, device=x_nhwc_u8.device)
+    assert out.is_contiguous() and tuple(out.shape) == (n, oh, ow, 64)
+    m3 = (C.c_float * 3)(*[float(v) for v in mean])
+    s3 = (C.c_float * 3)(*[float(v) for v in std])
+    meta = {"desc": f"stem(u8) conv7x7s2+bn+relu [{n},{h},{w},3]", "engine": "tcgen05-stem",
+            "flops": 2.0 * n * oh * ow * 64 * 147, "bytes": float(x_nhwc_u8.numel() + out.numel() * 2)}
+    _call("rmv_stem_conv_fwd_u8", meta, L.load().rmv_stem_conv_fwd_u8, x_nhwc_u8.data_ptr(), m3, s3,
+          w_packed.data_ptr(), L.ptr(scale), L.ptr(shift), out.data_ptr(), n, h, w, int(relu),
+          L.stream_ptr())
+    return out
+
+
 def nchw_to_nhwc(x_nchw, dtype):
     _need_cuda(x_nchw)
     assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()

@@ -144,6 +144,8 @@ class FeatRotationSymm(nn.Module):
         # main.py:239-240: StereoL1Loss(rel_weight=0.01, reference_decay=1.0), IterationLoss(0.5)
         self.loss_cfg = {"rel_weight": 0.01, "reference_decay": 1.0, "iter_decay": 0.5}
         self.fuse_loss = False  # dict API: also return data["loss"] from the fused head+loss kernel
+        # uint8 HWC input (images[B,V,H,W,3]): ToTensor + Normalize constants of main.py:38-39
+        self.input_mean, self.input_std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
         self._engines: Dict[str, E.InferenceEngine] = {}
 
     # -- engine management ---------------------------------------------------------------------
@@ -179,7 +181,7 @@ class FeatRotationSymm(nn.Module):
                 "train-mode forward runs through rotmv_b200.trainer.TrainStep (batch-statistic "
                 "BatchNorm + backward); module.forward is the inference path")
         if images.dim() != 5 or rotations is None or rotations.dim() != 5:
-            raise ValueError("expected images[B,V,3,H,W] and rotations[B,V,V,3,3]")
+            raise ValueError("expected images[B,V,3,H,W] (fp32) or [B,V,H,W,3] (uint8) and rotations[B,V,V,3,3]")
         return self.engine(precision).run(images, rotations, want_all=want_all, gt=gt)
 
     def _forward_dict(self, data: Dict[str, Any], precision) -> Dict[str, Any]:
