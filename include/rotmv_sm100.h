@@ -35,6 +35,11 @@ int rmv_version(void);
 const char* rmv_last_error(void);
 /* 0 when `device` is compute capability 10.x (B200); negative otherwise. */
 int rmv_device_check(int device);
+/* Kernel-variant switches, normally read once from the environment (RMV_<KEY>=digit): "PDL"
+ * (0/1/2 programmatic dependent launch level), "HALO" (halo-patch 3x3 kernel), "CTA2" (cta_group::2
+ * pair kernel: 0 off, 1 where it applies, 2 forced for every c_out % 256 == 0 layer),
+ * "WGRAD_ROWS" (tap-row weight-gradient kernel). This call overrides them at run time. */
+int rmv_set_tuning(const char* key, int value);
 
 /* ----------------------------------------------------------------------------------------------
  * Convolution / linear layer with fused epilogue:

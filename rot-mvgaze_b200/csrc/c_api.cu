@@ -6,6 +6,10 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <string>
+
 namespace rmv {
 
 static thread_local char g_err[1024] = "";
@@ -31,14 +35,23 @@ int num_sms() {
   return cached[dev];
 }
 
-int pdl_level() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("RMV_PDL");
-    cached = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
-  }
-  return cached;
+// Tuning switches: environment variable RMV_<KEY> (one digit), overridable at run time through
+// rmv_set_tuning (tests flip kernel variants inside one process).
+static std::mutex g_tune_mu;
+static std::map<std::string, int> g_tune;
+
+int tuning(const char* key, int dflt, int max_value) {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  auto it = g_tune.find(key);
+  if (it != g_tune.end()) return it->second;
+  const std::string env = std::string("RMV_") + key;
+  const char* e = getenv(env.c_str());
+  const int v = (e != nullptr && e[0] >= '0' && e[0] <= '0' + max_value && e[1] == 0) ? e[0] - '0' : dflt;
+  g_tune[key] = v;
+  return v;
 }
+
+int pdl_level() { return tuning("PDL", 1, 2); }
 
 }  // namespace rmv
 
@@ -93,4 +106,11 @@ extern "C" int rmv_conv2d_dgrad(const rmv_conv_args* args, void* stream) {
   RMV_CHECK_ARG(p.scale == nullptr && p.shift == nullptr && p.relu == 0,
                 "conv2d_dgrad: no scale/shift/relu epilogue");
   return conv_dgrad_tc(p, (cudaStream_t)stream);
+}
+
+extern "C" int rmv_set_tuning(const char* key, int value) {
+  RMV_CHECK_ARG(key != nullptr && value >= 0 && value <= 9, "set_tuning: bad key/value");
+  std::lock_guard<std::mutex> lk(rmv::g_tune_mu);
+  rmv::g_tune[key] = value;
+  return 0;
 }

@@ -522,6 +522,259 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for the tensor-bound layers with c_out % 256 == 0: two CTAs of a
+// cluster (the two SMs of a TPC) own two consecutive 128-row M tiles and ONE 256-wide N tile; each
+// loads its own A tile and HALF of the B tile (128 filter rows), the leader issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 256) which reads both halves of B from both CTAs' shared
+// memory and accumulates 128 x 256 in EACH CTA's TMEM. Per k-block a CTA now moves 32 KB through
+// L2->SM instead of 48 KB -- these layers run at the L2->SM rate with one CTA per tile (ncu:
+// l1tex__m_xbar2l1tex_read_bytes 13-14.6 TB/s), so that is a 1.5x lighter main loop.
+//   producer (warp 0, both CTAs): TMA with .cta_group::2, completion bytes signalled on the
+//       LEADER's full barrier (2 arrivals + 64 KB per stage);
+//   MMA (warp 1, leader): waits the leader's full barrier, commits with multicast to the empty /
+//       tmem_full barriers of both CTAs;
+//   epilogue (warps 2-9, both CTAs): as in igemm_kernel on the CTA's own accumulator; releases it by
+//       arriving on the leader's tmem_empty barrier (2 x 256 arrivals).
+// ---------------------------------------------------------------------------------------------
+constexpr int kPairStages = 5;
+constexpr int kPairHalfN = 128;
+constexpr int kPairBBytes = kPairHalfN * kBlockK * 2;                 // 16 KiB
+constexpr int kPairStageBytes = kABytes + kPairBBytes;               // 32 KiB
+constexpr int kPairSmem = kPairStages * kPairStageBytes + 2 * kChunkBytes + 2 * 256 * 4 + 256 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+igemm_pair_kernel(const __grid_constant__ IgemmArgs args) {
+  constexpr int BLOCK_N = 256;
+  constexpr int kChunkCols = 64, kChunks = BLOCK_N / kChunkCols;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + kPairStages * kABytes;
+  uint8_t* smem_out = smem_b + kPairStages * kPairBBytes;
+  float* s_scale = reinterpret_cast<float*>(smem_out + 2 * kChunkBytes);
+  float* s_shift = s_scale + BLOCK_N;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BLOCK_N);
+  uint64_t* full_bar = bars;                     // [stages] used in the leader
+  uint64_t* empty_bar = bars + kPairStages;      // [stages] both CTAs
+  uint64_t* tmem_full = bars + 2 * kPairStages;  // [2] both CTAs
+  uint64_t* tmem_empty = tmem_full + 2;          // [2] used in the leader
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&args.tmap_b);
+    tma_prefetch_desc(&args.tmap_a[0]);
+    tma_prefetch_desc(&args.tmap_out);
+    for (int s = 0; s < kPairStages; ++s) {
+      mbar_init(&full_bar[s], 2);   // one arrive.expect_tx per CTA of the pair
+      mbar_init(&empty_bar[s], 1);  // the leader's multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kEpiThreads);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / multicast commit
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  griddep_wait();
+  griddep_launch();
+
+  const int m_tiles = args.tiles_w * args.tiles_h * args.tiles_n;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int total_pairs = m_pairs * args.n_tiles;
+  const int n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  const int num_kb = args.num_taps * args.c_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
+        const int n_tile = pt % args.n_tiles;
+        const int m_tile = 2 * (pt / args.n_tiles) + (int)rank;
+        const int tw = m_tile % args.tiles_w;
+        const int th = (m_tile / args.tiles_w) % args.tiles_h;
+        const int tn = m_tile / (args.tiles_w * args.tiles_h);  // >= tiles_n for the odd tail: OOB
+        const int ow0 = tw * args.box_w, oh0 = th * args.box_h, n0 = tn * args.box_n;
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+          const uint32_t lead_full = mapa_u32(&full_bar[stage], 0);
+          mbar_expect_tx_cluster(lead_full, kPairStageBytes);
+          tma_load_4d_pair(smem_a + stage * kABytes, &args.tmap_a[args.tap_map[tap]], lead_full,
+                           cb * kBlockK, ow0 + args.tap_dw[tap], oh0 + args.tap_dh[tap], n0);
+          tma_load_2d_pair(smem_b + stage * kPairBBytes, &args.tmap_b, lead_full,
+                           (args.tap_w[tap] * args.c_blocks + cb) * kBlockK,
+                           n_tile * BLOCK_N + (int)rank * kPairHalfN);
+          if (++cb == args.c_blocks) { cb = 0; ++tap; }
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += n_clusters, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_cluster(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          if (lane == 0) {
+            const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * kABytes), 16, 1024);
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * kPairBBytes), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit_pair(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp != kResWarp) {
+    // ------------------------------- epilogue (warps 2..9) ----------------------
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    const int tid_e = threadIdx.x - 64;
+    const uint32_t sw = (uint32_t)(row & 7);
+    constexpr int kWarpCols = kChunkCols / 2;  // 32
+    int local = 0, cc = 0;
+    for (int pt = cluster_id; pt < total_pairs; pt += n_clusters, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int n_tile = pt % args.n_tiles;
+      const int m_tile = 2 * (pt / args.n_tiles) + (int)rank;
+      const int tw = m_tile % args.tiles_w;
+      const int th = (m_tile / args.tiles_w) % args.tiles_h;
+      const int tn = m_tile / (args.tiles_w * args.tiles_h);
+      const bool tile_ok = m_tile < m_tiles;   // the odd tail tile of the last pair does not exist
+      for (int i = tid_e; i < BLOCK_N; i += kEpiThreads) {
+        const int col = n_tile * BLOCK_N + i;
+        const bool ok = col < args.n_total;
+        s_scale[i] = (ok && args.scale != nullptr) ? __ldg(args.scale + col) : 1.f;
+        s_shift[i] = (ok && args.shift != nullptr) ? __ldg(args.shift + col) : 0.f;
+      }
+      mbar_wait_cluster(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c, ++cc) {
+        uint8_t* obuf = smem_out + (cc & 1) * kChunkBytes;
+        if (tid_e == 0) tma_store_wait_read<1>();
+        epi_bar_sync(1);
+        const int col_in_tile = c * kChunkCols + half * kWarpCols;
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + col_in_tile;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        if (c == kChunks - 1) {
+          tc_fence_before_sync();
+          mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));  // hand the accumulator back (leader)
+        }
+        float f[32];
+#pragma unroll
+        for (int q = 0; q < kWarpCols / 4; ++q) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + col_in_tile + q * 4);
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + col_in_tile + q * 4);
+          f[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]), sc.x, sh.x);
+          f[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]), sc.y, sh.y);
+          f[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]), sc.z, sh.z);
+          f[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]), sc.w, sh.w);
+        }
+        if (args.relu) {
+#pragma unroll
+          for (int j = 0; j < kWarpCols; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+          o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+          o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+          o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+          const uint32_t j = (uint32_t)(half * 4 + q);
+          *reinterpret_cast<uint4*>(obuf + row * 128 + ((j ^ sw) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        epi_bar_sync(2);
+        if (tid_e == 0 && tile_ok) {
+          tma_store_4d(&args.tmap_out, obuf, n_tile * BLOCK_N + c * kChunkCols, tw * args.box_w,
+                       th * args.box_h, tn * args.box_n);
+          tma_store_commit();
+        }
+      }
+    }
+    if (tid_e == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still read this CTA's B half / signal its barriers
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// RMV_CTA2: 1 (default) = use the CTA-pair kernel where it applies; 0 = never; 2 = also force 256-wide N
+// tiles for every c_out % 256 == 0 layer, however small (exercises the pair kernel in the tests)
+int cta2_mode() { return tuning("CTA2", 1, 2); }
+
+int pair_max_clusters_for_log = 0;
+int launch_pair(const IgemmArgs& a, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    RMV_CUDA(cudaFuncSetAttribute(igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kPairSmem));
+    attr_set = true;
+  }
+  // persistent kernel: exactly as many clusters as can be co-resident. That is NOT num_sms / 2:
+  // a CTA pair needs both SMs of one TPC, and floor-swept parts have TPCs with a single SM -- with
+  // 74 clusters on this B200 the leftover clusters ran as a second wave and doubled the time.
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms() / 2 * 2);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = kPairSmem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    RMV_CUDA(cudaOccupancyMaxActiveClusters(&n, igemm_pair_kernel, &cfg));
+    RMV_CHECK_ARG(n >= 1, "cta_group::2 kernel: no co-resident cluster possible");
+    max_clusters = n;
+  }
+  const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
+  const int pairs = ((m_tiles + 1) / 2) * a.n_tiles;
+  int clusters = max_clusters < pairs ? max_clusters : pairs;
+  igemm_pair_kernel<<<2 * clusters, kNumThreads, kPairSmem, stream>>>(a);
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
@@ -597,14 +850,7 @@ int launch(const IgemmArgs& a, int total_tiles, cudaStream_t stream) {
 // absolute shared-memory address (the same function TMA wrote the patch with), so a start address
 // that is a multiple of 128 B but not of 1024 B needs no base offset. 2 = set the base offset to
 // (addr >> 7) & 7 anyway (diagnostic: gives wrong results, kept to document the finding).
-int halo_mode() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("RMV_HALO");
-    cached = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
-  }
-  return cached;
-}
+int halo_mode() { return tuning("HALO", 1, 2); }
 
 template <int BLOCK_N>
 int dispatch(const IgemmArgs& a, int total, bool has_res, bool out_f32, cudaStream_t stream) {
@@ -726,15 +972,19 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
 
   const long m_tiles = (long)a.tiles_w * a.tiles_h * a.tiles_n;
   const int block_n = (p.block_n > 0) ? p.block_n
+                      : (cta2_mode() == 2 && p.c_out % 256 == 0) ? 256   // test mode: force pairs
                       : (p.c_out <= 64) ? 64
                       : (p.c_out % 256 == 0 && m_tiles * (p.c_out / 256) >= 2L * num_sms()) ? 256
                       : 128;
   RMV_CHECK_ARG(block_n == 64 || block_n == 128 || block_n == 256, "bad block_n %d", block_n);
+  // CTA pairs (cta_group::2): 256-wide N tiles, no residual / fp32 / statistics / halo variant
+  const bool pair = cta2_mode() >= 1 && block_n == 256 && p.block_n == 0 && !halo && !out_f32 &&
+                    p.residual == nullptr && p.stat_acc == nullptr && p.c_out % 256 == 0 && m_tiles >= 2;
   {
     const long long k_total = (long long)(taps ? taps->w_taps : a.num_taps) * p.c_in;
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)p.c_out};
     cuuint64_t strides[1] = {(cuuint64_t)(k_total * 2)};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(pair ? kPairHalfN : block_n)};
     int rc = encode_map(&a.tmap_b, p.w, 2, dims, strides, box);
     if (rc) return rc;
   }
@@ -762,6 +1012,7 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
   a.relu = p.relu;
   const int total = (int)(m_tiles * a.n_tiles);
   if (total == 0) return 0;
+  if (pair) return launch_pair(a, stream);
   if (p.stat_acc != nullptr) {
     RMV_CHECK_ARG(!out_f32 && p.residual == nullptr && p.stat_views == 2,
                   "tcgen05 conv: fused BatchNorm statistics need bf16 output, no residual, 2 views");

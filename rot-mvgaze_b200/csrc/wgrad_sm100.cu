@@ -296,14 +296,7 @@ wgrad_rows_kernel(const __grid_constant__ WgRowsArgs a) {
   if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem, 256); }
 }
 
-int wgrad_rows_enabled() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("RMV_WGRAD_ROWS");
-    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return cached;
-}
+int wgrad_rows_enabled() { return tuning("WGRAD_ROWS", 1, 1); }
 
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 

@@ -60,6 +60,7 @@ class PermuteJob(C.Structure):
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     "rmv_version": (_i, []),
+    "rmv_set_tuning": (_i, [C.c_char_p, _i]),
     "rmv_last_error": (C.c_char_p, []),
     "rmv_device_check": (_i, [_i]),
     "rmv_conv2d_dgrad": (_i, [C.POINTER(ConvArgs), _vp]),

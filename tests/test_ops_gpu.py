@@ -215,3 +215,43 @@ def test_conv3x3_halo_kernel(n, h, w):
     # the generic tap-by-tap kernel (block_n given explicitly) must agree to bf16 rounding
     y2 = RF.conv2d(x, wt, stride=1, pad=1, scale=scale, shift=shift, relu=True, engine=L.ENGINE_TC, block_n=64)
     assert (y.float() - y2.float()).abs().max().item() <= 4e-2 * ref.abs().max().item() / 8
+
+
+PAIR_CASES = [
+    # n, h, w, ci, co, k, stride, pad
+    (6, 14, 14, 256, 256, 3, 1, 1),     # boxed 2x2x32 tiles, odd number of M tiles (10 -> tail pair)
+    (7, 14, 14, 1024, 256, 1, 1, 0),    # flattened pointwise, K = 1024
+    (5, 7, 7, 512, 2048, 1, 1, 0),      # 8 N tiles
+    (4, 28, 28, 256, 256, 3, 2, 1),     # stride 2 (parity planes)
+    (3, 28, 28, 512, 1024, 1, 2, 0),    # stride-2 pointwise (downsample)
+    (1, 16, 16, 64, 256, 1, 1, 0),      # exactly one pair
+    (9, 7, 7, 512, 512, 3, 1, 1),       # 1x1x128 tiles
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_cta_pair_kernel(case):
+    """cta_group::2 pair kernel (RMV_CTA2 / rmv_set_tuning("CTA2", 2) forces it for every
+    c_out % 256 == 0 layer): same results as torch on the bf16-rounded operands, scale/shift/ReLU
+    epilogue included, and bit-identical to the single-CTA kernel's output."""
+    from rotmv_b200 import functional as RF, _lib as L
+
+    n, h, w, ci, co, k, stride, pad = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case) + 11)
+    x = torch.randn((n, h, w, ci), device="cuda", generator=g).bfloat16()
+    wt = (torch.randn((co, k, k, ci), device="cuda", generator=g) / math.sqrt(k * k * ci)).bfloat16()
+    scale = torch.rand((co,), device="cuda", generator=g) + 0.5
+    shift = torch.randn((co,), device="cuda", generator=g)
+    lib = L.load()
+    try:
+        L.check(lib.rmv_set_tuning(b"CTA2", 0), "set_tuning")
+        y1 = RF.conv2d(x, wt, stride=stride, pad=pad, scale=scale, shift=shift, relu=True, engine=L.ENGINE_TC)
+        L.check(lib.rmv_set_tuning(b"CTA2", 2), "set_tuning")
+        y2 = RF.conv2d(x, wt, stride=stride, pad=pad, scale=scale, shift=shift, relu=True, engine=L.ENGINE_TC)
+        torch.cuda.synchronize()
+    finally:
+        L.check(lib.rmv_set_tuning(b"CTA2", 1), "set_tuning")   # back to the default
+    ref = _ref_conv(x, wt, stride, pad, scale, shift, None, True)
+    err = (y2.float() - ref).abs().max().item()
+    assert err <= 1.2e-2 * ref.abs().max().item(), (case, err)
+    assert (y1.float() - y2.float()).abs().max().item() <= 8e-3 * ref.abs().max().item()
