@@ -334,6 +334,9 @@ def run_ours(args):
         recs, RF.PROFILE = RF.PROFILE, None
         tc = [(r[1], r[2].elapsed_time(r[3])) for r in recs if r[0] == "tcgen05"]
         pk = peaks()
+        # per-launch roofline bound (tensor or HBM, whichever is slower) summed over the igemm launches
+        bound_ms = sum(max(r[1] / (pk["tflops"] * 1e12), r[5].get("bytes", 0.0) / (pk["hbm_gbs"] * 1e9)) * 1e3
+                       for r in recs if r[0] == "tcgen05")
         if tc:
             flops = sum(f for f, _ in tc)
             ms = sum(t for _, t in tc)
@@ -348,6 +351,9 @@ def run_ours(args):
                 "frac": achieved / pk["tflops"], "traffic": traffic, "peak_source": pk["src"],
                 "launches_per_step": len(tc), "flops_per_launch": flops / len(tc),
                 "avg_launch_ms": ms / len(tc), "kernel_share_of_step": ms / ms_step,
+                "mixed_bound_frac": bound_ms / ms,   # sum over launches of max(flop, HBM) bound / measured
+                "note": "30 of the 53 convs are HBM-bound at bf16 (SURVEY 8d): frac is against the "
+                        "tensor peak alone, mixed_bound_frac against each launch's own roofline",
                 "whole_step_frac": (B * V * FLOPS_PER_VIEW / (ms_step * 1e-3) / 1e12) / pk["tflops"]}
         # ---- CPU baseline: the oracle on this box's host cores, bounded sample -----------------
         if n_gpus == 1 and not args.no_cpu:
