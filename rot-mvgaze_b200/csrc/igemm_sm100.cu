@@ -538,15 +538,24 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
 //   epilogue (warps 2-9, both CTAs): as in igemm_kernel on the CTA's own accumulator; releases it by
 //       arriving on the leader's tmem_empty barrier (2 x 256 arrivals).
 // ---------------------------------------------------------------------------------------------
-constexpr int kPairStages = 5;
-constexpr int kPairHalfN = 128;
-constexpr int kPairBBytes = kPairHalfN * kBlockK * 2;                 // 16 KiB
-constexpr int kPairStageBytes = kABytes + kPairBBytes;               // 32 KiB
-constexpr int kPairSmem = kPairStages * kPairStageBytes + 2 * kChunkBytes + 2 * 256 * 4 + 256 + 1024;
+template <int BLOCK_N>
+struct PairCfg {
+  static constexpr int kHalfN = BLOCK_N / 2;                     // filter rows each CTA loads
+  static constexpr int kBBytes = kHalfN * kBlockK * 2;           // 16 / 8 KiB
+  static constexpr int kStageBytes = kABytes + kBBytes;          // 32 / 24 KiB
+  static constexpr int kStages = BLOCK_N == 256 ? 5 : 7;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kSmem = kStages * kStageBytes + 2 * kChunkBytes + 2 * BLOCK_N * 4 + 256 + 1024;
+};
 
+template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 igemm_pair_kernel(const __grid_constant__ IgemmArgs args) {
-  constexpr int BLOCK_N = 256;
+  using PC = PairCfg<BLOCK_N>;
+  constexpr int kPairStages = PC::kStages;
+  constexpr int kPairHalfN = PC::kHalfN;
+  constexpr int kPairBBytes = PC::kBBytes;
+  constexpr int kPairStageBytes = PC::kStageBytes;
   constexpr int kChunkCols = 64, kChunks = BLOCK_N / kChunkCols;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -579,7 +588,7 @@ igemm_pair_kernel(const __grid_constant__ IgemmArgs args) {
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc_pair(tmem_ptr, 512);
+    tmem_alloc_pair(tmem_ptr, PC::kTmemCols);
     tmem_relinquish_pair();
   }
   tc_fence_before_sync();
@@ -733,7 +742,7 @@ igemm_pair_kernel(const __grid_constant__ IgemmArgs args) {
   cluster_sync_all();   // the peer may still read this CTA's B half / signal its barriers
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc_pair(tmem_base, 512);
+    tmem_dealloc_pair(tmem_base, PC::kTmemCols);
   }
 }
 
@@ -741,12 +750,13 @@ igemm_pair_kernel(const __grid_constant__ IgemmArgs args) {
 // tiles for every c_out % 256 == 0 layer, however small (exercises the pair kernel in the tests)
 int cta2_mode() { return tuning("CTA2", 1, 2); }
 
-int pair_max_clusters_for_log = 0;
+template <int BLOCK_N>
 int launch_pair(const IgemmArgs& a, cudaStream_t stream) {
+  constexpr int kPairSmem = PairCfg<BLOCK_N>::kSmem;
   static bool attr_set = false;
   if (!attr_set) {
-    RMV_CUDA(cudaFuncSetAttribute(igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kPairSmem));
+    RMV_CUDA(cudaFuncSetAttribute(igemm_pair_kernel<BLOCK_N>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
     attr_set = true;
   }
   // persistent kernel: exactly as many clusters as can be co-resident. That is NOT num_sms / 2:
@@ -763,14 +773,14 @@ int launch_pair(const IgemmArgs& a, cudaStream_t stream) {
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    RMV_CUDA(cudaOccupancyMaxActiveClusters(&n, igemm_pair_kernel, &cfg));
+    RMV_CUDA(cudaOccupancyMaxActiveClusters(&n, igemm_pair_kernel<BLOCK_N>, &cfg));
     RMV_CHECK_ARG(n >= 1, "cta_group::2 kernel: no co-resident cluster possible");
     max_clusters = n;
   }
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
   const int pairs = ((m_tiles + 1) / 2) * a.n_tiles;
   int clusters = max_clusters < pairs ? max_clusters : pairs;
-  igemm_pair_kernel<<<2 * clusters, kNumThreads, kPairSmem, stream>>>(a);
+  igemm_pair_kernel<BLOCK_N><<<2 * clusters, kNumThreads, kPairSmem, stream>>>(a);
   RMV_LAUNCH_CHECK();
   return 0;
 }
@@ -978,13 +988,17 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
                       : 128;
   RMV_CHECK_ARG(block_n == 64 || block_n == 128 || block_n == 256, "bad block_n %d", block_n);
   // CTA pairs (cta_group::2): 256-wide N tiles, no residual / fp32 / statistics / halo variant
-  const bool pair = cta2_mode() >= 1 && block_n == 256 && p.block_n == 0 && !halo && !out_f32 &&
-                    p.residual == nullptr && p.stat_acc == nullptr && p.c_out % 256 == 0 && m_tiles >= 2;
+  // measured: the 128-wide pair variant is 5-10 % SLOWER than the single-CTA kernel (N = 128 MMAs
+  // are too short to amortise the pair hand-shakes) -- it only runs in the forced test mode
+  const bool pair = cta2_mode() >= 1 && (block_n == 256 || (block_n == 128 && cta2_mode() == 2)) &&
+                    p.block_n == 0 && !halo &&
+                    !out_f32 && p.residual == nullptr && p.stat_acc == nullptr &&
+                    p.c_out % block_n == 0 && m_tiles >= 2;
   {
     const long long k_total = (long long)(taps ? taps->w_taps : a.num_taps) * p.c_in;
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)p.c_out};
     cuuint64_t strides[1] = {(cuuint64_t)(k_total * 2)};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(pair ? kPairHalfN : block_n)};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(pair ? block_n / 2 : block_n)};
     int rc = encode_map(&a.tmap_b, p.w, 2, dims, strides, box);
     if (rc) return rc;
   }
@@ -1012,7 +1026,7 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
   a.relu = p.relu;
   const int total = (int)(m_tiles * a.n_tiles);
   if (total == 0) return 0;
-  if (pair) return launch_pair(a, stream);
+  if (pair) return block_n == 256 ? launch_pair<256>(a, stream) : launch_pair<128>(a, stream);
   if (p.stat_acc != nullptr) {
     RMV_CHECK_ARG(!out_f32 && p.residual == nullptr && p.stat_views == 2,
                   "tcgen05 conv: fused BatchNorm statistics need bf16 output, no residual, 2 views");

@@ -226,6 +226,10 @@ PAIR_CASES = [
     (3, 28, 28, 512, 1024, 1, 2, 0),    # stride-2 pointwise (downsample)
     (1, 16, 16, 64, 256, 1, 1, 0),      # exactly one pair
     (9, 7, 7, 512, 512, 3, 1, 1),       # 1x1x128 tiles
+    (6, 28, 28, 128, 128, 3, 1, 1),     # 128-wide pair tiles (each CTA loads 64 filter rows)
+    (3, 56, 56, 128, 128, 3, 2, 1),     # 128-wide, stride 2
+    (5, 14, 14, 512, 384, 1, 1, 0),     # 3 N tiles of 128
+    (1, 1, 512, 3584, 1536, 1, 1, 0),   # the fuser Linear shape (M = 512 rows)
 ]
 
 
