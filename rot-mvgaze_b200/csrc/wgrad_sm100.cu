@@ -429,7 +429,10 @@ int conv_wgrad_tc(const ConvArgs& p, const void* dy, float* dw_scratch, cudaStre
   a.k_tiles = ceil_div(p.c_out, 128);
   a.c_tiles = p.c_in / n_tile;
   const long tiles = (long)a.k_tiles * a.c_tiles * a.num_taps;
-  long splits = (2L * num_sms() + tiles - 1) / tiles;
+  // pixel splits: one wave of one-CTA-per-SM blocks (WGRAD_WAVES = 1, default; measured 3.8 -> 3.3 ms
+  // per step against two waves: half the split-K reduce traffic, no second-wave ramp)
+  const int waves = tuning("WGRAD_WAVES", 1, 4);
+  long splits = waves == 1 ? (num_sms() / tiles) : ((long)waves * num_sms() + tiles - 1) / tiles;
   if (splits > a.m_blocks) splits = a.m_blocks;
   if (splits < 1) splits = 1;
   a.blocks_per_split = ceil_div(a.m_blocks, splits);
