@@ -68,6 +68,10 @@ struct IgemmArgs {
 // nine taps are nine UMMA descriptors into that patch (start shifted by (r*16+s) pixels = rows of
 // 128 B, stride 2048 B between the 8-row groups), instead of nine separate TMA boxes: 6x less
 // L2->SM traffic for A. The 72 KiB of filters stay resident in shared memory for the whole kernel.
+#ifndef RMV_RES256_STAGES
+#define RMV_RES256_STAGES 2
+#define RMV_RES256_SLOTS 4
+#endif
 constexpr int kHaloW = 16, kHaloH = 18;
 constexpr int kHaloABytes = kHaloW * kHaloH * 128;  // 36864
 constexpr int kHaloTaps = 9;
@@ -83,9 +87,9 @@ struct Cfg {
   // Layers with a residual (the expanding 1x1 convs) are HBM-bound with 1-8 k-blocks per tile: they
   // trade A/B stages for a deeper residual ring (4 x 16 KiB) so the residual loads run well ahead.
   static constexpr int kStages = HALO ? kHaloStages
-                                 : HAS_RES ? (BLOCK_N == 256 ? 2 : (BLOCK_N == 128 ? 3 : 4))
+                                 : HAS_RES ? (BLOCK_N == 256 ? RMV_RES256_STAGES : (BLOCK_N == 128 ? 3 : 4))
                                            : (BLOCK_N == 256 ? 3 : (STATS && BLOCK_N == 128 ? 4 : 6));
-  static constexpr int kResSlots = 4;
+  static constexpr int kResSlots = (HAS_RES && BLOCK_N == 256) ? RMV_RES256_SLOTS : 4;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
   static constexpr int kOutBytes = 2 * kChunkBytes;
   static constexpr int kResBytes = HAS_RES ? kResSlots * kChunkBytes : 0;
