@@ -91,3 +91,91 @@ def load_checkpoint(path: str, model, engine=None, strict: bool = True) -> None:
         engine.flat_m.copy_(opt["exp_avg"])
         engine.flat_v.copy_(opt["exp_avg_sq"])
         engine.hyper.copy_(opt["hyper"])
+
+
+def _stack_views(batch: Dict[str, torch.Tensor]):
+    """Accepts the reference loader's two-view dict (trainer.py:99-114: img_0/1, head_pose_0/1,
+    gt_gaze, gt_gaze_1) or the V-view form (images [B,V,3,H,W], head_pose [B,V,2], gt_gaze [B,V,2])."""
+    if "images" in batch:
+        return batch["images"], batch["head_pose"], batch["gt_gaze"]
+    images = torch.stack([batch["img_0"], batch["img_1"]], dim=1)
+    pose = torch.stack([batch["head_pose_0"], batch["head_pose_1"]], dim=1)
+    gt = torch.stack([batch["gt_gaze"], batch["gt_gaze_1"]], dim=1)
+    return images, pose, gt
+
+
+class Trainer:
+    """The step / epoch loop of the reference `Trainer` (trainer.py:54-62,84-96,116-147,164-199) on
+    the GPU engine: `optim.Adam(lr, weight_decay=1e-6)` with `CyclicLR(base 1e-6, max 1e-3,
+    triangular2)` stepped once per EPOCH (quirk Q2), CUDA-graph-captured steps fed from pinned host
+    batches with two steps in flight, evaluation with the on-device metric, checkpoints in the
+    reference's format. TensorBoard / image dumps / config files (trainer.py:66-82,130-139) are
+    outside the hot path and not reproduced. One instance per process (= per GPU); under
+    `torch.distributed` the gradients are all-reduced by the engine."""
+
+    def __init__(self, model, steps_per_epoch: int, batch: int, views: int = 2, *,
+                 precision: str = "bf16", base_lr: float = 1e-6, max_lr: float = 1e-3,
+                 weight_decay: float = 1e-6, decoupled: bool = False, process_group=None):
+        from .train import GraphedTrainStep, TrainEngine
+
+        self.model = model
+        self.step_size_up = int(steps_per_epoch // 2)            # trainer.py:56-58
+        self.step_size_down = steps_per_epoch - self.step_size_up
+        self.base_lr, self.max_lr = base_lr, max_lr
+        self.sched_steps = 0                                     # scheduler.step() calls so far
+        model.train()
+        self.engine = TrainEngine(model, precision=precision, lr=self._lr(), weight_decay=weight_decay,
+                                  decoupled=decoupled, process_group=process_group)
+        self.graph = GraphedTrainStep(self.engine, batch, views)
+        self.precision = precision
+        self.train_iter = 0
+
+    def _lr(self) -> float:
+        return cyclic_lr(self.sched_steps, max(self.step_size_up, 1), max(self.step_size_down, 1),
+                         self.base_lr, self.max_lr)
+
+    def train_one_epoch(self, batches: Iterable[Dict[str, torch.Tensor]]) -> float:
+        """trainer.py:116-147. Returns the mean training loss of the epoch (read back once)."""
+        self.model.train()
+        losses, prev = [], None
+        for batch in batches:
+            images, pose, gt = _stack_views(batch)
+            ticket = self.graph.submit(_pinned(images.float()), _pinned(pose.float()), _pinned(gt.float()))
+            if prev is not None:
+                losses.append(float(self.graph.result(prev)))
+            prev = ticket
+            self.train_iter += 1
+        if prev is not None:
+            losses.append(float(self.graph.result(prev)))
+        self.sched_steps += 1                                    # scheduler.step(), once per epoch (:147)
+        self.engine.set_lr(self._lr())
+        return sum(losses) / max(len(losses), 1)
+
+    def test(self, batches: Iterable[Dict[str, torch.Tensor]]) -> float:
+        """trainer.py:164-199: mean angular error (degrees) of view 0 over the loader."""
+        def adapt(b):
+            images, pose, gt = _stack_views(b)
+            return {"images": images, "head_pose": pose, "gt_gaze": gt[:, 0]}
+        err = Evaluator(self.model, precision=self.precision).run(adapt(b) for b in batches)
+        return err
+
+    def fit(self, train_batches, test_batches, epochs: int = 15, save_epoch: int = 0,
+            ckpt_dir: Optional[str] = None):
+        """trainer.py:84-96. `train_batches` / `test_batches` are callables returning a fresh
+        iterable per epoch. Returns [(epoch, train_loss, test_error)]."""
+        import os
+
+        history = [(-1, float("nan"), self.test(test_batches()))]
+        for epoch in range(epochs):
+            loss = self.train_one_epoch(train_batches())
+            error = self.test(test_batches())
+            history.append((epoch, loss, error))
+            if save_epoch and ckpt_dir and (epoch + 1) % save_epoch == 0:
+                name = "epoch_" + str(epoch + 1).zfill(2) + "_error=" + str(round(error, 2)) + ".pth.tar"
+                save_checkpoint(os.path.join(ckpt_dir, name), self.model, self.engine)
+        return history
+
+
+def _pinned(t: torch.Tensor) -> torch.Tensor:
+    t = t.contiguous()
+    return t if (t.is_cuda or t.is_pinned()) else t.pin_memory()

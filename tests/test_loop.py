@@ -51,3 +51,40 @@ def test_evaluator_matches_reference_metric(tmp_path):
     assert abs(Evaluator(other).run(batches) - err) <= 1e-6
     ora2 = O.build_model(num_iter=2, depth=18, seed=123)
     ora2.load_state_dict(sd, strict=True)   # and the reference-side module loads our file
+
+
+@pytest.mark.gpu
+def test_trainer_loop_schedule_eval_checkpoint(tmp_path):
+    """loop.Trainer: the reference's epoch loop (trainer.py:84-96,116-147): CyclicLR stepped once per
+    epoch, graph-captured steps from host batches in the reference loader's dict format, evaluation
+    and reference-format checkpoints."""
+    import glob
+    from rotmv_b200.loop import Trainer, cyclic_lr, load_checkpoint
+    from rotmv_b200.module import FeatRotationSymm
+
+    torch.manual_seed(0)
+    model = FeatRotationSymm(50, 2).cuda()
+    B, steps = 4, 3
+    g = torch.Generator().manual_seed(1)
+
+    def batches():
+        for _ in range(steps):
+            yield {"img_0": torch.randn((B, 3, 224, 224), generator=g), "img_1": torch.randn((B, 3, 224, 224), generator=g),
+                   "head_pose_0": torch.rand((B, 2), generator=g) - 0.5, "head_pose_1": torch.rand((B, 2), generator=g) - 0.5,
+                   "gt_gaze": torch.rand((B, 2), generator=g) - 0.5, "gt_gaze_1": torch.rand((B, 2), generator=g) - 0.5}
+
+    tr = Trainer(model, steps_per_epoch=steps, batch=B, views=2)
+    assert abs(float(tr.engine.hyper[0]) - 1e-6) < 1e-12               # CyclicLR step 0 = base_lr
+    p_before = tr.engine.flat_p.clone()
+    hist = tr.fit(batches, batches, epochs=2, save_epoch=2, ckpt_dir=str(tmp_path))
+    assert len(hist) == 3 and all(np.isfinite(h[2]) for h in hist) and all(np.isfinite(h[1]) for h in hist[1:])
+    assert tr.train_iter == 2 * steps and tr.sched_steps == 2
+    want_lr = cyclic_lr(2, max(steps // 2, 1), steps - steps // 2)
+    assert abs(float(tr.engine.hyper[0]) - want_lr) <= 1e-12            # scheduler stepped once per EPOCH
+    assert not torch.equal(tr.engine.flat_p, p_before)                  # the steps moved the weights
+    files = glob.glob(os.path.join(tmp_path, "epoch_02_error=*.pth.tar"))
+    assert len(files) == 1
+    other = FeatRotationSymm(50, 2).cuda()
+    load_checkpoint(files[0], other)
+    for (k, a), (_, b) in zip(model.state_dict().items(), other.state_dict().items()):
+        assert torch.equal(a.cpu(), b.cpu()), k
