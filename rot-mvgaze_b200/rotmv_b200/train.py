@@ -60,8 +60,9 @@ class TrainEngine:
         self.model, self.precision, self.dt = model, precision, _DT[precision]
         self.dtc = L.dtype_code(self.dt)
         trunk = model._feat_extractor[0]
-        if trunk.kind != "bottleneck":
-            raise NotImplementedError("TrainEngine covers backbone_depth=50 (the main.py config)")
+        if getattr(model, "_encode_rotmat", False) or getattr(model, "_share_feature", False):
+            raise NotImplementedError("TrainEngine covers the fuser of main.py (ImageFeatFuser); the "
+                                      "encode_rotmat / share_feature variants are inference-only")
         self.device = trunk.conv1.weight.device
         if self.device.type != "cuda":
             raise L.RotmvError("TrainEngine needs the model on a CUDA device; there is no CPU path")
@@ -111,8 +112,11 @@ class TrainEngine:
         self.stem_conv = trunk.conv1
         self.blocks = []
         for blk in trunk.blocks():
-            e = {"convs": [blk.conv1, blk.conv2, blk.conv3],
-                 "bns": [_BN(self, b, g[id(b.weight)], g[id(b.bias)]) for b in (blk.bn1, blk.bn2, blk.bn3)]}
+            # Bottleneck (models/resnet.py:99-148): 1x1, 3x3(stride), 1x1; BasicBlock (:50-96): 3x3(stride), 3x3
+            convs = [blk.conv1, blk.conv2, blk.conv3] if trunk.kind == "bottleneck" else [blk.conv1, blk.conv2]
+            bns = [blk.bn1, blk.bn2, blk.bn3] if trunk.kind == "bottleneck" else [blk.bn1, blk.bn2]
+            e = {"convs": convs,
+                 "bns": [_BN(self, b, g[id(b.weight)], g[id(b.bias)]) for b in bns]}
             if blk.downsample is not None:
                 e["ds_conv"] = blk.downsample[0]
                 d = blk.downsample[1]
@@ -402,19 +406,20 @@ class TrainEngine:
         pool_out = x
         saved = []
         for bi, e in enumerate(self.blocks):
-            c1, c2, c3 = e["convs"]
-            b1, b2, b3 = e["bns"]
+            convs, bns = e["convs"], e["bns"]
             x_in = x
             # conv -> (statistics in the epilogue) -> finalize -> apply, strictly in this order: the
             # fp64 accumulator `self.acc` is shared and reset by every finalize
-            z1, sd = self._conv_stats(x_in, self._w_fwd(c1, (bi, 1)),
-                                      out=self._buf(("z1", bi), (*x_in.shape[:3], c1.out_channels)))
-            y1 = self._bn_fwd(b1, z1, None, True, ("y1", bi), stats_done=sd)
-            s2 = c2.stride[0]
-            oh = (y1.shape[1] + 2 - 3) // s2 + 1
-            z2, sd = self._conv_stats(y1, self._w_fwd(c2, (bi, 2)), stride=s2, pad=1,
-                                      out=self._buf(("z2", bi), (m, oh, oh, c2.out_channels)))
-            y2 = self._bn_fwd(b2, z2, None, True, ("y2", bi), stats_done=sd)
+            t, zs, ys = x_in, [], []
+            for si in range(len(convs) - 1):
+                cv = convs[si]
+                k, st, pd = cv.kernel_size[0], cv.stride[0], cv.padding[0]
+                oh = (t.shape[1] + 2 * pd - k) // st + 1
+                z, sd = self._conv_stats(t, self._w_fwd(cv, (bi, si + 1)), stride=st, pad=pd,
+                                         out=self._buf((f"z{si + 1}", bi), (m, oh, oh, cv.out_channels)))
+                t = self._bn_fwd(bns[si], z, None, True, (f"y{si + 1}", bi), stats_done=sd)
+                zs.append(z); ys.append(t)
+            oh = t.shape[1]
             zd = None
             if "ds_conv" in e:
                 dc = e["ds_conv"]
@@ -423,10 +428,13 @@ class TrainEngine:
                 skip = self._bn_fwd(e["ds_bn"], zd, None, False, ("skip", bi), stats_done=sd)
             else:
                 skip = x_in
-            z3, sd = self._conv_stats(y2, self._w_fwd(c3, (bi, 3)),
-                                      out=self._buf(("z3", bi), (m, oh, oh, c3.out_channels)))
-            x = self._bn_fwd(b3, z3, skip, True, ("out", bi), stats_done=sd)
-            saved.append((x_in, z1, y1, z2, y2, z3, zd, x))
+            cv = convs[-1]
+            z, sd = self._conv_stats(t, self._w_fwd(cv, (bi, len(convs))), stride=cv.stride[0],
+                                     pad=cv.padding[0],
+                                     out=self._buf((f"z{len(convs)}", bi), (m, oh, oh, cv.out_channels)))
+            zs.append(z)
+            x = self._bn_fwd(bns[-1], z, skip, True, ("out", bi), stats_done=sd)
+            saved.append((x_in, zs, ys, zd, x))
         wide = self.fc_dim + 3 * self.nvec
         fd = self.fc_dim
         xs = [self._buf(("X", i), (m, wide)) for i in range(self.num_iter)]
@@ -488,31 +496,34 @@ class TrainEngine:
         if hook is not None:
             hook()
         # trunk
-        last = saved[-1][7]
+        last = saved[-1][4]
         d_out = self._buf(("dx", "avg"), last.shape)
         _ck("rmv_avgpool_bwd", dimg.data_ptr(), dimg.stride(0), d_out.data_ptr(), m,
             last.shape[1] * last.shape[2], last.shape[3], dtc)
         for bi in reversed(range(len(self.blocks))):
             e = self.blocks[bi]
-            c1, c2, c3 = e["convs"]
-            b1, b2, b3 = e["bns"]
-            x_in, z1, y1, z2, y2, z3, zd, out = saved[bi]
-            dz3, dyr = self._bn_bwd(b3, z3, d_out, out, (bi, 3), want_dyr=True)
-            self._wgrad(y2, dz3, c3, 1, 1, 1, 0)
-            dy2 = self._dgrad(dz3, c3, (bi, 3), y2.shape)
-            dz2, _ = self._bn_bwd(b2, z2, dy2, y2, (bi, 2))
-            self._wgrad(y1, dz2, c2, 3, 3, c2.stride[0], 1)
-            dy1 = self._dgrad(dz2, c2, (bi, 2), y1.shape)
-            dz1, _ = self._bn_bwd(b1, z1, dy1, y1, (bi, 1))
-            self._wgrad(x_in, dz1, c1, 1, 1, 1, 0)
-            if zd is not None:
-                dc = e["ds_conv"]
-                dzd, _ = self._bn_bwd(e["ds_bn"], zd, dyr, None, (bi, "d"))
-                self._wgrad(x_in, dzd, dc, 1, 1, dc.stride[0], 0)
-                res = self._dgrad(dzd, dc, (bi, "d"), x_in.shape)
-            else:
-                res = dyr
-            d_out = self._dgrad(dz1, c1, (bi, 1), x_in.shape, residual=res)
+            convs, bns = e["convs"], e["bns"]
+            x_in, zs, ys, zd, out = saved[bi]
+            n_st = len(convs)
+            # last conv of the block: its BatchNorm also yields the gradient of the skip branch
+            dz, dyr = self._bn_bwd(bns[-1], zs[-1], d_out, out, (bi, n_st), want_dyr=True)
+            for si in reversed(range(n_st)):
+                cv = convs[si]
+                k, st, pd = cv.kernel_size[0], cv.stride[0], cv.padding[0]
+                src = x_in if si == 0 else ys[si - 1]        # input of conv si
+                self._wgrad(src, dz, cv, k, k, st, pd)
+                if si > 0:
+                    dy = self._dgrad(dz, cv, (bi, si + 1), src.shape)
+                    dz, _ = self._bn_bwd(bns[si - 1], zs[si - 1], dy, ys[si - 1], (bi, si))
+                else:
+                    if zd is not None:
+                        dc = e["ds_conv"]
+                        dzd, _ = self._bn_bwd(e["ds_bn"], zd, dyr, None, (bi, "d"))
+                        self._wgrad(x_in, dzd, dc, 1, 1, dc.stride[0], 0)
+                        res = self._dgrad(dzd, dc, (bi, "d"), x_in.shape)
+                    else:
+                        res = dyr
+                    d_out = self._dgrad(dz, cv, (bi, 1), x_in.shape, residual=res)
         d_y0 = self._buf("dy_stem", y0.shape)
         _ck("rmv_maxpool3x3s2_bwd_idx", pool_idx.data_ptr(), d_out.data_ptr(), d_y0.data_ptr(), m,
             y0.shape[1], y0.shape[2], y0.shape[3], dtc)

