@@ -531,7 +531,9 @@ def test_maxpool_index_forward_backward(n, h, w, dt):
     assert (dx.float() - ref).abs().max().item() <= tol + 1e-6
 
 
-def test_depth18_step_fp32_vs_live_oracle_and_bf16():
+@pytest.mark.parametrize("flags", [dict(), dict(share_weights=True), dict(ignore_rotmat=True)],
+                         ids=["default", "share_weights", "ignore_rotmat"])
+def test_depth18_step_fp32_vs_live_oracle_and_bf16(flags):
     """backbone_depth=18 (BasicBlock trunk, models/resnet.py:50-96): one training step of the fp32
     engine against the CPU oracle's autograd step on the same batch/weights -- loss, every gradient
     norm, BatchNorm running statistics, parameters after Adam; the bf16 (tcgen05) engine within the
@@ -541,7 +543,7 @@ def test_depth18_step_fp32_vs_live_oracle_and_bf16():
     from rotmv_b200.train import TrainEngine
 
     B, V, lr = 6, 2, 1e-3
-    ora = O.build_model(num_iter=2, depth=18, seed=0)
+    ora = O.build_model(num_iter=2, depth=18, seed=0, **flags)
     sd0 = {k: v.clone() for k, v in ora.state_dict().items()}
     images, pose, gt = O.synthetic_batch(B, V, seed=2)
     rot = O.pairwise_rotations(pose)
@@ -552,7 +554,7 @@ def test_depth18_step_fp32_vs_live_oracle_and_bf16():
     ref_grads = {n: p.grad.clone() for n, p in ora.named_parameters() if p.grad is not None}
 
     for precision in ("fp32", "bf16"):
-        model = FeatRotationSymm(18, 2)
+        model = FeatRotationSymm(18, 2, **flags)
         model.load_state_dict(sd0, strict=True)
         model = model.cuda().train()
         eng = TrainEngine(model, precision=precision, lr=lr, weight_decay=1e-6)
