@@ -68,17 +68,17 @@ struct IgemmArgs {
 // nine taps are nine UMMA descriptors into that patch (start shifted by (r*16+s) pixels = rows of
 // 128 B, stride 2048 B between the 8-row groups), instead of nine separate TMA boxes: 6x less
 // L2->SM traffic for A. The 72 KiB of filters stay resident in shared memory for the whole kernel.
-#ifndef RMV_RES256_STAGES
-#define RMV_RES256_STAGES 2
-#define RMV_RES256_SLOTS 4
-#endif
 constexpr int kHaloW = 16, kHaloH = 18;
 constexpr int kHaloABytes = kHaloW * kHaloH * 128;  // 36864
 constexpr int kHaloTaps = 9;
 constexpr int kHaloStages = 3;
 
-template <int BLOCK_N, bool HAS_RES, bool HALO = false, bool STATS = false>
+// RES: 0 = no residual; 1 = residual, deep residual ring (the HBM-bound layers with 1-4 k-blocks per
+// tile); 2 = residual, deep A/B ring (K >= 512: 3 stages + 2 residual slots; measured 0.234 -> 0.184 ms
+// on the 7x7 512->2048 layers, slower on the shallow-K ones)
+template <int BLOCK_N, int RES, bool HALO = false, bool STATS = false>
 struct Cfg {
+  static constexpr bool HAS_RES = RES != 0;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageA = HALO ? kHaloABytes : kABytes;             // A bytes per stage
   static constexpr int kStageB = HALO ? 0 : kBBytes;                        // B bytes per stage
@@ -87,9 +87,9 @@ struct Cfg {
   // Layers with a residual (the expanding 1x1 convs) are HBM-bound with 1-8 k-blocks per tile: they
   // trade A/B stages for a deeper residual ring (4 x 16 KiB) so the residual loads run well ahead.
   static constexpr int kStages = HALO ? kHaloStages
-                                 : HAS_RES ? (BLOCK_N == 256 ? RMV_RES256_STAGES : (BLOCK_N == 128 ? 3 : 4))
+                                 : HAS_RES ? (BLOCK_N == 256 ? (RES == 2 ? 3 : 2) : (BLOCK_N == 128 ? 3 : 4))
                                            : (BLOCK_N == 256 ? 3 : (STATS && BLOCK_N == 128 ? 4 : 6));
-  static constexpr int kResSlots = (HAS_RES && BLOCK_N == 256) ? RMV_RES256_SLOTS : 4;
+  static constexpr int kResSlots = (BLOCK_N == 256 && RES == 2) ? 2 : 4;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
   static constexpr int kOutBytes = 2 * kChunkBytes;
   static constexpr int kResBytes = HAS_RES ? kResSlots * kChunkBytes : 0;
@@ -122,10 +122,11 @@ __device__ __forceinline__ void epi_bar_sync(int id) {
 }
 
 // OUT_F32: 32 fp32 columns per staged chunk; otherwise 64 bf16 columns (both 128 B per row).
-template <int BLOCK_N, bool HAS_RES, bool OUT_F32, bool HALO = false, bool STATS = false>
+template <int BLOCK_N, int RES, bool OUT_F32, bool HALO = false, bool STATS = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmArgs args) {
-  using C = Cfg<BLOCK_N, HAS_RES, HALO, STATS>;
+  constexpr bool HAS_RES = RES != 0;
+  using C = Cfg<BLOCK_N, RES, HALO, STATS>;
   static_assert(!STATS || (!HAS_RES && !OUT_F32), "STATS: bf16 output, no residual");
   constexpr int kChunkCols = OUT_F32 ? 32 : 64;
   constexpr int kChunks = BLOCK_N / kChunkCols;
@@ -838,9 +839,9 @@ namespace {
 
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-template <int BLOCK_N, bool HAS_RES, bool OUT_F32, bool HALO = false, bool STATS = false>
+template <int BLOCK_N, int RES, bool OUT_F32, bool HALO = false, bool STATS = false>
 int launch(const IgemmArgs& a, int total_tiles, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, HAS_RES, HALO, STATS>;
+  using C = Cfg<BLOCK_N, RES, HALO, STATS>;
   // STATS: [2][n_total][2] floats behind the fixed regions (they replace the 1 KiB alignment slack
   // at the end of kSmemBytes, which the 1024-byte aligned base may consume: keep it as well)
   const int stat_bytes = STATS ? (4 * a.n_total + 8 * 256) * (int)sizeof(float) + 1024 : 0;
@@ -849,12 +850,12 @@ int launch(const IgemmArgs& a, int total_tiles, cudaStream_t stream) {
                 a.n_total);
   static int attr_bytes = 0;
   if (smem > attr_bytes) {
-    RMV_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, HAS_RES, OUT_F32, HALO, STATS>,
+    RMV_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, RES, OUT_F32, HALO, STATS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_bytes = smem;
   }
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  RMV_CUDA(launch_pdl_tc(igemm_kernel<BLOCK_N, HAS_RES, OUT_F32, HALO, STATS>, dim3(grid),
+  RMV_CUDA(launch_pdl_tc(igemm_kernel<BLOCK_N, RES, OUT_F32, HALO, STATS>, dim3(grid),
                          dim3(kNumThreads), smem, stream, a));
   return 0;
 }
@@ -868,10 +869,15 @@ int halo_mode() { return tuning("HALO", 1, 2); }
 
 template <int BLOCK_N>
 int dispatch(const IgemmArgs& a, int total, bool has_res, bool out_f32, cudaStream_t stream) {
-  if (a.stat_acc != nullptr) return launch<BLOCK_N, false, false, false, true>(a, total, stream);
-  if (out_f32) return launch<BLOCK_N, false, true>(a, total, stream);
-  if (has_res) return launch<BLOCK_N, true, false>(a, total, stream);
-  return launch<BLOCK_N, false, false>(a, total, stream);
+  if (a.stat_acc != nullptr) return launch<BLOCK_N, 0, false, false, true>(a, total, stream);
+  if (out_f32) return launch<BLOCK_N, 0, true>(a, total, stream);
+  if (has_res) {
+    // K >= 512 (8+ k-blocks per tile): the main loop needs the shared memory more than the residual ring
+    if (BLOCK_N == 256 && a.num_taps * a.c_blocks >= 8 && tuning("RES_DEEPK", 1, 1) == 1)
+      return launch<BLOCK_N, 2, false>(a, total, stream);
+    return launch<BLOCK_N, 1, false>(a, total, stream);
+  }
+  return launch<BLOCK_N, 0, false>(a, total, stream);
 }
 
 }  // namespace
@@ -1048,8 +1054,8 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
   }
   if (halo) {
     a.halo_base_mode = halo_mode() == 2;
-    if (a.stat_acc != nullptr) return launch<64, false, false, true, true>(a, total, stream);
-    return launch<64, false, false, true>(a, total, stream);
+    if (a.stat_acc != nullptr) return launch<64, 0, false, true, true>(a, total, stream);
+    return launch<64, 0, false, true>(a, total, stream);
   }
   const bool has_res = p.residual != nullptr;
   switch (block_n) {
