@@ -144,6 +144,8 @@ class FeatRotationSymm(nn.Module):
         # main.py:239-240: StereoL1Loss(rel_weight=0.01, reference_decay=1.0), IterationLoss(0.5)
         self.loss_cfg = {"rel_weight": 0.01, "reference_decay": 1.0, "iter_decay": 0.5}
         self.fuse_loss = False  # dict API: also return data["loss"] from the fused head+loss kernel
+        self.auto_graph = True          # tensor API in eval mode: replay CUDA graphs for repeated input shapes
+        self.max_graph_sessions = 8
         # uint8 HWC input (images[B,V,H,W,3]): ToTensor + Normalize constants of main.py:38-39
         self.input_mean, self.input_std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
         self._engines: Dict[str, E.InferenceEngine] = {}
@@ -170,8 +172,45 @@ class FeatRotationSymm(nn.Module):
                 rotations: Optional[torch.Tensor] = None, *, precision: Optional[str] = None):
         if isinstance(data_or_images, dict):
             return self._forward_dict(data_or_images, precision)
-        out = self.forward_views(data_or_images, rotations, precision=precision, want_all=False)
+        images = data_or_images
+        if self.auto_graph and not self.training and images.is_cuda and rotations is not None:
+            pred = self._forward_graphed(images, rotations, precision)
+            if pred is not None:
+                return pred
+        out = self.forward_views(images, rotations, precision=precision, want_all=False)
         return out["pred_gaze"]
+
+    def _forward_graphed(self, images, rotations, precision):
+        """Serving path: the second call with an input signature (batch, views, size, dtype) captures
+        the forward as CUDA graphs and every later call replays them -- the eager path spends 1.6 ms of
+        host time per call in 72 launches + tensor-map encodes whatever the batch (B = 1: 0.69 ms
+        graphed). At most `max_graph_sessions` signatures are kept (least recently used first out)."""
+        eng = self.engine(precision)
+        if images.dim() != 5 or rotations.dim() != 5:
+            return None
+        key = (tuple(images.shape), images.dtype, tuple(rotations.shape))
+        cache = eng.__dict__.setdefault("_sessions", {})
+        seen = eng.__dict__.setdefault("_seen", set())
+        sess = cache.get(key)
+        if sess is None:
+            if key not in seen:          # first sighting: run eagerly, capture only if it comes back
+                seen.add(key)
+                return None
+            b, v = images.shape[0], images.shape[1]
+            u8 = images.dtype == torch.uint8
+            size = images.shape[2] if u8 else images.shape[3]
+            if (images.shape[2] != images.shape[3]) if u8 else (images.shape[3] != images.shape[4]):
+                return None              # GraphedForward sessions are square-image only
+            if images.dtype not in (torch.uint8, torch.float32):
+                return None
+            while len(cache) >= self.max_graph_sessions:
+                cache.pop(next(iter(cache)))
+            sess = E.GraphedForward(self, b, v, precision=precision, size=size,
+                                    input_dtype=torch.uint8 if u8 else torch.float32)
+            cache[key] = sess
+        else:
+            cache[key] = cache.pop(key)  # most recently used last
+        return sess(images.contiguous(), rotations.float().contiguous()).clone()
 
     def forward_views(self, images: torch.Tensor, rotations: torch.Tensor, *,
                       precision: Optional[str] = None, want_all: bool = True,
