@@ -140,6 +140,17 @@ class Trainer:
         losses, prev = [], None
         for batch in batches:
             images, pose, gt = _stack_views(batch)
+            if tuple(images.shape[:2]) != tuple(self.graph.images.shape[:2]):
+                # a short last batch (drop_last=False): the captured graphs are for the full batch
+                # size, this one runs as plain launches
+                if prev is not None:
+                    losses.append(float(self.graph.result(prev)))
+                    prev = None
+                dev = self.engine.device
+                rot = RF.pose_to_rotations(pose.float().to(dev).contiguous())
+                losses.append(float(self.engine.step(images.float().to(dev), rot, gt.float().to(dev))))
+                self.train_iter += 1
+                continue
             ticket = self.graph.submit(_pinned(images.float()), _pinned(pose.float()), _pinned(gt.float()))
             if prev is not None:
                 losses.append(float(self.graph.result(prev)))

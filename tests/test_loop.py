@@ -68,10 +68,11 @@ def test_trainer_loop_schedule_eval_checkpoint(tmp_path):
     g = torch.Generator().manual_seed(1)
 
     def batches():
-        for _ in range(steps):
-            yield {"img_0": torch.randn((B, 3, 224, 224), generator=g), "img_1": torch.randn((B, 3, 224, 224), generator=g),
-                   "head_pose_0": torch.rand((B, 2), generator=g) - 0.5, "head_pose_1": torch.rand((B, 2), generator=g) - 0.5,
-                   "gt_gaze": torch.rand((B, 2), generator=g) - 0.5, "gt_gaze_1": torch.rand((B, 2), generator=g) - 0.5}
+        for i in range(steps):
+            b = B if i < steps - 1 else B - 1      # a short last batch, as a loader with drop_last=False gives
+            yield {"img_0": torch.randn((b, 3, 224, 224), generator=g), "img_1": torch.randn((b, 3, 224, 224), generator=g),
+                   "head_pose_0": torch.rand((b, 2), generator=g) - 0.5, "head_pose_1": torch.rand((b, 2), generator=g) - 0.5,
+                   "gt_gaze": torch.rand((b, 2), generator=g) - 0.5, "gt_gaze_1": torch.rand((b, 2), generator=g) - 0.5}
 
     tr = Trainer(model, steps_per_epoch=steps, batch=B, views=2)
     assert abs(float(tr.engine.hyper[0]) - 1e-6) < 1e-12               # CyclicLR step 0 = base_lr
