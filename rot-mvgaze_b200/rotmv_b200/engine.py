@@ -198,9 +198,33 @@ class InferenceEngine:
             gt: Optional[torch.Tensor] = None) -> Dict[str, Any]:
         imgs, rot, b, v = self._check_inputs(images, rotations)
         m = b * v
+        if b == 0:
+            return self._empty_outputs(v, want_all, gt)
         for s in range(0, m, self.chunk):
             self.run_trunk(imgs, s, min(m, s + self.chunk))
         return self.run_fusion(b, v, rot, want_all=want_all, gt=gt)
+
+    def _empty_outputs(self, v: int, want_all: bool, gt) -> Dict[str, Any]:
+        """An empty batch launches nothing and returns empty tensors of the reference's shapes (the
+        reference in eval mode returns [0,2048] / [0,3,512] / [0,2] tensors for B = 0)."""
+        def z(*shape):
+            return torch.empty((0,) + shape, device=self.device, dtype=torch.float32)
+
+        out: Dict[str, Any] = {"num_iter": self.num_iter}
+        if want_all:
+            for k in range(v):
+                out[f"img_feat_{k}"] = z(3, self.nvec) if self.share_feat else z(self.fc_dim)
+                out[f"initial_rot_feat_{k}"] = z(3, self.nvec)
+        for i in range(self.num_iter):
+            if want_all or i == self.num_iter - 1:
+                it: Dict[str, Any] = {f"pred_gaze_{k}": z(2) for k in range(v)}
+                if want_all:
+                    it.update({f"feat_{k}": z(3, self.nvec) for k in range(v)})
+                out[f"iter_{i}"] = it
+        if gt is not None:   # mean over an empty batch, as torch.mean gives the reference
+            out["loss"] = torch.full((1,), float("nan"), device=self.device, dtype=torch.float32)
+        out["pred_gaze"] = out[f"iter_{self.num_iter - 1}"]["pred_gaze_0"]
+        return out
 
     def _check_inputs(self, images, rotations):
         if not images.is_cuda:

@@ -186,7 +186,7 @@ class FeatRotationSymm(nn.Module):
         host time per call in 72 launches + tensor-map encodes whatever the batch (B = 1: 0.69 ms
         graphed). At most `max_graph_sessions` signatures are kept (least recently used first out)."""
         eng = self.engine(precision)
-        if images.dim() != 5 or rotations.dim() != 5:
+        if images.dim() != 5 or rotations.dim() != 5 or images.shape[0] == 0:
             return None
         key = (tuple(images.shape), images.dtype, tuple(rotations.shape))
         cache = eng.__dict__.setdefault("_sessions", {})
@@ -217,8 +217,8 @@ class FeatRotationSymm(nn.Module):
                       gt: Optional[torch.Tensor] = None) -> Dict[str, Any]:
         if self.training:
             raise NotImplementedError(
-                "train-mode forward runs through rotmv_b200.trainer.TrainStep (batch-statistic "
-                "BatchNorm + backward); module.forward is the inference path")
+                "train-mode forward runs through rotmv_b200.train.TrainEngine / GraphedTrainStep "
+                "(batch-statistic BatchNorm + backward); module.forward is the inference path")
         if images.dim() != 5 or rotations is None or rotations.dim() != 5:
             raise ValueError("expected images[B,V,3,H,W] (fp32) or [B,V,H,W,3] (uint8) and rotations[B,V,V,3,3]")
         return self.engine(precision).run(images, rotations, want_all=want_all, gt=gt)
