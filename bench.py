@@ -359,7 +359,7 @@ def run_ours(args):
                 "whole_step_frac": (B * V * FLOPS_PER_VIEW / (ms_step * 1e-3) / 1e12) / pk["tflops"]}
         # ---- CPU baseline: the oracle on this box's host cores, bounded sample -----------------
         if n_gpus == 1 and not args.no_cpu:
-            times = time_cpu_oracle(V, 8, min_seconds=12.0, max_iters=40)
+            times = time_cpu_oracle(V, 8, min_seconds=12.0, max_iters=400)
             cpu_value = 8 / (sum(times) / len(times))
             line["cpu_baseline"] = {
                 "value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",

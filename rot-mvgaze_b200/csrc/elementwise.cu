@@ -290,7 +290,10 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-template <typename T>
+// One warp per row, grid-stride over rows. NCH = hid / 256 (1 or 2: the reference head has hid = 512)
+// keeps both weight rows in registers for the whole kernel; NCH = 0 is the generic form that
+// re-reads them (L1) per row. One loss atomic per block whatever the row count.
+template <typename T, int NCH>
 __global__ void __launch_bounds__(256)
 head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __restrict__ w2,
                  const float* __restrict__ b2, int rows, int hid, float* __restrict__ pred,
@@ -301,21 +304,40 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
 
   __shared__ float s_part[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
+  constexpr int R = NCH > 0 ? NCH : 1;
+  float wa[R][8], wb[R][8];
+  if (NCH > 0) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      Vec8<float>::load(w2 + j * 256 + lane * 8, wa[j]);
+      Vec8<float>::load(w2 + hid + j * 256 + lane * 8, wb[j]);
+    }
+  }
+  const float bias0 = __ldg(b2), bias1 = __ldg(b2 + 1);
   float ang = 0.f;
-  if (row < rows) {
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     float d0 = 0.f, d1 = 0.f;
     const T* hp = hidden + (long long)row * ld;
-    for (int k = lane * 8; k < hid; k += 256) {
-      float h[8], a[8], b[8];
-      Vec8<T>::load(hp + k, h);
-      Vec8<float>::load(w2 + k, a);
-      Vec8<float>::load(w2 + hid + k, b);
+    if (NCH > 0) {
+      float h[R][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { d0 = fmaf(h[i], a[i], d0); d1 = fmaf(h[i], b[i], d1); }
+      for (int j = 0; j < R; ++j) Vec8<T>::load(hp + j * 256 + lane * 8, h[j]);
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { d0 = fmaf(h[j][i], wa[j][i], d0); d1 = fmaf(h[j][i], wb[j][i], d1); }
+    } else {
+      for (int k = lane * 8; k < hid; k += 256) {
+        float h[8], a[8], b[8];
+        Vec8<T>::load(hp + k, h);
+        Vec8<float>::load(w2 + k, a);
+        Vec8<float>::load(w2 + hid + k, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { d0 = fmaf(h[i], a[i], d0); d1 = fmaf(h[i], b[i], d1); }
+      }
     }
-    d0 = warp_sum(d0) + __ldg(b2);
-    d1 = warp_sum(d1) + __ldg(b2 + 1);
+    d0 = warp_sum(d0) + bias0;
+    d1 = warp_sum(d1) + bias1;
     if (lane == 0) {
       pred[row * 2] = d0; pred[row * 2 + 1] = d1;
       if (gt != nullptr) {
@@ -324,7 +346,7 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
         pitchyaw_to_vec(d0, d1, vp);
         float sim = cos_sim_torch(vg, vp, 1e-6f);
         sim = fminf(fmaxf(sim, -1.f), 1.f);
-        ang = acosf(sim) * kRadToDeg * ((row % views) == 0 ? 1.f : aux_decay);
+        ang += acosf(sim) * kRadToDeg * ((row % views) == 0 ? 1.f : aux_decay);
       }
     }
   }
@@ -520,11 +542,23 @@ extern "C" int rmv_head_loss_fwd(const void* hidden, long long ld_hidden, int hi
   RMV_CHECK_ARG(views >= 1, "head_loss: views must be >= 1");
   if (rows == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (hid_dtype == RMV_DTYPE_BF16)
-    rmv::launch_pdl(head_loss_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, (const __nv_bfloat16*)hidden, ld_hidden, w2, b2, rows, hid, pred, gt, loss_scale, views, aux_decay, loss_out);
-  else
-    rmv::launch_pdl(head_loss_kernel<float>, dim3(grid), dim3(256), 0, s, (const float*)hidden, ld_hidden, w2, b2, rows, hid, pred, gt, loss_scale, views, aux_decay, loss_out);
+  // grid-stride over rows: at most 8 resident blocks per SM, one loss atomic per block
+  long blocks = ((long)rows + 7) / 8;
+  if (blocks > 8L * num_sms()) blocks = 8L * num_sms();
+  const dim3 grid((unsigned)blocks), block(256);
+#define RMV_HEAD_LAUNCH(T, NCH)                                                                    \
+  rmv::launch_pdl(head_loss_kernel<T, NCH>, grid, block, 0, s, (const T*)hidden, ld_hidden, w2, b2, \
+                  rows, hid, pred, gt, loss_scale, views, aux_decay, loss_out)
+  if (hid_dtype == RMV_DTYPE_BF16) {
+    if (hid == 512) RMV_HEAD_LAUNCH(__nv_bfloat16, 2);
+    else if (hid == 256) RMV_HEAD_LAUNCH(__nv_bfloat16, 1);
+    else RMV_HEAD_LAUNCH(__nv_bfloat16, 0);
+  } else {
+    if (hid == 512) RMV_HEAD_LAUNCH(float, 2);
+    else if (hid == 256) RMV_HEAD_LAUNCH(float, 1);
+    else RMV_HEAD_LAUNCH(float, 0);
+  }
+#undef RMV_HEAD_LAUNCH
   RMV_LAUNCH_CHECK();
   return 0;
 }

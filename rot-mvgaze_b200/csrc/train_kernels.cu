@@ -878,7 +878,12 @@ __device__ __forceinline__ void loss_grad_row(float p, float y, float gp, float 
   *dyw = dth * (g[0] * (cp * cy) + g[2] * (-cp * sy));
 }
 
-template <typename T>
+// One warp per row, grid-stride over rows. NCH = hid / 256 (1 or 2; the reference head has
+// hid = 512): each lane owns the same 8*NCH columns for every row it sees, so the weights and the
+// dw2 partial sums live in registers; the warps of a block meet in shared memory once and the block
+// issues one set of global atomics whatever the row count. NCH = 0: generic hid, shared-memory
+// accumulation per row.
+template <typename T, int NCH>
 __global__ void __launch_bounds__(256)
 head_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                      const T* __restrict__ hidden, long long ld_h, const float* __restrict__ w2,
@@ -888,35 +893,72 @@ head_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ g
   griddep_wait();    // PDL: predecessors complete + visible
   griddep_launch();  // let the next kernel of the stream get scheduled
 
-  // one warp per row; block-level partial dw2/db2 reduced through shared memory + atomics
   extern __shared__ float s_dw[];  // [2][hid] + [2]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 2 * hid + 2; i += blockDim.x) s_dw[i] = 0.f;
   __syncthreads();
-  const int row = blockIdx.x * 8 + warp;
-  if (row < rows) {
+  constexpr int R = NCH > 0 ? NCH : 1;
+  float wa[R][8], wb[R][8], ga[R][8], gb[R][8];
+  float g_dp = 0.f, g_dy = 0.f;
+  if (NCH > 0) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      V8<float>::load(w2 + j * 256 + lane * 8, wa[j]);
+      V8<float>::load(w2 + hid + j * 256 + lane * 8, wb[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { ga[j][i] = 0.f; gb[j][i] = 0.f; }
+    }
+  }
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     float dp, dyw;
     const float wgt = loss_scale * ((row % views) == 0 ? 1.f : aux_decay);
     loss_grad_row(__ldg(pred + row * 2), __ldg(pred + row * 2 + 1), __ldg(gt + row * 2),
                   __ldg(gt + row * 2 + 1), wgt, &dp, &dyw);
     if (lane == 0) {
       dpred_out[row * 2] = dp; dpred_out[row * 2 + 1] = dyw;
-      atomicAdd(&s_dw[2 * hid], dp); atomicAdd(&s_dw[2 * hid + 1], dyw);
+      g_dp += dp; g_dy += dyw;
     }
-    for (int k = lane * 8; k < hid; k += 256) {
-      float h[8], a[8], b[8], o[8];
-      V8<T>::load(hidden + (long long)row * ld_h + k, h);
-      V8<float>::load(w2 + k, a);
-      V8<float>::load(w2 + hid + k, b);
+    if (NCH > 0) {
+      float h[R][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        o[i] = h[i] > 0.f ? fmaf(dp, a[i], dyw * b[i]) : 0.f;
-        atomicAdd(&s_dw[k + i], dp * h[i]);
-        atomicAdd(&s_dw[hid + k + i], dyw * h[i]);
+      for (int j = 0; j < R; ++j) V8<T>::load(hidden + (long long)row * ld_h + j * 256 + lane * 8, h[j]);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = h[j][i] > 0.f ? fmaf(dp, wa[j][i], dyw * wb[j][i]) : 0.f;
+          ga[j][i] = fmaf(dp, h[j][i], ga[j][i]);
+          gb[j][i] = fmaf(dyw, h[j][i], gb[j][i]);
+        }
+        V8<T>::store(dhidden + (long long)row * ld_dh + j * 256 + lane * 8, o);
       }
-      V8<T>::store(dhidden + (long long)row * ld_dh + k, o);
+    } else {
+      for (int k = lane * 8; k < hid; k += 256) {
+        float h[8], a[8], b[8], o[8];
+        V8<T>::load(hidden + (long long)row * ld_h + k, h);
+        V8<float>::load(w2 + k, a);
+        V8<float>::load(w2 + hid + k, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = h[i] > 0.f ? fmaf(dp, a[i], dyw * b[i]) : 0.f;
+          atomicAdd(&s_dw[k + i], dp * h[i]);
+          atomicAdd(&s_dw[hid + k + i], dyw * h[i]);
+        }
+        V8<T>::store(dhidden + (long long)row * ld_dh + k, o);
+      }
     }
   }
+  if (NCH > 0) {
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&s_dw[j * 256 + lane * 8 + i], ga[j][i]);
+        atomicAdd(&s_dw[hid + j * 256 + lane * 8 + i], gb[j][i]);
+      }
+  }
+  if (lane == 0) { atomicAdd(&s_dw[2 * hid], g_dp); atomicAdd(&s_dw[2 * hid + 1], g_dy); }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * hid; i += blockDim.x) atomicAdd(dw2 + i, s_dw[i]);
   if (threadIdx.x < 2) atomicAdd(db2 + threadIdx.x, s_dw[2 * hid + threadIdx.x]);
@@ -1347,9 +1389,17 @@ extern "C" int rmv_head_loss_bwd(const float* pred, const float* gt, const void*
                 "head_loss_bwd: hid/ld must be multiples of 8");
   if (rows == 0) return 0;
   const int smem = (2 * hid + 2) * (int)sizeof(float);
-  DISPATCH_T(hid_dtype, (rmv::launch_pdl(head_loss_bwd_kernel<T>, dim3((rows + 7) / 8), dim3(256), smem, (cudaStream_t)stream, 
-      pred, gt, (const T*)hidden, ld_hidden, w2, rows, hid, loss_scale, views, aux_decay,
-      (T*)dhidden, ld_dhidden, dpred, dw2, db2)));
+  long blocks = ((long)rows + 7) / 8;
+  if (blocks > 4L * num_sms()) blocks = 4L * num_sms();   // grid-stride; one set of atomics per block
+  const dim3 grid((unsigned)blocks);
+#define RMV_HEAD_BWD(NCH)                                                                          \
+  DISPATCH_T(hid_dtype, (rmv::launch_pdl(head_loss_bwd_kernel<T, NCH>, grid, dim3(256), smem,       \
+      (cudaStream_t)stream, pred, gt, (const T*)hidden, ld_hidden, w2, rows, hid, loss_scale, views, \
+      aux_decay, (T*)dhidden, ld_dhidden, dpred, dw2, db2)))
+  if (hid == 512) { RMV_HEAD_BWD(2); }
+  else if (hid == 256) { RMV_HEAD_BWD(1); }
+  else { RMV_HEAD_BWD(0); }
+#undef RMV_HEAD_BWD
   RMV_LAUNCH_CHECK();
   return 0;
 }
