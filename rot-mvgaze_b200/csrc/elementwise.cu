@@ -14,6 +14,18 @@ constexpr float kRadToDeg = 57.29577951308232f;  // 180 / pi
 // ---- 8-wide vector helpers: bf16 x8 (16 B) or fp32 x8 (2 x 16 B) -> float[8] ----------------
 template <typename T> struct Vec8;
 template <> struct Vec8<__nv_bfloat16> {
+  typedef uint4 Raw;  // packed form: unrolled loads stay in 4 registers until they are consumed
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
+  }
+  static __device__ __forceinline__ void unpack(const Raw& u, float* f) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 v = unpack_bf16x2(w[i]);
+      f[2 * i] = v.x; f[2 * i + 1] = v.y;
+    }
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -31,6 +43,17 @@ template <> struct Vec8<__nv_bfloat16> {
   }
 };
 template <> struct Vec8<float> {
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw load_raw(const float* p) {
+    Raw r;
+    r.a = __ldg(reinterpret_cast<const float4*>(p));
+    r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    return r;
+  }
+  static __device__ __forceinline__ void unpack(const Raw& r, float* f) {
+    f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w;
+    f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+  }
   static __device__ __forceinline__ void load(const float* p, float* f) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p));
     const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -207,66 +230,91 @@ __global__ void avgpool_kernel(const T* __restrict__ x, int hw, int c, T* __rest
 // ---------------------------------------------------------------------------------------------
 // Rotation-constrained cross-view gather
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void rotate_gather_kernel(const T* __restrict__ feat, long long ld_feat,
-                                     const float* __restrict__ rot, T* __restrict__ dst,
-                                     long long ld_dst, int views, int nvec, int apply_rot,
-                                     long long total) {
+// One thread = 8 feature columns of VB consecutive output views of one sample: every partner row
+// F_u is loaded ONCE per thread and applied to all VB outputs (V = 2: both directions of the pair
+// from two row loads; V = 4: 4 row loads instead of 12; V = 8: 16 instead of 56), with all loads of
+// a partner in flight together. Each output still adds its partners in ascending view order.
+template <typename T, int VB>
+__global__ void __launch_bounds__(128)
+rotate_gather_kernel(const T* __restrict__ feat, long long ld_feat,
+                     const float* __restrict__ rot, T* __restrict__ dst,
+                     long long ld_dst, int views, int nvec, int apply_rot,
+                     long long total) {
   griddep_wait();    // PDL: predecessors complete + visible
   griddep_launch();  // let the next kernel of the stream get scheduled
 
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int kv = nvec / 8;
+  const int groups = (views + VB - 1) / VB;
   const int k0 = (int)(idx % kv) * 8;
-  const long long row = idx / kv;  // b*V + v
-  const int v = (int)(row % views);
-  const long long b = row / views;
-  float o[3][8];
+  const long long t = idx / kv;
+  const int v0 = (int)(t % groups) * VB;
+  const long long b = t / groups;
+  float o[VB][3][8];
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+  for (int j = 0; j < VB; ++j)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[r][i] = 0.f;
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[j][r][i] = 0.f;
+  const T* fbase = feat + b * views * ld_feat + k0;
+  typename Vec8<T>::Raw raw[3], nxt[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) raw[c] = Vec8<T>::load_raw(fbase + (long long)c * nvec);
   for (int u = 0; u < views; ++u) {
-    if (u == v) continue;
-    const T* fp = feat + (b * views + u) * ld_feat + k0;
+    if (u + 1 < views) {   // next partner's loads in flight while this one is applied
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        nxt[c] = Vec8<T>::load_raw(fbase + (long long)(u + 1) * ld_feat + (long long)c * nvec);
+    }
     float f[3][8];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) Vec8<T>::load(fp + (long long)c * nvec, f[c]);
-    float R[9];
-    if (apply_rot & 2) {
-      // backward of the gather: this row (self = v) receives rot[b,u,v]^T applied to d/dA of row u
-      const float* rp = rot + ((b * views + u) * views + v) * 9;
+    for (int c = 0; c < 3; ++c) { Vec8<T>::unpack(raw[c], f[c]); raw[c] = nxt[c]; }
 #pragma unroll
-      for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + (i % 3) * 3 + i / 3);
-    } else if (apply_rot & 1) {
-      const float* rp = rot + ((b * views + v) * views + u) * 9;
+    for (int j = 0; j < VB; ++j) {
+      const int v = v0 + j;
+      if (v >= views || v == u) continue;
+      float R[9];
+      if (apply_rot & 2) {
+        // backward of the gather: this row (self = v) receives rot[b,u,v]^T applied to d/dA of row u
+        const float* rp = rot + ((b * views + u) * views + v) * 9;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + i);
-    } else {
+        for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + (i % 3) * 3 + i / 3);
+      } else if (apply_rot & 1) {
+        const float* rp = rot + ((b * views + v) * views + u) * 9;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.f : 0.f;
-    }
+        for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + i);
+      } else {
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float t = R[r * 3 + 0] * f[0][i];
-        t = fmaf(R[r * 3 + 1], f[1][i], t);
-        t = fmaf(R[r * 3 + 2], f[2][i], t);
-        o[r][i] += t;
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.f : 0.f;
       }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a = R[r * 3 + 0] * f[0][i];
+          a = fmaf(R[r * 3 + 1], f[1][i], a);
+          a = fmaf(R[r * 3 + 2], f[2][i], a);
+          o[j][r][i] += a;
+        }
+    }
   }
-  if (views > 2) {
-    const float inv = 1.f / (float)(views - 1);
+  const float inv = views > 2 ? 1.f / (float)(views - 1) : 1.f;
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+  for (int j = 0; j < VB; ++j) {
+    const int v = v0 + j;
+    if (v >= views) continue;
+    if (views > 2) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[r][i] *= inv;
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[j][r][i] *= inv;
+    }
+    T* dp = dst + (b * views + v) * ld_dst + k0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) Vec8<T>::store(dp + (long long)r * nvec, o[j][r]);
   }
-  T* dp = dst + row * ld_dst + k0;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) Vec8<T>::store(dp + (long long)r * nvec, o[r]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -290,11 +338,15 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// One warp per row, grid-stride over rows. NCH = hid / 256 (1 or 2: the reference head has hid = 512)
+// One warp finishes kHeadRows rows per iteration (grid-stride): the loads of all of them are in
+// flight together, and lanes 0..kHeadRows-1 each do the transcendental tail (pitch-yaw -> vector,
+// cosine, acos) of one row in parallel. NCH = hid / 256 (1 or 2: the reference head has hid = 512)
 // keeps both weight rows in registers for the whole kernel; NCH = 0 is the generic form that
 // re-reads them (L1) per row. One loss atomic per block whatever the row count.
+constexpr int kHeadRows = 4;
+
 template <typename T, int NCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __restrict__ w2,
                  const float* __restrict__ b2, int rows, int hid, float* __restrict__ pred,
                  const float* __restrict__ gt, float loss_scale, int views, float aux_decay,
@@ -315,35 +367,58 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
   }
   const float bias0 = __ldg(b2), bias1 = __ldg(b2 + 1);
   float ang = 0.f;
-  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
-    float d0 = 0.f, d1 = 0.f;
-    const T* hp = hidden + (long long)row * ld;
+  for (int row0 = (blockIdx.x * 8 + warp) * kHeadRows; row0 < rows;
+       row0 += gridDim.x * 8 * kHeadRows) {
+    float d0[kHeadRows], d1[kHeadRows];
     if (NCH > 0) {
-      float h[R][8];
+      typename Vec8<T>::Raw raw[kHeadRows][R];
 #pragma unroll
-      for (int j = 0; j < R; ++j) Vec8<T>::load(hp + j * 256 + lane * 8, h[j]);
+      for (int r = 0; r < kHeadRows; ++r) {
+        const int row = min(row0 + r, rows - 1);  // past the end: re-read the last row, result dropped
 #pragma unroll
-      for (int j = 0; j < R; ++j)
+        for (int j = 0; j < R; ++j)
+          raw[r][j] = Vec8<T>::load_raw(hidden + (long long)row * ld + j * 256 + lane * 8);
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { d0 = fmaf(h[j][i], wa[j][i], d0); d1 = fmaf(h[j][i], wb[j][i], d1); }
+      for (int r = 0; r < kHeadRows; ++r) {
+        d0[r] = 0.f; d1[r] = 0.f;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          float h[8];
+          Vec8<T>::unpack(raw[r][j], h);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { d0[r] = fmaf(h[i], wa[j][i], d0[r]); d1[r] = fmaf(h[i], wb[j][i], d1[r]); }
+        }
+      }
     } else {
-      for (int k = lane * 8; k < hid; k += 256) {
-        float h[8], a[8], b[8];
-        Vec8<T>::load(hp + k, h);
-        Vec8<float>::load(w2 + k, a);
-        Vec8<float>::load(w2 + hid + k, b);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { d0 = fmaf(h[i], a[i], d0); d1 = fmaf(h[i], b[i], d1); }
+      for (int r = 0; r < kHeadRows; ++r) {
+        d0[r] = 0.f; d1[r] = 0.f;
+        const T* hp = hidden + (long long)min(row0 + r, rows - 1) * ld;
+        for (int k = lane * 8; k < hid; k += 256) {
+          float h[8], a[8], b[8];
+          Vec8<T>::load(hp + k, h);
+          Vec8<float>::load(w2 + k, a);
+          Vec8<float>::load(w2 + hid + k, b);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { d0[r] = fmaf(h[i], a[i], d0[r]); d1[r] = fmaf(h[i], b[i], d1[r]); }
+        }
       }
     }
-    d0 = warp_sum(d0) + bias0;
-    d1 = warp_sum(d1) + bias1;
-    if (lane == 0) {
-      pred[row * 2] = d0; pred[row * 2 + 1] = d1;
+    float p0 = 0.f, p1 = 0.f;   // lane r keeps row row0 + r
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) {
+      const float s0 = warp_sum(d0[r]) + bias0, s1 = warp_sum(d1[r]) + bias1;
+      if (lane == r) { p0 = s0; p1 = s1; }
+    }
+    const int row = row0 + lane;
+    if (lane < kHeadRows && row < rows) {
+      *reinterpret_cast<float2*>(pred + (long long)row * 2) = make_float2(p0, p1);
       if (gt != nullptr) {
         float vg[3], vp[3];
-        pitchyaw_to_vec(__ldg(gt + row * 2), __ldg(gt + row * 2 + 1), vg);
-        pitchyaw_to_vec(d0, d1, vp);
+        const float2 g2 = __ldg(reinterpret_cast<const float2*>(gt + (long long)row * 2));
+        pitchyaw_to_vec(g2.x, g2.y, vg);
+        pitchyaw_to_vec(p0, p1, vp);
         float sim = cos_sim_torch(vg, vp, 1e-6f);
         sim = fminf(fmaxf(sim, -1.f), 1.f);
         ang += acosf(sim) * kRadToDeg * ((row % views) == 0 ? 1.f : aux_decay);
@@ -351,6 +426,7 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
     }
   }
   if (gt != nullptr) {
+    ang = warp_sum(ang);
     if (lane == 0) s_part[warp] = ang;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -520,15 +596,20 @@ extern "C" int rmv_rotate_gather_fwd(const void* feat, long long ld_feat, const 
   RMV_CHECK_ARG(views >= 2, "rotate_gather: need >= 2 views, got %d", views);
   RMV_CHECK_ARG(nvec % 8 == 0 && ld_feat % 8 == 0 && ld_dst % 8 == 0,
                 "rotate_gather: nvec/ld must be multiples of 8");
-  const long long total = (long long)batch * views * (nvec / 8);
+  // V = 2: one thread produces both directions of the pair; V > 2: groups of four output views
+  const int vb = views == 2 ? 2 : 4;
+  const long long total = (long long)batch * ((views + vb - 1) / vb) * (nvec / 8);
   if (total == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == RMV_DTYPE_BF16)
-    rmv::launch_pdl(rotate_gather_kernel<__nv_bfloat16>, dim3(blocks_for(total, 128)), dim3(128), 0, s, 
-        (const __nv_bfloat16*)feat, ld_feat, rot, (__nv_bfloat16*)dst, ld_dst, views, nvec, apply_rot, total);
-  else
-    rmv::launch_pdl(rotate_gather_kernel<float>, dim3(blocks_for(total, 128)), dim3(128), 0, s, 
-        (const float*)feat, ld_feat, rot, (float*)dst, ld_dst, views, nvec, apply_rot, total);
+#define RMV_RG_LAUNCH(T, VB)                                                                      \
+  rmv::launch_pdl(rotate_gather_kernel<T, VB>, dim3(blocks_for(total, 128)), dim3(128), 0, s,      \
+                  (const T*)feat, ld_feat, rot, (T*)dst, ld_dst, views, nvec, apply_rot, total)
+  if (dtype == RMV_DTYPE_BF16) {
+    if (vb == 2) RMV_RG_LAUNCH(__nv_bfloat16, 2); else RMV_RG_LAUNCH(__nv_bfloat16, 4);
+  } else {
+    if (vb == 2) RMV_RG_LAUNCH(float, 2); else RMV_RG_LAUNCH(float, 4);
+  }
+#undef RMV_RG_LAUNCH
   RMV_LAUNCH_CHECK();
   return 0;
 }
@@ -542,9 +623,9 @@ extern "C" int rmv_head_loss_fwd(const void* hidden, long long ld_hidden, int hi
   RMV_CHECK_ARG(views >= 1, "head_loss: views must be >= 1");
   if (rows == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  // grid-stride over rows: at most 8 resident blocks per SM, one loss atomic per block
-  long blocks = ((long)rows + 7) / 8;
-  if (blocks > 8L * num_sms()) blocks = 8L * num_sms();
+  // grid-stride over groups of 8 warps x kHeadRows rows; one loss atomic per block
+  long blocks = ((long)rows + 8 * kHeadRows - 1) / (8 * kHeadRows);
+  if (blocks > 4L * num_sms()) blocks = 4L * num_sms();
   const dim3 grid((unsigned)blocks), block(256);
 #define RMV_HEAD_LAUNCH(T, NCH)                                                                    \
   rmv::launch_pdl(head_loss_kernel<T, NCH>, grid, block, 0, s, (const T*)hidden, ld_hidden, w2, b2, \

@@ -878,13 +878,16 @@ __device__ __forceinline__ void loss_grad_row(float p, float y, float gp, float 
   *dyw = dth * (g[0] * (cp * cy) + g[2] * (-cp * sy));
 }
 
-// One warp per row, grid-stride over rows. NCH = hid / 256 (1 or 2; the reference head has
-// hid = 512): each lane owns the same 8*NCH columns for every row it sees, so the weights and the
-// dw2 partial sums live in registers; the warps of a block meet in shared memory once and the block
-// issues one set of global atomics whatever the row count. NCH = 0: generic hid, shared-memory
-// accumulation per row.
+// One warp finishes kHeadRows rows per iteration (grid-stride): their loads are issued first, lanes
+// 0..kHeadRows-1 each compute the loss gradient of one row meanwhile and broadcast it by shuffle.
+// NCH = hid / 256 (1 or 2; the reference head has hid = 512): each lane owns the same 8*NCH columns
+// for every row it sees, so the dw2 partial sums live in registers; the warps of a block meet in
+// shared memory once and the block issues one set of global atomics whatever the row count.
+// NCH = 0: generic hid, shared-memory accumulation per row.
+constexpr int kHeadRows = 4;
+
 template <typename T, int NCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 2 : 1)
 head_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                      const T* __restrict__ hidden, long long ld_h, const float* __restrict__ w2,
                      int rows, int hid, float loss_scale, int views, float aux_decay,
@@ -898,54 +901,71 @@ head_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ g
   for (int i = threadIdx.x; i < 2 * hid + 2; i += blockDim.x) s_dw[i] = 0.f;
   __syncthreads();
   constexpr int R = NCH > 0 ? NCH : 1;
-  float wa[R][8], wb[R][8], ga[R][8], gb[R][8];
+  float ga[R][8], gb[R][8];
   float g_dp = 0.f, g_dy = 0.f;
-  if (NCH > 0) {
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      V8<float>::load(w2 + j * 256 + lane * 8, wa[j]);
-      V8<float>::load(w2 + hid + j * 256 + lane * 8, wb[j]);
+  for (int j = 0; j < R; ++j)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { ga[j][i] = 0.f; gb[j][i] = 0.f; }
-    }
-  }
-  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
-    float dp, dyw;
-    const float wgt = loss_scale * ((row % views) == 0 ? 1.f : aux_decay);
-    loss_grad_row(__ldg(pred + row * 2), __ldg(pred + row * 2 + 1), __ldg(gt + row * 2),
-                  __ldg(gt + row * 2 + 1), wgt, &dp, &dyw);
-    if (lane == 0) {
-      dpred_out[row * 2] = dp; dpred_out[row * 2 + 1] = dyw;
-      g_dp += dp; g_dy += dyw;
-    }
+    for (int i = 0; i < 8; ++i) { ga[j][i] = 0.f; gb[j][i] = 0.f; }
+  for (int row0 = (blockIdx.x * 8 + warp) * kHeadRows; row0 < rows;
+       row0 += gridDim.x * 8 * kHeadRows) {
+    typename V8<T>::Raw raw[kHeadRows][R];
     if (NCH > 0) {
-      float h[R][8];
 #pragma unroll
-      for (int j = 0; j < R; ++j) V8<T>::load(hidden + (long long)row * ld_h + j * 256 + lane * 8, h[j]);
+      for (int r = 0; r < kHeadRows; ++r) {
+        const int row = min(row0 + r, rows - 1);   // past the end: re-read the last row, dropped below
 #pragma unroll
-      for (int j = 0; j < R; ++j) {
-        float o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          o[i] = h[j][i] > 0.f ? fmaf(dp, wa[j][i], dyw * wb[j][i]) : 0.f;
-          ga[j][i] = fmaf(dp, h[j][i], ga[j][i]);
-          gb[j][i] = fmaf(dyw, h[j][i], gb[j][i]);
-        }
-        V8<T>::store(dhidden + (long long)row * ld_dh + j * 256 + lane * 8, o);
+        for (int j = 0; j < R; ++j)
+          raw[r][j] = V8<T>::load_raw(hidden + (long long)row * ld_h + j * 256 + lane * 8);
       }
-    } else {
-      for (int k = lane * 8; k < hid; k += 256) {
-        float h[8], a[8], b[8], o[8];
-        V8<T>::load(hidden + (long long)row * ld_h + k, h);
-        V8<float>::load(w2 + k, a);
-        V8<float>::load(w2 + hid + k, b);
+    }
+    // lane r: loss gradient of row row0 + r
+    float my_dp = 0.f, my_dy = 0.f;
+    {
+      const int row = row0 + lane;
+      if (lane < kHeadRows && row < rows) {
+        const float wgt = loss_scale * ((row % views) == 0 ? 1.f : aux_decay);
+        const float2 p2 = __ldg(reinterpret_cast<const float2*>(pred + (long long)row * 2));
+        const float2 g2 = __ldg(reinterpret_cast<const float2*>(gt + (long long)row * 2));
+        loss_grad_row(p2.x, p2.y, g2.x, g2.y, wgt, &my_dp, &my_dy);
+        *reinterpret_cast<float2*>(dpred_out + (long long)row * 2) = make_float2(my_dp, my_dy);
+        g_dp += my_dp; g_dy += my_dy;
+      }
+    }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          o[i] = h[i] > 0.f ? fmaf(dp, a[i], dyw * b[i]) : 0.f;
-          atomicAdd(&s_dw[k + i], dp * h[i]);
-          atomicAdd(&s_dw[hid + k + i], dyw * h[i]);
+    for (int r = 0; r < kHeadRows; ++r) {
+      const float dp = __shfl_sync(0xffffffffu, my_dp, r), dyw = __shfl_sync(0xffffffffu, my_dy, r);
+      const int row = row0 + r;
+      if (row >= rows) break;   // warp-uniform
+      if (NCH > 0) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          float h[8], a[8], b[8], o[8];
+          V8<T>::unpack(raw[r][j], h);
+          V8<float>::load(w2 + j * 256 + lane * 8, a);        // 4 KB table, L1-resident
+          V8<float>::load(w2 + hid + j * 256 + lane * 8, b);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            o[i] = h[i] > 0.f ? fmaf(dp, a[i], dyw * b[i]) : 0.f;
+            ga[j][i] = fmaf(dp, h[i], ga[j][i]);
+            gb[j][i] = fmaf(dyw, h[i], gb[j][i]);
+          }
+          V8<T>::store(dhidden + (long long)row * ld_dh + j * 256 + lane * 8, o);
         }
-        V8<T>::store(dhidden + (long long)row * ld_dh + k, o);
+      } else {
+        for (int k = lane * 8; k < hid; k += 256) {
+          float h[8], a[8], b[8], o[8];
+          V8<T>::load(hidden + (long long)row * ld_h + k, h);
+          V8<float>::load(w2 + k, a);
+          V8<float>::load(w2 + hid + k, b);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            o[i] = h[i] > 0.f ? fmaf(dp, a[i], dyw * b[i]) : 0.f;
+            atomicAdd(&s_dw[k + i], dp * h[i]);
+            atomicAdd(&s_dw[hid + k + i], dyw * h[i]);
+          }
+          V8<T>::store(dhidden + (long long)row * ld_dh + k, o);
+        }
       }
     }
   }
@@ -958,7 +978,7 @@ head_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ g
         atomicAdd(&s_dw[hid + j * 256 + lane * 8 + i], gb[j][i]);
       }
   }
-  if (lane == 0) { atomicAdd(&s_dw[2 * hid], g_dp); atomicAdd(&s_dw[2 * hid + 1], g_dy); }
+  if (lane < kHeadRows) { atomicAdd(&s_dw[2 * hid], g_dp); atomicAdd(&s_dw[2 * hid + 1], g_dy); }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * hid; i += blockDim.x) atomicAdd(dw2 + i, s_dw[i]);
   if (threadIdx.x < 2) atomicAdd(db2 + threadIdx.x, s_dw[2 * hid + threadIdx.x]);
@@ -1389,8 +1409,9 @@ extern "C" int rmv_head_loss_bwd(const float* pred, const float* gt, const void*
                 "head_loss_bwd: hid/ld must be multiples of 8");
   if (rows == 0) return 0;
   const int smem = (2 * hid + 2) * (int)sizeof(float);
-  long blocks = ((long)rows + 7) / 8;
-  if (blocks > 4L * num_sms()) blocks = 4L * num_sms();   // grid-stride; one set of atomics per block
+  // grid-stride over groups of 8 warps x kHeadRows rows; one set of global atomics per block
+  long blocks = ((long)rows + 8 * rmv::kHeadRows - 1) / (8 * rmv::kHeadRows);
+  if (blocks > 2L * num_sms()) blocks = 2L * num_sms();
   const dim3 grid((unsigned)blocks);
 #define RMV_HEAD_BWD(NCH)                                                                          \
   DISPATCH_T(hid_dtype, (rmv::launch_pdl(head_loss_bwd_kernel<T, NCH>, grid, dim3(256), smem,       \
