@@ -230,90 +230,137 @@ __global__ void avgpool_kernel(const T* __restrict__ x, int hw, int c, T* __rest
 // ---------------------------------------------------------------------------------------------
 // Rotation-constrained cross-view gather
 // ---------------------------------------------------------------------------------------------
-// One thread = 8 feature columns of VB consecutive output views of one sample: every partner row
-// F_u is loaded ONCE per thread and applied to all VB outputs (V = 2: both directions of the pair
-// from two row loads; V = 4: 4 row loads instead of 12; V = 8: 16 instead of 56), with all loads of
-// a partner in flight together. Each output still adds its partners in ascending view order.
-template <typename T, int VB>
-__global__ void __launch_bounds__(128)
-rotate_gather_kernel(const T* __restrict__ feat, long long ld_feat,
-                     const float* __restrict__ rot, T* __restrict__ dst,
-                     long long ld_dst, int views, int nvec, int apply_rot,
-                     long long total) {
+template <typename T>
+__global__ void rotate_gather_kernel(const T* __restrict__ feat, long long ld_feat,
+                                     const float* __restrict__ rot, T* __restrict__ dst,
+                                     long long ld_dst, int views, int nvec, int apply_rot,
+                                     long long total) {
   griddep_wait();    // PDL: predecessors complete + visible
   griddep_launch();  // let the next kernel of the stream get scheduled
 
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int kv = nvec / 8;
-  const int groups = (views + VB - 1) / VB;
   const int k0 = (int)(idx % kv) * 8;
-  const long long t = idx / kv;
-  const int v0 = (int)(t % groups) * VB;
-  const long long b = t / groups;
-  float o[VB][3][8];
+  const long long row = idx / kv;  // b*V + v
+  const int v = (int)(row % views);
+  const long long b = row / views;
+  float o[3][8];
 #pragma unroll
-  for (int j = 0; j < VB; ++j)
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[r][i] = 0.f;
+  for (int u = 0; u < views; ++u) {
+    if (u == v) continue;
+    const T* fp = feat + (b * views + u) * ld_feat + k0;
+    float f[3][8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Vec8<T>::load(fp + (long long)c * nvec, f[c]);
+    float R[9];
+    if (apply_rot & 2) {
+      // backward of the gather: this row (self = v) receives rot[b,u,v]^T applied to d/dA of row u
+      const float* rp = rot + ((b * views + u) * views + v) * 9;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + (i % 3) * 3 + i / 3);
+    } else if (apply_rot & 1) {
+      const float* rp = rot + ((b * views + v) * views + u) * 9;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.f : 0.f;
+    }
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[j][r][i] = 0.f;
-  const T* fbase = feat + b * views * ld_feat + k0;
-  typename Vec8<T>::Raw raw[3], nxt[3];
+      for (int i = 0; i < 8; ++i) {
+        float t = R[r * 3 + 0] * f[0][i];
+        t = fmaf(R[r * 3 + 1], f[1][i], t);
+        t = fmaf(R[r * 3 + 2], f[2][i], t);
+        o[r][i] += t;
+      }
+  }
+  if (views > 2) {
+    const float inv = 1.f / (float)(views - 1);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) raw[c] = Vec8<T>::load_raw(fbase + (long long)c * nvec);
-  for (int u = 0; u < views; ++u) {
-    if (u + 1 < views) {   // next partner's loads in flight while this one is applied
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        nxt[c] = Vec8<T>::load_raw(fbase + (long long)(u + 1) * ld_feat + (long long)c * nvec);
-    }
-    float f[3][8];
+      for (int i = 0; i < 8; ++i) o[r][i] *= inv;
+  }
+  T* dp = dst + row * ld_dst + k0;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { Vec8<T>::unpack(raw[c], f[c]); raw[c] = nxt[c]; }
+  for (int r = 0; r < 3; ++r) Vec8<T>::store(dp + (long long)r * nvec, o[r]);
+}
+
+// Two views (the reference's configuration, models/rot_mv.py:234,238): persistent grid-stride
+// kernel. One item = 8 feature columns of both views of one sample: the two partner slices (6 x
+// 16 B) are loaded together, the NEXT item's six loads are issued before this item is computed, and
+// both directions out_0 = R_01 F_1, out_1 = R_10 F_0 are produced from them (6 x 16 B stores).
+template <typename T>
+__global__ void __launch_bounds__(128)
+rotate_gather_pair_kernel(const T* __restrict__ feat, long long ld_feat,
+                          const float* __restrict__ rot, T* __restrict__ dst, long long ld_dst,
+                          int nvec, int apply_rot, long long total /* batch * nvec/8 */) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
+  const int kv = nvec / 8;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  typename Vec8<T>::Raw cur[2][3], nxt[2][3];
+  auto issue = [&](long long item, typename Vec8<T>::Raw (&r)[2][3]) {
+    const int k0 = (int)(item % kv) * 8;
+    const T* fp = feat + (item / kv) * 2 * ld_feat + k0;
 #pragma unroll
-    for (int j = 0; j < VB; ++j) {
-      const int v = v0 + j;
-      if (v >= views || v == u) continue;
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) r[u][c] = Vec8<T>::load_raw(fp + u * ld_feat + (long long)c * nvec);
+  };
+  issue(idx, cur);
+#pragma unroll 1
+  for (; idx < total; idx += step) {
+    const bool more = idx + step < total;
+    if (more) issue(idx + step, nxt);
+    const int k0 = (int)(idx % kv) * 8;
+    const long long b = idx / kv;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int u = 1 - v;
       float R[9];
-      if (apply_rot & 2) {
-        // backward of the gather: this row (self = v) receives rot[b,u,v]^T applied to d/dA of row u
-        const float* rp = rot + ((b * views + u) * views + v) * 9;
+      if (apply_rot & 2) {   // backward of the gather: rot[b,u,v]^T
+        const float* rp = rot + ((b * 2 + u) * 2 + v) * 9;
 #pragma unroll
         for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + (i % 3) * 3 + i / 3);
       } else if (apply_rot & 1) {
-        const float* rp = rot + ((b * views + v) * views + u) * 9;
+        const float* rp = rot + ((b * 2 + v) * 2 + u) * 9;
 #pragma unroll
         for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + i);
       } else {
 #pragma unroll
         for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.f : 0.f;
       }
+      float f[3][8], o[3][8];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Vec8<T>::unpack(cur[u][c], f[c]);
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float a = R[r * 3 + 0] * f[0][i];
           a = fmaf(R[r * 3 + 1], f[1][i], a);
-          a = fmaf(R[r * 3 + 2], f[2][i], a);
-          o[j][r][i] += a;
+          o[r][i] = fmaf(R[r * 3 + 2], f[2][i], a) + 0.f;   // same rounding as 0 + t of the general kernel
         }
+      T* dp = dst + (b * 2 + v) * ld_dst + k0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) Vec8<T>::store(dp + (long long)r * nvec, o[r]);
     }
-  }
-  const float inv = views > 2 ? 1.f / (float)(views - 1) : 1.f;
+    if (more) {
 #pragma unroll
-  for (int j = 0; j < VB; ++j) {
-    const int v = v0 + j;
-    if (v >= views) continue;
-    if (views > 2) {
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[j][r][i] *= inv;
+        for (int c = 0; c < 3; ++c) cur[u][c] = nxt[u][c];
     }
-    T* dp = dst + (b * views + v) * ld_dst + k0;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) Vec8<T>::store(dp + (long long)r * nvec, o[j][r]);
   }
 }
 
@@ -346,7 +393,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 constexpr int kHeadRows = 4;
 
 template <typename T, int NCH>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 2 : 1)
 head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __restrict__ w2,
                  const float* __restrict__ b2, int rows, int hid, float* __restrict__ pred,
                  const float* __restrict__ gt, float loss_scale, int views, float aux_decay,
@@ -357,38 +404,47 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
   __shared__ float s_part[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int R = NCH > 0 ? NCH : 1;
-  float wa[R][8], wb[R][8];
-  if (NCH > 0) {
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      Vec8<float>::load(w2 + j * 256 + lane * 8, wa[j]);
-      Vec8<float>::load(w2 + hid + j * 256 + lane * 8, wb[j]);
-    }
-  }
   const float bias0 = __ldg(b2), bias1 = __ldg(b2 + 1);
+  const int step = gridDim.x * 8 * kHeadRows;
   float ang = 0.f;
-  for (int row0 = (blockIdx.x * 8 + warp) * kHeadRows; row0 < rows;
-       row0 += gridDim.x * 8 * kHeadRows) {
+  typename Vec8<T>::Raw raw[kHeadRows][R], nxt[kHeadRows][R];
+  auto issue = [&](int row0, typename Vec8<T>::Raw (&dst)[kHeadRows][R]) {
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) {
+      const int row = min(row0 + r, rows - 1);  // past the end: re-read the last row, result dropped
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        dst[r][j] = Vec8<T>::load_raw(hidden + (long long)row * ld + j * 256 + lane * 8);
+    }
+  };
+  int row0 = (blockIdx.x * 8 + warp) * kHeadRows;
+  if (NCH > 0 && row0 < rows) issue(row0, raw);
+#pragma unroll 1
+  for (; row0 < rows; row0 += step) {
     float d0[kHeadRows], d1[kHeadRows];
     if (NCH > 0) {
-      typename Vec8<T>::Raw raw[kHeadRows][R];
+      const bool more = row0 + step < rows;
+      if (more) issue(row0 + step, nxt);   // next group's loads in flight during this group's tail
 #pragma unroll
-      for (int r = 0; r < kHeadRows; ++r) {
-        const int row = min(row0 + r, rows - 1);  // past the end: re-read the last row, result dropped
+      for (int r = 0; r < kHeadRows; ++r) { d0[r] = 0.f; d1[r] = 0.f; }
 #pragma unroll
-        for (int j = 0; j < R; ++j)
-          raw[r][j] = Vec8<T>::load_raw(hidden + (long long)row * ld + j * 256 + lane * 8);
-      }
+      for (int j = 0; j < R; ++j) {
+        float a[8], b[8];                  // 4 KB weight table: L1-resident, read once per group
+        Vec8<float>::load(w2 + j * 256 + lane * 8, a);
+        Vec8<float>::load(w2 + hid + j * 256 + lane * 8, b);
 #pragma unroll
-      for (int r = 0; r < kHeadRows; ++r) {
-        d0[r] = 0.f; d1[r] = 0.f;
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
+        for (int r = 0; r < kHeadRows; ++r) {
           float h[8];
           Vec8<T>::unpack(raw[r][j], h);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { d0[r] = fmaf(h[i], wa[j][i], d0[r]); d1[r] = fmaf(h[i], wb[j][i], d1[r]); }
+          for (int i = 0; i < 8; ++i) { d0[r] = fmaf(h[i], a[i], d0[r]); d1[r] = fmaf(h[i], b[i], d1[r]); }
         }
+      }
+      if (more) {
+#pragma unroll
+        for (int r = 0; r < kHeadRows; ++r)
+#pragma unroll
+          for (int j = 0; j < R; ++j) raw[r][j] = nxt[r][j];
       }
     } else {
 #pragma unroll
@@ -596,20 +652,34 @@ extern "C" int rmv_rotate_gather_fwd(const void* feat, long long ld_feat, const 
   RMV_CHECK_ARG(views >= 2, "rotate_gather: need >= 2 views, got %d", views);
   RMV_CHECK_ARG(nvec % 8 == 0 && ld_feat % 8 == 0 && ld_dst % 8 == 0,
                 "rotate_gather: nvec/ld must be multiples of 8");
-  // V = 2: one thread produces both directions of the pair; V > 2: groups of four output views
-  const int vb = views == 2 ? 2 : 4;
-  const long long total = (long long)batch * ((views + vb - 1) / vb) * (nvec / 8);
-  if (total == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-#define RMV_RG_LAUNCH(T, VB)                                                                      \
-  rmv::launch_pdl(rotate_gather_kernel<T, VB>, dim3(blocks_for(total, 128)), dim3(128), 0, s,      \
-                  (const T*)feat, ld_feat, rot, (T*)dst, ld_dst, views, nvec, apply_rot, total)
-  if (dtype == RMV_DTYPE_BF16) {
-    if (vb == 2) RMV_RG_LAUNCH(__nv_bfloat16, 2); else RMV_RG_LAUNCH(__nv_bfloat16, 4);
-  } else {
-    if (vb == 2) RMV_RG_LAUNCH(float, 2); else RMV_RG_LAUNCH(float, 4);
+  if (views == 2) {
+    // persistent pair kernel: as many blocks as stay resident (register-bound), grid-stride
+    const long long total = (long long)batch * (nvec / 8);
+    if (total == 0) return 0;
+    long long blocks = (total + 127) / 128;
+    if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+    if (dtype == RMV_DTYPE_BF16)
+      rmv::launch_pdl(rotate_gather_pair_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(128), 0, s,
+                      (const __nv_bfloat16*)feat, ld_feat, rot, (__nv_bfloat16*)dst, ld_dst, nvec,
+                      apply_rot, total);
+    else
+      rmv::launch_pdl(rotate_gather_pair_kernel<float>, dim3((unsigned)blocks), dim3(128), 0, s,
+                      (const float*)feat, ld_feat, rot, (float*)dst, ld_dst, nvec, apply_rot, total);
+    RMV_LAUNCH_CHECK();
+    return 0;
   }
-#undef RMV_RG_LAUNCH
+  // V > 2: one short thread per (row, 8 columns); the V-1 re-reads of a partner row by the rows of
+  // the same sample hit L1/L2 (measured: 0.92 / 1.04 of the HBM copy rate in algorithmic bytes at
+  // V = 4 / 8 -- a register-blocked variant that loaded each partner once per thread was slower)
+  const long long total = (long long)batch * views * (nvec / 8);
+  if (total == 0) return 0;
+  if (dtype == RMV_DTYPE_BF16)
+    rmv::launch_pdl(rotate_gather_kernel<__nv_bfloat16>, dim3(blocks_for(total, 128)), dim3(128), 0, s,
+        (const __nv_bfloat16*)feat, ld_feat, rot, (__nv_bfloat16*)dst, ld_dst, views, nvec, apply_rot, total);
+  else
+    rmv::launch_pdl(rotate_gather_kernel<float>, dim3(blocks_for(total, 128)), dim3(128), 0, s,
+        (const float*)feat, ld_feat, rot, (float*)dst, ld_dst, views, nvec, apply_rot, total);
   RMV_LAUNCH_CHECK();
   return 0;
 }
