@@ -390,7 +390,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // cosine, acos) of one row in parallel. NCH = hid / 256 (1 or 2: the reference head has hid = 512)
 // keeps both weight rows in registers for the whole kernel; NCH = 0 is the generic form that
 // re-reads them (L1) per row. One loss atomic per block whatever the row count.
-constexpr int kHeadRows = 4;
+constexpr int kHeadRows = 4;   // the shuffle tree in head_loss_kernel is written for 4
 
 template <typename T, int NCH>
 __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 2 : 1)
@@ -461,14 +461,38 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
         }
       }
     }
-    float p0 = 0.f, p1 = 0.f;   // lane r keeps row row0 + r
+    // eight warp sums in 9 shuffles: each butterfly level halves the number of values a lane still
+    // carries (same pairing and order of additions as warp_sum, so the sums are bit-identical);
+    // afterwards lane 4k holds value k (k < 4: d0[k], k >= 4: d1[k-4]); one more shuffle brings
+    // d1[r] next to d0[r] in lane 4r, which does the tail of row row0 + r
+    float x4[4], x2[2], x1;
+    {
+      const bool up = lane & 16;
 #pragma unroll
-    for (int r = 0; r < kHeadRows; ++r) {
-      const float s0 = warp_sum(d0[r]) + bias0, s1 = warp_sum(d1[r]) + bias1;
-      if (lane == r) { p0 = s0; p1 = s1; }
+      for (int i = 0; i < 4; ++i) {
+        const float keep = up ? d1[i] : d0[i], send = up ? d0[i] : d1[i];
+        x4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
     }
-    const int row = row0 + lane;
-    if (lane < kHeadRows && row < rows) {
+    {
+      const bool up = lane & 8;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float keep = up ? x4[i + 2] : x4[i], send = up ? x4[i] : x4[i + 2];
+        x2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+    }
+    {
+      const bool up = lane & 4;
+      const float keep = up ? x2[1] : x2[0], send = up ? x2[0] : x2[1];
+      x1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    x1 += __shfl_xor_sync(0xffffffffu, x1, 2);
+    x1 += __shfl_xor_sync(0xffffffffu, x1, 1);
+    const float p0 = x1 + bias0;
+    const float p1 = __shfl_down_sync(0xffffffffu, x1, 16) + bias1;
+    const int row = row0 + (lane >> 2);
+    if (lane < 4 * kHeadRows && (lane & 3) == 0 && row < rows) {
       *reinterpret_cast<float2*>(pred + (long long)row * 2) = make_float2(p0, p1);
       if (gt != nullptr) {
         float vg[3], vp[3];
