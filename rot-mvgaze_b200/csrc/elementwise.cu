@@ -385,15 +385,27 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// One warp finishes kHeadRows rows per iteration (grid-stride): the loads of all of them are in
-// flight together, and lanes 0..kHeadRows-1 each do the transcendental tail (pitch-yaw -> vector,
-// cosine, acos) of one row in parallel. NCH = hid / 256 (1 or 2: the reference head has hid = 512)
-// keeps both weight rows in registers for the whole kernel; NCH = 0 is the generic form that
-// re-reads them (L1) per row. One loss atomic per block whatever the row count.
-constexpr int kHeadRows = 4;   // the shuffle tree in head_loss_kernel is written for 4
+// One warp finishes kHeadRows rows per iteration (grid-stride). NCH = hid / 256 (1 or 2: the
+// reference head has hid = 512): the rows are staged through a per-thread ring in shared memory
+// with cp.async (kHeadStages groups of kHeadRows rows in flight per warp, no registers held by loads
+// in flight; every thread reads back exactly the 16-byte pieces it copied, so the ring needs no
+// barrier), the eight dot products of a group are reduced with a multi-value butterfly, and lanes
+// 0, 4, 8, 12 each do the transcendental tail (pitch-yaw -> vector, cosine, acos) of one row.
+// NCH = 0 is the generic form (any hid) without the ring. One loss atomic per block.
+constexpr int kHeadRows = 4;     // the shuffle tree in head_loss_kernel is written for 4
+constexpr int kHeadStages = 3;
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 template <typename T, int NCH>
-__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 2 : 1)
+__global__ void __launch_bounds__(256, 2)
 head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __restrict__ w2,
                  const float* __restrict__ b2, int rows, int hid, float* __restrict__ pred,
                  const float* __restrict__ gt, float loss_scale, int views, float aux_decay,
@@ -401,30 +413,49 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
   griddep_wait();    // PDL: predecessors complete + visible
   griddep_launch();  // let the next kernel of the stream get scheduled
 
+  using Raw = typename Vec8<T>::Raw;
+  constexpr int R = NCH > 0 ? NCH : 1;
+  constexpr int kPieces = (int)sizeof(Raw) / 16;           // 16-byte pieces per 8-element vector
+  extern __shared__ uint4 s_ring[];                        // [stage][row][chunk][piece][256 threads]
   __shared__ float s_part[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int R = NCH > 0 ? NCH : 1;
   const float bias0 = __ldg(b2), bias1 = __ldg(b2 + 1);
   const int step = gridDim.x * 8 * kHeadRows;
   float ang = 0.f;
-  typename Vec8<T>::Raw raw[kHeadRows][R], nxt[kHeadRows][R];
-  auto issue = [&](int row0, typename Vec8<T>::Raw (&dst)[kHeadRows][R]) {
+  auto slot = [&](int stage, int r, int j, int piece) -> uint4* {
+    return s_ring + ((((stage * kHeadRows + r) * R + j) * kPieces + piece) * 256 + threadIdx.x);
+  };
+  auto issue = [&](int row0, int stage) {   // always commits (possibly empty) so group counts line up
+    if (row0 < rows) {
 #pragma unroll
-    for (int r = 0; r < kHeadRows; ++r) {
-      const int row = min(row0 + r, rows - 1);  // past the end: re-read the last row, result dropped
+      for (int r = 0; r < kHeadRows; ++r) {
+        const int row = min(row0 + r, rows - 1);  // past the end: re-read the last row, result dropped
 #pragma unroll
-      for (int j = 0; j < R; ++j)
-        dst[r][j] = Vec8<T>::load_raw(hidden + (long long)row * ld + j * 256 + lane * 8);
+        for (int j = 0; j < R; ++j) {
+          const char* src = reinterpret_cast<const char*>(hidden + (long long)row * ld + j * 256 + lane * 8);
+#pragma unroll
+          for (int q = 0; q < kPieces; ++q) cp_async_16(slot(stage, r, j, q), src + 16 * q);
+        }
+      }
     }
+    cp_async_commit();
   };
   int row0 = (blockIdx.x * 8 + warp) * kHeadRows;
-  if (NCH > 0 && row0 < rows) issue(row0, raw);
+  if (NCH > 0) {
+#pragma unroll
+    for (int st = 0; st < kHeadStages - 1; ++st) issue(row0 + st * step, st);
+  }
+  int stage = 0;
 #pragma unroll 1
   for (; row0 < rows; row0 += step) {
     float d0[kHeadRows], d1[kHeadRows];
     if (NCH > 0) {
-      const bool more = row0 + step < rows;
-      if (more) issue(row0 + step, nxt);   // next group's loads in flight during this group's tail
+      {
+        int st_next = stage + kHeadStages - 1;
+        if (st_next >= kHeadStages) st_next -= kHeadStages;
+        issue(row0 + (kHeadStages - 1) * step, st_next);
+      }
+      cp_async_wait<kHeadStages - 1>();   // this thread's copies of the current group have landed
 #pragma unroll
       for (int r = 0; r < kHeadRows; ++r) { d0[r] = 0.f; d1[r] = 0.f; }
 #pragma unroll
@@ -434,18 +465,17 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
         Vec8<float>::load(w2 + hid + j * 256 + lane * 8, b);
 #pragma unroll
         for (int r = 0; r < kHeadRows; ++r) {
+          Raw raw;
+          uint4* rp = reinterpret_cast<uint4*>(&raw);
+#pragma unroll
+          for (int q = 0; q < kPieces; ++q) rp[q] = *slot(stage, r, j, q);
           float h[8];
-          Vec8<T>::unpack(raw[r][j], h);
+          Vec8<T>::unpack(raw, h);
 #pragma unroll
           for (int i = 0; i < 8; ++i) { d0[r] = fmaf(h[i], a[i], d0[r]); d1[r] = fmaf(h[i], b[i], d1[r]); }
         }
       }
-      if (more) {
-#pragma unroll
-        for (int r = 0; r < kHeadRows; ++r)
-#pragma unroll
-          for (int j = 0; j < R; ++j) raw[r][j] = nxt[r][j];
-      }
+      if (++stage == kHeadStages) stage = 0;
     } else {
 #pragma unroll
       for (int r = 0; r < kHeadRows; ++r) {
@@ -505,6 +535,7 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
       }
     }
   }
+  if (NCH > 0) cp_async_wait<0>();
   if (gt != nullptr) {
     ang = warp_sum(ang);
     if (lane == 0) s_part[warp] = ang;
@@ -719,18 +750,29 @@ extern "C" int rmv_head_loss_fwd(const void* hidden, long long ld_hidden, int hi
   cudaStream_t s = (cudaStream_t)stream;
   // grid-stride over groups of 8 warps x kHeadRows rows; one loss atomic per block
   long blocks = ((long)rows + 8 * kHeadRows - 1) / (8 * kHeadRows);
-  if (blocks > 4L * num_sms()) blocks = 4L * num_sms();
+  if (blocks > 2L * num_sms()) blocks = 2L * num_sms();
   const dim3 grid((unsigned)blocks), block(256);
+  const int nch = hid == 512 ? 2 : (hid == 256 ? 1 : 0);
+  const int esz = hid_dtype == RMV_DTYPE_BF16 ? 2 : 4;
+  const int smem = nch ? kHeadStages * kHeadRows * nch * 8 * esz * 256 : 0;   // bf16/512: 96 KB (2 blocks/SM), fp32/512: 192 KB
 #define RMV_HEAD_LAUNCH(T, NCH)                                                                    \
-  rmv::launch_pdl(head_loss_kernel<T, NCH>, grid, block, 0, s, (const T*)hidden, ld_hidden, w2, b2, \
-                  rows, hid, pred, gt, loss_scale, views, aux_decay, loss_out)
+  do {                                                                                             \
+    static int attr_done = 0; /* benign race: the attribute is idempotent */                       \
+    if (smem > 48 * 1024 && !attr_done) {                                                          \
+      RMV_CUDA(cudaFuncSetAttribute(head_loss_kernel<T, NCH>,                                       \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));            \
+      attr_done = 1;                                                                               \
+    }                                                                                              \
+    rmv::launch_pdl(head_loss_kernel<T, NCH>, grid, block, smem, s, (const T*)hidden, ld_hidden,   \
+                    w2, b2, rows, hid, pred, gt, loss_scale, views, aux_decay, loss_out);          \
+  } while (0)
   if (hid_dtype == RMV_DTYPE_BF16) {
-    if (hid == 512) RMV_HEAD_LAUNCH(__nv_bfloat16, 2);
-    else if (hid == 256) RMV_HEAD_LAUNCH(__nv_bfloat16, 1);
+    if (nch == 2) RMV_HEAD_LAUNCH(__nv_bfloat16, 2);
+    else if (nch == 1) RMV_HEAD_LAUNCH(__nv_bfloat16, 1);
     else RMV_HEAD_LAUNCH(__nv_bfloat16, 0);
   } else {
-    if (hid == 512) RMV_HEAD_LAUNCH(float, 2);
-    else if (hid == 256) RMV_HEAD_LAUNCH(float, 1);
+    if (nch == 2) RMV_HEAD_LAUNCH(float, 2);
+    else if (nch == 1) RMV_HEAD_LAUNCH(float, 1);
     else RMV_HEAD_LAUNCH(float, 0);
   }
 #undef RMV_HEAD_LAUNCH
