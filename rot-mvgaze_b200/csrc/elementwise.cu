@@ -404,6 +404,24 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// prediction write + loss term of one row per lane (models/backbones/blocks.py:41-60 output,
+// utils/math.py:52-60, losses/gaze_loss.py:42-52)
+__device__ __forceinline__ void head_tail(float p0, float p1, int row, int rows,
+                                          float* __restrict__ pred, const float* __restrict__ gt,
+                                          int views, float aux_decay, float& ang) {
+  if (row >= rows) return;
+  *reinterpret_cast<float2*>(pred + (long long)row * 2) = make_float2(p0, p1);
+  if (gt != nullptr) {
+    float vg[3], vp[3];
+    const float2 g2 = __ldg(reinterpret_cast<const float2*>(gt + (long long)row * 2));
+    pitchyaw_to_vec(g2.x, g2.y, vg);
+    pitchyaw_to_vec(p0, p1, vp);
+    float sim = cos_sim_torch(vg, vp, 1e-6f);
+    sim = fminf(fmaxf(sim, -1.f), 1.f);
+    ang += acosf(sim) * kRadToDeg * ((row % views) == 0 ? 1.f : aux_decay);
+  }
+}
+
 template <typename T, int NCH>
 __global__ void __launch_bounds__(256, 2)
 head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __restrict__ w2,
@@ -445,7 +463,8 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
 #pragma unroll
     for (int st = 0; st < kHeadStages - 1; ++st) issue(row0 + st * step, st);
   }
-  int stage = 0;
+  int stage = 0, pend = 0, qrow = rows;
+  float q0 = 0.f, q1 = 0.f;
 #pragma unroll 1
   for (; row0 < rows; row0 += step) {
     float d0[kHeadRows], d1[kHeadRows];
@@ -521,20 +540,17 @@ head_loss_kernel(const T* __restrict__ hidden, long long ld, const float* __rest
     x1 += __shfl_xor_sync(0xffffffffu, x1, 1);
     const float p0 = x1 + bias0;
     const float p1 = __shfl_down_sync(0xffffffffu, x1, 16) + bias1;
-    const int row = row0 + (lane >> 2);
-    if (lane < 4 * kHeadRows && (lane & 3) == 0 && row < rows) {
-      *reinterpret_cast<float2*>(pred + (long long)row * 2) = make_float2(p0, p1);
-      if (gt != nullptr) {
-        float vg[3], vp[3];
-        const float2 g2 = __ldg(reinterpret_cast<const float2*>(gt + (long long)row * 2));
-        pitchyaw_to_vec(g2.x, g2.y, vg);
-        pitchyaw_to_vec(p0, p1, vp);
-        float sim = cos_sim_torch(vg, vp, 1e-6f);
-        sim = fminf(fmaxf(sim, -1.f), 1.f);
-        ang += acosf(sim) * kRadToDeg * ((row % views) == 0 ? 1.f : aux_decay);
-      }
+    // park the four results in lanes 4*pend .. 4*pend+3; after eight groups every lane owns one
+    // row and the transcendental tail runs once for 32 rows with all lanes active
+    const float s0 = __shfl_sync(0xffffffffu, p0, 4 * (lane & 3));
+    const float s1 = __shfl_sync(0xffffffffu, p1, 4 * (lane & 3));
+    if ((lane >> 2) == pend) { q0 = s0; q1 = s1; qrow = row0 + (lane & 3); }
+    if (++pend == 8) {
+      head_tail(q0, q1, qrow, rows, pred, gt, views, aux_decay, ang);
+      pend = 0; qrow = rows;
     }
   }
+  if (pend != 0) head_tail(q0, q1, qrow, rows, pred, gt, views, aux_decay, ang);
   if (NCH > 0) cp_async_wait<0>();
   if (gt != nullptr) {
     ang = warp_sum(ang);
