@@ -330,79 +330,59 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(double* __restrict
 }
 
 // y = relu?(a[v,c] * z + b[v,c] + residual)
-// grid = (x, views * img_groups): every thread owns ONE 8-channel group of ONE view (its coefficients
-// live in registers) and kEwUnroll vector positions of the image plane; it walks the images
-// n = v + views * (grp + t * img_groups) of its view, with the NEXT image's loads (kEwUnroll
-// independent 16-byte loads per tensor) issued before the current image is computed and stored.
-// The host sizes grid.x so that gridDim.x * 256 * unroll covers the image plane.
+// grid = (x, n_img): every thread owns ONE 8-channel group (its coefficients live in registers) and
+// walks the image's pixels with 4 independent 16-byte loads in flight per tensor.
 constexpr int kEwUnroll = 4;
-template <typename T> struct EwUnroll { static constexpr int value = sizeof(T) == 2 ? kEwUnroll : 2; };
 
 template <typename T>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ a, const float* __restrict__ b,
                 const T* __restrict__ residual, T* __restrict__ y,
-                uint8_t* __restrict__ relu_bits, int pix, int c, int views, int relu, int n_img,
-                int img_groups) {
+                uint8_t* __restrict__ relu_bits, int pix, int c, int views, int relu) {
   griddep_wait();    // PDL: predecessors complete + visible
   griddep_launch();  // let the next kernel of the stream get scheduled
 
-  constexpr int U = EwUnroll<T>::value;
-  using Raw = typename V8<T>::Raw;
   const int cg = c / 8;
-  const int v = blockIdx.y % views, grp = blockIdx.y / views;
-  const long long per_img = (long long)pix * cg;  // 8-channel vectors in one image
+  const int n = blockIdx.y, v = n % views;
+  const long long per_img = (long long)pix * cg;  // 8-channel vectors in this image
   const long long stride = (long long)gridDim.x * blockDim.x;  // multiple of cg (cg | 256)
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int g = (int)(i0 % cg);
   float ca[8], cb[8];
   V8<float>::load(a + v * c + g * 8, ca);
   V8<float>::load(b + v * c + g * 8, cb);
-  const long long img_elems = (long long)pix * c;
-  const int n_step = views * img_groups;
-  Raw zr[U], rr[U], zn[U], rn[U];
-  auto issue = [&](int n, Raw (&zz)[U], Raw (&rz)[U]) {
-    const T* zi = z + (long long)n * img_elems;
-    const T* ri = residual ? residual + (long long)n * img_elems : nullptr;
+  const T* zi = z + (long long)n * pix * c;
+  const T* ri = residual ? residual + (long long)n * pix * c : nullptr;
+  T* yi = y + (long long)n * pix * c;
+  uint8_t* bi = relu_bits ? relu_bits + (long long)n * per_img : nullptr;
+  for (long long i = i0; i < per_img; i += stride * kEwUnroll) {
+    typename V8<T>::Raw zr[kEwUnroll], rr[kEwUnroll];
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const long long k = i0 + j * stride;
+    for (int j = 0; j < kEwUnroll; ++j) {
+      const long long k = i + j * stride;
       if (k < per_img) {
-        zz[j] = V8<T>::load_raw(zi + k * 8);
-        if (ri) rz[j] = V8<T>::load_raw(ri + k * 8);
+        zr[j] = V8<T>::load_raw(zi + k * 8);
+        if (ri) rr[j] = V8<T>::load_raw(ri + k * 8);
       }
     }
-  };
-  int n = v + views * grp;
-  if (n < n_img) issue(n, zr, rr);
-#pragma unroll 1
-  for (; n < n_img; n += n_step) {
-    const bool more = n + n_step < n_img;
-    if (more) issue(n + n_step, zn, rn);
-    T* yi = y + (long long)n * img_elems;
-    uint8_t* bi = relu_bits ? relu_bits + (long long)n * per_img : nullptr;
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const long long k = i0 + j * stride;
+    for (int j = 0; j < kEwUnroll; ++j) {
+      const long long k = i + j * stride;
       if (k < per_img) {
         float f[8], r[8], o[8];
         V8<T>::unpack(zr[j], f);
-        if (residual) V8<T>::unpack(rr[j], r);
+        if (ri) V8<T>::unpack(rr[j], r);
         uint32_t bits = 0;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           o[e] = fmaf(f[e], ca[e], cb[e]);
-          if (residual) o[e] += r[e];
+          if (ri) o[e] += r[e];
           bits |= (o[e] > 0.f ? 1u : 0u) << e;
           if (relu) o[e] = fmaxf(o[e], 0.f);
         }
         V8<T>::store(yi + k * 8, o);
         if (bi) bi[k] = (uint8_t)bits;
       }
-    }
-    if (more) {
-#pragma unroll
-      for (int j = 0; j < U; ++j) { zr[j] = zn[j]; rr[j] = rn[j]; }
     }
   }
 }
@@ -1263,17 +1243,9 @@ extern "C" int rmv_bn_apply(const void* z, const float* a, const float* b, const
                             int views, int relu, void* stream) {
   RMV_CHECK_ARG(c % 8 == 0 && 256 % (c / 8) == 0, "bn_apply: c=%d must be 8*2^k, <= 2048", c);
   if ((long long)n_img * pix == 0) return 0;
-  RMV_CHECK_ARG(views >= 1 && n_img % views == 0, "bn_apply: n_img not a multiple of views");
-  // persistent over the images of a view: about two waves of blocks (2 resident per SM), each
-  // walking n_img / (views * groups) images with the next image's loads in flight
-  const unsigned bx = ew_blocks_x(pix, c, n_img, dtype == RMV_DTYPE_BF16 ? rmv::kEwUnroll : 2);
-  const int per_view = n_img / views;
-  long groups = (4L * num_sms() + (long)bx * views / 2) / ((long)bx * views);
-  if (groups < 1) groups = 1;
-  if (groups > per_view) groups = per_view;
-  const dim3 grid(bx, (unsigned)(views * groups));
+  const dim3 grid(ew_blocks_x(pix, c, n_img), (unsigned)n_img);
   DISPATCH_T(dtype, (rmv::launch_pdl(bn_apply_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
-      (const T*)z, a, b, (const T*)residual, (T*)y, relu_bits, pix, c, views, relu, n_img, (int)groups)));
+      (const T*)z, a, b, (const T*)residual, (T*)y, relu_bits, pix, c, views, relu)));
   RMV_LAUNCH_CHECK();
   return 0;
 }
