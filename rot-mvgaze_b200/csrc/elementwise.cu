@@ -230,6 +230,15 @@ __global__ void avgpool_kernel(const T* __restrict__ x, int hw, int c, T* __rest
 // ---------------------------------------------------------------------------------------------
 // Rotation-constrained cross-view gather
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <typename T>
 __global__ void rotate_gather_kernel(const T* __restrict__ feat, long long ld_feat,
                                      const float* __restrict__ rot, T* __restrict__ dst,
@@ -290,6 +299,90 @@ __global__ void rotate_gather_kernel(const T* __restrict__ feat, long long ld_fe
   T* dp = dst + row * ld_dst + k0;
 #pragma unroll
   for (int r = 0; r < 3; ++r) Vec8<T>::store(dp + (long long)r * nvec, o[r]);
+}
+
+// More than two views: every feature row of a sample is a partner of the V-1 other
+// rows. One thread = 8 feature columns of ALL views of one sample: the V x 3 slices are copied once
+// with cp.async into a per-thread scratch in shared memory (all V*3 16-byte copies in flight at
+// once, no registers held, no barrier: a thread reads back only what it copied), then the V outputs
+// are produced one after the other from that scratch -- HBM sees every row once instead of V-1
+// times. Partners are added in ascending view order, as in the general kernel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rotate_gather_staged_kernel(const T* __restrict__ feat, long long ld_feat,
+                            const float* __restrict__ rot, T* __restrict__ dst, long long ld_dst,
+                            int views, int nvec, int apply_rot, long long total /* batch * nvec/8 */) {
+  griddep_wait();    // PDL: predecessors complete + visible
+  griddep_launch();  // let the next kernel of the stream get scheduled
+
+  using Raw = typename Vec8<T>::Raw;
+  constexpr int kPieces = (int)sizeof(Raw) / 16;
+  extern __shared__ uint4 s_stage[];   // [view][component][piece][256 threads]
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int kv = nvec / 8;
+  const int k0 = (int)(idx % kv) * 8;
+  const long long b = idx / kv;
+  const T* fbase = feat + b * views * ld_feat + k0;
+  for (int u = 0; u < views; ++u)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const char* src = reinterpret_cast<const char*>(fbase + u * ld_feat + (long long)c * nvec);
+#pragma unroll
+      for (int q = 0; q < kPieces; ++q)
+        cp_async_16(s_stage + ((u * 3 + c) * kPieces + q) * 256 + threadIdx.x, src + 16 * q);
+    }
+  cp_async_commit();
+  cp_async_wait<0>();
+  const float inv = 1.f / (float)(views - 1);
+  for (int v = 0; v < views; ++v) {
+    float o[3][8];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[r][i] = 0.f;
+    for (int u = 0; u < views; ++u) {
+      if (u == v) continue;
+      float f[3][8];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        Raw raw;
+        uint4* rp = reinterpret_cast<uint4*>(&raw);
+#pragma unroll
+        for (int q = 0; q < kPieces; ++q) rp[q] = s_stage[((u * 3 + c) * kPieces + q) * 256 + threadIdx.x];
+        Vec8<T>::unpack(raw, f[c]);
+      }
+      float R[9];
+      if (apply_rot & 2) {   // backward of the gather: rot[b,u,v]^T
+        const float* rp = rot + ((b * views + u) * views + v) * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + (i % 3) * 3 + i / 3);
+      } else if (apply_rot & 1) {
+        const float* rp = rot + ((b * views + v) * views + u) * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = __ldg(rp + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.f : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float t = R[r * 3 + 0] * f[0][i];
+          t = fmaf(R[r * 3 + 1], f[1][i], t);
+          t = fmaf(R[r * 3 + 2], f[2][i], t);
+          o[r][i] += t;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[r][i] *= inv;
+    T* dp = dst + (b * views + v) * ld_dst + k0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) Vec8<T>::store(dp + (long long)r * nvec, o[r]);
+  }
 }
 
 // Two views (the reference's configuration, models/rot_mv.py:234,238): persistent grid-stride
@@ -395,14 +488,6 @@ __device__ __forceinline__ float warp_sum(float v) {
 constexpr int kHeadRows = 4;     // the shuffle tree in head_loss_kernel is written for 4
 constexpr int kHeadStages = 3;
 
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
-                   (uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 // prediction write + loss term of one row per lane (models/backbones/blocks.py:41-60 output,
 // utils/math.py:52-60, losses/gaze_loss.py:42-52)
@@ -740,9 +825,32 @@ extern "C" int rmv_rotate_gather_fwd(const void* feat, long long ld_feat, const 
     RMV_LAUNCH_CHECK();
     return 0;
   }
-  // V > 2: one short thread per (row, 8 columns); the V-1 re-reads of a partner row by the rows of
-  // the same sample hit L1/L2 (measured: 0.92 / 1.04 of the HBM copy rate in algorithmic bytes at
-  // V = 4 / 8 -- a register-blocked variant that loaded each partner once per thread was slower)
+  const int esz = dtype == RMV_DTYPE_BF16 ? 2 : 4;
+  const int stage_bytes = views * 3 * 8 * esz * 256;   // V x 12 KB (bf16) / V x 24 KB (fp32) per block
+  if (stage_bytes <= 200 * 1024) {
+    // 3..8 views (16 in bf16): every row read from HBM once, staged per thread in shared memory
+    const long long total = (long long)batch * (nvec / 8);
+    if (total == 0) return 0;
+    if (dtype == RMV_DTYPE_BF16) {
+      if (stage_bytes > 48 * 1024)
+        RMV_CUDA(cudaFuncSetAttribute(rotate_gather_staged_kernel<__nv_bfloat16>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      rmv::launch_pdl(rotate_gather_staged_kernel<__nv_bfloat16>, dim3(blocks_for(total, 256)), dim3(256),
+                      stage_bytes, s, (const __nv_bfloat16*)feat, ld_feat, rot, (__nv_bfloat16*)dst,
+                      ld_dst, views, nvec, apply_rot, total);
+    } else {
+      if (stage_bytes > 48 * 1024)
+        RMV_CUDA(cudaFuncSetAttribute(rotate_gather_staged_kernel<float>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      rmv::launch_pdl(rotate_gather_staged_kernel<float>, dim3(blocks_for(total, 256)), dim3(256),
+                      stage_bytes, s, (const float*)feat, ld_feat, rot, (float*)dst, ld_dst, views, nvec,
+                      apply_rot, total);
+    }
+    RMV_LAUNCH_CHECK();
+    return 0;
+  }
+  // more views than the staging buffer holds: one short thread per (row, 8 columns); the V-1
+  // re-reads of a partner row by the rows of the same sample hit L1/L2
   const long long total = (long long)batch * views * (nvec / 8);
   if (total == 0) return 0;
   if (dtype == RMV_DTYPE_BF16)

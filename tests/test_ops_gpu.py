@@ -136,8 +136,12 @@ def test_maxpool_avgpool():
         assert torch.equal(o0, o1) and o0[:, 2048:].abs().max().item() == 0
 
 
-@pytest.mark.parametrize("views", [2, 4])
+@pytest.mark.parametrize("views", [2, 3, 4, 8, 20])
 def test_rotate_gather(views):
+    """models/rot_mv.py:234,238 generalised to V views: the pair kernel (V = 2), the
+    shared-memory staged kernel (3 <= V <= 8 in fp32) and the general kernel (V = 20) against the
+    formula, fp32 and bf16; the transposed mode (backward of the gather) through the adjoint identity
+    <A x, y> = <x, A^T y>."""
     from rotmv_b200 import functional as RF
 
     g = torch.Generator(device="cuda").manual_seed(11)
@@ -156,6 +160,30 @@ def test_rotate_gather(views):
     ref /= (views - 1)
     assert (dst[:, 2048:].reshape(b, views, 3, 512) - ref).abs().max().item() < 1e-5
     assert dst[:, :2048].abs().max().item() == 0
+    # bf16 storage: same arithmetic on the rounded inputs, one rounding of the result
+    f16 = feat.bfloat16()
+    d16 = torch.zeros((b * views, 1536), device="cuda", dtype=torch.bfloat16)
+    RF.rotate_gather(f16, rot, d16, b, views)
+    ref16 = torch.zeros_like(f3)
+    f3r = f16.float().view(b, views, 3, 512)
+    for v in range(views):
+        for u in range(views):
+            if u != v:
+                ref16[:, v] += rot[:, v, u] @ f3r[:, u]
+    ref16 /= (views - 1)
+    assert (d16.float().view(b, views, 3, 512) - ref16).abs().max().item() <= 2e-2 * ref16.abs().max().item()
+    # identity mode (ignore_rotmat): plain partner mean
+    RF.rotate_gather(feat, rot, dst[:, 2048:], b, views, 512, False)
+    mean_ref = (f3.sum(1, keepdim=True) - f3) / (views - 1)
+    assert (dst[:, 2048:].reshape(b, views, 3, 512) - mean_ref).abs().max().item() < 1e-5
+    # transposed mode = adjoint of the forward gather
+    y = torch.randn((b * views, 1536), device="cuda", generator=g)
+    aty = torch.empty_like(y)
+    RF.rotate_gather(y, rot, aty, b, views, 512, True, transpose=True)
+    ax = torch.empty_like(feat)
+    RF.rotate_gather(feat, rot, ax, b, views, 512, True)
+    lhs, rhs = (ax.double() * y.double()).sum().item(), (feat.double() * aty.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs)), (lhs, rhs)
 
 
 def test_stem_im2col_matches_conv():

@@ -582,3 +582,42 @@ def test_depth18_step_fp32_vs_live_oracle_and_bf16(flags):
         p0 = eng.flat_p.clone()
         eng.step(images.cuda(), rot.cuda(), gt.cuda())
         assert torch.isfinite(eng.flat_p).all() and not torch.equal(p0, eng.flat_p)
+
+
+def test_three_view_step_fp32_vs_live_oracle():
+    """V = 3 training step (SURVEY D1 generalisation; BatchNorm statistics per view, partner mean
+    in the fusion and its transposed gather in the backward pass): fp32 engine against the CPU
+    oracle's autograd on the same batch and weights."""
+    from oracle import rotmv_oracle as O
+    from rotmv_b200.module import FeatRotationSymm
+    from rotmv_b200.train import TrainEngine
+
+    B, V = 4, 3
+    ora = O.build_model(num_iter=2, depth=18, seed=0)
+    sd0 = {k: v.clone() for k, v in ora.state_dict().items()}
+    images, pose, gt = O.synthetic_batch(B, V, seed=4)
+    rot = O.pairwise_rotations(pose)
+    ora.train()
+    out = ora.forward_views(images, rot)
+    loss_ref = O.iteration_loss(out, [gt[:, v] for v in range(V)])
+    loss_ref.backward()
+    ref_grads = {n: p.grad.clone() for n, p in ora.named_parameters() if p.grad is not None}
+    model = FeatRotationSymm(18, 2)
+    model.load_state_dict(sd0, strict=True)
+    model = model.cuda().train()
+    eng = TrainEngine(model, precision="fp32", lr=1e-3, weight_decay=1e-6)
+    res = eng.forward_backward(images.cuda(), rot.cuda(), gt.cuda())
+    loss = res["loss"].item()
+    assert abs(loss - loss_ref.item()) <= 1e-4 * abs(loss_ref.item()), (loss, loss_ref.item())
+    named = dict(model.named_parameters())
+    errs = []
+    for n, g_ref in ref_grads.items():
+        g = eng.grads[id(named[n])].cpu().double()
+        errs.append((abs(g.norm().item() - g_ref.double().norm().item()) / max(g_ref.double().norm().item(), 1e-12), n))
+    errs.sort(reverse=True)
+    assert len(errs) == len(ref_grads) and errs[0][0] <= 2e-2, errs[:3]
+    assert errs[len(errs) // 2][0] <= 2e-3, errs[len(errs) // 2]
+    # lifter gradient element-wise (it collects every path through the rotated gathers)
+    n = "_lifter._lifter.blocks.1.0.bias"
+    assert rel_l2(eng.grads[id(named[n])].cpu(), ref_grads[n]) <= 2e-2
+    assert int(model._feat_extractor[0].bn1.num_batches_tracked) == V
