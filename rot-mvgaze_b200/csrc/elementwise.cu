@@ -827,8 +827,11 @@ extern "C" int rmv_rotate_gather_fwd(const void* feat, long long ld_feat, const 
   }
   const int esz = dtype == RMV_DTYPE_BF16 ? 2 : 4;
   const int stage_bytes = views * 3 * 8 * esz * 256;   // V x 12 KB (bf16) / V x 24 KB (fp32) per block
-  if (stage_bytes <= 200 * 1024) {
-    // 3..8 views (16 in bf16): every row read from HBM once, staged per thread in shared memory
+  if (views <= 4) {
+    // 3 or 4 views: every row read from HBM once, staged per thread in shared memory (measured at
+    // B=32768, V=4: 239 us vs 271 us for the general kernel). From 5 views on the V(V-1) 3x3
+    // products per column make the kernel instruction-bound and the staging's lower occupancy costs
+    // more than the saved L2 re-reads (V=8: 568 us staged vs 476 us general), so those stay general.
     const long long total = (long long)batch * (nvec / 8);
     if (total == 0) return 0;
     if (dtype == RMV_DTYPE_BF16) {
@@ -849,8 +852,8 @@ extern "C" int rmv_rotate_gather_fwd(const void* feat, long long ld_feat, const 
     RMV_LAUNCH_CHECK();
     return 0;
   }
-  // more views than the staging buffer holds: one short thread per (row, 8 columns); the V-1
-  // re-reads of a partner row by the rows of the same sample hit L1/L2
+  // general kernel: one short thread per (row, 8 columns); the V-1 re-reads of a partner row by
+  // the rows of the same sample hit L1/L2
   const long long total = (long long)batch * views * (nvec / 8);
   if (total == 0) return 0;
   if (dtype == RMV_DTYPE_BF16)

@@ -139,7 +139,7 @@ def test_maxpool_avgpool():
 @pytest.mark.parametrize("views", [2, 3, 4, 8, 20])
 def test_rotate_gather(views):
     """models/rot_mv.py:234,238 generalised to V views: the pair kernel (V = 2), the
-    shared-memory staged kernel (3 <= V <= 8 in fp32) and the general kernel (V = 20) against the
+    shared-memory staged kernel (V = 3, 4) and the general kernel (V = 8, 20) against the
     formula, fp32 and bf16; the transposed mode (backward of the gather) through the adjoint identity
     <A x, y> = <x, A^T y>."""
     from rotmv_b200 import functional as RF
