@@ -334,8 +334,11 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(double* __restrict
 // walks the image's pixels with 4 independent 16-byte loads in flight per tensor.
 constexpr int kEwUnroll = 4;
 
-template <typename T>
-__global__ void __launch_bounds__(256, 3)
+// UNROLL = kEwUnroll with a residual (two input streams); without one (most launches: bn1/bn2 of
+// every block, the stem, the downsample branches) twice that, so that a thread keeps the same
+// 128 bytes of loads in flight either way.
+template <typename T, int UNROLL, bool HAS_RES>
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2)
 bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ a, const float* __restrict__ b,
                 const T* __restrict__ residual, T* __restrict__ y,
                 uint8_t* __restrict__ relu_bits, int pix, int c, int views, int relu) {
@@ -352,31 +355,31 @@ bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ a, const floa
   V8<float>::load(a + v * c + g * 8, ca);
   V8<float>::load(b + v * c + g * 8, cb);
   const T* zi = z + (long long)n * pix * c;
-  const T* ri = residual ? residual + (long long)n * pix * c : nullptr;
+  const T* ri = HAS_RES ? residual + (long long)n * pix * c : nullptr;
   T* yi = y + (long long)n * pix * c;
   uint8_t* bi = relu_bits ? relu_bits + (long long)n * per_img : nullptr;
-  for (long long i = i0; i < per_img; i += stride * kEwUnroll) {
-    typename V8<T>::Raw zr[kEwUnroll], rr[kEwUnroll];
+  for (long long i = i0; i < per_img; i += stride * UNROLL) {
+    typename V8<T>::Raw zr[UNROLL], rr[HAS_RES ? UNROLL : 1];
 #pragma unroll
-    for (int j = 0; j < kEwUnroll; ++j) {
+    for (int j = 0; j < UNROLL; ++j) {
       const long long k = i + j * stride;
       if (k < per_img) {
         zr[j] = V8<T>::load_raw(zi + k * 8);
-        if (ri) rr[j] = V8<T>::load_raw(ri + k * 8);
+        if (HAS_RES) rr[j] = V8<T>::load_raw(ri + k * 8);
       }
     }
 #pragma unroll
-    for (int j = 0; j < kEwUnroll; ++j) {
+    for (int j = 0; j < UNROLL; ++j) {
       const long long k = i + j * stride;
       if (k < per_img) {
         float f[8], r[8], o[8];
         V8<T>::unpack(zr[j], f);
-        if (ri) V8<T>::unpack(rr[j], r);
+        if (HAS_RES) V8<T>::unpack(rr[j], r);
         uint32_t bits = 0;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           o[e] = fmaf(f[e], ca[e], cb[e]);
-          if (ri) o[e] += r[e];
+          if (HAS_RES) o[e] += r[e];
           bits |= (o[e] > 0.f ? 1u : 0u) << e;
           if (relu) o[e] = fmaxf(o[e], 0.f);
         }
@@ -1151,6 +1154,12 @@ using namespace rmv;
   if ((dtype) == RMV_DTYPE_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
   else { using T = float; __VA_ARGS__; }
 
+// RMV_BN_APPLY_U8=0 keeps the 4-deep form for launches without a residual (A/B switch)
+static bool apply_unroll8() {
+  static const int on = [] { const char* e = getenv("RMV_BN_APPLY_U8"); return e ? atoi(e) : 1; }();
+  return on != 0;
+}
+
 // blocks along x for the per-image elementwise kernels: enough threads for kEwUnroll vectors each,
 // but at least ~4 waves of blocks over the whole launch
 static unsigned ew_blocks_x(int pix, int c, int n_img, int unroll = rmv::kEwUnroll) {
@@ -1243,9 +1252,22 @@ extern "C" int rmv_bn_apply(const void* z, const float* a, const float* b, const
                             int views, int relu, void* stream) {
   RMV_CHECK_ARG(c % 8 == 0 && 256 % (c / 8) == 0, "bn_apply: c=%d must be 8*2^k, <= 2048", c);
   if ((long long)n_img * pix == 0) return 0;
+  if (residual == nullptr && dtype == RMV_DTYPE_BF16 && apply_unroll8()) {
+    const dim3 grid(ew_blocks_x(pix, c, n_img, 2 * rmv::kEwUnroll), (unsigned)n_img);
+    rmv::launch_pdl(bn_apply_kernel<__nv_bfloat16, 2 * rmv::kEwUnroll, false>, dim3(grid), dim3(256), 0,
+                    (cudaStream_t)stream, (const __nv_bfloat16*)z, a, b, (const __nv_bfloat16*)nullptr,
+                    (__nv_bfloat16*)y, relu_bits, pix, c, views, relu);
+    RMV_LAUNCH_CHECK();
+    return 0;
+  }
   const dim3 grid(ew_blocks_x(pix, c, n_img), (unsigned)n_img);
-  DISPATCH_T(dtype, (rmv::launch_pdl(bn_apply_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
-      (const T*)z, a, b, (const T*)residual, (T*)y, relu_bits, pix, c, views, relu)));
+  if (residual != nullptr) {
+    DISPATCH_T(dtype, (rmv::launch_pdl(bn_apply_kernel<T, rmv::kEwUnroll, true>, dim3(grid), dim3(256), 0,
+        (cudaStream_t)stream, (const T*)z, a, b, (const T*)residual, (T*)y, relu_bits, pix, c, views, relu)));
+  } else {
+    DISPATCH_T(dtype, (rmv::launch_pdl(bn_apply_kernel<T, rmv::kEwUnroll, false>, dim3(grid), dim3(256), 0,
+        (cudaStream_t)stream, (const T*)z, a, b, (const T*)nullptr, (T*)y, relu_bits, pix, c, views, relu)));
+  }
   RMV_LAUNCH_CHECK();
   return 0;
 }
