@@ -60,9 +60,11 @@ class TrainEngine:
         self.model, self.precision, self.dt = model, precision, _DT[precision]
         self.dtc = L.dtype_code(self.dt)
         trunk = model._feat_extractor[0]
-        if getattr(model, "_encode_rotmat", False) or getattr(model, "_share_feature", False):
-            raise NotImplementedError("TrainEngine covers the fuser of main.py (ImageFeatFuser); the "
-                                      "encode_rotmat / share_feature variants are inference-only")
+        # constructor variants, two views only like the reference: encode_rotmat
+        # (ImageRotmatFeatFuser, models/rot_mv.py:53-67,225-231) and share_feature (RotFeatFuser +
+        # IntensityBatchNorm, :13-32,70-85,201-203,243-248)
+        self.encode_rot = bool(getattr(model, "_encode_rotmat", False)) and not model._ignore_rotmat
+        self.share_feat = bool(getattr(model, "_share_feature", False))
         self.device = trunk.conv1.weight.device
         if self.device.type != "cuda":
             raise L.RotmvError("TrainEngine needs the model on a CUDA device; there is no CPU path")
@@ -124,7 +126,7 @@ class TrainEngine:
             self.blocks.append(e)
         lif = model._lifter._lifter.blocks
         self.lift = [lif[0][0], lif[1][0]]
-        self.fusers = [[m._fuser.blocks[0][0], m._fuser.blocks[1][0]] for m in model._img_fusers]
+        self.fusers = [[blk[0] for blk in m._fuser.blocks] for m in model._img_fusers]
         self.heads = [[m.blocks[0][0], m.blocks[1][0]] for m in model._gaze_estimators]
         self.acc = torch.zeros((max_views, 2048, 2), device=self.device, dtype=torch.float64)
         self.ticket = torch.zeros((1,), device=self.device, dtype=torch.int32)
@@ -267,8 +269,9 @@ class TrainEngine:
         return dz, dyr
 
     # ---- convolution gradients -----------------------------------------------------------------
-    def _wgrad(self, x, dy, conv_or_lin, kh, kw, stride, pad, x_strides=None):
-        """dW (fp32, parameter layout) += sum_p dy[p,k] x[p+(r,s), c]."""
+    def _wgrad(self, x, dy, conv_or_lin, kh, kw, stride, pad, x_strides=None, grad=None):
+        """dW (fp32, parameter layout) += sum_p dy[p,k] x[p+(r,s), c]. `grad` overrides the
+        destination (default: the parameter's slice of the flat gradient buffer)."""
         a = L.ConvArgs()
         a.x_dtype = L.dtype_code(x.dtype)
         a.x = x.data_ptr()
@@ -282,7 +285,8 @@ class TrainEngine:
         a.y_sn, a.y_sh, a.y_sw = dy.stride(0), dy.stride(1), dy.stride(2)
         a.out_h, a.out_w = dy.shape[1], dy.shape[2]
         assert L.dtype_code(dy.dtype) == a.x_dtype
-        grad = self.grads[id(conv_or_lin.weight)]
+        if grad is None:
+            grad = self.grads[id(conv_or_lin.weight)]
         if self.use_tc_wgrad and x.dtype == torch.bfloat16 and c % 64 == 0 and a.x_sc == 1:
             # tcgen05 weight gradient into an fp32 [k][r][s][c] buffer; 1x1 / Linear: that IS the
             # parameter layout, so accumulate straight into the (zeroed) flat gradient slice.
@@ -303,8 +307,7 @@ class TrainEngine:
         RF._call("rmv_conv2d_wgrad", {"desc": f"wgrad {kh}x{kw}s{stride} [{n},{h},{w},{c}]->{dy.shape[3]}",
                                       "engine": "ffma-wgrad",
                                       "flops": 2.0 * n * dy.shape[1] * dy.shape[2] * dy.shape[3] * kh * kw * c},
-                 L.load().rmv_conv2d_wgrad, C.byref(a), dy.data_ptr(),
-                 self.grads[id(conv_or_lin.weight)].data_ptr(), L.stream_ptr())
+                 L.load().rmv_conv2d_wgrad, C.byref(a), dy.data_ptr(), grad.data_ptr(), L.stream_ptr())
 
     def _dgrad(self, dz, conv, tag, in_shape, residual=None):
         """dx = conv_transpose(dz, w) (+ residual) via the forward kernel with flipped filters."""
@@ -331,7 +334,7 @@ class TrainEngine:
     def _lin_bwd(self, lin, tag, x, dy, dx_out, need_dx=True):
         """bias grad, weight grad and (optionally) input grad of y = x W^T + b."""
         m, n = dy.shape
-        _ck("rmv_colsum", dy.data_ptr(), dy.stride(0), m, n, self.dtc, self.grads[id(lin.bias)].data_ptr())
+        self._colsum(dy, n, self.grads[id(lin.bias)])
         x4 = x.as_strided((1, 1, m, x.shape[1]), (0, 0, x.stride(0), 1), x.storage_offset())
         d4 = dy.as_strided((1, 1, m, n), (0, 0, dy.stride(0), 1), dy.storage_offset())
         self._wgrad(x4, d4, lin, 1, 1, 1, 0)
@@ -362,6 +365,290 @@ class TrainEngine:
             1.0 / self.world)
         self.launches_last_step = L.STATS["launches"] - before
         return self.loss
+
+    # ---- fusion stage: forward + loss + backward down to d(loss)/d(pooled image feature) ----------
+    def _fusion_default(self, x, rot, gt_flat, b, v, cfg):
+        """ImageFeatFuser configuration (the one main.py builds; models/rot_mv.py:35-50,198-254)."""
+        m = b * v
+        dt, dtc = self.dt, self.dtc
+        wide = self.fc_dim + 3 * self.nvec
+        fd = self.fc_dim
+        xs = [self._buf(("X", i), (m, wide)) for i in range(self.num_iter)]
+        ys = [self._buf(("Y", i), (m, wide)) for i in range(self.num_iter)]
+        hs = [self._buf(("H", i), (m, wide)) for i in range(self.num_iter)]
+        gs = [self._buf(("G", i), (m, 512)) for i in range(self.num_iter)]
+        preds = [self._buf(("pred", i), (m, 2), torch.float32) for i in range(self.num_iter)]
+        y_init = self._buf("Yinit", (m, wide))
+        RF.avgpool(x, y_init, xs[0])
+        img = y_init[:, :fd]
+        for i in range(self.num_iter):
+            if i > 0:
+                self._add(img, xs[i][:, :fd])
+            self._add(img, ys[i][:, :fd])
+        l1 = self._buf("L1", (m, 3 * self.nvec))
+        self._lin(img, self._lin_fwd(self.lift[0], "l0"), self.lift[0].bias, True, l1)
+        self._lin(l1, self._lin_fwd(self.lift[1], "l1"), self.lift[1].bias, False, y_init[:, fd:])
+        scales = []
+        for i in range(self.num_iter):
+            f_prev = (y_init if i == 0 else ys[i - 1])[:, fd:]
+            RF.rotate_gather(f_prev, rot, xs[i][:, fd:], b, v, self.nvec, self.apply_rot)
+            f1, f2 = self.fusers[i]
+            self._lin(xs[i], self._lin_fwd(f1, ("f1", i)), f1.bias, True, hs[i])
+            self._lin(hs[i], self._lin_fwd(f2, ("f2", i)), f2.bias, False, ys[i][:, fd:])
+            h1, h2 = self.heads[i]
+            self._lin(ys[i], self._lin_fwd(h1, ("h1", i)), h1.bias, True, gs[i])
+            scale = (cfg["iter_decay"] ** (self.num_iter - 1 - i)) * cfg["rel_weight"] / b
+            scales.append(scale)
+            RF.head_loss(gs[i], h2.weight.detach(), h2.bias.detach(), preds[i], gt_flat, scale,
+                         self.loss, views=v, aux_decay=cfg["reference_decay"])
+
+        # ================================ backward ================================
+        dimg = self._buf("dimg", (m, fd))
+        dimg.zero_()
+        d_f_next = None
+        for i in reversed(range(self.num_iter)):
+            h1, h2 = self.heads[i]
+            f1, f2 = self.fusers[i]
+            dg = self._buf("dG", (m, 512))
+            dpred = self._buf("dpred", (m, 2), torch.float32)
+            self._head_bwd(preds[i], gt_flat, gs[i], h2, scales[i], v, cfg, dg, dpred)
+            d_y = self._lin_bwd(h1, ("h1", i), ys[i], dg, self._buf("dY", (m, wide)))
+            self._add(d_y[:, :fd], dimg, add=dimg)
+            d_f = self._buf("dF", (m, 3 * self.nvec))
+            self._add(d_y[:, fd:], d_f, add=d_f_next)
+            d_h = self._lin_bwd(f2, ("f2", i), hs[i], d_f, self._buf("dH", (m, wide)))
+            self._add(d_h, d_h, mask=hs[i])
+            d_x = self._lin_bwd(f1, ("f1", i), xs[i], d_h, self._buf("dX", (m, wide)))
+            self._add(d_x[:, :fd], dimg, add=dimg)
+            d_f_next = self._buf("dFn", (m, 3 * self.nvec))
+            RF.rotate_gather(d_x[:, fd:], rot, d_f_next, b, v, self.nvec, self.apply_rot, transpose=True)
+        d_l1 = self._lin_bwd(self.lift[1], "l1", l1, d_f_next, self._buf("dL1", (m, 3 * self.nvec)))
+        self._add(d_l1, d_l1, mask=l1)
+        d_img2 = self._lin_bwd(self.lift[0], "l0", img, d_l1, self._buf("dimg2", (m, fd)))
+        self._add(d_img2, dimg, add=dimg)
+        return dimg, preds
+
+    # ---- constructor variants (SURVEY 8f n3; two views) --------------------------------------------
+    # The GEMMs, weight gradients, rotation gathers, head/loss kernels are the sm_100a kernels of the
+    # default configuration. What these variants add -- zero-padding the 3593-wide layers to a
+    # multiple of 64, the 9 rotation entries per row, the [3][2][512] interleave of RotFeatFuser and
+    # IntensityBatchNorm's 512-element statistics -- is done with plain tensor copies / small torch
+    # reductions: they are not on the path main.py builds.
+    def _colsum(self, dy, n, dst):
+        """dst[:n] += column sums of dy[:, :n] (bias gradient)."""
+        _ck("rmv_colsum", dy.data_ptr(), dy.stride(0), dy.shape[0], n, self.dtc, dst.data_ptr())
+
+    def _head_bwd(self, pred, gt_flat, g, h2, scale, views, cfg, dg, dpred):
+        """Backward of the fused head tail + loss (rmv_head_loss_bwd): d hidden, d pred, dW2, db2."""
+        _ck("rmv_head_loss_bwd", pred.data_ptr(), gt_flat.data_ptr(), g.data_ptr(), g.stride(0), self.dtc,
+            h2.weight.data_ptr(), g.shape[0], g.shape[1], scale, views, cfg["reference_decay"],
+            dg.data_ptr(), dg.stride(0), dpred.data_ptr(), self.grads[id(h2.weight)].data_ptr(),
+            self.grads[id(h2.bias)].data_ptr())
+
+    def _padded_linear(self, lin, tag, pk, pn):
+        """bf16/fp32 copies of lin.weight zero-padded to [pn, pk] and its transpose [pk, pn], the
+        bias zero-padded to [pn] (refreshed every step: the fp32 masters move in the Adam kernel)."""
+        n, k = lin.weight.shape
+        key = ("padw", tag)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.zeros((pn, pk), device=self.device, dtype=self.dt),
+                               torch.zeros((pk, pn), device=self.device, dtype=self.dt),
+                               torch.zeros((pn,), device=self.device, dtype=torch.float32))
+        w, wt, bias = self._bufs[key]
+        w[:n, :k].copy_(lin.weight.detach())
+        wt[:k, :n].copy_(lin.weight.detach().t())
+        bias[:n].copy_(lin.bias.detach())
+        return w, wt, bias
+
+    def _padded_lin_bwd(self, lin, wt, x, dy, dx_out):
+        """Backward of y = x Wp^T + bp on zero-padded operands: x [m, pk], dy [m, pn] (padding
+        columns are zero). The weight gradient is formed at the padded size in an fp32 scratch and its
+        [n, k] corner added to the parameter's gradient (+=: share_weights aliases one fuser)."""
+        n, k = lin.weight.shape
+        m, pn = dy.shape
+        pk = x.shape[1]
+        self._colsum(dy, n, self.grads[id(lin.bias)])
+        scratch = self._buf(("padg", pn, pk), (pn, pk), torch.float32)
+        scratch.zero_()
+        x4 = x.as_strided((1, 1, m, pk), (0, 0, x.stride(0), 1), x.storage_offset())
+        d4 = dy.as_strided((1, 1, m, pn), (0, 0, dy.stride(0), 1), dy.storage_offset())
+        self._wgrad(x4, d4, lin, 1, 1, 1, 0, grad=scratch)
+        self.grads[id(lin.weight)].add_(scratch[:n, :k])
+        if dx_out is not None:
+            RF.linear(dy, wt, None, out=dx_out)
+        return dx_out
+
+    def _fusion_encode_rotmat(self, x, rot, gt_flat, b, cfg):
+        """ImageRotmatFeatFuser (models/rot_mv.py:53-67,225-231): the partner feature is NOT rotated;
+        the 9 entries of R_{self<-partner} are appended to the fuser input instead. Fuser = three
+        Linear layers of width fc+1536+9 (3593 for ResNet-50), run zero-padded to a multiple of 64."""
+        v, m = 2, 2 * b
+        dt, dtc = self.dt, self.dtc
+        fd, nv3, n_it = self.fc_dim, 3 * self.nvec, self.num_iter
+        wide = fd + nv3
+        w_true = wide + 9
+        p = (w_true + 63) // 64 * 64
+        xs = [self._buf(("Xe", i), (m, p)) for i in range(n_it)]
+        h1s = [self._buf(("He1", i), (m, p)) for i in range(n_it)]
+        h2s = [self._buf(("He2", i), (m, p)) for i in range(n_it)]
+        ys = [self._buf(("Y", i), (m, wide)) for i in range(n_it)]
+        gs = [self._buf(("G", i), (m, 512)) for i in range(n_it)]
+        preds = [self._buf(("pred", i), (m, 2), torch.float32) for i in range(n_it)]
+        y_init = self._buf("Yinit", (m, wide))
+        for t in xs:
+            t.zero_()
+        RF.avgpool(x, y_init, xs[0])
+        img = y_init[:, :fd]
+        # row (b, view) gets R_{view <- partner}: rot[b,0,1] = rot_10, rot[b,1,0] = rot_01 (:193-194)
+        pair = torch.stack([rot[:, 0, 1], rot[:, 1, 0]], dim=1).reshape(m, 9)
+        for i in range(n_it):
+            if i > 0:
+                self._add(img, xs[i][:, :fd])
+            self._add(img, ys[i][:, :fd])
+            xs[i][:, wide:w_true].copy_(pair)
+        l1 = self._buf("L1", (m, nv3))
+        self._lin(img, self._lin_fwd(self.lift[0], "l0"), self.lift[0].bias, True, l1)
+        self._lin(l1, self._lin_fwd(self.lift[1], "l1"), self.lift[1].bias, False, y_init[:, fd:])
+        scales, padded = [], []
+        for i in range(n_it):
+            f_prev = (y_init if i == 0 else ys[i - 1])[:, fd:]
+            RF.rotate_gather(f_prev, rot, xs[i][:, fd:wide], b, v, self.nvec, False)   # partner, unrotated
+            f1, f2, f3 = self.fusers[i]
+            pw = [self._padded_linear(f1, ("e1", i), p, p), self._padded_linear(f2, ("e2", i), p, p),
+                  self._padded_linear(f3, ("e3", i), p, nv3)]
+            padded.append(pw)
+            self._lin(xs[i], pw[0][0], pw[0][2], True, h1s[i])
+            self._lin(h1s[i], pw[1][0], pw[1][2], True, h2s[i])
+            self._lin(h2s[i], pw[2][0], pw[2][2], False, ys[i][:, fd:])
+            h1, h2 = self.heads[i]
+            self._lin(ys[i], self._lin_fwd(h1, ("h1", i)), h1.bias, True, gs[i])
+            scale = (cfg["iter_decay"] ** (n_it - 1 - i)) * cfg["rel_weight"] / b
+            scales.append(scale)
+            RF.head_loss(gs[i], h2.weight.detach(), h2.bias.detach(), preds[i], gt_flat, scale,
+                         self.loss, views=v, aux_decay=cfg["reference_decay"])
+        # backward
+        dimg = self._buf("dimg", (m, fd))
+        dimg.zero_()
+        d_f_next = None
+        for i in reversed(range(n_it)):
+            h1, h2 = self.heads[i]
+            f1, f2, f3 = self.fusers[i]
+            pw = padded[i]
+            dg = self._buf("dG", (m, 512))
+            dpred = self._buf("dpred", (m, 2), torch.float32)
+            self._head_bwd(preds[i], gt_flat, gs[i], h2, scales[i], v, cfg, dg, dpred)
+            d_y = self._lin_bwd(h1, ("h1", i), ys[i], dg, self._buf("dY", (m, wide)))
+            self._add(d_y[:, :fd], dimg, add=dimg)
+            d_f = self._buf("dF", (m, nv3))
+            self._add(d_y[:, fd:], d_f, add=d_f_next)
+            d_h2 = self._padded_lin_bwd(f3, pw[2][1], h2s[i], d_f, self._buf("dHe2", (m, p)))
+            self._add(d_h2, d_h2, mask=h2s[i])
+            d_h1 = self._padded_lin_bwd(f2, pw[1][1], h1s[i], d_h2, self._buf("dHe1", (m, p)))
+            self._add(d_h1, d_h1, mask=h1s[i])
+            d_x = self._padded_lin_bwd(f1, pw[0][1], xs[i], d_h1, self._buf("dXe", (m, p)))
+            self._add(d_x[:, :fd], dimg, add=dimg)
+            d_f_next = self._buf("dFn", (m, nv3))
+            RF.rotate_gather(d_x[:, fd:wide], rot, d_f_next, b, v, self.nvec, False, transpose=True)
+        d_l1 = self._lin_bwd(self.lift[1], "l1", l1, d_f_next, self._buf("dL1", (m, nv3)))
+        self._add(d_l1, d_l1, mask=l1)
+        d_img2 = self._lin_bwd(self.lift[0], "l0", img, d_l1, self._buf("dimg2", (m, fd)))
+        self._add(d_img2, dimg, add=dimg)
+        return dimg, preds
+
+    def _intensity_scale(self, bn, feat_bv):
+        """Train-mode IntensityBatchNorm (models/rot_mv.py:13-32) of one call: feat_bv [B, 3, 512].
+        Updates the running STD (buffer `running_mean`) from the batch and returns the per-vector
+        scale 1 / (running_std + eps) [512] that this call applies; the norm is detached in the
+        reference, so the scale is a constant of the backward pass."""
+        intensity = feat_bv.float().norm(dim=-2, keepdim=True)                      # [B, 1, 512]
+        var = intensity.var(dim=0, unbiased=False, keepdim=True)
+        std = var.clamp_min(bn.eps).sqrt()
+        bn.running_mean.copy_(bn.running_mean * (1 - bn.momentum) + std * bn.momentum)
+        return (1.0 / (bn.running_mean.reshape(-1) + bn.eps)).to(self.dt)
+
+    def _fusion_share_feature(self, x, rot, gt_flat, b, cfg):
+        """share_feature=True (models/rot_mv.py:70-85,160-171,201-203,243-248): the lifted feature
+        replaces the image feature; fuser input = cat(BN(F_init), BN(R F_partner), -1).flatten() of
+        two [3,512] features = the [3][2][512] interleave, three Linear layers of width 3072; head
+        input = cat(F_init, F_new, -1).flatten(). IntensityBatchNorm runs in train mode: four
+        sequential running-std updates per iteration (view 0: own, rotated partner; view 1: same)."""
+        v, m = 2, 2 * b
+        dt, dtc = self.dt, self.dtc
+        fd, nv, n_it = self.fc_dim, self.nvec, self.num_iter
+        nv3, w6 = 3 * nv, 6 * nv
+        xs = [self._buf(("Xs", i), (m, w6)) for i in range(n_it)]
+        h1s = [self._buf(("Hs1", i), (m, w6)) for i in range(n_it)]
+        h2s = [self._buf(("Hs2", i), (m, w6)) for i in range(n_it)]
+        ys = [self._buf(("Ys", i), (m, w6)) for i in range(n_it)]
+        fs = [self._buf(("Fs", i), (m, nv3)) for i in range(n_it)]
+        gs = [self._buf(("G", i), (m, 512)) for i in range(n_it)]
+        preds = [self._buf(("pred", i), (m, 2), torch.float32) for i in range(n_it)]
+        img = self._buf("img", (m, fd))
+        RF.avgpool(x, img, None)
+        l1 = self._buf("L1", (m, nv3))
+        f_init = self._buf("Finit", (m, nv3))
+        self._lin(img, self._lin_fwd(self.lift[0], "l0"), self.lift[0].bias, True, l1)
+        self._lin(l1, self._lin_fwd(self.lift[1], "l1"), self.lift[1].bias, False, f_init)
+        fi4 = f_init.view(b, v, 3, nv)
+        rotf = self._buf("rotF", (m, nv3))
+        scales, bn_scales = [], []
+        for i in range(n_it):
+            f_prev = f_init if i == 0 else fs[i - 1]
+            RF.rotate_gather(f_prev, rot, rotf, b, v, nv, self.apply_rot)       # R_{self<-partner} F_partner
+            r4 = rotf.view(b, v, 3, nv)
+            bn = self.model._img_fusers[i]._batchnorm
+            xv = xs[i].view(b, v, 3, 2, nv)
+            sc = torch.empty((v, 2, nv), device=self.device, dtype=dt)
+            for k in range(v):                                                   # view order, as the reference
+                sc[k, 0] = self._intensity_scale(bn, fi4[:, k])
+                xv[:, k, :, 0] = fi4[:, k] * sc[k, 0]
+                sc[k, 1] = self._intensity_scale(bn, r4[:, k])
+                xv[:, k, :, 1] = r4[:, k] * sc[k, 1]
+            bn_scales.append(sc)
+            f1, f2, f3 = self.fusers[i]
+            self._lin(xs[i], self._lin_fwd(f1, ("f1", i)), f1.bias, True, h1s[i])
+            self._lin(h1s[i], self._lin_fwd(f2, ("f2", i)), f2.bias, True, h2s[i])
+            self._lin(h2s[i], self._lin_fwd(f3, ("f3", i)), f3.bias, False, fs[i])
+            yv = ys[i].view(m, 3, 2, nv)
+            yv[:, :, 0].copy_(f_init.view(m, 3, nv))
+            yv[:, :, 1].copy_(fs[i].view(m, 3, nv))
+            h1, h2 = self.heads[i]
+            self._lin(ys[i], self._lin_fwd(h1, ("h1", i)), h1.bias, True, gs[i])
+            scale = (cfg["iter_decay"] ** (n_it - 1 - i)) * cfg["rel_weight"] / b
+            scales.append(scale)
+            RF.head_loss(gs[i], h2.weight.detach(), h2.bias.detach(), preds[i], gt_flat, scale,
+                         self.loss, views=v, aux_decay=cfg["reference_decay"])
+        # backward
+        d_init = torch.zeros((m, nv3), device=self.device, dtype=torch.float32)   # d loss / d F_init
+        d_f_next = None
+        for i in reversed(range(n_it)):
+            h1, h2 = self.heads[i]
+            f1, f2, f3 = self.fusers[i]
+            dg = self._buf("dG", (m, 512))
+            dpred = self._buf("dpred", (m, 2), torch.float32)
+            self._head_bwd(preds[i], gt_flat, gs[i], h2, scales[i], v, cfg, dg, dpred)
+            d_y = self._lin_bwd(h1, ("h1", i), ys[i], dg, self._buf("dYs", (m, w6))).view(m, 3, 2, nv)
+            d_init += d_y[:, :, 0].reshape(m, nv3)
+            d_f = self._buf("dF", (m, nv3))
+            d_f.copy_(d_y[:, :, 1].reshape(m, nv3) if d_f_next is None
+                      else d_y[:, :, 1].reshape(m, nv3) + d_f_next)
+            d_h2 = self._lin_bwd(f3, ("f3", i), h2s[i], d_f, self._buf("dHs2", (m, w6)))
+            self._add(d_h2, d_h2, mask=h2s[i])
+            d_h1 = self._lin_bwd(f2, ("f2", i), h1s[i], d_h2, self._buf("dHs1", (m, w6)))
+            self._add(d_h1, d_h1, mask=h1s[i])
+            d_x = self._lin_bwd(f1, ("f1", i), xs[i], d_h1, self._buf("dXs", (m, w6))).view(b, v, 3, 2, nv)
+            sc = bn_scales[i].float()
+            d_init += (d_x[:, :, :, 0].float() * sc[:, 0].view(1, v, 1, nv)).reshape(m, nv3)
+            d_rotf = self._buf("dRotF", (m, nv3))
+            d_rotf.copy_((d_x[:, :, :, 1].float() * sc[:, 1].view(1, v, 1, nv)).reshape(m, nv3))
+            d_f_next = self._buf("dFn", (m, nv3))
+            RF.rotate_gather(d_rotf, rot, d_f_next, b, v, nv, self.apply_rot, transpose=True)
+        d_total = self._buf("dFinit", (m, nv3))
+        d_total.copy_(d_init + d_f_next.float())    # iteration 0 gathered F_init itself
+        d_l1 = self._lin_bwd(self.lift[1], "l1", l1, d_total, self._buf("dL1", (m, nv3)))
+        self._add(d_l1, d_l1, mask=l1)
+        dimg = self._lin_bwd(self.lift[0], "l0", img, d_l1, self._buf("dimg", (m, fd)))
+        return dimg, preds
 
     def forward_backward(self, images, rotations, gt, hook=None) -> Dict[str, Any]:
         """Forward + loss + backward into the flat gradient buffer. `hook()` is called once, between
@@ -435,64 +722,14 @@ class TrainEngine:
             zs.append(z)
             x = self._bn_fwd(bns[-1], z, skip, True, ("out", bi), stats_done=sd)
             saved.append((x_in, zs, ys, zd, x))
-        wide = self.fc_dim + 3 * self.nvec
-        fd = self.fc_dim
-        xs = [self._buf(("X", i), (m, wide)) for i in range(self.num_iter)]
-        ys = [self._buf(("Y", i), (m, wide)) for i in range(self.num_iter)]
-        hs = [self._buf(("H", i), (m, wide)) for i in range(self.num_iter)]
-        gs = [self._buf(("G", i), (m, 512)) for i in range(self.num_iter)]
-        preds = [self._buf(("pred", i), (m, 2), torch.float32) for i in range(self.num_iter)]
-        y_init = self._buf("Yinit", (m, wide))
-        RF.avgpool(x, y_init, xs[0])
-        img = y_init[:, :fd]
-        for i in range(self.num_iter):
-            if i > 0:
-                self._add(img, xs[i][:, :fd])
-            self._add(img, ys[i][:, :fd])
-        l1 = self._buf("L1", (m, 3 * self.nvec))
-        self._lin(img, self._lin_fwd(self.lift[0], "l0"), self.lift[0].bias, True, l1)
-        self._lin(l1, self._lin_fwd(self.lift[1], "l1"), self.lift[1].bias, False, y_init[:, fd:])
-        scales = []
-        for i in range(self.num_iter):
-            f_prev = (y_init if i == 0 else ys[i - 1])[:, fd:]
-            RF.rotate_gather(f_prev, rot, xs[i][:, fd:], b, v, self.nvec, self.apply_rot)
-            f1, f2 = self.fusers[i]
-            self._lin(xs[i], self._lin_fwd(f1, ("f1", i)), f1.bias, True, hs[i])
-            self._lin(hs[i], self._lin_fwd(f2, ("f2", i)), f2.bias, False, ys[i][:, fd:])
-            h1, h2 = self.heads[i]
-            self._lin(ys[i], self._lin_fwd(h1, ("h1", i)), h1.bias, True, gs[i])
-            scale = (cfg["iter_decay"] ** (self.num_iter - 1 - i)) * cfg["rel_weight"] / b
-            scales.append(scale)
-            RF.head_loss(gs[i], h2.weight.detach(), h2.bias.detach(), preds[i], gt_flat, scale,
-                         self.loss, views=v, aux_decay=cfg["reference_decay"])
-
-        # ================================ backward ================================
-        dimg = self._buf("dimg", (m, fd))
-        dimg.zero_()
-        d_f_next = None
-        for i in reversed(range(self.num_iter)):
-            h1, h2 = self.heads[i]
-            f1, f2 = self.fusers[i]
-            dg = self._buf("dG", (m, 512))
-            dpred = self._buf("dpred", (m, 2), torch.float32)
-            _ck("rmv_head_loss_bwd", preds[i].data_ptr(), gt_flat.data_ptr(), gs[i].data_ptr(),
-                gs[i].stride(0), dtc, h2.weight.data_ptr(), m, 512, scales[i], v,
-                cfg["reference_decay"], dg.data_ptr(), dg.stride(0), dpred.data_ptr(),
-                self.grads[id(h2.weight)].data_ptr(), self.grads[id(h2.bias)].data_ptr())
-            d_y = self._lin_bwd(h1, ("h1", i), ys[i], dg, self._buf("dY", (m, wide)))
-            self._add(d_y[:, :fd], dimg, add=dimg)
-            d_f = self._buf("dF", (m, 3 * self.nvec))
-            self._add(d_y[:, fd:], d_f, add=d_f_next)
-            d_h = self._lin_bwd(f2, ("f2", i), hs[i], d_f, self._buf("dH", (m, wide)))
-            self._add(d_h, d_h, mask=hs[i])
-            d_x = self._lin_bwd(f1, ("f1", i), xs[i], d_h, self._buf("dX", (m, wide)))
-            self._add(d_x[:, :fd], dimg, add=dimg)
-            d_f_next = self._buf("dFn", (m, 3 * self.nvec))
-            RF.rotate_gather(d_x[:, fd:], rot, d_f_next, b, v, self.nvec, self.apply_rot, transpose=True)
-        d_l1 = self._lin_bwd(self.lift[1], "l1", l1, d_f_next, self._buf("dL1", (m, 3 * self.nvec)))
-        self._add(d_l1, d_l1, mask=l1)
-        d_img2 = self._lin_bwd(self.lift[0], "l0", img, d_l1, self._buf("dimg2", (m, fd)))
-        self._add(d_img2, dimg, add=dimg)
+        if self.encode_rot or self.share_feat:
+            if v != 2:
+                raise NotImplementedError("encode_rotmat / share_feature are two-view configurations "
+                                          "(the reference defines nothing else)")
+            fusion = self._fusion_encode_rotmat if self.encode_rot else self._fusion_share_feature
+            dimg, preds = fusion(x, rot, gt_flat, b, cfg)
+        else:
+            dimg, preds = self._fusion_default(x, rot, gt_flat, b, v, cfg)
         if hook is not None:
             hook()
         # trunk

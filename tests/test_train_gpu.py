@@ -531,8 +531,11 @@ def test_maxpool_index_forward_backward(n, h, w, dt):
     assert (dx.float() - ref).abs().max().item() <= tol + 1e-6
 
 
-@pytest.mark.parametrize("flags", [dict(), dict(share_weights=True), dict(ignore_rotmat=True)],
-                         ids=["default", "share_weights", "ignore_rotmat"])
+@pytest.mark.parametrize("flags", [dict(), dict(share_weights=True), dict(ignore_rotmat=True),
+                                   dict(encode_rotmat=True), dict(share_feature=True),
+                                   dict(encode_rotmat=True, share_weights=True)],
+                         ids=["default", "share_weights", "ignore_rotmat", "encode_rotmat",
+                              "share_feature", "encode_rotmat+share_weights"])
 def test_depth18_step_fp32_vs_live_oracle_and_bf16(flags):
     """backbone_depth=18 (BasicBlock trunk, models/resnet.py:50-96): one training step of the fp32
     engine against the CPU oracle's autograd step on the same batch/weights -- loss, every gradient
@@ -575,6 +578,12 @@ def test_depth18_step_fp32_vs_live_oracle_and_bf16(flags):
             assert torch.allclose(bn.running_mean.cpu(), obn.running_mean, rtol=1e-3, atol=1e-5)
             assert torch.allclose(bn.running_var.cpu(), obn.running_var, rtol=1e-3, atol=1e-5)
             assert int(bn.num_batches_tracked) == V
+            if flags.get("share_feature"):
+                # IntensityBatchNorm (models/rot_mv.py:13-32): running STD after 4 train-mode calls
+                for i in range(2):
+                    got = model._img_fusers[i]._batchnorm.running_mean.cpu()
+                    want = ora._img_fusers[i]._batchnorm.running_mean
+                    assert torch.allclose(got, want, rtol=1e-4, atol=1e-6), i
         else:
             assert abs(loss - loss_ref.item()) <= 3e-2 * abs(loss_ref.item()), (loss, loss_ref.item())
             assert errs[len(errs) // 2][0] <= 0.1, errs[len(errs) // 2]   # median gradient norm within 10 %
