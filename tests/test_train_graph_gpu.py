@@ -68,3 +68,36 @@ def test_stem_wgrad_tcgen05_matches_autograd():
                                         n, h, w, L.stream_ptr()), "rmv_stem_wgrad")
         err = (dw - wt.grad).abs().max().item()
         assert err <= 2e-4 * wt.grad.abs().max().item() + 1e-3, (n, h, w, err, wt.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("flags", [dict(share_feature=True), dict(encode_rotmat=True)],
+                         ids=["share_feature", "encode_rotmat"])
+def test_graphed_step_variants_match_eager(flags):
+    """The constructor variants use a few torch copies / reductions inside the step (padding,
+    interleave, IntensityBatchNorm statistics): they capture into the same graphs."""
+    from rotmv_b200 import functional as RF
+    from rotmv_b200.module import FeatRotationSymm
+    from rotmv_b200.train import GraphedTrainStep, TrainEngine
+
+    g = torch.Generator(device="cuda").manual_seed(6)
+    images = torch.randn((4, 2, 3, 224, 224), device="cuda", generator=g)
+    rot = RF.pose_to_rotations(torch.rand((4, 2, 2), device="cuda", generator=g) - 0.5)
+    gt = torch.rand((4, 2, 2), device="cuda", generator=g) - 0.5
+
+    def make():
+        torch.manual_seed(0)
+        model = FeatRotationSymm(18, 2, **flags).cuda().train()
+        return model, TrainEngine(model, precision="bf16", lr=1e-4)
+
+    model_a, eng_a = make()
+    eager = [eng_a.step(images, rot, gt).item() for _ in range(3)]
+    model_b, eng_b = make()
+    graphed = GraphedTrainStep(eng_b, 4, 2)
+    got = [graphed.step(images, rot, gt).item() for _ in range(3)]
+    for a, b in zip(eager, got):
+        assert abs(a - b) <= 5e-3 * abs(a), (eager, got)
+    if flags.get("share_feature"):
+        ra = model_a._img_fusers[1]._batchnorm.running_mean
+        rb = model_b._img_fusers[1]._batchnorm.running_mean
+        assert not torch.equal(rb, torch.ones_like(rb))
+        assert torch.allclose(ra, rb, rtol=2e-2, atol=1e-4)
