@@ -873,7 +873,9 @@ int dispatch(const IgemmArgs& a, int total, bool has_res, bool out_f32, cudaStre
   if (out_f32) return launch<BLOCK_N, 0, true>(a, total, stream);
   if (has_res) {
     // K >= 512 (8+ k-blocks per tile): the main loop needs the shared memory more than the residual ring
-    if (BLOCK_N == 256 && a.num_taps * a.c_blocks >= 8 && tuning("RES_DEEPK", 1, 1) == 1)
+    // (RMV_RES_DEEPK: 0 = never, 1 = K >= 512, 2 = K >= 256)
+    const int deepk = tuning("RES_DEEPK", 1, 2);
+    if (BLOCK_N == 256 && deepk != 0 && a.num_taps * a.c_blocks >= (deepk == 2 ? 4 : 8))
       return launch<BLOCK_N, 2, false>(a, total, stream);
     return launch<BLOCK_N, 1, false>(a, total, stream);
   }

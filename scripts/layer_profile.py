@@ -11,6 +11,7 @@ B = int(os.environ.get("B", 256)); V = int(os.environ.get("V", 2)); chunk = int(
 pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650, "bf16_tflops_sustained": 1400}
 torch.manual_seed(0)
 model = FeatRotationSymm(50, 3, trunk_chunk=chunk).cuda().eval()
+model.auto_graph = False   # per-launch events need the eager launches, not graph replays
 images = torch.randn((B, V, 3, 224, 224), device="cuda")
 rot = RF.pose_to_rotations(torch.rand((B, V, 2), device="cuda") - 0.5)
 with torch.no_grad():
