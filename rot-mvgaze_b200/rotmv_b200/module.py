@@ -90,6 +90,39 @@ class _TrunkParams(nn.Module):
                 yield blk
 
 
+class _TrainStepFunction(torch.autograd.Function):
+    """Autograd bridge for train mode: `forward` runs the engine's forward pass (batch-statistic
+    BatchNorm, activations kept in the engine's buffers) and returns the per-iteration predictions;
+    `backward` receives d(loss)/d(pred) from whatever loss the caller built on them (the reference's
+    `IterationLoss`, losses/stereo_loss.py:65-84) and runs the engine's backward kernels, handing the
+    parameter gradients to autograd -- so `loss.backward(); optimizer.step()` of trainer.py:141-143
+    work unchanged. One backward per forward (no double backward, no retain_graph)."""
+
+    @staticmethod
+    def forward(ctx, engine, images, rotations, *params):
+        gen = engine._fwd_bwd(images, rotations, None)
+        preds = next(gen)
+        ctx.gen, ctx.engine = gen, engine
+        ctx.pids = [id(p) for p in params]
+        ctx.shape = tuple(preds[0].shape)
+        return tuple(p.clone() for p in preds)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *dpreds):
+        eng, gen = ctx.engine, ctx.gen
+        if gen is None:
+            raise RuntimeError("FeatRotationSymm (train mode): backward called twice for one forward")
+        ctx.gen = None
+        ext = [d if d is not None else torch.zeros(ctx.shape, device=eng.device) for d in dpreds]
+        try:
+            gen.send(ext)
+        except StopIteration:
+            pass
+        grads = tuple(eng.grads[pid].clone() if pid in eng.grads else None for pid in ctx.pids)
+        return (None, None, None) + grads
+
+
 class FeatRotationSymm(nn.Module):
     def __init__(self, backbone_depth: int = 50, num_iter: Optional[int] = None,
                  share_weights: bool = False, encode_rotmat: bool = False,
@@ -149,6 +182,7 @@ class FeatRotationSymm(nn.Module):
         # uint8 HWC input (images[B,V,H,W,3]): ToTensor + Normalize constants of main.py:38-39
         self.input_mean, self.input_std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
         self._engines: Dict[str, E.InferenceEngine] = {}
+        self._train_engine = None        # rotmv_b200.train.TrainEngine behind the train-mode forward
 
     # -- engine management ---------------------------------------------------------------------
     def engine(self, precision: Optional[str] = None) -> "E.InferenceEngine":
@@ -173,6 +207,8 @@ class FeatRotationSymm(nn.Module):
         if isinstance(data_or_images, dict):
             return self._forward_dict(data_or_images, precision)
         images = data_or_images
+        if self.training:
+            return self._forward_train(images, rotations, precision)["pred_gaze"]
         if self.auto_graph and not self.training and images.is_cuda and rotations is not None:
             pred = self._forward_graphed(images, rotations, precision)
             if pred is not None:
@@ -233,6 +269,33 @@ class FeatRotationSymm(nn.Module):
         gt = None
         if "gt_gaze" in data and "gt_gaze_1" in data and self.fuse_loss:
             gt = torch.stack([data["gt_gaze"], data["gt_gaze_1"]], dim=1)
-        out = self.forward_views(images, rotations, precision=precision, want_all=True, gt=gt)
+        if self.training:
+            out = self._forward_train(images, rotations, precision)
+        else:
+            out = self.forward_views(images, rotations, precision=precision, want_all=True, gt=gt)
         data.update(out)
         return data
+
+    def _forward_train(self, images: torch.Tensor, rotations: torch.Tensor, precision) -> Dict[str, Any]:
+        """Train-mode forward through the training engine, connected to autograd by
+        `_TrainStepFunction`: returns `num_iter`, `iter_i` -> {`pred_gaze_k`} and `pred_gaze` -- what
+        `IterationLoss` (losses/stereo_loss.py:66-76) and `Trainer` (trainer.py:122-126) read; the
+        intermediate features of the eval-mode dict are not materialised. The fused, CUDA-graph
+        captured step (`rotmv_b200.train.GraphedTrainStep`, `rotmv_b200.loop.Trainer`) is the fast
+        path; this is the drop-in one."""
+        from .train import TrainEngine
+
+        precision = precision or self.precision
+        eng = self._train_engine
+        if eng is None or eng.precision != precision:
+            eng = self._train_engine = TrainEngine(self, precision=precision, lr=0.0, weight_decay=0.0)
+        if images.dim() != 5 or rotations is None or rotations.dim() != 5:
+            raise ValueError("expected images[B,V,3,H,W] (fp32) and rotations[B,V,V,3,3]")
+        b, v = images.shape[0], images.shape[1]
+        preds = _TrainStepFunction.apply(eng, images, rotations, *self.parameters())
+        out: Dict[str, Any] = {"num_iter": self._num_iter}
+        for i, p in enumerate(preds):
+            pv = p.view(b, v, 2)
+            out[f"iter_{i}"] = {f"pred_gaze_{k}": pv[:, k] for k in range(v)}
+        out["pred_gaze"] = out[f"iter_{self._output_index}"]["pred_gaze_0"]
+        return out

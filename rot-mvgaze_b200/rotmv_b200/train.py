@@ -403,6 +403,7 @@ class TrainEngine:
                          self.loss, views=v, aux_decay=cfg["reference_decay"])
 
         # ================================ backward ================================
+        ext = yield preds   # None: gradient of the fused loss; else d(loss)/d(pred) per iteration
         dimg = self._buf("dimg", (m, fd))
         dimg.zero_()
         d_f_next = None
@@ -411,7 +412,10 @@ class TrainEngine:
             f1, f2 = self.fusers[i]
             dg = self._buf("dG", (m, 512))
             dpred = self._buf("dpred", (m, 2), torch.float32)
-            self._head_bwd(preds[i], gt_flat, gs[i], h2, scales[i], v, cfg, dg, dpred)
+            if ext is None:
+                self._head_bwd(preds[i], gt_flat, gs[i], h2, scales[i], v, cfg, dg, dpred)
+            else:
+                self._head_bwd_ext(ext[i], gs[i], h2, dg)
             d_y = self._lin_bwd(h1, ("h1", i), ys[i], dg, self._buf("dY", (m, wide)))
             self._add(d_y[:, :fd], dimg, add=dimg)
             d_f = self._buf("dF", (m, 3 * self.nvec))
@@ -444,6 +448,16 @@ class TrainEngine:
             h2.weight.data_ptr(), g.shape[0], g.shape[1], scale, views, cfg["reference_decay"],
             dg.data_ptr(), dg.stride(0), dpred.data_ptr(), self.grads[id(h2.weight)].data_ptr(),
             self.grads[id(h2.bias)].data_ptr())
+
+    def _head_bwd_ext(self, dpred, g, h2, dg):
+        """Backward of the head's last Linear(512,2) and the ReLU before it for an EXTERNAL
+        d(loss)/d(pred) [m,2] (the autograd bridge: the caller's own loss objects produced it). Three
+        tiny torch ops on a [m,2] operand; the fused path uses rmv_head_loss_bwd instead."""
+        dp = dpred.detach().float().contiguous()
+        w = h2.weight.detach().float()
+        dg.copy_(torch.where(g > 0, dp @ w, torch.zeros((), device=dp.device)))
+        self.grads[id(h2.weight)].add_(dp.t() @ g.float())
+        self.grads[id(h2.bias)].add_(dp.sum(0))
 
     def _padded_linear(self, lin, tag, pk, pn):
         """bf16/fp32 copies of lin.weight zero-padded to [pn, pk] and its transpose [pk, pn], the
@@ -527,6 +541,7 @@ class TrainEngine:
             RF.head_loss(gs[i], h2.weight.detach(), h2.bias.detach(), preds[i], gt_flat, scale,
                          self.loss, views=v, aux_decay=cfg["reference_decay"])
         # backward
+        ext = yield preds   # None: gradient of the fused loss; else d(loss)/d(pred) per iteration
         dimg = self._buf("dimg", (m, fd))
         dimg.zero_()
         d_f_next = None
@@ -536,7 +551,10 @@ class TrainEngine:
             pw = padded[i]
             dg = self._buf("dG", (m, 512))
             dpred = self._buf("dpred", (m, 2), torch.float32)
-            self._head_bwd(preds[i], gt_flat, gs[i], h2, scales[i], v, cfg, dg, dpred)
+            if ext is None:
+                self._head_bwd(preds[i], gt_flat, gs[i], h2, scales[i], v, cfg, dg, dpred)
+            else:
+                self._head_bwd_ext(ext[i], gs[i], h2, dg)
             d_y = self._lin_bwd(h1, ("h1", i), ys[i], dg, self._buf("dY", (m, wide)))
             self._add(d_y[:, :fd], dimg, add=dimg)
             d_f = self._buf("dF", (m, nv3))
@@ -619,6 +637,7 @@ class TrainEngine:
             RF.head_loss(gs[i], h2.weight.detach(), h2.bias.detach(), preds[i], gt_flat, scale,
                          self.loss, views=v, aux_decay=cfg["reference_decay"])
         # backward
+        ext = yield preds   # None: gradient of the fused loss; else d(loss)/d(pred) per iteration
         d_init = torch.zeros((m, nv3), device=self.device, dtype=torch.float32)   # d loss / d F_init
         d_f_next = None
         for i in reversed(range(n_it)):
@@ -626,7 +645,10 @@ class TrainEngine:
             f1, f2, f3 = self.fusers[i]
             dg = self._buf("dG", (m, 512))
             dpred = self._buf("dpred", (m, 2), torch.float32)
-            self._head_bwd(preds[i], gt_flat, gs[i], h2, scales[i], v, cfg, dg, dpred)
+            if ext is None:
+                self._head_bwd(preds[i], gt_flat, gs[i], h2, scales[i], v, cfg, dg, dpred)
+            else:
+                self._head_bwd_ext(ext[i], gs[i], h2, dg)
             d_y = self._lin_bwd(h1, ("h1", i), ys[i], dg, self._buf("dYs", (m, w6))).view(m, 3, 2, nv)
             d_init += d_y[:, :, 0].reshape(m, nv3)
             d_f = self._buf("dF", (m, nv3))
@@ -655,6 +677,19 @@ class TrainEngine:
         the backward of the fusion stage (all lifter/fuser/head gradients are final) and the backward
         of the trunk: the data-parallel step starts the all-reduce of those gradients there, the
         graph-captured step splits its two graphs there."""
+        gen = self._fwd_bwd(images, rotations, gt, hook)
+        next(gen)                 # forward + fused loss
+        try:
+            gen.send(None)        # backward from the fused loss
+        except StopIteration as done:
+            return done.value
+        raise RuntimeError("forward_backward: the step generator yielded twice")
+
+    def _fwd_bwd(self, images, rotations, gt, hook=None):
+        """The step as a generator: runs the forward, yields the per-iteration predictions
+        (list of [B*V, 2] fp32), and on `send(ext)` runs the backward -- from the fused loss when
+        `ext` is None (`gt` required), from the caller's d(loss)/d(pred) list otherwise (`gt` may be
+        None: rotmv_b200.module's autograd bridge). Returns {"loss", "preds", "pool_out"}."""
         if not images.is_cuda:
             raise L.RotmvError("images must be CUDA tensors (there is no CPU path)")
         b, v = images.shape[0], images.shape[1]
@@ -666,7 +701,7 @@ class TrainEngine:
         cfg = self.model.loss_cfg
         imgs = images.reshape(m, *images.shape[2:]).float().contiguous()
         rot = rotations.float().contiguous()
-        gt_flat = gt.float().reshape(m, 2).contiguous()
+        gt_flat = None if gt is None else gt.float().reshape(m, 2).contiguous()
         self.flat_g.zero_()
         self.loss.zero_()
         if self._wjobs_ready:
@@ -727,9 +762,9 @@ class TrainEngine:
                 raise NotImplementedError("encode_rotmat / share_feature are two-view configurations "
                                           "(the reference defines nothing else)")
             fusion = self._fusion_encode_rotmat if self.encode_rot else self._fusion_share_feature
-            dimg, preds = fusion(x, rot, gt_flat, b, cfg)
+            dimg, preds = yield from fusion(x, rot, gt_flat, b, cfg)
         else:
-            dimg, preds = self._fusion_default(x, rot, gt_flat, b, v, cfg)
+            dimg, preds = yield from self._fusion_default(x, rot, gt_flat, b, v, cfg)
         if hook is not None:
             hook()
         # trunk

@@ -114,9 +114,10 @@ FLAGS = [dict(), dict(share_weights=True), dict(ignore_rotmat=True), dict(encode
          dict(share_feature=True), dict(encode_rotmat=True, share_weights=True)]
 
 
+@pytest.mark.parametrize("external", [False, True], ids=["fused_loss", "external_dpred"])
 @pytest.mark.parametrize("flags", FLAGS, ids=["default", "share_weights", "ignore_rotmat", "encode_rotmat",
                                               "share_feature", "encode_rotmat+share_weights"])
-def test_fusion_stage_host_logic_matches_oracle_autograd(torch_kernels, flags):
+def test_fusion_stage_host_logic_matches_oracle_autograd(torch_kernels, flags, external):
     b, v, n_it = 5, 2, 2
     ora = O.build_model(num_iter=n_it, depth=18, seed=0, **flags).train()
     model = FeatRotationSymm(18, n_it, **flags)
@@ -137,14 +138,35 @@ def test_fusion_stage_host_logic_matches_oracle_autograd(torch_kernels, flags):
     eng = HostEngine(model)
     cfg = model.loss_cfg
     gt_flat = gt.reshape(b * v, 2).contiguous()
-    if eng.encode_rot:
-        dimg, preds = eng._fusion_encode_rotmat(trunk_out, rot, gt_flat, b, cfg)
-    elif eng.share_feat:
-        dimg, preds = eng._fusion_share_feature(trunk_out, rot, gt_flat, b, cfg)
-    else:
-        dimg, preds = eng._fusion_default(trunk_out, rot, gt_flat, b, v, cfg)
 
-    assert abs(eng.loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item()), (eng.loss.item(), loss_ref.item())
+    def stage(gt_arg):
+        if eng.encode_rot:
+            return eng._fusion_encode_rotmat(trunk_out, rot, gt_arg, b, cfg)
+        if eng.share_feat:
+            return eng._fusion_share_feature(trunk_out, rot, gt_arg, b, cfg)
+        return eng._fusion_default(trunk_out, rot, gt_arg, b, v, cfg)
+
+    gen = stage(None if external else gt_flat)
+    fwd_preds = next(gen)                       # forward (+ fused loss when the labels are given)
+    ext = None
+    if external:
+        # the autograd bridge: the caller's own loss objects (here the oracle's IterationLoss
+        # restatement) turn the predictions into d(loss)/d(pred) per iteration
+        leaves = [p.detach().clone().requires_grad_(True) for p in fwd_preds]
+        fake = {"num_iter": n_it}
+        for i, p in enumerate(leaves):
+            fake[f"iter_{i}"] = {f"pred_gaze_{k}": p.view(b, v, 2)[:, k] for k in range(v)}
+        loss_ext = O.iteration_loss(fake, [gt[:, k] for k in range(v)])
+        loss_ext.backward()
+        ext = [p.grad for p in leaves]
+        assert abs(loss_ext.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    try:
+        gen.send(ext)
+        raise AssertionError("the fusion stage must finish after the backward")
+    except StopIteration as done:
+        dimg, preds = done.value
+    if not external:
+        assert abs(eng.loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item()), (eng.loss.item(), loss_ref.item())
     for k in range(v):
         want = out[f"iter_{n_it - 1}"][f"pred_gaze_{k}"].detach()
         assert torch.allclose(preds[-1].view(b, v, 2)[:, k], want, rtol=1e-4, atol=1e-5)

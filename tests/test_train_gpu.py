@@ -630,3 +630,70 @@ def test_three_view_step_fp32_vs_live_oracle():
     n = "_lifter._lifter.blocks.1.0.bias"
     assert rel_l2(eng.grads[id(named[n])].cpu(), ref_grads[n]) <= 2e-2
     assert int(model._feat_extractor[0].bn1.num_batches_tracked) == V
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_autograd_bridge_reference_style_step(precision):
+    """The reference's own step, unchanged (trainer.py:119-123,141-143): `data = model(data)` in
+    train mode, the loss built OUTSIDE the model on the returned predictions (IterationLoss
+    restatement, torch ops), `zero_grad(); loss.backward(); torch.optim.Adam.step()`. The module's
+    autograd bridge runs the engine's forward/backward kernels underneath; loss and gradients are
+    checked against the CPU oracle's autograd, the update against torch's Adam on the oracle."""
+    from oracle import rotmv_oracle as O
+    from rotmv_b200.module import FeatRotationSymm
+
+    B, V, lr = 6, 2, 1e-3
+    ora = O.build_model(num_iter=2, depth=18, seed=0)
+    sd0 = {k: v.clone() for k, v in ora.state_dict().items()}
+    images, pose, gt = O.synthetic_batch(B, V, seed=2)
+    rot = O.pairwise_rotations(pose)
+    ora.train()
+    oopt = O.make_adam(ora, lr=lr)
+    loss_ref = O.iteration_loss(ora.forward_views(images, rot), [gt[:, 0], gt[:, 1]])
+    oopt.zero_grad(); loss_ref.backward()
+    ref_grads = {n: p.grad.clone() for n, p in ora.named_parameters() if p.grad is not None}
+    oopt.step()
+
+    model = FeatRotationSymm(18, 2, precision=precision)
+    model.load_state_dict(sd0, strict=True)
+    model = model.cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=1e-6)      # trainer.py:54
+    r = O.rotation_matrix_2d(pose.reshape(-1, 2)).view(B, V, 3, 3)
+    data = {"img_0": images[:, 0].cuda(), "img_1": images[:, 1].cuda(), "rot_0": r[:, 0].cuda(),
+            "rot_1": r[:, 1].cuda(), "gt_gaze": gt[:, 0].cuda(), "gt_gaze_1": gt[:, 1].cuda()}
+    out = model(data)
+    assert out is data and out["num_iter"] == 2 and out["pred_gaze"].requires_grad
+    loss = O.iteration_loss(out, [data["gt_gaze"], data["gt_gaze_1"]])
+    opt.zero_grad(); loss.backward()
+    tol_loss, tol_med = (1e-4, 2e-3) if precision == "fp32" else (3e-2, 0.1)
+    assert abs(loss.item() - loss_ref.item()) <= tol_loss * abs(loss_ref.item()), (loss.item(), loss_ref.item())
+    errs = []
+    for n, p in model.named_parameters():
+        if n.startswith("_feat_extractor.0.fc."):
+            assert p.grad is None, n                                        # Q4
+            continue
+        g_ref = ref_grads[n].double()
+        errs.append(abs(p.grad.double().cpu().norm().item() - g_ref.norm().item()) / max(g_ref.norm().item(), 1e-12))
+    errs.sort()
+    assert errs[len(errs) // 2] <= tol_med, errs[len(errs) // 2]
+    if precision == "fp32":
+        assert errs[-1] <= 2e-2, errs[-1]
+    opt.step()
+    w = "_gaze_estimators.1.blocks.1.0.weight"
+    moved = (model.state_dict()[w].cpu() - sd0[w]).abs().max().item()
+    assert 0.5 * lr <= moved <= 1.5 * lr, moved                            # first Adam step: ~lr per element
+    if precision == "fp32":
+        assert (model.state_dict()[w].cpu() - ora.state_dict()[w]).abs().max().item() <= 2 * lr
+    bn = model._feat_extractor[0].bn1
+    assert int(bn.num_batches_tracked) == V
+    # the next step starts from the updated weights; the tensor form returns pred_gaze [B, 2]
+    images_d = torch.stack([data["img_0"], data["img_1"]], 1)
+    pred = model(images_d, rot.cuda())
+    assert tuple(pred.shape) == (B, 2) and pred.requires_grad
+    pred.sum().backward()
+    assert torch.isfinite(model._lifter._lifter.blocks[0][0].weight.grad).all()
+    # and eval mode serves inference from the trained weights
+    model.eval()
+    with torch.no_grad():
+        p_eval = model(images_d, rot.cuda())
+    assert torch.isfinite(p_eval).all()
