@@ -114,9 +114,13 @@ FLAGS = [dict(), dict(share_weights=True), dict(ignore_rotmat=True), dict(encode
          dict(share_feature=True), dict(encode_rotmat=True, share_weights=True)]
 
 
-@pytest.mark.parametrize("external", [False, True], ids=["fused_loss", "external_dpred"])
-@pytest.mark.parametrize("flags", FLAGS, ids=["default", "share_weights", "ignore_rotmat", "encode_rotmat",
-                                              "share_feature", "encode_rotmat+share_weights"])
+IDS = ["default", "share_weights", "ignore_rotmat", "encode_rotmat", "share_feature", "encode_rotmat+share_weights"]
+# every flag set with the fused loss; the external-d(pred) path (autograd bridge) once per fusion method
+CASES = [pytest.param(f, False, id=i + "-fused_loss") for f, i in zip(FLAGS, IDS)] + \
+        [pytest.param(FLAGS[k], True, id=IDS[k] + "-external_dpred") for k in (0, 3, 4)]
+
+
+@pytest.mark.parametrize("flags,external", CASES)
 def test_fusion_stage_host_logic_matches_oracle_autograd(torch_kernels, flags, external):
     b, v, n_it = 5, 2, 2
     ora = O.build_model(num_iter=n_it, depth=18, seed=0, **flags).train()
