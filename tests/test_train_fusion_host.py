@@ -192,3 +192,45 @@ def test_fusion_stage_host_logic_matches_oracle_autograd(torch_kernels, flags, e
             got = model._img_fusers[i]._batchnorm.running_mean
             want = ora._img_fusers[i]._batchnorm.running_mean
             assert torch.allclose(got, want, rtol=1e-5, atol=1e-7), i
+
+
+def test_autograd_bridge_plumbing_with_a_stub_engine():
+    """`module._TrainStepFunction` alone (CPU, stub engine): predictions come back connected to
+    autograd, the caller's d(loss)/d(pred) reaches the engine's backward half, parameter gradients
+    are returned in parameter order (None for tensors the engine has no gradient for, e.g. fc.*),
+    an output that does not take part in the loss arrives as zeros, and a second backward is refused."""
+    from rotmv_b200.module import _TrainStepFunction
+
+    w0 = torch.nn.Parameter(torch.tensor([[1.0, 2.0]]))
+    w1 = torch.nn.Parameter(torch.tensor([[-1.0, 0.5]]))
+    unused = torch.nn.Parameter(torch.ones(3))
+    x = torch.arange(4.0).view(4, 1)                      # stands for the images
+
+    class StubEngine:
+        device = torch.device("cpu")
+
+        def __init__(self):
+            self.grads = {id(w0): torch.zeros_like(w0), id(w1): torch.zeros_like(w1)}
+            self.seen = None
+
+        def _fwd_bwd(self, images, rotations, gt, hook=None):
+            assert gt is None
+            preds = [images @ w0.detach(), images @ w1.detach()]          # two "iterations", [4, 2] each
+            ext = yield preds
+            self.seen = [e.clone() for e in ext]
+            for w, e in zip((w0, w1), ext):
+                self.grads[id(w)].copy_(images.t() @ e)
+            return {}
+
+    eng = StubEngine()
+    p0, p1 = _TrainStepFunction.apply(eng, x, None, w0, unused, w1)
+    assert p0.requires_grad and p1.requires_grad and torch.equal(p0, x @ w0.detach())
+    loss = (p0 * torch.tensor([1.0, -2.0])).sum()         # p1 does not take part
+    loss.backward()
+    assert torch.equal(eng.seen[0], torch.tensor([1.0, -2.0]).expand(4, 2)) and eng.seen[1].abs().sum() == 0
+    assert torch.equal(w0.grad, x.t() @ eng.seen[0]) and torch.equal(w1.grad, torch.zeros_like(w1))
+    assert unused.grad is None
+    q0, _ = _TrainStepFunction.apply(eng, x, None, w0, unused, w1)
+    q0.sum().backward(retain_graph=True)
+    with pytest.raises(RuntimeError):
+        q0.sum().backward()
