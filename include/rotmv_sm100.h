@@ -19,6 +19,8 @@
 #ifndef ROTMV_SM100_H_
 #define ROTMV_SM100_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -116,6 +118,19 @@ int rmv_stem_conv_fwd_u8(const unsigned char* x_nhwc_u8, const float* mean3, con
  * rows are rebuilt in shared memory exactly as in the forward. scratch: fp32 [192*64] workspace. */
 int rmv_stem_wgrad(const float* x_nchw, const void* dz_nhwc, float* scratch, float* dw_oihw,
                    int n_img, int in_h, int in_w, void* stream);
+
+/* Workspace queries (boundary B2: the library never allocates device memory -- the caller owns
+ * every buffer and sizes the scratch regions with these; all are pure host functions).
+ *   rmv_stem_wgrad_workspace_bytes        `scratch` of rmv_stem_wgrad
+ *   rmv_bn_workspace_bytes                the fp64 accumulator `acc` shared by the rmv_bn_* calls and
+ *                                         the conv epilogue statistics (stat_acc), for layers of up
+ *                                         to `max_channels` channels and `views` views; the `ticket`
+ *                                         counter those calls take is one more zero-initialised int
+ *   rmv_conv2d_wgrad_tc_workspace_bytes   the fp32 [c_out][kh][kw][c_in] accumulation buffer
+ *                                         `dw_krsc` of rmv_conv2d_wgrad_tc (zeroed by the caller) */
+size_t rmv_stem_wgrad_workspace_bytes(void);
+size_t rmv_bn_workspace_bytes(int max_channels, int views);
+size_t rmv_conv2d_wgrad_tc_workspace_bytes(const rmv_conv_args* args);
 
 /* fp32 NCHW -> NHWC (fp32 or bf16) layout change (the reference keeps NCHW, trainer.py:100-106). */
 int rmv_nchw_to_nhwc(const float* x, void* y, int n_img, int c, int h, int w, int y_dtype,
@@ -267,7 +282,10 @@ int rmv_avgpool_bwd(const void* dfeat, long long ld, void* dx, int n_img, int hw
                     void* stream);
 /* Analytic gradient of the weighted angular loss w.r.t. pred (zero where the cosine saturates,
  * like F.hardtanh) + backward of the head's last Linear(512,2) and the ReLU before it:
- * dhidden = (hidden>0) * dpred w2; dw2 += dpred^T hidden; db2 += colsum(dpred). */
+ * dhidden = (hidden>0) * dpred w2; dw2 += dpred^T hidden; db2 += colsum(dpred).
+ * gt == NULL: `dpred` [rows,2] is an INPUT -- d(loss)/d(pred) from the caller's own loss objects
+ * (losses/stereo_loss.py:65-84 under torch.autograd, trainer.py:141-142); pred/loss_scale/views/
+ * aux_decay are ignored and only the Linear(512,2) + ReLU backward runs. */
 int rmv_head_loss_bwd(const float* pred, const float* gt, const void* hidden, long long ld_hidden,
                       int hid_dtype, const float* w2, int rows, int hid, float loss_scale,
                       int views, float aux_decay, void* dhidden, long long ld_dhidden,

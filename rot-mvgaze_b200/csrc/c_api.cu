@@ -87,6 +87,10 @@ extern "C" int rmv_conv2d_fwd(const rmv_conv_args* args, void* stream) {
     return conv_fwd_tc(p, s);
   }
   if (p.engine == RMV_ENGINE_AUTO && tc_ok) return conv_fwd_tc(p, s);
+  // the FFMA engine has no statistics epilogue: refuse instead of leaving the accumulator empty
+  RMV_CHECK_ARG(p.stat_acc == nullptr,
+                "conv2d_fwd: fused BatchNorm statistics (stat_acc) need the tcgen05 engine "
+                "(bf16, c_in %% 64 == 0)");
   return conv_fwd_simt(p, s);
 }
 
@@ -106,6 +110,18 @@ extern "C" int rmv_conv2d_dgrad(const rmv_conv_args* args, void* stream) {
   RMV_CHECK_ARG(p.scale == nullptr && p.shift == nullptr && p.relu == 0,
                 "conv2d_dgrad: no scale/shift/relu epilogue");
   return conv_dgrad_tc(p, (cudaStream_t)stream);
+}
+
+extern "C" size_t rmv_stem_wgrad_workspace_bytes(void) { return (size_t)192 * 64 * sizeof(float); }
+
+extern "C" size_t rmv_bn_workspace_bytes(int max_channels, int views) {
+  if (max_channels <= 0 || views <= 0) return 0;
+  return (size_t)views * (size_t)max_channels * 2 * sizeof(double);
+}
+
+extern "C" size_t rmv_conv2d_wgrad_tc_workspace_bytes(const rmv_conv_args* args) {
+  if (args == nullptr || args->c_out <= 0 || args->c_in <= 0 || args->kh <= 0 || args->kw <= 0) return 0;
+  return (size_t)args->c_out * args->kh * args->kw * args->c_in * sizeof(float);
 }
 
 extern "C" int rmv_set_tuning(const char* key, int value) {

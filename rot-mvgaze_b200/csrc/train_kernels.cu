@@ -927,11 +927,17 @@ head_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ g
     {
       const int row = row0 + lane;
       if (lane < kHeadRows && row < rows) {
-        const float wgt = loss_scale * ((row % views) == 0 ? 1.f : aux_decay);
-        const float2 p2 = __ldg(reinterpret_cast<const float2*>(pred + (long long)row * 2));
-        const float2 g2 = __ldg(reinterpret_cast<const float2*>(gt + (long long)row * 2));
-        loss_grad_row(p2.x, p2.y, g2.x, g2.y, wgt, &my_dp, &my_dy);
-        *reinterpret_cast<float2*>(dpred_out + (long long)row * 2) = make_float2(my_dp, my_dy);
+        if (gt != nullptr) {
+          const float wgt = loss_scale * ((row % views) == 0 ? 1.f : aux_decay);
+          const float2 p2 = __ldg(reinterpret_cast<const float2*>(pred + (long long)row * 2));
+          const float2 g2 = __ldg(reinterpret_cast<const float2*>(gt + (long long)row * 2));
+          loss_grad_row(p2.x, p2.y, g2.x, g2.y, wgt, &my_dp, &my_dy);
+          *reinterpret_cast<float2*>(dpred_out + (long long)row * 2) = make_float2(my_dp, my_dy);
+        } else {
+          // external d(loss)/d(pred): the caller's own loss produced it (autograd bridge)
+          const float2 d2 = *reinterpret_cast<const float2*>(dpred_out + (long long)row * 2);
+          my_dp = d2.x; my_dy = d2.y;
+        }
         g_dp += my_dp; g_dy += my_dy;
       }
     }
@@ -1429,6 +1435,8 @@ extern "C" int rmv_head_loss_bwd(const float* pred, const float* gt, const void*
                                  float* db2, void* stream) {
   RMV_CHECK_ARG(hid % 8 == 0 && ld_hidden % 8 == 0 && ld_dhidden % 8 == 0,
                 "head_loss_bwd: hid/ld must be multiples of 8");
+  RMV_CHECK_ARG(dpred != nullptr && (gt == nullptr || pred != nullptr),
+                "head_loss_bwd: dpred (and pred when gt is given) must not be null");
   if (rows == 0) return 0;
   const int smem = (2 * hid + 2) * (int)sizeof(float);
   // grid-stride over groups of 8 warps x kHeadRows rows; one set of global atomics per block

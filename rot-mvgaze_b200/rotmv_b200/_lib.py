@@ -70,6 +70,9 @@ SIGNATURES = {
     "rmv_stem_conv_fwd_u8": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rmv_stem_conv_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rmv_stem_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "rmv_stem_wgrad_workspace_bytes": (C.c_size_t, []),
+    "rmv_bn_workspace_bytes": (C.c_size_t, [_i, _i]),
+    "rmv_conv2d_wgrad_tc_workspace_bytes": (C.c_size_t, [C.POINTER(ConvArgs)]),
     "rmv_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rmv_maxpool3x3s2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rmv_avgpool_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp]),

@@ -65,32 +65,59 @@ class Evaluator:
             pred = self.model(images, rot, precision=self.precision)
             gt = batch["gt_gaze"].to(dev, non_blocking=True).float().contiguous()
             RF.angular_error_accum(pred, gt, acc)
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(acc)   # every rank evaluated its own shard: combine [sum, count]
         s, n = acc.tolist()  # the only device->host read of the whole evaluation
         return s / max(n, 1.0)
 
 
+def _optim_path(path: str) -> str:
+    return path + ".optim.pt"
+
+
+def _is_rank0() -> bool:
+    import torch.distributed as dist
+
+    return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
+
 def save_checkpoint(path: str, model, engine=None) -> None:
-    """Reference format: the bare state_dict (trainer.py:150-160). With `engine`, the Adam moments,
-    hyper-parameters and step count are stored next to it under '__optimizer__'."""
+    """Reference format: `path` holds the BARE state_dict (trainer.py:150-160), so the reference's
+    `model.load_state_dict(torch.load(path), strict=True)` (trainer.py:45-48) accepts it. With
+    `engine`, the Adam moments, hyper-parameters and step count -- which the reference forgets -- go
+    to the sidecar file `<path>.optim.pt`. Under torch.distributed only rank 0 writes."""
+    if not _is_rank0():
+        return
     sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
-    if engine is not None:
-        sd["__optimizer__"] = {"exp_avg": engine.flat_m.cpu(), "exp_avg_sq": engine.flat_v.cpu(),
-                               "hyper": engine.hyper.cpu(), "names": list(engine.names)}
     torch.save(sd, path)
+    if engine is not None:
+        torch.save({"exp_avg": engine.flat_m.cpu(), "exp_avg_sq": engine.flat_v.cpu(),
+                    "hyper": engine.hyper.cpu(), "names": list(engine.names)}, _optim_path(path))
 
 
 def load_checkpoint(path: str, model, engine=None, strict: bool = True) -> None:
+    """Loads a reference-format checkpoint (bare state_dict; a legacy '__optimizer__' entry is
+    accepted) and, with `engine`, the optimizer sidecar if it exists. The engine's replicas are
+    re-synchronised from rank 0 afterwards."""
+    import os
+
     sd = torch.load(path, map_location="cpu")
     opt = sd.pop("__optimizer__", None)
+    if opt is None and os.path.exists(_optim_path(path)):
+        opt = torch.load(_optim_path(path), map_location="cpu")
     model.load_state_dict(sd, strict=strict)
     if hasattr(model, "invalidate"):
         model.invalidate()
-    if engine is not None and opt is not None:
-        if list(opt["names"]) != list(engine.names):
-            raise ValueError("optimizer state does not match this model's parameter list")
-        engine.flat_m.copy_(opt["exp_avg"])
-        engine.flat_v.copy_(opt["exp_avg_sq"])
-        engine.hyper.copy_(opt["hyper"])
+    if engine is not None:
+        if opt is not None:
+            if list(opt["names"]) != list(engine.names):
+                raise ValueError("optimizer state does not match this model's parameter list")
+            engine.flat_m.copy_(opt["exp_avg"])
+            engine.flat_v.copy_(opt["exp_avg_sq"])
+            engine.hyper.copy_(opt["hyper"])
+        engine.sync_replicas()
 
 
 def _stack_views(batch: Dict[str, torch.Tensor]):

@@ -278,11 +278,13 @@ class FeatRotationSymm(nn.Module):
 
     def _forward_train(self, images: torch.Tensor, rotations: torch.Tensor, precision) -> Dict[str, Any]:
         """Train-mode forward through the training engine, connected to autograd by
-        `_TrainStepFunction`: returns `num_iter`, `iter_i` -> {`pred_gaze_k`} and `pred_gaze` -- what
-        `IterationLoss` (losses/stereo_loss.py:66-76) and `Trainer` (trainer.py:122-126) read; the
-        intermediate features of the eval-mode dict are not materialised. The fused, CUDA-graph
-        captured step (`rotmv_b200.train.GraphedTrainStep`, `rotmv_b200.loop.Trainer`) is the fast
-        path; this is the drop-in one."""
+        `_TrainStepFunction`: returns the reference's full dict (models/rot_mv.py:205-211,256-266):
+        `num_iter`, `img_feat_k`, `initial_rot_feat_k`, `iter_i` -> {`feat_k`, `pred_gaze_k`} and
+        `pred_gaze`. The predictions carry the autograd graph (what `IterationLoss`,
+        losses/stereo_loss.py:66-76, differentiates); the feature entries are detached fp32 copies of
+        the engine's buffers (nothing in the reference's step differentiates through them). The fused,
+        CUDA-graph captured step (`rotmv_b200.train.GraphedTrainStep`, `rotmv_b200.loop.Trainer`)
+        is the fast path; this is the drop-in one."""
         from .train import TrainEngine
 
         precision = precision or self.precision
@@ -294,8 +296,23 @@ class FeatRotationSymm(nn.Module):
         b, v = images.shape[0], images.shape[1]
         preds = _TrainStepFunction.apply(eng, images, rotations, *self.parameters())
         out: Dict[str, Any] = {"num_iter": self._num_iter}
+        feats = eng.last_feats
+        nv = self._num_feat_vec
+
+        def per_view(t2d, tail):
+            t = t2d.detach().float().reshape(b, v, *tail)
+            return [t[:, k].contiguous() for k in range(v)]
+
+        img_tail = (3, nv) if self._share_feature else (self._fc_dim,)
+        for k, t in enumerate(per_view(feats["img"], img_tail)):
+            out[f"img_feat_{k}"] = t
+        for k, t in enumerate(per_view(feats["init"], (3, nv))):
+            out[f"initial_rot_feat_{k}"] = t
         for i, p in enumerate(preds):
             pv = p.view(b, v, 2)
-            out[f"iter_{i}"] = {f"pred_gaze_{k}": pv[:, k] for k in range(v)}
+            it = {f"pred_gaze_{k}": pv[:, k] for k in range(v)}
+            for k, t in enumerate(per_view(feats["iters"][i], (3, nv))):
+                it[f"feat_{k}"] = t
+            out[f"iter_{i}"] = it
         out["pred_gaze"] = out[f"iter_{self._output_index}"]["pred_gaze_0"]
         return out

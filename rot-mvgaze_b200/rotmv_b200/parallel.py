@@ -32,6 +32,42 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
+def flat_layout(named_params, align: int = 64, skip_prefix: str = "_feat_extractor.0.fc."):
+    """Offsets of every trained parameter inside the flat fp32 buffers (parameters, gradients, Adam
+    moments), in `named_parameters()` order, each padded to `align` elements. `fc.*` never receives a
+    gradient and is left out. Returns (names, offsets, total)."""
+    names, offs, total = [], [], 0
+    for n, p in named_params:
+        if n.startswith(skip_prefix):
+            continue
+        names.append(n)
+        offs.append(total)
+        total += (p.numel() + align - 1) // align * align
+    return names, offs, total
+
+
+def gradient_buckets(names, offs, total, trunk_prefix: str = "_feat_extractor.0."):
+    """Contiguous slices of the flat gradient buffer in the order the backward pass completes them:
+    the fusion stage (lifter / fusers / heads: everything behind the trunk in parameter order, 74 % of
+    the bytes, final before the trunk backward starts), then layer4, layer3, and layer2 + layer1 + stem
+    together (1.4 M parameters). Returns [(name, begin, end)]; the slices partition [0, total)."""
+    def first(prefix, default):
+        return next((o for n, o in zip(names, offs) if n.startswith(prefix)), default)
+    split = next((o for n, o in zip(names, offs) if not n.startswith(trunk_prefix)), total)
+    o4 = first(trunk_prefix + "layer4.", split)
+    o3 = first(trunk_prefix + "layer3.", o4)
+    return [("fusion", split, total), ("layer4", o4, split), ("layer3", o3, o4), ("layer2-stem", 0, o3)]
+
+
+def broadcast_state_(tensors, module=None, src: int = 0, group=None) -> None:
+    """Make rank `src`'s optimizer/parameter tensors (and the module's buffers) every replica's."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)
+        if module is not None:
+            broadcast_buffers_(module, src=src, group=group)
+
+
 class OverlappedAllReduce:
     """Sum-all-reduce of a flat gradient buffer in the order its slices become final, each slice as
     an asynchronous collective (NCCL runs it on its own stream, ordered after the work already
@@ -39,8 +75,8 @@ class OverlappedAllReduce:
     that is still producing the late ones. `finish()` makes the caller's stream wait for all of
     them (the host does not block on NCCL). With no process group (single process) it is a no-op.
 
-    The Rot-MV step uses two slices: [grad_split:] (lifter/fuser/head gradients, complete before the
-    trunk backward starts) and [:grad_split] (trunk gradients)."""
+    The Rot-MV step uses the four slices of `gradient_buckets` (fusion stage, layer4, layer3,
+    layer2..stem), each started right after the backward kernels that write it have been queued."""
 
     def __init__(self, flat: torch.Tensor, group=None):
         self.flat, self.group, self.works = flat, group, []

@@ -83,11 +83,9 @@ class TrainEngine:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         # ---- flat parameter / gradient / moment buffers (fc.* never gets a gradient: SURVEY Q4) ----
-        named = [(n, p) for n, p in model.named_parameters() if not n.startswith("_feat_extractor.0.fc.")]
-        offs, total = [], 0
-        for _, p in named:
-            offs.append(total)
-            total += (p.numel() + 63) // 64 * 64
+        names, offs, total = P.flat_layout(model.named_parameters())
+        params = dict(model.named_parameters())
+        named = [(n, params[n]) for n in names]
         self.flat_p = torch.zeros(total, device=self.device, dtype=torch.float32)
         self.flat_g = torch.zeros_like(self.flat_p)
         self.flat_m = torch.zeros_like(self.flat_p)
@@ -106,6 +104,11 @@ class TrainEngine:
         # before the trunk backward starts) -- the second slice is all-reduced while the trunk
         # backward runs
         self.grad_split = next((o for (n, _), o in zip(named, offs) if not n.startswith("_feat_extractor.")), total)
+        # gradient buckets in the order the backward pass completes them (parallel.gradient_buckets):
+        # `forward_backward` reports each through its hook as soon as the last kernel writing into it
+        # has been launched
+        self.buckets = P.gradient_buckets(names, offs, total)
+        self._bucket_by_stage = {4: self.buckets[1], 3: self.buckets[2]}
         self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 0.0],
                                   device=self.device, dtype=torch.float64)
         # ---- layer table ----
@@ -128,13 +131,31 @@ class TrainEngine:
         self.lift = [lif[0][0], lif[1][0]]
         self.fusers = [[blk[0] for blk in m._fuser.blocks] for m in model._img_fusers]
         self.heads = [[m.blocks[0][0], m.blocks[1][0]] for m in model._gaze_estimators]
-        self.acc = torch.zeros((max_views, 2048, 2), device=self.device, dtype=torch.float64)
+        c_max = max(2048, self.fc_dim)
+        assert L.load().rmv_bn_workspace_bytes(c_max, max_views) == max_views * c_max * 2 * 8
+        self.acc = torch.zeros((max_views, c_max, 2), device=self.device, dtype=torch.float64)
         self.ticket = torch.zeros((1,), device=self.device, dtype=torch.int32)
         self._bufs: Dict[Any, torch.Tensor] = {}
         self._bits: Dict[int, Optional[torch.Tensor]] = {}   # id(ReLU output) -> packed mask
         self.loss = torch.zeros((1,), device=self.device, dtype=torch.float32)
         self.launches_last_step = 0
         self._wjobs, self._wjob_tags, self._wjobs_ready = [], set(), False
+        self.last_feats = None   # views of the last forward's features (train-mode dict contract)
+        # first block index of every trunk stage (layer1..layer4), for the per-stage gradient buckets
+        self._stage_first, bi = {}, 0
+        for li in range(1, 5):
+            self._stage_first[bi] = li
+            bi += len(getattr(trunk, f"layer{li}"))
+        self.sync_replicas()
+
+    def sync_replicas(self, src: int = 0) -> None:
+        """Data parallel: make rank `src`'s parameters, Adam moments, hyper-parameters (incl. the
+        step count) and BatchNorm buffers the state of every replica. Called at construction and
+        after loading a checkpoint -- the gradient all-reduce averages gradients, which is only
+        meaningful when all replicas hold the same weights."""
+        if self.world > 1:
+            P.broadcast_state_((self.flat_p, self.flat_m, self.flat_v, self.hyper), self.model,
+                               src=src, group=self.pg)
 
     # ------------------------------------------------------------------------------------------
     def set_lr(self, lr: float) -> None:
@@ -297,6 +318,7 @@ class TrainEngine:
                 RF._call("rmv_conv2d_wgrad_tc", meta, L.load().rmv_conv2d_wgrad_tc, C.byref(a),
                          dy.data_ptr(), grad.data_ptr(), L.stream_ptr())
             else:
+                assert L.load().rmv_conv2d_wgrad_tc_workspace_bytes(C.byref(a)) == k * kh * kw * c * 4
                 scratch = self._buf(("wg", id(conv_or_lin)), (k, kh, kw, c), torch.float32)
                 scratch.zero_()
                 RF._call("rmv_conv2d_wgrad_tc", meta, L.load().rmv_conv2d_wgrad_tc, C.byref(a),
@@ -355,15 +377,17 @@ class TrainEngine:
         before = L.STATS["launches"]
         ar = P.OverlappedAllReduce(self.flat_g, self.pg)
         n = self.flat_g.numel()
-        split = self.grad_split if self.dp_overlap else n
-        self.forward_backward(images, rotations, gt,
-                              hook=(lambda: ar.start(split, n)) if ar.active else None)
-        ar.start(0, split)
+        if ar.active and self.dp_overlap:   # every bucket is all-reduced as soon as it is final
+            self.forward_backward(images, rotations, gt, hook=lambda name, b, e: ar.start(b, e))
+        else:
+            self.forward_backward(images, rotations, gt)
+            ar.start(0, n)
         ar.finish()   # the current stream waits for NCCL's stream; the host does not block
         _ck("rmv_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
             self.flat_v.data_ptr(), self.hyper.data_ptr(), self.flat_p.numel(), int(self.decoupled),
             1.0 / self.world)
         self.launches_last_step = L.STATS["launches"] - before
+        self.model.invalidate()   # cached inference weights / graph sessions are stale now
         return self.loss
 
     # ---- fusion stage: forward + loss + backward down to d(loss)/d(pooled image feature) ----------
@@ -402,6 +426,7 @@ class TrainEngine:
             RF.head_loss(gs[i], h2.weight.detach(), h2.bias.detach(), preds[i], gt_flat, scale,
                          self.loss, views=v, aux_decay=cfg["reference_decay"])
 
+        self.last_feats = {"img": img, "init": y_init[:, fd:], "iters": [y[:, fd:] for y in ys]}
         # ================================ backward ================================
         ext = yield preds   # None: gradient of the fused loss; else d(loss)/d(pred) per iteration
         dimg = self._buf("dimg", (m, fd))
@@ -451,13 +476,13 @@ class TrainEngine:
 
     def _head_bwd_ext(self, dpred, g, h2, dg):
         """Backward of the head's last Linear(512,2) and the ReLU before it for an EXTERNAL
-        d(loss)/d(pred) [m,2] (the autograd bridge: the caller's own loss objects produced it). Three
-        tiny torch ops on a [m,2] operand; the fused path uses rmv_head_loss_bwd instead."""
-        dp = dpred.detach().float().contiguous()
-        w = h2.weight.detach().float()
-        dg.copy_(torch.where(g > 0, dp @ w, torch.zeros((), device=dp.device)))
-        self.grads[id(h2.weight)].add_(dp.t() @ g.float())
-        self.grads[id(h2.bias)].add_(dp.sum(0))
+        d(loss)/d(pred) [m,2] (the autograd bridge: the caller's own loss objects produced it):
+        rmv_head_loss_bwd with gt == NULL reads `dpred` instead of computing the loss gradient."""
+        dp = self._buf("dpred_ext", (g.shape[0], 2), torch.float32)
+        dp.copy_(dpred.detach().reshape(g.shape[0], 2))
+        _ck("rmv_head_loss_bwd", None, None, g.data_ptr(), g.stride(0), self.dtc, h2.weight.data_ptr(),
+            g.shape[0], g.shape[1], 0.0, 1, 1.0, dg.data_ptr(), dg.stride(0), dp.data_ptr(),
+            self.grads[id(h2.weight)].data_ptr(), self.grads[id(h2.bias)].data_ptr())
 
     def _padded_linear(self, lin, tag, pk, pn):
         """bf16/fp32 copies of lin.weight zero-padded to [pn, pk] and its transpose [pk, pn], the
@@ -540,6 +565,7 @@ class TrainEngine:
             scales.append(scale)
             RF.head_loss(gs[i], h2.weight.detach(), h2.bias.detach(), preds[i], gt_flat, scale,
                          self.loss, views=v, aux_decay=cfg["reference_decay"])
+        self.last_feats = {"img": img, "init": y_init[:, fd:], "iters": [y[:, fd:] for y in ys]}
         # backward
         ext = yield preds   # None: gradient of the fused loss; else d(loss)/d(pred) per iteration
         dimg = self._buf("dimg", (m, fd))
@@ -636,6 +662,8 @@ class TrainEngine:
             scales.append(scale)
             RF.head_loss(gs[i], h2.weight.detach(), h2.bias.detach(), preds[i], gt_flat, scale,
                          self.loss, views=v, aux_decay=cfg["reference_decay"])
+        # share_feature: the lifted feature IS the "image feature" of the dict (models/rot_mv.py:201-203)
+        self.last_feats = {"img": f_init, "init": f_init, "iters": list(fs)}
         # backward
         ext = yield preds   # None: gradient of the fused loss; else d(loss)/d(pred) per iteration
         d_init = torch.zeros((m, nv3), device=self.device, dtype=torch.float32)   # d loss / d F_init
@@ -673,10 +701,10 @@ class TrainEngine:
         return dimg, preds
 
     def forward_backward(self, images, rotations, gt, hook=None) -> Dict[str, Any]:
-        """Forward + loss + backward into the flat gradient buffer. `hook()` is called once, between
-        the backward of the fusion stage (all lifter/fuser/head gradients are final) and the backward
-        of the trunk: the data-parallel step starts the all-reduce of those gradients there, the
-        graph-captured step splits its two graphs there."""
+        """Forward + loss + backward into the flat gradient buffer. `hook(name, begin, end)` is called
+        once per gradient bucket (`self.buckets`: fusion stage, layer4, layer3, layer2..stem), right
+        after the last kernel writing into flat_g[begin:end] has been launched: the data-parallel step
+        starts that bucket's all-reduce there, the graph-captured step splits its graphs there."""
         gen = self._fwd_bwd(images, rotations, gt, hook)
         next(gen)                 # forward + fused loss
         try:
@@ -766,7 +794,7 @@ class TrainEngine:
         else:
             dimg, preds = yield from self._fusion_default(x, rot, gt_flat, b, v, cfg)
         if hook is not None:
-            hook()
+            hook(*self.buckets[0])
         # trunk
         last = saved[-1][4]
         d_out = self._buf(("dx", "avg"), last.shape)
@@ -796,6 +824,8 @@ class TrainEngine:
                     else:
                         res = dyr
                     d_out = self._dgrad(dz, cv, (bi, 1), x_in.shape, residual=res)
+            if hook is not None and self._stage_first.get(bi) in self._bucket_by_stage:
+                hook(*self._bucket_by_stage[self._stage_first[bi]])   # this stage's gradients are final
         d_y0 = self._buf("dy_stem", y0.shape)
         _ck("rmv_maxpool3x3s2_bwd_idx", pool_idx.data_ptr(), d_out.data_ptr(), d_y0.data_ptr(), m,
             y0.shape[1], y0.shape[2], y0.shape[3], dtc)
@@ -804,11 +834,14 @@ class TrainEngine:
             RF._call("rmv_stem_wgrad", {"desc": "stem wgrad (tcgen05)", "engine": "tcgen05-wgrad",
                                         "flops": 2.0 * m * y0.shape[1] * y0.shape[2] * 64 * 147},
                      L.load().rmv_stem_wgrad, imgs.data_ptr(), dz0.data_ptr(),
-                     self._buf("stem_wg", (192 * 64,), torch.float32).data_ptr(),
+                     self._buf("stem_wg", (L.load().rmv_stem_wgrad_workspace_bytes() // 4,),
+                               torch.float32).data_ptr(),
                      self.grads[id(self.stem_conv.weight)].data_ptr(), m, imgs.shape[2], imgs.shape[3],
                      L.stream_ptr())
         else:
             self._wgrad(stem_x, dz0, self.stem_conv, 7, 7, 2, 3, x_strides=stem_xs)
+        if hook is not None:
+            hook(*self.buckets[3])
         if not self._wjobs_ready:
             self._finish_wjobs()
         return {"loss": self.loss, "preds": preds, "pool_out": pool_out}
@@ -817,12 +850,14 @@ class TrainEngine:
 class GraphedTrainStep:
     """CUDA-graph-captured training step (north_star: "trainer.py step loop (CUDA-graph captured)").
 
-    forward + loss + fusion-stage backward are one graph, the trunk backward a second, the Adam
-    update a third. In a data-parallel job the fusion-stage gradients (74 % of the bytes) are
-    all-reduced over NCCL while the trunk-backward graph runs, the trunk gradients after it. Per
-    step the host replays three graphs (and issues two collectives); learning rate and step count live in device
-    memory (`TrainEngine.hyper`), so `set_lr` needs no re-capture. The per-step D2H of the reference
-    (trainer.py:128) is gone: `loss` stays on the device until the caller reads it.
+    The step is captured as one graph per gradient bucket (`TrainEngine.buckets`): forward + loss +
+    fusion-stage backward, then the trunk backward split after layer4, after layer3 and at the end,
+    plus the Adam update. In a data-parallel job every bucket of the flat fp32 gradient is all-reduced
+    over NCCL as soon as its graph has been queued, so the collectives run on NCCL's stream while the
+    next graph computes; only the last bucket (layer2 + layer1 + stem, 5.7 MB) is exposed. Per step
+    the host replays five graphs (and issues four collectives); learning rate and step count live in
+    device memory (`TrainEngine.hyper`), so `set_lr` needs no re-capture. The per-step D2H of the
+    reference (trainer.py:128) is gone: `loss` stays on the device until the caller reads it.
     """
 
     def __init__(self, engine: TrainEngine, batch: int, views: int, size: int = 224):
@@ -831,10 +866,13 @@ class GraphedTrainStep:
         self.images = torch.zeros((batch, views, 3, size, size), device=dev)
         self.rotations = torch.eye(3, device=dev).expand(batch, views, views, 3, 3).contiguous()
         self.gt = torch.zeros((batch, views, 2), device=dev)
+        self.skip_allreduce = False   # bench.py: time the step without its collectives
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        # warm-up on a side stream allocates every cached buffer; restore what it touched
-        saved_p = engine.flat_p.clone()
+        # warm-up on a side stream allocates every cached buffer; everything it touched (parameters,
+        # BatchNorm buffers, Adam state) is restored afterwards -- a checkpoint loaded before the
+        # capture survives it
+        saved = [t.clone() for t in (engine.flat_p, engine.flat_m, engine.flat_v, engine.hyper)]
         bufs = [b.clone() for b in engine.model.buffers()]
         with torch.cuda.stream(side):
             for _ in range(2):
@@ -842,37 +880,44 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         n0 = L.STATS["launches"]
-        # graph 1: weight re-layout, forward, loss, backward of the fusion stage; graph 2: backward
-        # of the trunk. Split so that a data-parallel step can all-reduce the fusion-stage gradients
-        # (flat_g[grad_split:]) on NCCL's stream while graph 2 runs.
-        self.fwd_bwd = torch.cuda.CUDAGraph()
-        self.trunk_bwd = torch.cuda.CUDAGraph()
+        self.graphs = [torch.cuda.CUDAGraph()]
+        self.bucket_of_graph = []
 
-        def split():
-            self.fwd_bwd.capture_end()
-            self.trunk_bwd.capture_begin(pool=self.fwd_bwd.pool())
+        def split(name, begin, end):
+            self.bucket_of_graph.append((name, begin, end))
+            self.graphs[-1].capture_end()
+            if len(self.bucket_of_graph) < len(engine.buckets):
+                g = torch.cuda.CUDAGraph()
+                g.capture_begin(pool=self.graphs[0].pool())
+                self.graphs.append(g)
 
         cap = torch.cuda.Stream(device=dev)
         cap.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(cap):
-            self.fwd_bwd.capture_begin()
+            self.graphs[0].capture_begin()
             engine.forward_backward(self.images, self.rotations, self.gt, hook=split)
-            self.trunk_bwd.capture_end()
         torch.cuda.current_stream(dev).wait_stream(cap)
+        assert len(self.graphs) == len(self.bucket_of_graph) == len(engine.buckets)
         self.adam = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.adam, pool=self.fwd_bwd.pool()):
+        with torch.cuda.graph(self.adam, pool=self.graphs[0].pool()):
             _ck("rmv_adam_step", engine.flat_p.data_ptr(), engine.flat_g.data_ptr(),
                 engine.flat_m.data_ptr(), engine.flat_v.data_ptr(), engine.hyper.data_ptr(),
                 engine.flat_p.numel(), int(engine.decoupled), 1.0 / engine.world)
         self.launches_per_step = L.STATS["launches"] - n0
-        engine.flat_p.copy_(saved_p)
-        for b, s in zip(engine.model.buffers(), bufs):
-            b.copy_(s)
-        engine.flat_m.zero_(); engine.flat_v.zero_()
-        engine.hyper[5] = 0.0
+        for t, c in zip((engine.flat_p, engine.flat_m, engine.flat_v, engine.hyper), saved):
+            t.copy_(c)
+        for b, c in zip(engine.model.buffers(), bufs):
+            b.copy_(c)
         torch.cuda.synchronize(dev)
         self._pipe = None
         self._copy_stream = torch.cuda.Stream(device=dev)
+
+    def collective_desc(self) -> str:
+        eng = self.engine
+        if not eng.dp_overlap:
+            return "one all-reduce of the whole flat gradient after the backward pass"
+        return "; ".join(f"{n}: {(e - b) * 4 / 1e6:.1f} MB" for n, b, e in self.bucket_of_graph) + \
+            " -- each all-reduced (NCCL, async) right after its graph is queued"
 
     def step(self, images=None, rotations=None, gt=None) -> torch.Tensor:
         if images is not None:
@@ -882,14 +927,24 @@ class GraphedTrainStep:
         if gt is not None:
             self.gt.copy_(gt, non_blocking=True)
         eng = self.engine
-        self.fwd_bwd.replay()
+        for p in (eng.model._feat_extractor[0].conv1.weight,):
+            # the parameters must still be views of the flat buffer Adam updates (a later
+            # model.to()/.float() would silently detach them)
+            if not (eng.flat_p.data_ptr() <= p.data_ptr() < eng.flat_p.data_ptr() + eng.flat_p.numel() * 4):
+                raise L.RotmvError("GraphedTrainStep: model parameters were moved after TrainEngine "
+                                   "was built (model.to()/.float()?); rebuild the engine")
         ar = P.OverlappedAllReduce(eng.flat_g, eng.pg)
-        split = eng.grad_split if eng.dp_overlap else eng.flat_g.numel()
-        ar.start(split, eng.flat_g.numel())   # overlaps the trunk-backward graph
-        self.trunk_bwd.replay()
-        ar.start(0, split)
+        if self.skip_allreduce:
+            ar.active = False
+        for g, (_, begin, end) in zip(self.graphs, self.bucket_of_graph):
+            g.replay()
+            if eng.dp_overlap:
+                ar.start(begin, end)   # overlaps the next graph
+        if not eng.dp_overlap:
+            ar.start(0, eng.flat_g.numel())
         ar.finish()
         self.adam.replay()
+        eng.model.invalidate()
         return eng.loss
 
     # ---- host-buffer entry, two steps in flight -------------------------------------------------

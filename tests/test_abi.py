@@ -120,4 +120,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["config"]["workload"].startswith("configs[1]")
+    # the default run carries the training half of the metric (configs[3]) in the `train` block
+    t = d["train"]
+    assert t["impl"] == "reference" and t["value"] > 0 and t["config"]["workload"].startswith("configs[3]")
+    assert "fwd+bwd" in t["metric"] and t["cpu_baseline"]["kind"] == "port"

@@ -73,6 +73,53 @@ def _oracle_on_subset(O, ora, images, pose, idx):
         return ora.forward_views(images[idx].cpu(), O.pairwise_rotations(pose[idx].cpu()))
 
 
+def _dist(d):
+    q = torch.quantile(d.double(), torch.tensor([0.5, 0.9, 0.99], dtype=torch.float64))
+    return {"mean": d.mean().item(), "p50": q[0].item(), "p90": q[1].item(), "p99": q[2].item(),
+            "max": d.max().item(), "n": d.numel()}
+
+
+def _fmt(st):
+    return (f"n={st['n']} mean {st['mean']:.3f} p50 {st['p50']:.3f} p90 {st['p90']:.3f} "
+            f"p99 {st['p99']:.3f} max {st['max']:.3f} deg")
+
+
+def test_bf16_delta_no_worse_than_reference_autocast(calibrated):
+    """THE bf16 tolerance statement: the angular delta of the tcgen05 bf16 engine
+    against the reference's fp32 predictions must be no worse than the delta of the REFERENCE'S OWN
+    bf16 path (`torch.autocast("cpu", bfloat16)` over the unmodified models/rot_mv.py) on the same 64
+    two-view samples and the same BN-calibrated weights. Both fp32 and autocast predictions of the
+    reference are the committed fixture tests/golden/rotmv_r50_bf16_autocast_b64.npz
+    (oracle/make_golden_bf16.py; reference distribution over its 384 predictions: mean 1.58, p50
+    1.47, p90 2.68, p99 3.88, max 4.35 deg -- the 0.46-2.98 deg of BASELINE.md section 2 is the same
+    statistic on 8 samples). Bounds: mean, p50, p90 <= 1.10x the reference's, p99 <= 1.15x, max <=
+    1.25x (the max of 384 draws of a chaotic random-init network is the noisiest statistic)."""
+    import os
+
+    import numpy as np
+
+    O, ora, model = calibrated
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                             "rotmv_r50_bf16_autocast_b64.npz"))
+    p32, p16 = torch.tensor(g["pred_fp32"]), torch.tensor(g["pred_bf16_autocast"])   # [3, 2, 64, 2]
+    b = int(g["batch"])
+    images, pose, _ = O.synthetic_batch(b, 2, seed=int(g["seed"]))
+    rot = O.pairwise_rotations(pose)
+    with torch.no_grad():
+        o32 = model.forward_views(images.cuda(), rot.cuda(), precision="fp32", want_all=False)
+        o16 = model.forward_views(images.cuda(), rot.cuda(), precision="bf16", want_all=True)
+    ours16 = torch.stack([torch.stack([o16[f"iter_{i}"][f"pred_gaze_{v}"].cpu() for v in range(2)]) for i in range(3)])
+    # the fixture's fp32 predictions are the same function the fp32 engine computes (rtol 1e-4)
+    ok, info = close(o32["iter_2"]["pred_gaze_0"], p32[2, 0])
+    assert ok, info
+    ref = _dist(_ang(p16.reshape(-1, 2), p32.reshape(-1, 2)))
+    ours = _dist(_ang(ours16.reshape(-1, 2), p32.reshape(-1, 2)))
+    print(f"bf16 angular delta vs reference fp32, 64 samples:\n  reference autocast: {_fmt(ref)}\n"
+          f"  tcgen05 bf16 engine: {_fmt(ours)}")
+    for key, slack in (("mean", 1.10), ("p50", 1.10), ("p90", 1.10), ("p99", 1.15), ("max", 1.25)):
+        assert ours[key] <= slack * ref[key], (key, ours[key], ref[key])
+
+
 def test_config1_scattered_samples_match_oracle(calibrated):
     """configs[1] (B=256, V=2): 8 samples scattered over the batch (first/last rows of tiles and of
     the batch) against the CPU oracle on those samples alone."""
@@ -93,9 +140,18 @@ def test_config1_scattered_samples_match_oracle(calibrated):
             deltas.append(_ang(out16[f"iter_{i}"][f"pred_gaze_{v}"][idx].cpu(),
                                ref[f"iter_{i}"][f"pred_gaze_{v}"]))
     d = torch.cat(deltas)
-    print(f"full-size bf16 angular delta: mean {d.mean():.3f} max {d.max():.3f} deg")
-    # the stated bf16 tolerance (tests/test_module_gpu.py::test_bf16_angular_delta)
-    assert d.mean().item() <= 2.0 and d.max().item() <= 6.4, (d.mean().item(), d.max().item())
+    print(f"full-size bf16 angular delta vs the oracle on 8 scattered samples: {_fmt(_dist(d))}")
+    # whole batch: the bf16 engine against the fp32 engine (which the lines above pin to the oracle at
+    # rtol 1e-4) over all 256 samples x 2 views x 3 iterations = 1536 predictions. Bounds = the
+    # reference's own bf16-autocast distribution (test_bf16_delta_no_worse_than_reference_autocast:
+    # mean 1.58, p99 3.88, max 4.35 deg over 384 predictions) with the same slack; the max of a
+    # 4x larger draw gets the 6.4 deg of the uncalibrated regime only as a sanity ceiling.
+    full = torch.cat([_ang(out16[f"iter_{i}"][f"pred_gaze_{v}"].cpu(), out32[f"iter_{i}"][f"pred_gaze_{v}"].cpu())
+                      for v in range(2) for i in range(3)])
+    st = _dist(full)
+    print(f"full-size bf16 angular delta vs the fp32 engine, all 256 samples: {_fmt(st)}")
+    assert d.max().item() <= 3.0, d.max().item()      # the scattered subset (48 values)
+    assert st["mean"] <= 1.10 * 1.58 and st["p99"] <= 1.15 * 3.88 and st["max"] <= 6.4, st
     assert torch.isfinite(out16["pred_gaze"]).all() and tuple(out16["pred_gaze"].shape) == (256, 2)
 
 
@@ -139,8 +195,10 @@ def test_config2_four_views_full_size(calibrated):
         preds = [out[f"pred_gaze_{k}"].clone() for k in range(4)]
     deltas = [_ang(preds[k][idx].cpu(), ref["iter_2"][f"pred_gaze_{k}"]) for k in range(4)]
     d = torch.cat(deltas)
-    print(f"V=4 full-size bf16 angular delta: mean {d.mean():.3f} max {d.max():.3f} deg")
-    assert d.mean().item() <= 2.0 and d.max().item() <= 6.4, (d.mean().item(), d.max().item())
+    print(f"V=4 full-size bf16 angular delta (5 scattered samples): {_fmt(_dist(d))}")
+    # same statement as test_bf16_delta_no_worse_than_reference_autocast (reference autocast: mean 1.58,
+    # max 4.35 deg); V=4 has no reference bf16 path of its own
+    assert d.mean().item() <= 1.10 * 1.58 and d.max().item() <= 1.25 * 4.35, (d.mean().item(), d.max().item())
     sigma = [2, 0, 3, 1]
     with torch.no_grad():
         o = model.forward_views(images[:, sigma].contiguous(), rot[:, sigma][:, :, sigma].contiguous(),

@@ -85,7 +85,47 @@ def test_trainer_loop_schedule_eval_checkpoint(tmp_path):
     assert not torch.equal(tr.engine.flat_p, p_before)                  # the steps moved the weights
     files = glob.glob(os.path.join(tmp_path, "epoch_02_error=*.pth.tar"))
     assert len(files) == 1
+    # the file Trainer.fit wrote is a BARE state_dict: the reference's strict load accepts it
+    # (trainer.py:45-48); the optimizer state lives in the sidecar
+    from oracle import rotmv_oracle as O
+    sd = torch.load(files[0])
+    assert "__optimizer__" not in sd
+    O.build_model(num_iter=2, depth=50, seed=5).load_state_dict(sd, strict=True)
+    assert os.path.exists(files[0] + ".optim.pt")
     other = FeatRotationSymm(50, 2).cuda()
     load_checkpoint(files[0], other)
     for (k, a), (_, b) in zip(model.state_dict().items(), other.state_dict().items()):
         assert torch.equal(a.cpu(), b.cpu()), k
+
+
+def test_checkpoint_with_engine_is_bare_state_dict(tmp_path):
+    """a checkpoint saved WITH optimizer state must still load into the reference with
+    strict=True (trainer.py:45-48). CPU: a stub engine stands in for TrainEngine."""
+    import types
+    from oracle import rotmv_oracle as O
+    from rotmv_b200.loop import load_checkpoint, save_checkpoint
+    from rotmv_b200.module import FeatRotationSymm
+
+    model = FeatRotationSymm(18, 2)
+    eng = types.SimpleNamespace(flat_m=torch.ones(8), flat_v=torch.full((8,), 2.0),
+                                hyper=torch.tensor([1e-3, 0.9, 0.999, 1e-8, 1e-6, 7.0], dtype=torch.float64),
+                                names=["a", "b"], sync_replicas=lambda: None)
+    path = os.path.join(tmp_path, "epoch_01_error=9.99.pth.tar")
+    save_checkpoint(path, model, eng)
+    sd = torch.load(path)
+    assert all(isinstance(v, torch.Tensor) for v in sd.values())
+    assert list(sd.keys()) == list(model.state_dict().keys())
+    O.build_model(num_iter=2, depth=18, seed=1).load_state_dict(sd, strict=True)
+    from oracle import ref_loader
+    if ref_loader.available():          # the unmodified reference module, when present (build container)
+        ref = ref_loader.load().FeatRotationSymm(backbone_depth=18, num_iter=2)
+        ref.load_state_dict(torch.load(path), strict=True)   # trainer.py:45-48
+    eng2 = types.SimpleNamespace(flat_m=torch.zeros(8), flat_v=torch.zeros(8),
+                                 hyper=torch.zeros(6, dtype=torch.float64), names=["a", "b"],
+                                 sync_replicas=lambda: None)
+    other = FeatRotationSymm(18, 2)
+    load_checkpoint(path, other, eng2)
+    assert torch.equal(eng2.flat_m, eng.flat_m) and torch.equal(eng2.flat_v, eng.flat_v)
+    assert float(eng2.hyper[5]) == 7.0
+    for (k, a), (_, b) in zip(model.state_dict().items(), other.state_dict().items()):
+        assert torch.equal(a, b), k

@@ -40,20 +40,30 @@ def _worker(rank, world, port, out_dir):
     loss.backward()
     params = [p for p in model.parameters() if p.grad is not None]
     flat = torch.cat([p.grad.flatten() for p in params])
-    # two-slice overlapped all-reduce (the order the training step produces the gradients in): the
-    # tail slice is reduced first, the head is still being written while that collective runs
-    flat2 = flat.clone()
-    split = flat2.numel() // 3
+    # bucketed, overlapped all-reduce in the order the training step completes its gradient buckets
+    # (fusion stage, layer4, layer3, layer2..stem): later buckets are still being written while the
+    # earlier collectives run
+    names, offs, total = P.flat_layout(model.named_parameters())
+    named = dict(model.named_parameters())
+    flat2 = torch.zeros(total)
+    for n, o in zip(names, offs):
+        flat2[o:o + named[n].numel()] = named[n].grad.flatten()
+    expect = flat2.clone()
+    buckets = P.gradient_buckets(names, offs, total)
     ar = P.OverlappedAllReduce(flat2)
     assert ar.active
-    ar.start(split, flat2.numel())
-    flat2[:split] += 1.0            # "trunk backward" finishing the head slice
-    ar.start(0, split)
+    for i, (_, b0, e0) in enumerate(buckets):
+        flat2[b0:e0] += float(i)              # the "backward" finishing this bucket just before its reduce
+        expect[b0:e0] += float(i)
+        ar.start(b0, e0)
     ar.finish()
     flat2.mul_(1.0 / world)
-    flat_head_bias = flat.clone(); flat_head_bias[:split] += 1.0
-    P.allreduce_mean_(flat_head_bias)
-    overlap_ok = torch.allclose(flat2, flat_head_bias, rtol=1e-6, atol=1e-7)
+    P.allreduce_mean_(expect)
+    overlap_ok = torch.allclose(flat2, expect, rtol=1e-6, atol=1e-7)
+    # replica synchronisation at start-up: rank 0's state everywhere
+    state = [torch.full((7,), float(rank + 1)), torch.full((3,), 10.0 * (rank + 1), dtype=torch.float64)]
+    P.broadcast_state_(state, None, src=0)
+    overlap_ok = overlap_ok and float(state[0][0]) == 1.0 and float(state[1][0]) == 10.0
     P.allreduce_mean_(flat)
     t = P.max_over_ranks(1.0 + rank)
     bn = next(m for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d))
@@ -64,6 +74,33 @@ def _worker(rank, world, port, out_dir):
                os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def test_gradient_buckets_partition_the_flat_buffer():
+    """parallel.flat_layout / gradient_buckets on the real parameter tree: the four buckets are
+    contiguous, disjoint, cover [0, total) and come in backward-completion order."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "rot-mvgaze_b200"))
+    from rotmv_b200 import parallel as P
+    from rotmv_b200.module import FeatRotationSymm
+
+    for depth in (50, 18):
+        m = FeatRotationSymm(depth, 3)
+        names, offs, total = P.flat_layout(m.named_parameters())
+        assert not any(n.startswith("_feat_extractor.0.fc.") for n in names)           # Q4
+        assert all(o % 64 == 0 for o in offs) and total % 64 == 0
+        b = P.gradient_buckets(names, offs, total)
+        assert [x[0] for x in b] == ["fusion", "layer4", "layer3", "layer2-stem"]
+        assert b[0][2] == total and b[3][1] == 0
+        assert all(b[i][1] == b[i + 1][2] for i in range(3))                            # contiguous, descending
+        assert all(e > s for _, s, e in b)
+        where = dict(zip(names, offs))
+        assert b[1][1] == where["_feat_extractor.0.layer4.0.conv1.weight"]
+        assert b[2][1] == where["_feat_extractor.0.layer3.0.conv1.weight"]
+        assert b[0][1] == where["_lifter._lifter.blocks.0.0.weight"]
+        if depth == 50:
+            assert sum(p.numel() for n, p in m.named_parameters() if n in where) == 89591366
 
 
 def test_shard_range_covers_batch():
@@ -94,7 +131,7 @@ def test_gloo_two_ranks_gradient_average_equals_global_batch(tmp_path):
     assert r0["range"] == (0, 3) and r1["range"] == (3, 5)
     assert torch.equal(r0["flat"], r1["flat"])          # every rank holds the same averaged gradient
     assert r0["tmax"] == r1["tmax"] == 2.0              # slowest rank wins
-    assert r0["overlap_ok"] and r1["overlap_ok"]        # two-slice overlapped all-reduce == one all-reduce
+    assert r0["overlap_ok"] and r1["overlap_ok"]        # bucketed overlapped all-reduce == one all-reduce; replica sync
     assert torch.equal(r0["rm"], r1["rm"]) and float(r1["rm"][0]) == 1.0   # rank 0's buffers
     # single-process gradient on the global batch
     model = O.build_model(num_iter=2, depth=18, seed=0).eval()

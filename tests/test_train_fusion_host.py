@@ -65,6 +65,14 @@ class HostEngine(T.TrainEngine):
         self.grads[id(h2.bias)] += p.grad.sum(0)
 
 
+    def _head_bwd_ext(self, dpred, g, h2, dg):
+        """rmv_head_loss_bwd with gt == NULL (external d(loss)/d(pred)): Linear(512,2) + ReLU backward."""
+        dp = dpred.detach().float().reshape(g.shape[0], 2)
+        dg.copy_((g > 0).float() * (dp @ h2.weight.detach()))
+        self.grads[id(h2.weight)] += dp.t() @ g
+        self.grads[id(h2.bias)] += dp.sum(0)
+
+
 def _head_loss_value(pred, gt, scale, views, aux_decay):
     """scale * sum over rows of w_row * angular(pred, gt) in degrees (losses/gaze_loss.py:42-52)."""
     a, b = O.pitchyaw_to_vector(gt), O.pitchyaw_to_vector(pred)

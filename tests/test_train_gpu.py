@@ -649,7 +649,8 @@ def test_autograd_bridge_reference_style_step(precision):
     rot = O.pairwise_rotations(pose)
     ora.train()
     oopt = O.make_adam(ora, lr=lr)
-    loss_ref = O.iteration_loss(ora.forward_views(images, rot), [gt[:, 0], gt[:, 1]])
+    ref_out = ora.forward_views(images, rot)
+    loss_ref = O.iteration_loss(ref_out, [gt[:, 0], gt[:, 1]])
     oopt.zero_grad(); loss_ref.backward()
     ref_grads = {n: p.grad.clone() for n, p in ora.named_parameters() if p.grad is not None}
     oopt.step()
@@ -663,6 +664,17 @@ def test_autograd_bridge_reference_style_step(precision):
             "rot_1": r[:, 1].cuda(), "gt_gaze": gt[:, 0].cuda(), "gt_gaze_1": gt[:, 1].cuda()}
     out = model(data)
     assert out is data and out["num_iter"] == 2 and out["pred_gaze"].requires_grad
+    # the train-mode dict carries every key of the reference's (models/rot_mv.py:205-211,256-266)
+    tol_feat = 1e-3 if precision == "fp32" else 0.1
+    for k in range(V):
+        for key, shape in ((f"img_feat_{k}", (B, 512)), (f"initial_rot_feat_{k}", (B, 3, 512))):
+            assert tuple(out[key].shape) == shape, (key, tuple(out[key].shape))
+            assert rel_l2(out[key].cpu(), ref_out[key].detach()) <= tol_feat, key
+        for i in range(2):
+            f = out[f"iter_{i}"][f"feat_{k}"]
+            assert tuple(f.shape) == (B, 3, 512)
+            assert rel_l2(f.cpu(), ref_out[f"iter_{i}"][f"feat_{k}"].detach()) <= tol_feat, (i, k)
+            assert tuple(out[f"iter_{i}"][f"pred_gaze_{k}"].shape) == (B, 2)
     loss = O.iteration_loss(out, [data["gt_gaze"], data["gt_gaze_1"]])
     opt.zero_grad(); loss.backward()
     tol_loss, tol_med = (1e-4, 2e-3) if precision == "fp32" else (3e-2, 0.1)
