@@ -74,6 +74,25 @@ typedef struct rmv_conv_args {
    * to view n % stat_views. NULL = off. Only stat_views == 2 is implemented. */
   double* stat_acc;
   int stat_views;
+  /* Training, RECOMPUTED BatchNorm of the expanding 1x1 convolutions (tcgen05 engine, bf16, two
+   * views: image n belongs to view n & 1). The conv output z is never written to HBM; the
+   * statistics come from rmv_conv_bn_stats / rmv_conv_bn_bwd_reduce, the apply passes are epilogue
+   * modes of this call with per-(view, channel) coefficient tables [2][c_out] (scale/shift unset):
+   *   bn_mode 1 (forward):  y = relu?( bn_a*z + bn_b + residual );  bn_bits (optional) receives the
+   *                         sign mask of the pre-ReLU value
+   *   bn_mode 2 (backward): y = dz = bn_a*dy + bn_b*z + bn_c, with dy passed as `residual`
+   * Packed masks hold 1 bit per element of a tensor with y's geometry: element offset
+   * n*y_sn + oh*y_sh + ow*y_sw + k (+ mask_off) -> bit (off % 8) of byte off / 8.
+   * mask_bits (any tcgen05 launch with bf16 output): the value about to be stored is zeroed where its
+   * mask bit is 0 -- the data gradient of a block input arrives already multiplied by the ReLU
+   * derivative of that tensor (models/resnet.py:146). */
+  int bn_mode;
+  const float* bn_a;
+  const float* bn_b;
+  const float* bn_c;
+  void* bn_bits;
+  const void* mask_bits;
+  long long mask_off;
 } rmv_conv_args;
 
 int rmv_conv2d_fwd(const rmv_conv_args* args, void* stream);
@@ -88,6 +107,19 @@ int rmv_conv2d_fwd(const rmv_conv_args* args, void* stream);
  * four parity-class convolutions over the undilated dy (1x1 filters: dx is zero-filled first and
  * must be dense). */
 int rmv_conv2d_dgrad(const rmv_conv_args* args, void* stream);
+
+/* BatchNorm(train) reductions over the RECOMPUTED output z = conv1x1(x, w) (stride 1 or 2, bf16,
+ * c_in % 64 == 0, c_out % 128 == 0; `args` describes the forward conv, y is not touched). The GEMM
+ * runs transposed on the tensor cores (channels = TMEM lanes), the accumulator is reduced on the
+ * fly and z never reaches HBM. acc = fp64 [2][c_out][2] (rmv_bn_workspace_bytes), accumulated into:
+ *   rmv_conv_bn_stats:       (sum z, sum z^2) per (view, channel)            -> rmv_bn_finalize
+ *   rmv_conv_bn_bwd_reduce:  (sum dy, sum dy*xhat), xhat = (z - mean)*invstd -> rmv_bn_bwd_finalize
+ * dy (bf16) has the geometry args->y_s* of the conv output and is expected to be already masked by
+ * the ReLU that follows the BatchNorm. Replaces the statistics passes of nn.BatchNorm2d behind
+ * models/resnet.py:122-123,139-146,229-230 (autograd at trainer.py:142). */
+int rmv_conv_bn_stats(const rmv_conv_args* args, double* acc, void* stream);
+int rmv_conv_bn_bwd_reduce(const rmv_conv_args* args, const void* dy, const float* mean,
+                           const float* invstd, double* acc, void* stream);
 
 /* Stem im2col: x fp32 NCHW [n,3,224,224]-like -> A[n*out_h*out_w, k_pad] (bf16 or fp32), row =
  * (kh,kw,c)-ordered 7x7x3 patch (stride 2, pad 3) zero-padded to k_pad columns. Feeds the stem
@@ -280,6 +312,10 @@ int rmv_maxpool3x3s2_bwd_idx(const void* idx, const void* dy, void* dx, int n_im
                              int in_w, int c, int dtype, void* stream);
 int rmv_avgpool_bwd(const void* dfeat, long long ld, void* dx, int n_img, int hw, int c, int dtype,
                     void* stream);
+/* dst[i] = (bit i of the packed mask `bits`) ? src[i] : 0 over n elements (n % 8 == 0; dst may alias
+ * src): a gradient times the derivative of the ReLU whose sign mask rmv_bn_apply / bn_mode 1 packed
+ * (models/resnet.py:146 under autograd). */
+int rmv_mask_bits(const void* src, const void* bits, void* dst, long long n, int dtype, void* stream);
 /* Analytic gradient of the weighted angular loss w.r.t. pred (zero where the cosine saturates,
  * like F.hardtanh) + backward of the head's last Linear(512,2) and the ReLU before it:
  * dhidden = (hidden>0) * dpred w2; dw2 += dpred^T hidden; db2 += colsum(dpred).

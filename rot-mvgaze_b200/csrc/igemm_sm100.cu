@@ -60,6 +60,17 @@ struct IgemmArgs {
   int stat_ppi_shift;  // boxed tiles: image of tile row r is tn*box_n + (r >> stat_ppi_shift),
   int stat_bw_shift;   //   its pixel (th*box_h + ((r >> stat_bw_shift) & (box_h-1)), tw*box_w + (r & (box_w-1)))
   int stat_w, stat_h, stat_n;  // output extent
+  // BNM kernels (training, recomputed BatchNorm): per-(view, channel) coefficient tables [2][n_total]
+  //   BNM 1 (forward apply):  y = relu?(bn_a*z + bn_b (+ residual)); bn_bits <- sign mask of the pre-ReLU value
+  //   BNM 2 (backward apply): y = bn_a*dy + bn_b*z + bn_c with dy = the "residual" tile
+  const float* bn_a;
+  const float* bn_b;
+  const float* bn_c;
+  // packed ReLU sign masks, 1 bit per element of a tensor with the geometry of y (element offset =
+  // n*m_sn + oh*m_sh + ow*m_sw + channel, + mask_off; bit e of byte off/8 = element off, e = off%8):
+  uint32_t* bn_bits;          // BNM 1: written
+  const uint32_t* mask_bits;  // any kernel: the value about to be stored is zeroed where the bit is 0
+  long long m_sn, m_sh, m_sw, mask_off;
 };
 
 // HALO variant (3x3, stride 1, pad 1, 64 -> 64 channels; BLOCK_N = 64): the producer loads ONE
@@ -76,7 +87,7 @@ constexpr int kHaloStages = 3;
 // RES: 0 = no residual; 1 = residual, deep residual ring (the HBM-bound layers with 1-4 k-blocks per
 // tile); 2 = residual, deep A/B ring (K >= 512: 3 stages + 2 residual slots; measured 0.234 -> 0.184 ms
 // on the 7x7 512->2048 layers, slower on the shallow-K ones)
-template <int BLOCK_N, int RES, bool HALO = false, bool STATS = false>
+template <int BLOCK_N, int RES, bool HALO = false, bool STATS = false, int BNM = 0>
 struct Cfg {
   static constexpr bool HAS_RES = RES != 0;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -88,12 +99,13 @@ struct Cfg {
   // trade A/B stages for a deeper residual ring (4 x 16 KiB) so the residual loads run well ahead.
   static constexpr int kStages = HALO ? kHaloStages
                                  : HAS_RES ? (BLOCK_N == 256 ? (RES == 2 ? 3 : 2) : (BLOCK_N == 128 ? 3 : 4))
-                                           : (BLOCK_N == 256 ? 3 : (STATS && BLOCK_N == 128 ? 4 : 6));
+                                           : (BLOCK_N == 256 ? 3 : ((STATS || BNM != 0) && BLOCK_N == 128 ? 4 : 6));
   static constexpr int kResSlots = (BLOCK_N == 256 && RES == 2) ? 2 : 4;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
   static constexpr int kOutBytes = 2 * kChunkBytes;
   static constexpr int kResBytes = HAS_RES ? kResSlots * kChunkBytes : 0;
-  static constexpr int kVecBytes = 2 * BLOCK_N * 4;  // scale + shift of the current N tile
+  // scale + shift of the current N tile; BNM: 2 (a, b) or 3 (a, b, c) tables for each of the 2 views
+  static constexpr int kVecBytes = (BNM == 0 ? 2 : (BNM == 1 ? 4 : 6)) * BLOCK_N * 4;
   static constexpr int kSmemBytes = kStages * kStageBytes + kResidentB + kOutBytes + kResBytes +
                                     kVecBytes + 256 /*barriers*/ + 1024 /*align*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
@@ -122,12 +134,14 @@ __device__ __forceinline__ void epi_bar_sync(int id) {
 }
 
 // OUT_F32: 32 fp32 columns per staged chunk; otherwise 64 bf16 columns (both 128 B per row).
-template <int BLOCK_N, int RES, bool OUT_F32, bool HALO = false, bool STATS = false>
+template <int BLOCK_N, int RES, bool OUT_F32, bool HALO = false, bool STATS = false, int BNM = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmArgs args) {
   constexpr bool HAS_RES = RES != 0;
-  using C = Cfg<BLOCK_N, RES, HALO, STATS>;
+  using C = Cfg<BLOCK_N, RES, HALO, STATS, BNM>;
   static_assert(!STATS || (!HAS_RES && !OUT_F32), "STATS: bf16 output, no residual");
+  static_assert(BNM == 0 || (!OUT_F32 && !HALO && !STATS), "BNM: bf16 output, plain tiles");
+  static_assert(BNM != 2 || HAS_RES, "BNM 2 reads dy through the residual ring");
   constexpr int kChunkCols = OUT_F32 ? 32 : 64;
   constexpr int kChunks = BLOCK_N / kChunkCols;
   extern __shared__ uint8_t smem_raw[];
@@ -139,8 +153,8 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   uint8_t* smem_out = smem_b + C::kStages * C::kStageB + C::kResidentB;  // [2][128 rows][128 B], SW128
   uint8_t* smem_res = smem_out + C::kOutBytes;           // [2][128 rows][128 B], SW128
   float* s_scale = reinterpret_cast<float*>(smem_res + C::kResBytes);
-  float* s_shift = s_scale + BLOCK_N;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BLOCK_N);
+  float* s_shift = s_scale + (BNM == 0 ? 1 : 2) * BLOCK_N;   // BNM: [2 views][BLOCK_N] per table
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_res + C::kResBytes + C::kVecBytes);
   uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + C::kStages;        // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * C::kStages;    // [2]        MMA -> epilogue
@@ -370,12 +384,48 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       }
       // per-channel scale/shift of this N tile -> smem (all readers of the previous tile's values
       // are behind the last epi_bar_sync(2) of that tile)
-      for (int i = tid_e; i < BLOCK_N; i += kEpiThreads) {
-        const int col = n_tile * BLOCK_N + i;
-        const bool ok = col < args.n_total;
-        s_scale[i] = (ok && args.scale != nullptr) ? __ldg(args.scale + col) : 1.f;
-        s_shift[i] = (ok && args.shift != nullptr) ? __ldg(args.shift + col) : 0.f;
+      if (BNM == 0) {
+        for (int i = tid_e; i < BLOCK_N; i += kEpiThreads) {
+          const int col = n_tile * BLOCK_N + i;
+          const bool ok = col < args.n_total;
+          s_scale[i] = (ok && args.scale != nullptr) ? __ldg(args.scale + col) : 1.f;
+          s_shift[i] = (ok && args.shift != nullptr) ? __ldg(args.shift + col) : 0.f;
+        }
+      } else {
+        for (int i = tid_e; i < 2 * BLOCK_N; i += kEpiThreads) {
+          const int vi = i / BLOCK_N, col = n_tile * BLOCK_N + (i - vi * BLOCK_N);
+          const bool ok = col < args.n_total;
+          s_scale[i] = ok ? __ldg(args.bn_a + vi * args.n_total + col) : 0.f;
+          s_shift[i] = ok ? __ldg(args.bn_b + vi * args.n_total + col) : 0.f;
+          if (BNM == 2) s_shift[2 * BLOCK_N + i] = ok ? __ldg(args.bn_c + vi * args.n_total + col) : 0.f;
+        }
       }
+      // this thread's output row: validity, image (-> view) and element offset inside a tensor of
+      // y's geometry (for the packed ReLU masks)
+      bool row_ok = true;
+      int row_view = 0;
+      long long row_off = 0;
+      if (BNM != 0 || args.mask_bits != nullptr) {
+        int ow, oh, n;
+        if (args.stat_pix > 0) {
+          const long long p = (long long)tw * args.box_w + row;
+          row_ok = p < args.stat_rows;
+          n = (int)(p / args.stat_pix);
+          ow = (int)p; oh = 0;
+          row_off = p * args.m_sw + args.mask_off;
+        } else {
+          ow = tw * args.box_w + (row & (args.box_w - 1));
+          oh = th * args.box_h + ((row >> args.stat_bw_shift) & (args.box_h - 1));
+          n = tn * args.box_n + (row >> args.stat_ppi_shift);
+          row_ok = ow < args.stat_w && oh < args.stat_h && n < args.stat_n;
+          row_off = (long long)n * args.m_sn + (long long)oh * args.m_sh + (long long)ow * args.m_sw +
+                    args.mask_off;
+        }
+        row_view = n & 1;
+      }
+      const float* t_a = s_scale + row_view * BLOCK_N;
+      const float* t_b = s_shift + row_view * BLOCK_N;
+      const float* t_c = s_shift + (2 + row_view) * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
 #pragma unroll 1
@@ -401,12 +451,20 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
         float f[32];
 #pragma unroll
         for (int q = 0; q < kWarpCols / 4; ++q) {
-          const float4 sc = *reinterpret_cast<const float4*>(s_scale + col_in_tile + q * 4);
-          const float4 sh = *reinterpret_cast<const float4*>(s_shift + col_in_tile + q * 4);
-          f[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]), sc.x, sh.x);
-          f[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]), sc.y, sh.y);
-          f[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]), sc.z, sh.z);
-          f[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]), sc.w, sh.w);
+          const float4 sc = *reinterpret_cast<const float4*>((BNM ? t_a : s_scale) + col_in_tile + q * 4);
+          const float4 sh = *reinterpret_cast<const float4*>((BNM ? t_b : s_shift) + col_in_tile + q * 4);
+          if (BNM == 2) {   // dz = a*dy + b*z + c: the b*z + c part (dy comes from the residual tile)
+            const float4 sc2 = *reinterpret_cast<const float4*>(t_c + col_in_tile + q * 4);
+            f[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]), sh.x, sc2.x);
+            f[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]), sh.y, sc2.y);
+            f[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]), sh.z, sc2.z);
+            f[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]), sh.w, sc2.w);
+          } else {
+            f[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]), sc.x, sh.x);
+            f[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]), sc.y, sh.y);
+            f[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]), sc.z, sh.z);
+            f[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]), sc.w, sh.w);
+          }
         }
         if (HAS_RES) {
 #pragma unroll
@@ -414,12 +472,37 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
             const uint32_t j = (uint32_t)(half * 4 + q);  // 16-byte unit within the 128-byte row
             const uint4 r = *reinterpret_cast<const uint4*>(rbuf + row * 128 + ((j ^ sw) << 4));
             const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+            float ka[8];
+            if (BNM == 2) {
+              *reinterpret_cast<float4*>(ka) = *reinterpret_cast<const float4*>(t_a + col_in_tile + q * 8);
+              *reinterpret_cast<float4*>(ka + 4) = *reinterpret_cast<const float4*>(t_a + col_in_tile + q * 8 + 4);
+            }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const float2 p = unpack_bf16x2(w[t]);
-              f[q * 8 + t * 2] += p.x;
-              f[q * 8 + t * 2 + 1] += p.y;
+              if (BNM == 2) {
+                f[q * 8 + t * 2] = fmaf(p.x, ka[t * 2], f[q * 8 + t * 2]);
+                f[q * 8 + t * 2 + 1] = fmaf(p.y, ka[t * 2 + 1], f[q * 8 + t * 2 + 1]);
+              } else {
+                f[q * 8 + t * 2] += p.x;
+                f[q * 8 + t * 2 + 1] += p.y;
+              }
             }
+          }
+        }
+        if (!OUT_F32) {
+          // packed ReLU masks: 32 consecutive channels of this row = one 32-bit word
+          const long long woff = (row_off + n_tile * BLOCK_N + col_in_tile) >> 5;
+          if (BNM == 1 && args.bn_bits != nullptr && row_ok) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) word |= (f[j] > 0.f ? 1u : 0u) << j;
+            args.bn_bits[woff] = word;
+          }
+          if (args.mask_bits != nullptr) {
+            const uint32_t word = row_ok ? __ldg(args.mask_bits + woff) : 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = (word >> j) & 1u ? f[j] : 0.f;
           }
         }
         if (args.relu) {
@@ -839,9 +922,9 @@ namespace {
 
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-template <int BLOCK_N, int RES, bool OUT_F32, bool HALO = false, bool STATS = false>
+template <int BLOCK_N, int RES, bool OUT_F32, bool HALO = false, bool STATS = false, int BNM = 0>
 int launch(const IgemmArgs& a, int total_tiles, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, RES, HALO, STATS>;
+  using C = Cfg<BLOCK_N, RES, HALO, STATS, BNM>;
   // STATS: [2][n_total][2] floats behind the fixed regions (they replace the 1 KiB alignment slack
   // at the end of kSmemBytes, which the 1024-byte aligned base may consume: keep it as well)
   const int stat_bytes = STATS ? (4 * a.n_total + 8 * 256) * (int)sizeof(float) + 1024 : 0;
@@ -850,12 +933,12 @@ int launch(const IgemmArgs& a, int total_tiles, cudaStream_t stream) {
                 a.n_total);
   static int attr_bytes = 0;
   if (smem > attr_bytes) {
-    RMV_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, RES, OUT_F32, HALO, STATS>,
+    RMV_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, RES, OUT_F32, HALO, STATS, BNM>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_bytes = smem;
   }
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  RMV_CUDA(launch_pdl_tc(igemm_kernel<BLOCK_N, RES, OUT_F32, HALO, STATS>, dim3(grid),
+  RMV_CUDA(launch_pdl_tc(igemm_kernel<BLOCK_N, RES, OUT_F32, HALO, STATS, BNM>, dim3(grid),
                          dim3(kNumThreads), smem, stream, a));
   return 0;
 }
@@ -868,7 +951,12 @@ int launch(const IgemmArgs& a, int total_tiles, cudaStream_t stream) {
 int halo_mode() { return tuning("HALO", 1, 2); }
 
 template <int BLOCK_N>
-int dispatch(const IgemmArgs& a, int total, bool has_res, bool out_f32, cudaStream_t stream) {
+int dispatch(const IgemmArgs& a, int total, bool has_res, bool out_f32, int bn_mode, cudaStream_t stream) {
+  if (bn_mode == 1) {   // recomputed-BatchNorm forward apply (+ residual): HBM-bound, deep residual ring
+    if (has_res) return launch<BLOCK_N, 1, false, false, false, 1>(a, total, stream);
+    return launch<BLOCK_N, 0, false, false, false, 1>(a, total, stream);
+  }
+  if (bn_mode == 2) return launch<BLOCK_N, 1, false, false, false, 2>(a, total, stream);
   if (a.stat_acc != nullptr) return launch<BLOCK_N, 0, false, false, true>(a, total, stream);
   if (out_f32) return launch<BLOCK_N, 0, true>(a, total, stream);
   if (has_res) {
@@ -1005,6 +1093,7 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
   const bool pair = cta2_mode() >= 1 && (block_n == 256 || (block_n == 128 && cta2_mode() == 2)) &&
                     p.block_n == 0 && !halo &&
                     !out_f32 && p.residual == nullptr && p.stat_acc == nullptr &&
+                    p.bn_mode == 0 && p.mask_bits == nullptr &&
                     p.c_out % block_n == 0 && m_tiles >= 2;
   {
     const long long k_total = (long long)(taps ? taps->w_taps : a.num_taps) * p.c_in;
@@ -1039,9 +1128,11 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
   const int total = (int)(m_tiles * a.n_tiles);
   if (total == 0) return 0;
   if (pair) return block_n == 256 ? launch_pair<256>(a, stream) : launch_pair<128>(a, stream);
-  if (p.stat_acc != nullptr) {
-    RMV_CHECK_ARG(!out_f32 && p.residual == nullptr && p.stat_views == 2,
+  if (p.stat_acc != nullptr)
+    RMV_CHECK_ARG(!out_f32 && p.residual == nullptr && p.stat_views == 2 && p.bn_mode == 0,
                   "tcgen05 conv: fused BatchNorm statistics need bf16 output, no residual, 2 views");
+  if (p.stat_acc != nullptr || p.bn_mode != 0 || p.mask_bits != nullptr) {
+    // row bookkeeping of the epilogue: image (view) and pixel of every tile row
     a.stat_acc = p.stat_acc;
     const bool flattened = (out_h == 1 && n_img == 1 && (p.out_h != 1 || p.n_img != 1));
     a.stat_pix = flattened ? p.out_h * p.out_w : 0;
@@ -1053,6 +1144,25 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
     while ((1 << sh) < a.box_w) ++sh;
     a.stat_bw_shift = sh;
     a.stat_w = out_w; a.stat_h = out_h; a.stat_n = n_img;
+    a.m_sn = y_sn; a.m_sh = y_sh; a.m_sw = y_sw; a.mask_off = p.mask_off;
+  }
+  if (p.bn_mode != 0 || p.mask_bits != nullptr) {
+    RMV_CHECK_ARG(!out_f32 && !halo && p.c_out % 32 == 0 && p.y_sw % 32 == 0 && p.y_sh % 32 == 0 &&
+                      p.y_sn % 32 == 0 && p.mask_off % 32 == 0,
+                  "tcgen05 conv: BatchNorm-apply modes / ReLU masks need bf16 output and channel counts, "
+                  "strides and mask offsets that are multiples of 32");
+    RMV_CHECK_ARG(p.bn_mode == 0 || (p.bn_a != nullptr && p.bn_b != nullptr && p.scale == nullptr &&
+                                     p.shift == nullptr && block_n >= 128),
+                  "tcgen05 conv: bn_mode needs bn_a/bn_b, no scale/shift and c_out >= 128");
+    RMV_CHECK_ARG(p.bn_mode != 2 || (p.bn_c != nullptr && p.residual != nullptr && p.relu == 0),
+                  "tcgen05 conv: bn_mode 2 needs bn_c and dy in `residual`, no ReLU");
+    RMV_CHECK_ARG(p.bn_mode >= 0 && p.bn_mode <= 2, "tcgen05 conv: bad bn_mode %d", p.bn_mode);
+    a.bn_a = p.bn_a; a.bn_b = p.bn_b; a.bn_c = p.bn_c;
+    a.bn_bits = reinterpret_cast<uint32_t*>(p.bn_bits);
+    a.mask_bits = reinterpret_cast<const uint32_t*>(p.mask_bits);
+    RMV_CHECK_ARG((reinterpret_cast<uintptr_t>(p.bn_bits) & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.mask_bits) & 3) == 0,
+                  "tcgen05 conv: mask pointers must be 4-byte aligned");
   }
   if (halo) {
     a.halo_base_mode = halo_mode() == 2;
@@ -1061,9 +1171,9 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
   }
   const bool has_res = p.residual != nullptr;
   switch (block_n) {
-    case 64: return dispatch<64>(a, total, has_res, out_f32, stream);
-    case 128: return dispatch<128>(a, total, has_res, out_f32, stream);
-    default: return dispatch<256>(a, total, has_res, out_f32, stream);
+    case 64: return dispatch<64>(a, total, has_res, out_f32, 0, stream);
+    case 128: return dispatch<128>(a, total, has_res, out_f32, p.bn_mode, stream);
+    default: return dispatch<256>(a, total, has_res, out_f32, p.bn_mode, stream);
   }
 }
 
@@ -1129,6 +1239,7 @@ int conv_dgrad_tc(const ConvArgs& p, cudaStream_t stream) {
         q.residual = (const char*)p.residual + ((long long)pa * p.r_sh + (long long)pb * p.r_sw) * 2;
         q.r_sh = 2 * p.r_sh; q.r_sw = 2 * p.r_sw;
       }
+      q.mask_off = p.mask_off + (long long)pa * p.y_sh + (long long)pb * p.y_sw;
       if (int rc = conv_taps_tc(q, &tl[pa][pb], stream)) return rc;
     }
   return 0;

@@ -484,6 +484,22 @@ __global__ void relu_bwd_kernel(const T* __restrict__ src, long long ld_src,
   V8<T>::store(dst + row * ld_dst + g * 8, s);
 }
 
+// dst[i] = bit i of `bits` ? src[i] : 0 over a flat tensor (8 elements / one mask byte per thread):
+// multiplies a gradient by the ReLU derivative recorded as a packed sign mask.
+template <typename T>
+__global__ void mask_bits_kernel(const T* __restrict__ src, const uint8_t* __restrict__ bits,
+                                 T* __restrict__ dst, long long n8) {
+  griddep_wait();
+  griddep_launch();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    V8<T>::load(src + i * 8, f);
+    apply_bits(f, bits[i]);
+    V8<T>::store(dst + i * 8, f);
+  }
+}
+
 // out[col] (+)= sum_rows x[row, col]  (fp32 output; bias gradients)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -1424,6 +1440,20 @@ extern "C" int rmv_avgpool_bwd(const void* dfeat, long long ld, void* dx, int n_
   if (total == 0) return 0;
   DISPATCH_T(dtype, (rmv::launch_pdl(avgpool_bwd_kernel<T>, dim3(nblk(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const T*)dfeat, ld, (T*)dx, hw, c, total)));
+  RMV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rmv_mask_bits(const void* src, const void* bits, void* dst, long long n, int dtype,
+                             void* stream) {
+  RMV_CHECK_ARG(n % 8 == 0, "mask_bits: element count must be a multiple of 8");
+  if (n == 0) return 0;
+  RMV_CHECK_ARG(src && bits && dst, "mask_bits: null pointer");
+  long blocks = (n / 8 + 255) / 256;
+  if (blocks > 8L * num_sms()) blocks = 8L * num_sms();
+  DISPATCH_T(dtype, (rmv::launch_pdl(mask_bits_kernel<T>, dim3((unsigned)blocks), dim3(256), 0,
+                                     (cudaStream_t)stream, (const T*)src, (const uint8_t*)bits, (T*)dst,
+                                     n / 8)));
   RMV_LAUNCH_CHECK();
   return 0;
 }

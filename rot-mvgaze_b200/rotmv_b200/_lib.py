@@ -42,6 +42,8 @@ class ConvArgs(C.Structure):
         ("r_sn", C.c_longlong), ("r_sh", C.c_longlong), ("r_sw", C.c_longlong),
         ("relu", C.c_int),
         ("stat_acc", C.c_void_p), ("stat_views", C.c_int),
+        ("bn_mode", C.c_int), ("bn_a", C.c_void_p), ("bn_b", C.c_void_p), ("bn_c", C.c_void_p),
+        ("bn_bits", C.c_void_p), ("mask_bits", C.c_void_p), ("mask_off", C.c_longlong),
     ]
 
 
@@ -65,6 +67,8 @@ SIGNATURES = {
     "rmv_device_check": (_i, [_i]),
     "rmv_conv2d_dgrad": (_i, [C.POINTER(ConvArgs), _vp]),
     "rmv_conv2d_fwd": (_i, [C.POINTER(ConvArgs), _vp]),
+    "rmv_conv_bn_stats": (_i, [C.POINTER(ConvArgs), _vp, _vp]),
+    "rmv_conv_bn_bwd_reduce": (_i, [C.POINTER(ConvArgs), _vp, _vp, _vp, _vp, _vp]),
     "rmv_stem_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rmv_stem_pack_weights": (_i, [_vp, _vp, _vp]),
     "rmv_stem_conv_fwd_u8": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -100,6 +104,7 @@ SIGNATURES = {
     "rmv_maxpool3x3s2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rmv_maxpool3x3s2_fwd_idx": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rmv_maxpool3x3s2_bwd_idx": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rmv_mask_bits": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
     "rmv_avgpool_bwd": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _vp]),
     "rmv_head_loss_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _vp, _i, _i, _f, _i, _f, _vp, _ll, _vp, _vp,
                                _vp, _vp]),

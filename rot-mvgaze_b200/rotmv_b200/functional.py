@@ -33,8 +33,62 @@ def _need_cuda(*ts):
             raise L.RotmvError("rotmv_b200 ops need CUDA tensors (there is no CPU path)")
 
 
+def _conv_args(x, w, out, stride, pad):
+    """rmv_conv_args of y = conv(x, w) for NHWC x [N,H,W,C], KRSC w, NHWC out."""
+    n, h, wd, c = x.shape
+    k, kh, kw, _ = w.shape
+    a = L.ConvArgs()
+    a.x_dtype = L.dtype_code(x.dtype)
+    a.y_dtype = L.dtype_code(out.dtype if out is not None else x.dtype)
+    a.x = x.data_ptr()
+    a.x_sn, a.x_sh, a.x_sw, a.x_sc = x.stride(0), x.stride(1), x.stride(2), 1
+    a.n_img, a.in_h, a.in_w, a.c_in = n, h, wd, c
+    a.w = w.data_ptr()
+    a.c_out, a.kh, a.kw, a.stride, a.pad = k, kh, kw, stride, pad
+    a.out_h = (h + 2 * pad - kh) // stride + 1
+    a.out_w = (wd + 2 * pad - kw) // stride + 1
+    if out is not None:
+        a.y = out.data_ptr()
+        a.y_sn, a.y_sh, a.y_sw = out.stride(0), out.stride(1), out.stride(2)
+    return a
+
+
+def conv_bn_stats(x, w, acc, *, stride=1):
+    """acc[v][k] += (sum z, sum z^2) of z = conv1x1(x, w), recomputed on the tensor cores (z is never
+    written; rmv_conv_bn_stats). x [N,H,W,C] bf16, w [K,1,1,C] bf16, acc fp64 [>=2, K, 2]."""
+    _need_cuda(x, w, acc)
+    assert w.shape[1] == w.shape[2] == 1 and w.is_contiguous() and w.dtype == x.dtype == torch.bfloat16
+    a = _conv_args(x, w, None, stride, 0)
+    meta = {}
+    if PROFILE is not None:
+        n, h, wd, c = x.shape
+        meta = {"engine": "tcgen05-bnstat", "flops": 2.0 * n * a.out_h * a.out_w * w.shape[0] * c,
+                "bytes": float(n * a.out_h * a.out_w * c * 2),
+                "desc": f"conv-bn stats 1x1s{stride} [{n},{h},{wd},{c}]->{w.shape[0]}"}
+    _call("rmv_conv_bn_stats", meta, L.load().rmv_conv_bn_stats, C.byref(a), acc.data_ptr(), L.stream_ptr())
+
+
+def conv_bn_bwd_reduce(x, w, dy, mean, invstd, acc, *, stride=1):
+    """acc[v][k] += (sum dy, sum dy*xhat) with xhat from the recomputed z = conv1x1(x, w)
+    (rmv_conv_bn_bwd_reduce); dy [N,OH,OW,K] bf16, already ReLU-masked."""
+    _need_cuda(x, w, dy, mean, invstd, acc)
+    assert w.shape[1] == w.shape[2] == 1 and w.is_contiguous() and w.dtype == x.dtype == dy.dtype == torch.bfloat16
+    a = _conv_args(x, w, None, stride, 0)
+    assert tuple(dy.shape) == (x.shape[0], a.out_h, a.out_w, w.shape[0]) and dy.stride(3) == 1
+    a.y_sn, a.y_sh, a.y_sw = dy.stride(0), dy.stride(1), dy.stride(2)
+    meta = {}
+    if PROFILE is not None:
+        n, h, wd, c = x.shape
+        meta = {"engine": "tcgen05-bnstat", "flops": 2.0 * dy.numel() * c,
+                "bytes": float(n * a.out_h * a.out_w * c * 2 + dy.numel() * 2),
+                "desc": f"conv-bn bwd reduce 1x1s{stride} [{n},{h},{wd},{c}]->{w.shape[0]}"}
+    _call("rmv_conv_bn_bwd_reduce", meta, L.load().rmv_conv_bn_bwd_reduce, C.byref(a), dy.data_ptr(),
+          mean.data_ptr(), invstd.data_ptr(), acc.data_ptr(), L.stream_ptr())
+
+
 def conv2d(x, w, *, stride=1, pad=0, scale=None, shift=None, residual=None, relu=False,
-           out=None, out_dtype=None, engine=L.ENGINE_AUTO, block_n=0, stat_acc=None, stat_views=0):
+           out=None, out_dtype=None, engine=L.ENGINE_AUTO, block_n=0, stat_acc=None, stat_views=0,
+           bn_mode=0, bn_a=None, bn_b=None, bn_c=None, bn_bits=None, mask_bits=None):
     """y = act(scale * conv(x, w) + shift + residual).
 
     x: [N, H, W, C] (any pixel strides, channel stride 1); w: [K, kh, kw, C] contiguous, same
@@ -78,6 +132,14 @@ def conv2d(x, w, *, stride=1, pad=0, scale=None, shift=None, residual=None, relu
         assert stat_acc.dtype == torch.float64 and stat_acc.is_contiguous() and stat_acc.numel() >= stat_views * k * 2
         a.stat_acc = stat_acc.data_ptr()
         a.stat_views = stat_views
+    if bn_mode:
+        # recomputed-BatchNorm epilogues (rmv_conv_args.bn_mode): per-(view, channel) tables [2][K]
+        for t in (bn_a, bn_b) + ((bn_c,) if bn_mode == 2 else ()):
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() >= 2 * k
+        a.bn_mode = bn_mode
+        a.bn_a, a.bn_b, a.bn_c = bn_a.data_ptr(), bn_b.data_ptr(), L.ptr(bn_c)
+        a.bn_bits = L.ptr(bn_bits)
+    a.mask_bits = L.ptr(mask_bits)
     meta = {}
     if PROFILE is not None:
         tc = x.dtype == torch.bfloat16 and engine != L.ENGINE_SIMT and c % 64 == 0
@@ -91,7 +153,7 @@ def conv2d(x, w, *, stride=1, pad=0, scale=None, shift=None, residual=None, relu
     return out
 
 
-def conv2d_dgrad(dy, wt, *, stride, pad, in_hw, residual=None, out=None):
+def conv2d_dgrad(dy, wt, *, stride, pad, in_hw, residual=None, out=None, mask_bits=None):
     """dx (+ residual) of y = conv(x, w, stride, pad) on the tcgen05 engine.
 
     dy: [N, OH, OW, K] bf16; wt: [C, kh, kw, K] = w reversed and transposed
@@ -121,6 +183,7 @@ def conv2d_dgrad(dy, wt, *, stride, pad, in_hw, residual=None, out=None):
         assert tuple(residual.shape) == tuple(out.shape) and residual.dtype == out.dtype
         a.residual = residual.data_ptr()
         a.r_sn, a.r_sh, a.r_sw = residual.stride(0), residual.stride(1), residual.stride(2)
+    a.mask_bits = L.ptr(mask_bits)   # dx is zeroed where the packed ReLU mask of that tensor is 0
     meta = {}
     if PROFILE is not None:
         meta = {"engine": "tcgen05", "flops": 2.0 * n * oh * ow * k * kh * kw * c,

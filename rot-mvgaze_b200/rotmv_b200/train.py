@@ -72,6 +72,10 @@ class TrainEngine:
         self.use_tc_wgrad = True  # bf16: weight gradients on tcgen05 (False -> FFMA kernel)
         # bf16, V == 2: BatchNorm statistics in the conv epilogue (RMV_FUSE_BN_STATS=0: separate pass)
         self.fuse_bn_stats = os.environ.get("RMV_FUSE_BN_STATS", "1") != "0"
+        # bf16, V == 2, bottleneck blocks: the BatchNorm of the expanding 1x1 convolutions (conv3,
+        # downsample) never materialises the conv output -- statistics and apply passes recompute it on
+        # the tensor cores (RMV_BN_RECOMPUTE=0: the conv writes z and the HBM-bound passes read it)
+        self.recompute_bn = os.environ.get("RMV_BN_RECOMPUTE", "1") != "0" and trunk.kind == "bottleneck"
         # data parallel: all-reduce the fusion-stage gradients while the trunk backward runs
         # (RMV_DP_OVERLAP=0: one all-reduce of the whole buffer after the backward pass)
         self.dp_overlap = os.environ.get("RMV_DP_OVERLAP", "1") != "0"
@@ -289,6 +293,45 @@ class TrainEngine:
             desc="rmv_bn_bwd_apply" + shp)
         return dz, dyr
 
+    # ---- BatchNorm over a recomputed 1x1 convolution (conv3 / downsample of the bottlenecks) ------
+    def _use_recompute(self, conv) -> bool:
+        return (self.recompute_bn and self.precision == "bf16" and self.views == 2
+                and conv.kernel_size[0] == 1 and conv.out_channels % 128 == 0 and conv.in_channels % 64 == 0)
+
+    def _conv_bn_fwd(self, bn: _BN, x, w, stride, residual, relu, tag):
+        """y = relu?(BN_train(conv1x1(x, w)) + residual) without writing the conv output: statistics
+        from the transposed recompute GEMM (rmv_conv_bn_stats), coefficients (rmv_bn_finalize), then
+        the conv again with the BatchNorm-apply epilogue (bn_mode 1), which also packs the ReLU mask."""
+        n, h, wd, _ = x.shape
+        oh, ow = (h - 1) // stride + 1, (wd - 1) // stride + 1
+        c, v = w.shape[0], self.views
+        RF.conv_bn_stats(x, w, self.acc, stride=stride)
+        _ck("rmv_bn_finalize", self.acc.data_ptr(), bn.gamma.data_ptr(), bn.beta.data_ptr(),
+            bn.rm.data_ptr(), bn.rv.data_ptr(), bn.nbt.data_ptr(), bn.mean.data_ptr(),
+            bn.invstd.data_ptr(), bn.a.data_ptr(), bn.b.data_ptr(), c, v, (n // v) * oh * ow, bn.eps,
+            bn.momentum)
+        y = self._buf(tag, (n, oh, ow, c))
+        bits = self._buf(("bits", tag), (n * oh * ow * c // 8,), torch.uint8) if relu else None
+        RF.conv2d(x, w, stride=stride, residual=residual, relu=relu, out=y, bn_mode=1, bn_a=bn.a,
+                  bn_b=bn.b, bn_bits=bits)
+        self._bits[id(y)] = bits
+        return y
+
+    def _conv_bn_bwd(self, bn: _BN, x, w, stride, dy, tag):
+        """dz of z = conv1x1(x, w) under y = BN_train(z) for a dy that is ALREADY multiplied by the
+        derivative of the ReLU behind the BatchNorm: reductions over the recomputed z
+        (rmv_conv_bn_bwd_reduce), coefficients (rmv_bn_bwd_finalize), then the conv again with the
+        backward-apply epilogue (bn_mode 2: dz = k0*dy + k1*z + k2)."""
+        n, oh, ow, c = dy.shape
+        v = self.views
+        RF.conv_bn_bwd_reduce(x, w, dy, bn.mean, bn.invstd, self.acc, stride=stride)
+        _ck("rmv_bn_bwd_finalize", self.acc.data_ptr(), bn.gamma.data_ptr(), bn.mean.data_ptr(),
+            bn.invstd.data_ptr(), bn.dgamma.data_ptr(), bn.dbeta.data_ptr(), bn.k0.data_ptr(),
+            bn.k1.data_ptr(), bn.k2.data_ptr(), c, v, (n // v) * oh * ow)
+        dz = self._buf(("dz", tag), dy.shape)
+        RF.conv2d(x, w, stride=stride, residual=dy, out=dz, bn_mode=2, bn_a=bn.k0, bn_b=bn.k1, bn_c=bn.k2)
+        return dz
+
     # ---- convolution gradients -----------------------------------------------------------------
     def _wgrad(self, x, dy, conv_or_lin, kh, kw, stride, pad, x_strides=None, grad=None):
         """dW (fp32, parameter layout) += sum_p dy[p,k] x[p+(r,s), c]. `grad` overrides the
@@ -331,14 +374,18 @@ class TrainEngine:
                                       "flops": 2.0 * n * dy.shape[1] * dy.shape[2] * dy.shape[3] * kh * kw * c},
                  L.load().rmv_conv2d_wgrad, C.byref(a), dy.data_ptr(), grad.data_ptr(), L.stream_ptr())
 
-    def _dgrad(self, dz, conv, tag, in_shape, residual=None):
-        """dx = conv_transpose(dz, w) (+ residual) via the forward kernel with flipped filters."""
+    def _dgrad(self, dz, conv, tag, in_shape, residual=None, mask_bits=None):
+        """dx = conv_transpose(dz, w) (+ residual) via the forward kernel with flipped filters;
+        `mask_bits` (bf16 engine): packed ReLU mask of the tensor dx is the gradient of -- dx is
+        zeroed where that ReLU was inactive."""
         wt = self._w_dgrad(conv, tag)
         r = conv.kernel_size[0]
         stride, pad = conv.stride[0], conv.padding[0]
         if self.precision == "bf16":
             return RF.conv2d_dgrad(dz, wt, stride=stride, pad=pad, in_hw=in_shape[1:3],
-                                   residual=residual, out=self._buf(("dx", tag), in_shape))
+                                   residual=residual, out=self._buf(("dx", tag), in_shape),
+                                   mask_bits=mask_bits)
+        assert mask_bits is None
         src = dz
         if stride == 2:
             n, oh, ow, k = dz.shape
@@ -773,17 +820,25 @@ class TrainEngine:
             zd = None
             if "ds_conv" in e:
                 dc = e["ds_conv"]
-                zd, sd = self._conv_stats(x_in, self._w_fwd(dc, (bi, "d")), stride=dc.stride[0],
-                                          out=self._buf(("zd", bi), (m, oh, oh, dc.out_channels)))
-                skip = self._bn_fwd(e["ds_bn"], zd, None, False, ("skip", bi), stats_done=sd)
+                if self._use_recompute(dc):
+                    skip = self._conv_bn_fwd(e["ds_bn"], x_in, self._w_fwd(dc, (bi, "d")), dc.stride[0],
+                                             None, False, ("skip", bi))
+                else:
+                    zd, sd = self._conv_stats(x_in, self._w_fwd(dc, (bi, "d")), stride=dc.stride[0],
+                                              out=self._buf(("zd", bi), (m, oh, oh, dc.out_channels)))
+                    skip = self._bn_fwd(e["ds_bn"], zd, None, False, ("skip", bi), stats_done=sd)
             else:
                 skip = x_in
             cv = convs[-1]
-            z, sd = self._conv_stats(t, self._w_fwd(cv, (bi, len(convs))), stride=cv.stride[0],
-                                     pad=cv.padding[0],
-                                     out=self._buf((f"z{len(convs)}", bi), (m, oh, oh, cv.out_channels)))
-            zs.append(z)
-            x = self._bn_fwd(bns[-1], z, skip, True, ("out", bi), stats_done=sd)
+            if self._use_recompute(cv):
+                zs.append(None)   # never materialised
+                x = self._conv_bn_fwd(bns[-1], t, self._w_fwd(cv, (bi, len(convs))), 1, skip, True, ("out", bi))
+            else:
+                z, sd = self._conv_stats(t, self._w_fwd(cv, (bi, len(convs))), stride=cv.stride[0],
+                                         pad=cv.padding[0],
+                                         out=self._buf((f"z{len(convs)}", bi), (m, oh, oh, cv.out_channels)))
+                zs.append(z)
+                x = self._bn_fwd(bns[-1], z, skip, True, ("out", bi), stats_done=sd)
             saved.append((x_in, zs, ys, zd, x))
         if self.encode_rot or self.share_feat:
             if v != 2:
@@ -800,13 +855,27 @@ class TrainEngine:
         d_out = self._buf(("dx", "avg"), last.shape)
         _ck("rmv_avgpool_bwd", dimg.data_ptr(), dimg.stride(0), d_out.data_ptr(), m,
             last.shape[1] * last.shape[2], last.shape[3], dtc)
+        pre_masked = False   # d_out already multiplied by the ReLU derivative of the block output
+        if self.precision == "bf16" and self._bits.get(id(last)) is not None and self._use_recompute(self.blocks[-1]["convs"][-1]):
+            _ck("rmv_mask_bits", d_out.data_ptr(), self._bits[id(last)].data_ptr(), d_out.data_ptr(),
+                d_out.numel(), dtc)
+            pre_masked = True
         for bi in reversed(range(len(self.blocks))):
             e = self.blocks[bi]
             convs, bns = e["convs"], e["bns"]
             x_in, zs, ys, zd, out = saved[bi]
             n_st = len(convs)
             # last conv of the block: its BatchNorm also yields the gradient of the skip branch
-            dz, dyr = self._bn_bwd(bns[-1], zs[-1], d_out, out, (bi, n_st), want_dyr=True)
+            if zs[-1] is None:    # recomputed BatchNorm: d_out arrives masked, dyr IS d_out
+                assert pre_masked
+                dz = self._conv_bn_bwd(bns[-1], ys[-1], self._w_fwd(convs[-1], (bi, n_st)), 1, d_out, (bi, n_st))
+                dyr = d_out
+            else:
+                dz, dyr = self._bn_bwd(bns[-1], zs[-1], d_out, out, (bi, n_st), want_dyr=True)
+            # the data gradient this block hands to the previous one is masked by that block's ReLU
+            # when its packed mask exists (bf16 engine); blocks of the old path mask again (idempotent)
+            in_bits = self._bits.get(id(x_in)) if (self.precision == "bf16" and bi > 0) else None
+            pre_masked = in_bits is not None
             for si in reversed(range(n_st)):
                 cv = convs[si]
                 k, st, pd = cv.kernel_size[0], cv.stride[0], cv.padding[0]
@@ -816,14 +885,18 @@ class TrainEngine:
                     dy = self._dgrad(dz, cv, (bi, si + 1), src.shape)
                     dz, _ = self._bn_bwd(bns[si - 1], zs[si - 1], dy, ys[si - 1], (bi, si))
                 else:
-                    if zd is not None:
+                    if "ds_conv" in e:
                         dc = e["ds_conv"]
-                        dzd, _ = self._bn_bwd(e["ds_bn"], zd, dyr, None, (bi, "d"))
+                        if zd is None:
+                            dzd = self._conv_bn_bwd(e["ds_bn"], x_in, self._w_fwd(dc, (bi, "d")), dc.stride[0],
+                                                    dyr, (bi, "d"))
+                        else:
+                            dzd, _ = self._bn_bwd(e["ds_bn"], zd, dyr, None, (bi, "d"))
                         self._wgrad(x_in, dzd, dc, 1, 1, dc.stride[0], 0)
                         res = self._dgrad(dzd, dc, (bi, "d"), x_in.shape)
                     else:
                         res = dyr
-                    d_out = self._dgrad(dz, cv, (bi, 1), x_in.shape, residual=res)
+                    d_out = self._dgrad(dz, cv, (bi, 1), x_in.shape, residual=res, mask_bits=in_bits)
             if hook is not None and self._stage_first.get(bi) in self._bucket_by_stage:
                 hook(*self._bucket_by_stage[self._stage_first[bi]])   # this stage's gradients are final
         d_y0 = self._buf("dy_stem", y0.shape)
