@@ -43,6 +43,32 @@ int rmv_device_check(int device);
  * "WGRAD_ROWS" (tap-row weight-gradient kernel). This call overrides them at run time. */
 int rmv_set_tuning(const char* key, int value);
 
+/* BatchNorm(train) finalize parameters. Passed (non-NULL) to a statistics / reduction call, the LAST
+ * thread block of that launch turns the fp64 sums into the coefficients of the apply pass, so no
+ * separate rmv_bn_finalize / rmv_bn_bwd_finalize launch is needed. `ticket`: one zero-initialised
+ * unsigned int in device memory (reset by the call). Forward: mean, invstd, a = gamma*invstd,
+ * b = beta - mean*a per (view, channel) [views][c]; running statistics updated in view order
+ * (momentum, unbiased variance), num_batches += views. Backward: dgamma, dbeta [c] and
+ * k0, k1, k2 [views][c] of dz = k0*dy + k1*z + k2. Unused fields may be NULL. */
+typedef struct rmv_bn_params {
+  unsigned int* ticket;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  long long* num_batches;
+  float* mean;
+  float* invstd;
+  float* a;
+  float* b;
+  float* dgamma;
+  float* dbeta;
+  float* k0;
+  float* k1;
+  float* k2;
+  float eps, momentum;
+} rmv_bn_params;
+
 /* ----------------------------------------------------------------------------------------------
  * Convolution / linear layer with fused epilogue:
  *     y = act( scale[k] * conv(x, w)[..., k] + shift[k] + residual )
@@ -74,6 +100,7 @@ typedef struct rmv_conv_args {
    * to view n % stat_views. NULL = off. Only stat_views == 2 is implemented. */
   double* stat_acc;
   int stat_views;
+  const void* stat_finalize; /* const rmv_bn_params* or NULL: finalize inside this launch (forward fields) */
   /* Training, RECOMPUTED BatchNorm of the expanding 1x1 convolutions (tcgen05 engine, bf16, two
    * views: image n belongs to view n & 1). The conv output z is never written to HBM; the
    * statistics come from rmv_conv_bn_stats / rmv_conv_bn_bwd_reduce, the apply passes are epilogue
@@ -114,12 +141,15 @@ int rmv_conv2d_dgrad(const rmv_conv_args* args, void* stream);
  * fly and z never reaches HBM. acc = fp64 [2][c_out][2] (rmv_bn_workspace_bytes), accumulated into:
  *   rmv_conv_bn_stats:       (sum z, sum z^2) per (view, channel)            -> rmv_bn_finalize
  *   rmv_conv_bn_bwd_reduce:  (sum dy, sum dy*xhat), xhat = (z - mean)*invstd -> rmv_bn_bwd_finalize
+ * or, with `finalize` != NULL, finalized by the last block of the launch itself (acc is reset).
  * dy (bf16) has the geometry args->y_s* of the conv output and is expected to be already masked by
  * the ReLU that follows the BatchNorm. Replaces the statistics passes of nn.BatchNorm2d behind
  * models/resnet.py:122-123,139-146,229-230 (autograd at trainer.py:142). */
-int rmv_conv_bn_stats(const rmv_conv_args* args, double* acc, void* stream);
+int rmv_conv_bn_stats(const rmv_conv_args* args, double* acc, const rmv_bn_params* finalize,
+                      void* stream);
 int rmv_conv_bn_bwd_reduce(const rmv_conv_args* args, const void* dy, const float* mean,
-                           const float* invstd, double* acc, void* stream);
+                           const float* invstd, double* acc, const rmv_bn_params* finalize,
+                           void* stream);
 
 /* Stem im2col: x fp32 NCHW [n,3,224,224]-like -> A[n*out_h*out_w, k_pad] (bf16 or fp32), row =
  * (kh,kw,c)-ordered 7x7x3 patch (stride 2, pad 3) zero-padded to k_pad columns. Feeds the stem

@@ -21,6 +21,7 @@
 // Replaces the statistics half of nn.BatchNorm2d (train mode) forward/backward behind
 // models/resnet.py:139-146 (autograd at trainer.py:142).
 #include "common.cuh"
+#include "bn_finalize.cuh"
 #include "ops.h"
 
 namespace rmv {
@@ -44,6 +45,7 @@ struct TStatArgs {
   double* acc;           // [2][c_out][2]
   const float* mean;     // BWD: [2][c_out]
   const float* invstd;
+  BnFinalize fin;        // ticket != null: the last CTA turns the sums into coefficients
 };
 
 template <int N_PX, bool BWD>
@@ -260,6 +262,8 @@ tstat_kernel(const __grid_constant__ TStatArgs a) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 2 * N_PX);
   }
+  __shared__ unsigned int s_ticket;
+  bn_last_block_finalize<BWD>(a.acc, a.fin, a.c_out, 2, gridDim.x, &s_ticket, a.mean, a.invstd);
 }
 
 template <int N_PX, bool BWD>
@@ -285,7 +289,8 @@ int launch_tstat(const TStatArgs& a, cudaStream_t stream) {
 // p describes the forward 1x1 convolution (x, w, strides, shapes; stride 1 or 2, pad 0). BWD: `dy`
 // has the geometry (p.y_sn, p.y_sh, p.y_sw) of the conv output.
 int conv_bn_reduce_tc(const ConvArgs& p, bool bwd, const void* dy, const float* mean,
-                      const float* invstd, double* acc, cudaStream_t stream) {
+                      const float* invstd, double* acc, const rmv_bn_params* finalize,
+                      cudaStream_t stream) {
   RMV_CHECK_ARG(p.kh == 1 && p.kw == 1 && p.pad == 0 && (p.stride == 1 || p.stride == 2),
                 "conv_bn_reduce: 1x1 convolutions (stride 1 or 2) only");
   RMV_CHECK_ARG(p.x_dtype == RMV_DTYPE_BF16 && p.c_in % 64 == 0 && p.c_out % 128 == 0,
@@ -328,6 +333,10 @@ int conv_bn_reduce_tc(const ConvArgs& p, bool bwd, const void* dy, const float* 
   a.n_ct = p.c_out / 128;
   a.c_out = p.c_out;
   a.acc = acc; a.mean = mean; a.invstd = invstd;
+  RMV_CHECK_ARG(finalize == nullptr || (finalize->ticket != nullptr && p.n_img % 2 == 0 &&
+                                        (long long)(p.n_img / 2) * p.out_h * p.out_w > 1),
+                "conv_bn_reduce: finalize needs a ticket counter and an even image count");
+  a.fin = bn_finalize_args(finalize, bwd, (long long)(p.n_img / 2) * p.out_h * p.out_w);
   if ((long)a.tiles_w * a.tiles_h * a.tiles_n == 0) return 0;
   {
     cuuint64_t dims[2] = {(cuuint64_t)p.c_in, (cuuint64_t)p.c_out};
@@ -356,13 +365,16 @@ int conv_bn_reduce_tc(const ConvArgs& p, bool bwd, const void* dy, const float* 
 
 }  // namespace rmv
 
-extern "C" int rmv_conv_bn_stats(const rmv_conv_args* args, double* acc, void* stream) {
+extern "C" int rmv_conv_bn_stats(const rmv_conv_args* args, double* acc,
+                                 const rmv_bn_params* finalize, void* stream) {
   RMV_CHECK_ARG(args != nullptr && args->x && args->w, "conv_bn_stats: null pointer");
-  return rmv::conv_bn_reduce_tc(*args, false, nullptr, nullptr, nullptr, acc, (cudaStream_t)stream);
+  return rmv::conv_bn_reduce_tc(*args, false, nullptr, nullptr, nullptr, acc, finalize,
+                                (cudaStream_t)stream);
 }
 
 extern "C" int rmv_conv_bn_bwd_reduce(const rmv_conv_args* args, const void* dy, const float* mean,
-                                      const float* invstd, double* acc, void* stream) {
+                                      const float* invstd, double* acc,
+                                      const rmv_bn_params* finalize, void* stream) {
   RMV_CHECK_ARG(args != nullptr && args->x && args->w, "conv_bn_bwd_reduce: null pointer");
-  return rmv::conv_bn_reduce_tc(*args, true, dy, mean, invstd, acc, (cudaStream_t)stream);
+  return rmv::conv_bn_reduce_tc(*args, true, dy, mean, invstd, acc, finalize, (cudaStream_t)stream);
 }

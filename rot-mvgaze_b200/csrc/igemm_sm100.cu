@@ -16,6 +16,7 @@
 // Replaces the cuDNN/cuBLAS calls behind nn.Conv2d / nn.BatchNorm2d / nn.ReLU / nn.Linear at
 // reference models/resnet.py:31-47,128-148 and models/backbones/blocks.py:41-60.
 #include "common.cuh"
+#include "bn_finalize.cuh"
 #include "ops.h"
 
 #include <mutex>
@@ -71,6 +72,7 @@ struct IgemmArgs {
   uint32_t* bn_bits;          // BNM 1: written
   const uint32_t* mask_bits;  // any kernel: the value about to be stored is zeroed where the bit is 0
   long long m_sn, m_sh, m_sw, mask_off;
+  BnFinalize stat_fin;        // STATS: ticket != null -> the last CTA finalizes the statistics
 };
 
 // HALO variant (3x3, stride 1, pad 1, 64 -> 64 channels; BLOCK_N = 64): the producer loads ONE
@@ -607,6 +609,10 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+  if (STATS) {
+    __shared__ unsigned int s_ticket;
+    bn_last_block_finalize<false>(args.stat_acc, args.stat_fin, args.n_total, 2, gridDim.x, &s_ticket);
   }
 }
 
@@ -1145,6 +1151,13 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
     a.stat_bw_shift = sh;
     a.stat_w = out_w; a.stat_h = out_h; a.stat_n = n_img;
     a.m_sn = y_sn; a.m_sh = y_sh; a.m_sw = y_sw; a.mask_off = p.mask_off;
+    if (p.stat_acc != nullptr && p.stat_finalize != nullptr) {
+      const rmv_bn_params* fp = reinterpret_cast<const rmv_bn_params*>(p.stat_finalize);
+      RMV_CHECK_ARG(fp->ticket != nullptr && p.n_img % 2 == 0 &&
+                        (long long)(p.n_img / 2) * p.out_h * p.out_w > 1,
+                    "tcgen05 conv: stat_finalize needs a ticket counter and an even image count");
+      a.stat_fin = bn_finalize_args(fp, false, (long long)(p.n_img / 2) * p.out_h * p.out_w);
+    }
   }
   if (p.bn_mode != 0 || p.mask_bits != nullptr) {
     RMV_CHECK_ARG(!out_f32 && !halo && p.c_out % 32 == 0 && p.y_sw % 32 == 0 && p.y_sh % 32 == 0 &&

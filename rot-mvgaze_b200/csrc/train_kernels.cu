@@ -5,6 +5,7 @@
 // gradient dilation for stride-2 dgrad, the FFMA weight-gradient GEMM and the fused multi-tensor
 // Adam step (coupled L2 = torch.optim.Adam(weight_decay) as in trainer.py:54, or decoupled).
 #include "common.cuh"
+#include "bn_finalize.cuh"
 #include "ops.h"
 
 namespace rmv {
@@ -76,119 +77,6 @@ inline unsigned nblk(long long total, int threads) { return (unsigned)((total + 
 __device__ __forceinline__ void apply_bits(float* d, uint32_t bits) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) d[i] = (bits >> i) & 1u ? d[i] : 0.f;
-}
-
-// Arguments of the finalize step the LAST block of a reduction launch runs (null ticket = none).
-struct BnFinalize {
-  unsigned int* ticket;  // zero on entry; the block that draws the last ticket finalizes + resets
-  const float* gamma; const float* beta;
-  float* running_mean; float* running_var; long long* nbt;
-  float* mean; float* invstd; float* a; float* b;            // forward outputs
-  float* dgamma; float* dbeta; float* k0; float* k1; float* k2;  // backward outputs
-  double count; float eps, momentum;
-};
-
-// Finalize, written for a SINGLE block with plenty of memory-level parallelism (it is the serial
-// tail of the reduction launch): phase 1 is one item per (view, channel), four items in flight per
-// thread; phase 2 (running statistics in VIEW ORDER / dgamma, dbeta) is one item per channel.
-// Forward: mean / invstd, fused affine (a = gamma*invstd, b = beta - mean*a), running stats
-// (rm <- (1-m) rm + m mean_v for v = 0..V-1; unbiased variance), accumulator reset.
-__device__ __forceinline__ void bn_finalize_block(double* acc, const BnFinalize& f, int c, int views,
-                                                  int tid, int nthreads) {
-  const int items = views * c;
-  const double inv_count = 1.0 / f.count;
-  for (int i0 = tid; i0 < items; i0 += nthreads * 4) {
-    double s1[4], s2[4];
-    float ga[4], be[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = i0 + j * nthreads;
-      if (i < items) {
-        s1[j] = __ldcg(acc + 2 * (long long)i);
-        s2[j] = __ldcg(acc + 2 * (long long)i + 1);
-        ga[j] = __ldg(f.gamma + i % c);
-        be[j] = __ldg(f.beta + i % c);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = i0 + j * nthreads;
-      if (i < items) {
-        const double m = s1[j] * inv_count;
-        double var = s2[j] * inv_count - m * m;
-        if (var < 0.0) var = 0.0;
-        const float is = (float)(1.0 / sqrt(var + (double)f.eps));
-        f.mean[i] = (float)m;
-        f.invstd[i] = is;
-        const float av = ga[j] * is;
-        f.a[i] = av;
-        f.b[i] = be[j] - (float)m * av;
-        acc[2 * (long long)i] = m;       // parked for phase 2
-        acc[2 * (long long)i + 1] = var;
-      }
-    }
-  }
-  __syncthreads();
-  const double unb = f.count / (f.count - 1.0);
-  for (int ch = tid; ch < c; ch += nthreads) {
-    float rm = f.running_mean ? f.running_mean[ch] : 0.f, rv = f.running_var ? f.running_var[ch] : 0.f;
-    for (int v = 0; v < views; ++v) {
-      double* p = acc + ((long long)v * c + ch) * 2;
-      const float m = (float)p[0], unbiased = (float)(p[1] * unb);
-      p[0] = 0.0; p[1] = 0.0;
-      rm = (1.f - f.momentum) * rm + f.momentum * m;
-      rv = (1.f - f.momentum) * rv + f.momentum * unbiased;
-    }
-    if (f.running_mean) f.running_mean[ch] = rm;
-    if (f.running_var) f.running_var[ch] = rv;
-  }
-}
-
-// Backward: dgamma/dbeta (=), per-(v,c) coefficients for the apply pass
-//   dz = k0 * dyr + k1 * z + k2  with  k0 = gamma*invstd, k1 = -k0*invstd*s2/cnt,
-//   k2 = -k0*s1/cnt - k1*mean   (from dz = gamma*invstd*(dyr - s1/cnt - xhat*s2/cnt))
-__device__ __forceinline__ void bn_bwd_finalize_block(double* acc, const BnFinalize& f,
-                                                      const float* mean, const float* invstd, int c,
-                                                      int views, int tid, int nthreads) {
-  const int items = views * c;
-  const double inv_count = 1.0 / f.count;
-  for (int i0 = tid; i0 < items; i0 += nthreads * 4) {
-    double s1[4], s2[4];
-    float ga[4], is[4], mu[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = i0 + j * nthreads;
-      if (i < items) {
-        s1[j] = __ldcg(acc + 2 * (long long)i);
-        s2[j] = __ldcg(acc + 2 * (long long)i + 1);
-        ga[j] = __ldg(f.gamma + i % c);
-        is[j] = invstd[i];
-        mu[j] = mean[i];
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = i0 + j * nthreads;
-      if (i < items) {
-        const double c0 = (double)ga[j] * (double)is[j];
-        const double c1 = -c0 * (double)is[j] * s2[j] * inv_count;
-        f.k0[i] = (float)c0;
-        f.k1[i] = (float)c1;
-        f.k2[i] = (float)(-c0 * s1[j] * inv_count - c1 * (double)mu[j]);
-      }
-    }
-  }
-  __syncthreads();
-  for (int ch = tid; ch < c; ch += nthreads) {
-    double dg = 0.0, db = 0.0;
-    for (int v = 0; v < views; ++v) {
-      double* p = acc + ((long long)v * c + ch) * 2;
-      db += __ldcg(p); dg += __ldcg(p + 1);
-      p[0] = 0.0; p[1] = 0.0;
-    }
-    f.dgamma[ch] = (float)dg;
-    f.dbeta[ch] = (float)db;
-  }
 }
 
 // grid = (G, views) with G*views = the number of co-resident blocks (one balanced wave, no tail):

@@ -41,10 +41,20 @@ class ConvArgs(C.Structure):
         ("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
         ("r_sn", C.c_longlong), ("r_sh", C.c_longlong), ("r_sw", C.c_longlong),
         ("relu", C.c_int),
-        ("stat_acc", C.c_void_p), ("stat_views", C.c_int),
+        ("stat_acc", C.c_void_p), ("stat_views", C.c_int), ("stat_finalize", C.c_void_p),
         ("bn_mode", C.c_int), ("bn_a", C.c_void_p), ("bn_b", C.c_void_p), ("bn_c", C.c_void_p),
         ("bn_bits", C.c_void_p), ("mask_bits", C.c_void_p), ("mask_off", C.c_longlong),
     ]
+
+
+class BnParams(C.Structure):
+    """Mirror of `struct rmv_bn_params`."""
+
+    _fields_ = [("ticket", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches", C.c_void_p),
+                ("mean", C.c_void_p), ("invstd", C.c_void_p), ("a", C.c_void_p), ("b", C.c_void_p),
+                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("k0", C.c_void_p), ("k1", C.c_void_p),
+                ("k2", C.c_void_p), ("eps", C.c_float), ("momentum", C.c_float)]
 
 
 class PermuteJob(C.Structure):
@@ -67,8 +77,8 @@ SIGNATURES = {
     "rmv_device_check": (_i, [_i]),
     "rmv_conv2d_dgrad": (_i, [C.POINTER(ConvArgs), _vp]),
     "rmv_conv2d_fwd": (_i, [C.POINTER(ConvArgs), _vp]),
-    "rmv_conv_bn_stats": (_i, [C.POINTER(ConvArgs), _vp, _vp]),
-    "rmv_conv_bn_bwd_reduce": (_i, [C.POINTER(ConvArgs), _vp, _vp, _vp, _vp, _vp]),
+    "rmv_conv_bn_stats": (_i, [C.POINTER(ConvArgs), _vp, C.POINTER(BnParams), _vp]),
+    "rmv_conv_bn_bwd_reduce": (_i, [C.POINTER(ConvArgs), _vp, _vp, _vp, _vp, C.POINTER(BnParams), _vp]),
     "rmv_stem_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rmv_stem_pack_weights": (_i, [_vp, _vp, _vp]),
     "rmv_stem_conv_fwd_u8": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

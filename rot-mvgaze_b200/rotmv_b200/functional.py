@@ -53,7 +53,7 @@ def _conv_args(x, w, out, stride, pad):
     return a
 
 
-def conv_bn_stats(x, w, acc, *, stride=1):
+def conv_bn_stats(x, w, acc, *, stride=1, finalize=None):
     """acc[v][k] += (sum z, sum z^2) of z = conv1x1(x, w), recomputed on the tensor cores (z is never
     written; rmv_conv_bn_stats). x [N,H,W,C] bf16, w [K,1,1,C] bf16, acc fp64 [>=2, K, 2]."""
     _need_cuda(x, w, acc)
@@ -65,10 +65,11 @@ def conv_bn_stats(x, w, acc, *, stride=1):
         meta = {"engine": "tcgen05-bnstat", "flops": 2.0 * n * a.out_h * a.out_w * w.shape[0] * c,
                 "bytes": float(n * a.out_h * a.out_w * c * 2),
                 "desc": f"conv-bn stats 1x1s{stride} [{n},{h},{wd},{c}]->{w.shape[0]}"}
-    _call("rmv_conv_bn_stats", meta, L.load().rmv_conv_bn_stats, C.byref(a), acc.data_ptr(), L.stream_ptr())
+    _call("rmv_conv_bn_stats", meta, L.load().rmv_conv_bn_stats, C.byref(a), acc.data_ptr(),
+          None if finalize is None else C.byref(finalize), L.stream_ptr())
 
 
-def conv_bn_bwd_reduce(x, w, dy, mean, invstd, acc, *, stride=1):
+def conv_bn_bwd_reduce(x, w, dy, mean, invstd, acc, *, stride=1, finalize=None):
     """acc[v][k] += (sum dy, sum dy*xhat) with xhat from the recomputed z = conv1x1(x, w)
     (rmv_conv_bn_bwd_reduce); dy [N,OH,OW,K] bf16, already ReLU-masked."""
     _need_cuda(x, w, dy, mean, invstd, acc)
@@ -83,12 +84,13 @@ def conv_bn_bwd_reduce(x, w, dy, mean, invstd, acc, *, stride=1):
                 "bytes": float(n * a.out_h * a.out_w * c * 2 + dy.numel() * 2),
                 "desc": f"conv-bn bwd reduce 1x1s{stride} [{n},{h},{wd},{c}]->{w.shape[0]}"}
     _call("rmv_conv_bn_bwd_reduce", meta, L.load().rmv_conv_bn_bwd_reduce, C.byref(a), dy.data_ptr(),
-          mean.data_ptr(), invstd.data_ptr(), acc.data_ptr(), L.stream_ptr())
+          mean.data_ptr(), invstd.data_ptr(), acc.data_ptr(),
+          None if finalize is None else C.byref(finalize), L.stream_ptr())
 
 
 def conv2d(x, w, *, stride=1, pad=0, scale=None, shift=None, residual=None, relu=False,
            out=None, out_dtype=None, engine=L.ENGINE_AUTO, block_n=0, stat_acc=None, stat_views=0,
-           bn_mode=0, bn_a=None, bn_b=None, bn_c=None, bn_bits=None, mask_bits=None):
+           bn_mode=0, bn_a=None, bn_b=None, bn_c=None, bn_bits=None, mask_bits=None, stat_finalize=None):
     """y = act(scale * conv(x, w) + shift + residual).
 
     x: [N, H, W, C] (any pixel strides, channel stride 1); w: [K, kh, kw, C] contiguous, same
@@ -132,6 +134,8 @@ def conv2d(x, w, *, stride=1, pad=0, scale=None, shift=None, residual=None, relu
         assert stat_acc.dtype == torch.float64 and stat_acc.is_contiguous() and stat_acc.numel() >= stat_views * k * 2
         a.stat_acc = stat_acc.data_ptr()
         a.stat_views = stat_views
+        if stat_finalize is not None:   # L.BnParams: coefficients by the last CTA of this launch
+            a.stat_finalize = C.addressof(stat_finalize)
     if bn_mode:
         # recomputed-BatchNorm epilogues (rmv_conv_args.bn_mode): per-(view, channel) tables [2][K]
         for t in (bn_a, bn_b) + ((bn_c,) if bn_mode == 2 else ()):

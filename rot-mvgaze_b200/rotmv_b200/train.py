@@ -48,6 +48,15 @@ class _BN:
         v, dev = eng.max_views, eng.device
         f = lambda: torch.empty((v, c), device=dev, dtype=torch.float32)  # noqa: E731
         self.mean, self.invstd, self.a, self.b, self.k0, self.k1, self.k2 = (f() for _ in range(7))
+        # rmv_bn_params: lets the last thread block of a statistics launch finalize the coefficients
+        p = self.params = L.BnParams()
+        p.ticket = eng.ticket.data_ptr()
+        p.gamma, p.beta = self.gamma.data_ptr(), self.beta.data_ptr()
+        p.running_mean, p.running_var, p.num_batches = self.rm.data_ptr(), self.rv.data_ptr(), self.nbt.data_ptr()
+        p.mean, p.invstd, p.a, p.b = (t.data_ptr() for t in (self.mean, self.invstd, self.a, self.b))
+        p.dgamma, p.dbeta = self.dgamma.data_ptr(), self.dbeta.data_ptr()
+        p.k0, p.k1, p.k2 = self.k0.data_ptr(), self.k1.data_ptr(), self.k2.data_ptr()
+        p.eps, p.momentum = self.eps, self.momentum
 
 
 class TrainEngine:
@@ -115,6 +124,7 @@ class TrainEngine:
         self._bucket_by_stage = {4: self.buckets[1], 3: self.buckets[2]}
         self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 0.0],
                                   device=self.device, dtype=torch.float64)
+        self.ticket = torch.zeros((1,), device=self.device, dtype=torch.int32)
         # ---- layer table ----
         g = self.grads
         self.stem_bn = _BN(self, trunk.bn1, g[id(trunk.bn1.weight)], g[id(trunk.bn1.bias)])
@@ -138,7 +148,6 @@ class TrainEngine:
         c_max = max(2048, self.fc_dim)
         assert L.load().rmv_bn_workspace_bytes(c_max, max_views) == max_views * c_max * 2 * 8
         self.acc = torch.zeros((max_views, c_max, 2), device=self.device, dtype=torch.float64)
-        self.ticket = torch.zeros((1,), device=self.device, dtype=torch.int32)
         self._bufs: Dict[Any, torch.Tensor] = {}
         self._bits: Dict[int, Optional[torch.Tensor]] = {}   # id(ReLU output) -> packed mask
         self.loss = torch.zeros((1,), device=self.device, dtype=torch.float32)
@@ -239,29 +248,27 @@ class TrainEngine:
                  self._wjob_blocks, L.stream_ptr())
 
     # ---- BatchNorm -----------------------------------------------------------------------------
-    def _conv_stats(self, x, w, *, stride=1, pad=0, out=None):
+    def _conv_stats(self, x, w, *, stride=1, pad=0, out=None, bn=None):
         """Forward conv of the training step. bf16 / two views: the BatchNorm batch statistics of
-        the output are accumulated by the conv epilogue itself (returns stats_done=True)."""
+        the output are accumulated by the conv epilogue itself and turned into the coefficients of
+        `bn` by the last thread block of the launch (returns stats_done=True)."""
         fused = self.fuse_bn_stats and self.precision == "bf16" and self.views == 2
         # measured (B=128, V=2): free for the tensor-bound 3x3 and the reducing 1x1 convs, but the
         # expanding 1x1 convs are HBM-bound with the epilogue on the critical path (+70 % with the
         # statistics in it) -- those keep the separate one-wave reduction
         if w.shape[1] == 1 and w.shape[0] > w.shape[3]:
             fused = False
+        fused = fused and bn is not None and x.shape[0] % 2 == 0
         z = RF.conv2d(x, w, stride=stride, pad=pad, out=out,
-                      stat_acc=self.acc if fused else None, stat_views=2 if fused else 0)
+                      stat_acc=self.acc if fused else None, stat_views=2 if fused else 0,
+                      stat_finalize=bn.params if fused else None)
         return z, fused
 
     def _bn_fwd(self, bn: _BN, z, residual, relu, tag, stats_done=False):
         n, h, w, c = z.shape
         v = self.views
         shp = f" [{n},{h},{w},{c}]" if RF.PROFILE is not None else ""
-        if stats_done:   # sums already in self.acc (fused conv epilogue): coefficients only
-            _ck("rmv_bn_finalize", self.acc.data_ptr(), bn.gamma.data_ptr(), bn.beta.data_ptr(),
-                bn.rm.data_ptr(), bn.rv.data_ptr(), bn.nbt.data_ptr(), bn.mean.data_ptr(),
-                bn.invstd.data_ptr(), bn.a.data_ptr(), bn.b.data_ptr(), c, v, (n // v) * h * w, bn.eps,
-                bn.momentum)
-        else:
+        if not stats_done:   # else: statistics AND coefficients came out of the conv launch itself
             _ck("rmv_bn_stats_finalize", z.data_ptr(), self.dtc, n, h * w, c, v, self.acc.data_ptr(),
                 self.ticket.data_ptr(), bn.gamma.data_ptr(), bn.beta.data_ptr(), bn.rm.data_ptr(),
                 bn.rv.data_ptr(), bn.nbt.data_ptr(), bn.mean.data_ptr(), bn.invstd.data_ptr(),
@@ -305,11 +312,7 @@ class TrainEngine:
         n, h, wd, _ = x.shape
         oh, ow = (h - 1) // stride + 1, (wd - 1) // stride + 1
         c, v = w.shape[0], self.views
-        RF.conv_bn_stats(x, w, self.acc, stride=stride)
-        _ck("rmv_bn_finalize", self.acc.data_ptr(), bn.gamma.data_ptr(), bn.beta.data_ptr(),
-            bn.rm.data_ptr(), bn.rv.data_ptr(), bn.nbt.data_ptr(), bn.mean.data_ptr(),
-            bn.invstd.data_ptr(), bn.a.data_ptr(), bn.b.data_ptr(), c, v, (n // v) * oh * ow, bn.eps,
-            bn.momentum)
+        RF.conv_bn_stats(x, w, self.acc, stride=stride, finalize=bn.params)   # sums + coefficients
         y = self._buf(tag, (n, oh, ow, c))
         bits = self._buf(("bits", tag), (n * oh * ow * c // 8,), torch.uint8) if relu else None
         RF.conv2d(x, w, stride=stride, residual=residual, relu=relu, out=y, bn_mode=1, bn_a=bn.a,
@@ -324,10 +327,7 @@ class TrainEngine:
         backward-apply epilogue (bn_mode 2: dz = k0*dy + k1*z + k2)."""
         n, oh, ow, c = dy.shape
         v = self.views
-        RF.conv_bn_bwd_reduce(x, w, dy, bn.mean, bn.invstd, self.acc, stride=stride)
-        _ck("rmv_bn_bwd_finalize", self.acc.data_ptr(), bn.gamma.data_ptr(), bn.mean.data_ptr(),
-            bn.invstd.data_ptr(), bn.dgamma.data_ptr(), bn.dbeta.data_ptr(), bn.k0.data_ptr(),
-            bn.k1.data_ptr(), bn.k2.data_ptr(), c, v, (n // v) * oh * ow)
+        RF.conv_bn_bwd_reduce(x, w, dy, bn.mean, bn.invstd, self.acc, stride=stride, finalize=bn.params)
         dz = self._buf(("dz", tag), dy.shape)
         RF.conv2d(x, w, stride=stride, residual=dy, out=dz, bn_mode=2, bn_a=bn.k0, bn_b=bn.k1, bn_c=bn.k2)
         return dz
@@ -812,7 +812,7 @@ class TrainEngine:
                 cv = convs[si]
                 k, st, pd = cv.kernel_size[0], cv.stride[0], cv.padding[0]
                 oh = (t.shape[1] + 2 * pd - k) // st + 1
-                z, sd = self._conv_stats(t, self._w_fwd(cv, (bi, si + 1)), stride=st, pad=pd,
+                z, sd = self._conv_stats(t, self._w_fwd(cv, (bi, si + 1)), stride=st, pad=pd, bn=bns[si],
                                          out=self._buf((f"z{si + 1}", bi), (m, oh, oh, cv.out_channels)))
                 t = self._bn_fwd(bns[si], z, None, True, (f"y{si + 1}", bi), stats_done=sd)
                 zs.append(z); ys.append(t)
@@ -824,7 +824,7 @@ class TrainEngine:
                     skip = self._conv_bn_fwd(e["ds_bn"], x_in, self._w_fwd(dc, (bi, "d")), dc.stride[0],
                                              None, False, ("skip", bi))
                 else:
-                    zd, sd = self._conv_stats(x_in, self._w_fwd(dc, (bi, "d")), stride=dc.stride[0],
+                    zd, sd = self._conv_stats(x_in, self._w_fwd(dc, (bi, "d")), stride=dc.stride[0], bn=e["ds_bn"],
                                               out=self._buf(("zd", bi), (m, oh, oh, dc.out_channels)))
                     skip = self._bn_fwd(e["ds_bn"], zd, None, False, ("skip", bi), stats_done=sd)
             else:
@@ -835,7 +835,7 @@ class TrainEngine:
                 x = self._conv_bn_fwd(bns[-1], t, self._w_fwd(cv, (bi, len(convs))), 1, skip, True, ("out", bi))
             else:
                 z, sd = self._conv_stats(t, self._w_fwd(cv, (bi, len(convs))), stride=cv.stride[0],
-                                         pad=cv.padding[0],
+                                         pad=cv.padding[0], bn=bns[-1],
                                          out=self._buf((f"z{len(convs)}", bi), (m, oh, oh, cv.out_channels)))
                 zs.append(z)
                 x = self._bn_fwd(bns[-1], z, skip, True, ("out", bi), stats_done=sd)

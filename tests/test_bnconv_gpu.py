@@ -84,6 +84,97 @@ def test_conv_bn_bwd_reduce_matches_torch(case):
     assert (acc[:, :, 1] - ref2).abs().max().item() <= 5e-5 * s2
 
 
+def _bn_params(c, momentum=0.1, eps=1e-5):
+    from rotmv_b200 import _lib as L
+
+    t = {"ticket": torch.zeros((1,), device="cuda", dtype=torch.int32),
+         "gamma": torch.rand((c,), device="cuda") + 0.5, "beta": torch.randn((c,), device="cuda"),
+         "running_mean": torch.randn((c,), device="cuda") * 0.1, "running_var": torch.rand((c,), device="cuda") + 0.5,
+         "num_batches": torch.zeros((), device="cuda", dtype=torch.int64)}
+    for k in ("mean", "invstd", "a", "b", "k0", "k1", "k2"):
+        t[k] = torch.full((2, c), float("nan"), device="cuda")
+    for k in ("dgamma", "dbeta"):
+        t[k] = torch.full((c,), float("nan"), device="cuda")
+    p = L.BnParams()
+    for k, v in t.items():
+        setattr(p, k, v.data_ptr())
+    p.eps, p.momentum = eps, momentum
+    return p, t
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[4], (6, 7, 7, 512, 2048, 1)])
+@pytest.mark.parametrize("via", ["recompute", "epilogue"])
+def test_statistics_finalized_inside_the_launch(case, via):
+    """The last thread block of the statistics launch produces the BatchNorm coefficients and the
+    running statistics (two sequential view updates, unbiased variance, num_batches += 2: SURVEY Q1)
+    -- against nn.BatchNorm2d semantics applied view by view; the accumulator is left zeroed.
+    `recompute` = rmv_conv_bn_stats, `epilogue` = the STATS epilogue of rmv_conv2d_fwd."""
+    from rotmv_b200 import functional as RF
+
+    n, h, w, ci, co, s_ = case
+    _, x, wt, z = _inputs(case, seed=4)
+    torch.manual_seed(3)
+    p, t = _bn_params(co)
+    rm0, rv0 = t["running_mean"].clone(), t["running_var"].clone()
+    acc = torch.zeros((2, co, 2), device="cuda", dtype=torch.float64)
+    if via == "recompute":
+        RF.conv_bn_stats(x, wt, acc, stride=s_, finalize=p)
+        zz = z
+    else:
+        y = RF.conv2d(x, wt, stride=s_, stat_acc=acc, stat_views=2, stat_finalize=p)
+        zz = y.float()                      # the epilogue statistics are those of the bf16 values stored
+    torch.cuda.synchronize()
+    assert int(t["ticket"]) == 0 and int(t["num_batches"]) == 2 and float(acc.abs().max()) == 0.0
+    rm, rv = rm0.clone(), rv0.clone()
+    for v in range(2):
+        zv = zz[v::2].double().reshape(-1, co)
+        mean, var = zv.mean(0), zv.var(0, unbiased=False)
+        invstd = 1.0 / torch.sqrt(var + 1e-5)
+        assert (t["mean"][v].double() - mean).abs().max().item() <= 1e-4 * max(mean.abs().max().item(), 1e-2)
+        assert ((t["invstd"][v].double() - invstd) / invstd).abs().max().item() <= 1e-3
+        a = t["gamma"].double() * invstd
+        assert ((t["a"][v].double() - a) / a).abs().max().item() <= 1e-3
+        assert (t["b"][v].double() - (t["beta"].double() - mean * a)).abs().max().item() <= 1e-3
+        cnt = zv.shape[0]
+        rm = 0.9 * rm + 0.1 * mean.float()
+        rv = 0.9 * rv + 0.1 * (var * cnt / (cnt - 1)).float()
+    assert (t["running_mean"] - rm).abs().max().item() <= 1e-4
+    assert ((t["running_var"] - rv) / rv).abs().max().item() <= 1e-3
+
+
+def test_bwd_reduce_finalized_inside_the_launch():
+    """rmv_conv_bn_bwd_reduce with finalize: dgamma, dbeta and the (k0, k1, k2) of
+    dz = k0*dy + k1*z + k2 against autograd through F.batch_norm applied per view."""
+    from rotmv_b200 import functional as RF
+
+    case = (6, 14, 14, 64, 256, 1)
+    g, x, wt, z = _inputs(case, seed=5)
+    co = case[4]
+    torch.manual_seed(4)
+    p, t = _bn_params(co)
+    dy = torch.randn(z.shape, device="cuda", generator=g).bfloat16()
+    zr = z.clone().requires_grad_(True)
+    gamma = t["gamma"].clone().requires_grad_(True)
+    beta = t["beta"].clone().requires_grad_(True)
+    outs = [F.batch_norm(zr[v::2].permute(0, 3, 1, 2), None, None, gamma, beta, True, 0.1, 1e-5) for v in range(2)]
+    loss = sum((o.permute(0, 2, 3, 1) * dy[v::2].float()).sum() for v, o in enumerate(outs))
+    loss.backward()
+    for v in range(2):
+        zv = z[v::2].double().reshape(-1, co)
+        t["mean"][v] = zv.mean(0).float()
+        t["invstd"][v] = (1.0 / torch.sqrt(zv.var(0, unbiased=False) + 1e-5)).float()
+    acc = torch.zeros((2, co, 2), device="cuda", dtype=torch.float64)
+    RF.conv_bn_bwd_reduce(x, wt, dy, t["mean"], t["invstd"], acc, finalize=p)
+    torch.cuda.synchronize()
+    assert float(acc.abs().max()) == 0.0 and int(t["ticket"]) == 0
+    assert (t["dbeta"] - beta.grad).abs().max().item() <= 2e-3 * beta.grad.abs().max().item()
+    assert (t["dgamma"] - gamma.grad).abs().max().item() <= 2e-3 * gamma.grad.abs().max().item()
+    dz = torch.empty_like(z)
+    for v in range(2):
+        dz[v::2] = t["k0"][v] * dy[v::2].float() + t["k1"][v] * z[v::2] + t["k2"][v]
+    assert (dz - zr.grad).abs().max().item() <= 2e-3 * zr.grad.abs().max().item()
+
+
 def _unpack_bits(bits, shape):
     b = bits.view(-1, 1).int()
     return ((b >> torch.arange(8, device=bits.device).view(1, 8)) & 1).bool().view(shape)

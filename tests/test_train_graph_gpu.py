@@ -29,7 +29,7 @@ def test_graphed_step_matches_eager(precision):
 
     model_b, eng_b = _make(precision)
     graphed = GraphedTrainStep(eng_b, 4, 2)
-    assert graphed.launches_per_step > 400
+    assert graphed.launches_per_step > 300
     got = [graphed.step(images, rot, gt).item() for _ in range(3)]
     # fp32 atomics (weight-gradient split-K, loss sum) make runs non-bit-reproducible
     for a, b in zip(eager, got):
