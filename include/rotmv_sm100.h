@@ -120,6 +120,13 @@ typedef struct rmv_conv_args {
   void* bn_bits;
   const void* mask_bits;
   long long mask_off;
+  /* Optional scratch for split-K (tcgen05 engine; pointwise / Linear GEMMs whose tile count is far
+   * below the SM count -- the lifter / fuser / head layers of models/rot_mv.py:35-50,91-98,179-184
+   * at M = B*V rows): S CTAs share one output tile along K, write fp32 partial tiles here and a
+   * second kernel adds them in a fixed order (bit-reproducible). NULL or too small = no split.
+   * rmv_splitk_workspace_bytes() is always enough. 16-byte aligned device memory. */
+  void* workspace;
+  size_t workspace_bytes;
 } rmv_conv_args;
 
 int rmv_conv2d_fwd(const rmv_conv_args* args, void* stream);
@@ -189,8 +196,10 @@ int rmv_stem_wgrad(const float* x_nchw, const void* dz_nhwc, float* scratch, flo
  *                                         to `max_channels` channels and `views` views; the `ticket`
  *                                         counter those calls take is one more zero-initialised int
  *   rmv_conv2d_wgrad_tc_workspace_bytes   the fp32 [c_out][kh][kw][c_in] accumulation buffer
- *                                         `dw_krsc` of rmv_conv2d_wgrad_tc (zeroed by the caller) */
+ *                                         `dw_krsc` of rmv_conv2d_wgrad_tc (zeroed by the caller)
+ *   rmv_splitk_workspace_bytes            upper bound of rmv_conv_args.workspace for any launch */
 size_t rmv_stem_wgrad_workspace_bytes(void);
+size_t rmv_splitk_workspace_bytes(void);
 size_t rmv_bn_workspace_bytes(int max_channels, int views);
 size_t rmv_conv2d_wgrad_tc_workspace_bytes(const rmv_conv_args* args);
 

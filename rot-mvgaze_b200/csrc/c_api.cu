@@ -114,6 +114,11 @@ extern "C" int rmv_conv2d_dgrad(const rmv_conv_args* args, void* stream) {
 
 extern "C" size_t rmv_stem_wgrad_workspace_bytes(void) { return (size_t)192 * 64 * sizeof(float); }
 
+// split-K only runs when (m, n) tiles x splits <= SMs: at most one 128 x 256 fp32 tile per SM
+extern "C" size_t rmv_splitk_workspace_bytes(void) {
+  return (size_t)rmv::num_sms() * 128 * 256 * sizeof(float);
+}
+
 extern "C" size_t rmv_bn_workspace_bytes(int max_channels, int views) {
   if (max_channels <= 0 || views <= 0) return 0;
   return (size_t)views * (size_t)max_channels * 2 * sizeof(double);

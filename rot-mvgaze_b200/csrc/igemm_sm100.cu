@@ -73,6 +73,10 @@ struct IgemmArgs {
   const uint32_t* mask_bits;  // any kernel: the value about to be stored is zeroed where the bit is 0
   long long m_sn, m_sh, m_sw, mask_off;
   BnFinalize stat_fin;        // STATS: ticket != null -> the last CTA finalizes the statistics
+  // split-K (small-M linear layers): tile = split * (m_tiles * n_tiles) + (m, n) tile; split s owns the
+  // k-blocks [s * kb_per_split, (s+1) * kb_per_split) and stores its fp32 partial tile into slice s
+  // of a workspace (4th coordinate of tmap_out); splitk_reduce_kernel adds the slices in order.
+  int k_splits, kb_per_split;
 };
 
 // HALO variant (3x3, stride 1, pad 1, 64 -> 64 channels; BLOCK_N = 64): the producer loads ONE
@@ -107,7 +111,7 @@ struct Cfg {
   static constexpr int kOutBytes = 2 * kChunkBytes;
   static constexpr int kResBytes = HAS_RES ? kResSlots * kChunkBytes : 0;
   // scale + shift of the current N tile; BNM: 2 (a, b) or 3 (a, b, c) tables for each of the 2 views
-  static constexpr int kVecBytes = (BNM == 0 ? 2 : (BNM == 1 ? 4 : 6)) * BLOCK_N * 4;
+  static constexpr int kVecBytes = (BNM == 1 ? 4 : (BNM == 2 ? 6 : 2)) * BLOCK_N * 4;
   static constexpr int kSmemBytes = kStages * kStageBytes + kResidentB + kOutBytes + kResBytes +
                                     kVecBytes + 256 /*barriers*/ + 1024 /*align*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
@@ -143,6 +147,8 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   using C = Cfg<BLOCK_N, RES, HALO, STATS, BNM>;
   static_assert(!STATS || (!HAS_RES && !OUT_F32), "STATS: bf16 output, no residual");
   static_assert(BNM == 0 || (!OUT_F32 && !HALO && !STATS), "BNM: bf16 output, plain tiles");
+  constexpr bool MASK = BNM == 3;       // plain epilogue + packed ReLU mask applied to the stored value
+  constexpr bool BNT = BNM == 1 || BNM == 2;   // per-view BatchNorm coefficient tables
   static_assert(BNM != 2 || HAS_RES, "BNM 2 reads dy through the residual ring");
   constexpr int kChunkCols = OUT_F32 ? 32 : 64;
   constexpr int kChunks = BLOCK_N / kChunkCols;
@@ -155,7 +161,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   uint8_t* smem_out = smem_b + C::kStages * C::kStageB + C::kResidentB;  // [2][128 rows][128 B], SW128
   uint8_t* smem_res = smem_out + C::kOutBytes;           // [2][128 rows][128 B], SW128
   float* s_scale = reinterpret_cast<float*>(smem_res + C::kResBytes);
-  float* s_shift = s_scale + (BNM == 0 ? 1 : 2) * BLOCK_N;   // BNM: [2 views][BLOCK_N] per table
+  float* s_shift = s_scale + (BNT ? 2 : 1) * BLOCK_N;   // BNT: [2 views][BLOCK_N] per table
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_res + C::kResBytes + C::kVecBytes);
   uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + C::kStages;        // [kStages]  MMA -> TMA
@@ -205,7 +211,8 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   griddep_launch();
 
   const int m_tiles = args.tiles_w * args.tiles_h * args.tiles_n;
-  const int total_tiles = m_tiles * args.n_tiles;
+  const int mn_tiles = m_tiles * args.n_tiles;
+  const int total_tiles = mn_tiles * args.k_splits;
   const int num_kb = args.num_taps * args.c_blocks;
 
   if (warp == 0) {
@@ -231,14 +238,18 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % args.n_tiles;
-        const int m_tile = tile / args.n_tiles;
+        int split = 0, mn = tile;
+        if (args.k_splits > 1) { split = tile / mn_tiles; mn = tile - split * mn_tiles; }
+        const int n_tile = mn % args.n_tiles;
+        const int m_tile = mn / args.n_tiles;
         const int tw = m_tile % args.tiles_w;
         const int th = (m_tile / args.tiles_w) % args.tiles_h;
         const int tn = m_tile / (args.tiles_w * args.tiles_h);
         const int ow0 = tw * args.box_w, oh0 = th * args.box_h, n0 = tn * args.box_n;
-        int tap = 0, cb = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = split * args.kb_per_split;
+        const int kb1 = (kb0 + args.kb_per_split < num_kb) ? kb0 + args.kb_per_split : num_kb;
+        int tap = kb0 / args.c_blocks, cb = kb0 - tap * args.c_blocks;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
           tma_load_4d(smem_a + stage * kABytes, &args.tmap_a[args.tap_map[tap]], &full_bar[stage],
@@ -287,7 +298,10 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         continue;
       }
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int split = args.k_splits > 1 ? tile / mn_tiles : 0;
+      const int kb0 = split * args.kb_per_split;
+      const int kb1 = (kb0 + args.kb_per_split < num_kb) ? kb0 + args.kb_per_split : num_kb;
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
         if (lane == 0) {
@@ -296,10 +310,10 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // +32 bytes per K=16 step inside the 128-byte swizzle row (>>4 -> +2)
-            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -311,7 +325,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       tma_prefetch_desc(&args.tmap_res);
       int slot = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {   // k_splits == 1 with a residual
         const int n_tile = tile % args.n_tiles;
         const int m_tile = tile / args.n_tiles;
         const int tw = m_tile % args.tiles_w;
@@ -350,8 +364,10 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int n_tile = tile % args.n_tiles;
-      const int m_tile = tile / args.n_tiles;
+      int split = 0, mn = tile;
+      if (args.k_splits > 1) { split = tile / mn_tiles; mn = tile - split * mn_tiles; }
+      const int n_tile = mn % args.n_tiles;
+      const int m_tile = mn / args.n_tiles;
       const int tw = m_tile % args.tiles_w;
       const int th = (m_tile / args.tiles_w) % args.tiles_h;
       const int tn = m_tile / (args.tiles_w * args.tiles_h);
@@ -386,7 +402,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       }
       // per-channel scale/shift of this N tile -> smem (all readers of the previous tile's values
       // are behind the last epi_bar_sync(2) of that tile)
-      if (BNM == 0) {
+      if (!BNT) {
         for (int i = tid_e; i < BLOCK_N; i += kEpiThreads) {
           const int col = n_tile * BLOCK_N + i;
           const bool ok = col < args.n_total;
@@ -407,7 +423,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       bool row_ok = true;
       int row_view = 0;
       long long row_off = 0;
-      if (BNM != 0 || args.mask_bits != nullptr) {
+      if (BNM != 0) {
         int ow, oh, n;
         if (args.stat_pix > 0) {
           const long long p = (long long)tw * args.box_w + row;
@@ -453,8 +469,8 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
         float f[32];
 #pragma unroll
         for (int q = 0; q < kWarpCols / 4; ++q) {
-          const float4 sc = *reinterpret_cast<const float4*>((BNM ? t_a : s_scale) + col_in_tile + q * 4);
-          const float4 sh = *reinterpret_cast<const float4*>((BNM ? t_b : s_shift) + col_in_tile + q * 4);
+          const float4 sc = *reinterpret_cast<const float4*>((BNT ? t_a : s_scale) + col_in_tile + q * 4);
+          const float4 sh = *reinterpret_cast<const float4*>((BNT ? t_b : s_shift) + col_in_tile + q * 4);
           if (BNM == 2) {   // dz = a*dy + b*z + c: the b*z + c part (dy comes from the residual tile)
             const float4 sc2 = *reinterpret_cast<const float4*>(t_c + col_in_tile + q * 4);
             f[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]), sh.x, sc2.x);
@@ -492,7 +508,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
             }
           }
         }
-        if (!OUT_F32) {
+        if (BNM == 1 || MASK) {
           // packed ReLU masks: 32 consecutive channels of this row = one 32-bit word
           const long long woff = (row_off + n_tile * BLOCK_N + col_in_tile) >> 5;
           if (BNM == 1 && args.bn_bits != nullptr && row_ok) {
@@ -501,7 +517,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
             for (int j = 0; j < 32; ++j) word |= (f[j] > 0.f ? 1u : 0u) << j;
             args.bn_bits[woff] = word;
           }
-          if (args.mask_bits != nullptr) {
+          if (MASK) {
             const uint32_t word = row_ok ? __ldg(args.mask_bits + woff) : 0u;
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = (word >> j) & 1u ? f[j] : 0.f;
@@ -535,7 +551,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
         epi_bar_sync(2);
         if (tid_e == 0) {
           tma_store_4d(&args.tmap_out, obuf, n_tile * BLOCK_N + c * kChunkCols, tw * args.box_w,
-                       th * args.box_h, tn * args.box_n);
+                       th * args.box_h, args.k_splits > 1 ? split : tn * args.box_n);
           tma_store_commit();
         }
         if (STATS) {
@@ -840,6 +856,54 @@ igemm_pair_kernel(const __grid_constant__ IgemmArgs args) {
   }
 }
 
+// Split-K fix-up: out[m, n] = act(scale[n] * sum_s ws[s][m][n] + shift[n]); the slices are added in
+// the fixed order s = 0, 1, ... so the result does not depend on which CTA finished first.
+template <typename TO>
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long rows, int n_total,
+                     const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                     TO* __restrict__ out, long long ld_out) {
+  griddep_wait();
+  griddep_launch();
+  const int ng = n_total / 8;
+  const long long total = rows * ng;
+  const long long slice = rows * (long long)n_total;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ng;
+    const int c0 = (int)(i - r * ng) * 8;
+    const float* src = ws + r * n_total + c0;
+    float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
+    for (int s = 1; s < splits; ++s) {
+      const float4 b0 = *reinterpret_cast<const float4*>(src + s * slice);
+      const float4 b1 = *reinterpret_cast<const float4*>(src + s * slice + 4);
+      a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+      a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+    }
+    float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float sc = scale ? __ldg(scale + c0 + e) : 1.f, sh = shift ? __ldg(shift + c0 + e) : 0.f;
+      f[e] = fmaf(f[e], sc, sh);
+      if (relu) f[e] = fmaxf(f[e], 0.f);
+    }
+    TO* dst = out + r * ld_out + c0;
+    if (sizeof(TO) == 2) {
+      uint4 o;
+      o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+      o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(dst) = o;
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+}
+
+// RMV_SPLITK: 1 (default) = split the reduction of small-M pointwise GEMMs when a workspace is given;
+// 0 = never
+int splitk_mode() { return tuning("SPLITK", 1, 1); }
+
 // RMV_CTA2: 1 (default) = use the CTA-pair kernel where it applies; 0 = never; 2 = also force 256-wide N
 // tiles for every c_out % 256 == 0 layer, however small (exercises the pair kernel in the tests)
 int cta2_mode() { return tuning("CTA2", 1, 2); }
@@ -963,6 +1027,10 @@ int dispatch(const IgemmArgs& a, int total, bool has_res, bool out_f32, int bn_m
     return launch<BLOCK_N, 0, false, false, false, 1>(a, total, stream);
   }
   if (bn_mode == 2) return launch<BLOCK_N, 1, false, false, false, 2>(a, total, stream);
+  if (bn_mode == 3) {   // plain epilogue (+ residual) with the packed ReLU mask applied: training data gradients
+    if (has_res) return launch<BLOCK_N, 1, false, false, false, 3>(a, total, stream);
+    return launch<BLOCK_N, 0, false, false, false, 3>(a, total, stream);
+  }
   if (a.stat_acc != nullptr) return launch<BLOCK_N, 0, false, false, true>(a, total, stream);
   if (out_f32) return launch<BLOCK_N, 0, true>(a, total, stream);
   if (has_res) {
@@ -1101,6 +1169,33 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
                     !out_f32 && p.residual == nullptr && p.stat_acc == nullptr &&
                     p.bn_mode == 0 && p.mask_bits == nullptr &&
                     p.c_out % block_n == 0 && m_tiles >= 2;
+  // Split-K for the small-M pointwise GEMMs (the lifter / fuser / head Linear layers at M = B*V rows and
+  // their data gradients): with m_tiles * n_tiles well below the SM count every CTA would stream the
+  // whole K axis alone; S splits fill the machine, their fp32 partial tiles go to the caller's
+  // workspace and splitk_reduce_kernel adds them in a fixed order (bit-reproducible).
+  int k_splits = 1, kb_per_split = a.num_taps * (p.c_in / kBlockK);
+  {
+    const int num_kb = a.num_taps * (p.c_in / kBlockK);
+    const long mn = m_tiles * ceil_div(p.c_out, block_n);
+    if (splitk_mode() != 0 && p.workspace != nullptr && taps == nullptr && !halo && !pair &&
+        out_h == 1 && n_img == 1 && p.residual == nullptr && p.stat_acc == nullptr &&
+        p.bn_mode == 0 && p.mask_bits == nullptr && num_kb >= 8 && mn > 0 && 2 * mn <= num_sms() &&
+        p.c_out % 8 == 0 && y_sw % 8 == 0) {
+      int s_want = (int)(num_sms() / mn);
+      if (s_want > num_kb / 4) s_want = num_kb / 4;
+      if (s_want > 16) s_want = 16;
+      if (s_want >= 2) {
+        const int per = ceil_div(num_kb, s_want);
+        const int s_eff = ceil_div(num_kb, per);
+        const size_t need = (size_t)s_eff * (size_t)out_w * (size_t)p.c_out * sizeof(float);
+        if (s_eff >= 2 && need <= p.workspace_bytes &&
+            (reinterpret_cast<uintptr_t>(p.workspace) & 15) == 0) {
+          k_splits = s_eff; kb_per_split = per;
+        }
+      }
+    }
+  }
+  const bool splitk = k_splits > 1;
   {
     const long long k_total = (long long)(taps ? taps->w_taps : a.num_taps) * p.c_in;
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)p.c_out};
@@ -1117,7 +1212,16 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
                          (cuuint32_t)a.box_n};
     cuuint64_t ystr[3] = {(cuuint64_t)(y_sw * y_es), (cuuint64_t)(y_sh * y_es),
                           (cuuint64_t)(y_sn * y_es)};
-    int rc = encode_map(&a.tmap_out, p.y, 4, dims, ystr, box, out_f32);
+    int rc;
+    if (splitk) {   // fp32 partial tiles: slice s of the workspace = [out_w rows][c_out]
+      cuuint64_t wdims[4] = {(cuuint64_t)p.c_out, (cuuint64_t)out_w, 1, (cuuint64_t)k_splits};
+      const cuuint64_t slice = (cuuint64_t)out_w * p.c_out * 4;
+      cuuint64_t wstr[3] = {(cuuint64_t)p.c_out * 4, slice, slice};
+      cuuint32_t wbox[4] = {32, (cuuint32_t)a.box_w, 1, 1};
+      rc = encode_map(&a.tmap_out, p.workspace, 4, wdims, wstr, wbox, true);
+    } else {
+      rc = encode_map(&a.tmap_out, p.y, 4, dims, ystr, box, out_f32);
+    }
     if (rc) return rc;
     if (p.residual != nullptr) {
       cuuint64_t rstr[3] = {(cuuint64_t)(r_sw * 2), (cuuint64_t)(r_sh * 2), (cuuint64_t)(r_sn * 2)};
@@ -1128,11 +1232,32 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
   a.n_total = p.c_out;
   a.n_tiles = ceil_div(p.c_out, block_n);
   a.c_blocks = p.c_in / kBlockK;
-  a.scale = p.scale;
-  a.shift = p.shift;
-  a.relu = p.relu;
-  const int total = (int)(m_tiles * a.n_tiles);
+  a.scale = splitk ? nullptr : p.scale;
+  a.shift = splitk ? nullptr : p.shift;
+  a.relu = splitk ? 0 : p.relu;
+  a.k_splits = k_splits;
+  a.kb_per_split = kb_per_split;
+  const int total = (int)(m_tiles * a.n_tiles) * k_splits;
   if (total == 0) return 0;
+  if (splitk) {
+    int rc = (block_n == 64)    ? launch<64, 0, true>(a, total, stream)
+             : (block_n == 128) ? launch<128, 0, true>(a, total, stream)
+                                : launch<256, 0, true>(a, total, stream);
+    if (rc) return rc;
+    const long long groups = (long long)out_w * (p.c_out / 8);
+    long blocks = (long)((groups + 255) / 256);
+    if (blocks > 8L * num_sms()) blocks = 8L * num_sms();
+    if (out_f32) {
+      RMV_CUDA(launch_pdl(splitk_reduce_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, stream,
+                          (const float*)p.workspace, k_splits, (long long)out_w, p.c_out, p.scale,
+                          p.shift, p.relu, (float*)p.y, y_sw));
+    } else {
+      RMV_CUDA(launch_pdl(splitk_reduce_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(256), 0,
+                          stream, (const float*)p.workspace, k_splits, (long long)out_w, p.c_out,
+                          p.scale, p.shift, p.relu, (__nv_bfloat16*)p.y, y_sw));
+    }
+    return 0;
+  }
   if (pair) return block_n == 256 ? launch_pair<256>(a, stream) : launch_pair<128>(a, stream);
   if (p.stat_acc != nullptr)
     RMV_CHECK_ARG(!out_f32 && p.residual == nullptr && p.stat_views == 2 && p.bn_mode == 0,
@@ -1165,8 +1290,9 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
                   "tcgen05 conv: BatchNorm-apply modes / ReLU masks need bf16 output and channel counts, "
                   "strides and mask offsets that are multiples of 32");
     RMV_CHECK_ARG(p.bn_mode == 0 || (p.bn_a != nullptr && p.bn_b != nullptr && p.scale == nullptr &&
-                                     p.shift == nullptr && block_n >= 128),
-                  "tcgen05 conv: bn_mode needs bn_a/bn_b, no scale/shift and c_out >= 128");
+                                     p.shift == nullptr && p.mask_bits == nullptr),
+                  "tcgen05 conv: bn_mode needs bn_a/bn_b, no scale/shift, no mask_bits");
+    RMV_CHECK_ARG(p.stat_acc == nullptr, "tcgen05 conv: statistics cannot be combined with bn_mode / mask_bits");
     RMV_CHECK_ARG(p.bn_mode != 2 || (p.bn_c != nullptr && p.residual != nullptr && p.relu == 0),
                   "tcgen05 conv: bn_mode 2 needs bn_c and dy in `residual`, no ReLU");
     RMV_CHECK_ARG(p.bn_mode >= 0 && p.bn_mode <= 2, "tcgen05 conv: bad bn_mode %d", p.bn_mode);
@@ -1183,10 +1309,11 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
     return launch<64, 0, false, true>(a, total, stream);
   }
   const bool has_res = p.residual != nullptr;
+  const int epi_mode = p.mask_bits != nullptr ? 3 : p.bn_mode;
   switch (block_n) {
-    case 64: return dispatch<64>(a, total, has_res, out_f32, 0, stream);
-    case 128: return dispatch<128>(a, total, has_res, out_f32, p.bn_mode, stream);
-    default: return dispatch<256>(a, total, has_res, out_f32, p.bn_mode, stream);
+    case 64: return dispatch<64>(a, total, has_res, out_f32, epi_mode, stream);
+    case 128: return dispatch<128>(a, total, has_res, out_f32, epi_mode, stream);
+    default: return dispatch<256>(a, total, has_res, out_f32, epi_mode, stream);
   }
 }
 

@@ -44,6 +44,7 @@ class ConvArgs(C.Structure):
         ("stat_acc", C.c_void_p), ("stat_views", C.c_int), ("stat_finalize", C.c_void_p),
         ("bn_mode", C.c_int), ("bn_a", C.c_void_p), ("bn_b", C.c_void_p), ("bn_c", C.c_void_p),
         ("bn_bits", C.c_void_p), ("mask_bits", C.c_void_p), ("mask_off", C.c_longlong),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -85,6 +86,7 @@ SIGNATURES = {
     "rmv_stem_conv_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rmv_stem_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "rmv_stem_wgrad_workspace_bytes": (C.c_size_t, []),
+    "rmv_splitk_workspace_bytes": (C.c_size_t, []),
     "rmv_bn_workspace_bytes": (C.c_size_t, [_i, _i]),
     "rmv_conv2d_wgrad_tc_workspace_bytes": (C.c_size_t, [C.POINTER(ConvArgs)]),
     "rmv_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

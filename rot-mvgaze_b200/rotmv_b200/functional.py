@@ -33,6 +33,21 @@ def _need_cuda(*ts):
             raise L.RotmvError("rotmv_b200 ops need CUDA tensors (there is no CPU path)")
 
 
+_WORKSPACE = {}
+
+
+def splitk_workspace(device):
+    """Per-device scratch of rmv_splitk_workspace_bytes() for the split-K GEMMs (allocated on first
+    use -- the engines' warm-up passes run before any CUDA-graph capture; launches on one stream
+    use it one after the other)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    t = _WORKSPACE.get(key)
+    if t is None:
+        t = torch.empty((L.load().rmv_splitk_workspace_bytes(),), dtype=torch.uint8, device=device)
+        _WORKSPACE[key] = t
+    return t
+
+
 def _conv_args(x, w, out, stride, pad):
     """rmv_conv_args of y = conv(x, w) for NHWC x [N,H,W,C], KRSC w, NHWC out."""
     n, h, wd, c = x.shape
@@ -144,6 +159,9 @@ def conv2d(x, w, *, stride=1, pad=0, scale=None, shift=None, residual=None, relu
         a.bn_a, a.bn_b, a.bn_c = bn_a.data_ptr(), bn_b.data_ptr(), L.ptr(bn_c)
         a.bn_bits = L.ptr(bn_bits)
     a.mask_bits = L.ptr(mask_bits)
+    if kh == 1 and kw == 1 and x.dtype == torch.bfloat16 and n * oh * ow <= 4096:
+        ws = splitk_workspace(x.device)       # small-M pointwise GEMM: the library may split K
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     meta = {}
     if PROFILE is not None:
         tc = x.dtype == torch.bfloat16 and engine != L.ENGINE_SIMT and c % 64 == 0

@@ -53,7 +53,7 @@ def test_conv_args_struct_layout():
         decl = decl.strip()
         if not decl:
             continue
-        decl = re.sub(r"^(const\s+)?(void|float|double|int|long long)\s*\*?\s*", "", decl)
+        decl = re.sub(r"^(const\s+)?(void|float|double|int|long long|size_t)\s*\*?\s*", "", decl)
         names += [n.strip().lstrip("*") for n in decl.split(",")]
     assert names == [f[0] for f in L.ConvArgs._fields_]
 

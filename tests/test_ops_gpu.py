@@ -91,7 +91,10 @@ def test_conv_tc_fp32_out_tight(block_n):
 
 
 LINEAR_CASES = [(300, 2048, 1536), (16, 3584, 3584), (513, 3584, 512), (128, 1536, 1536),
-                (1024, 3584, 1536)]
+                (1024, 3584, 1536),
+                # the fusion-stage shapes at M = B*V rows (models/rot_mv.py:35-50,91-98,179-184): split-K
+                (2, 3584, 512), (16, 2048, 1536), (512, 3584, 3584), (512, 3584, 1536), (512, 3584, 512),
+                (512, 2048, 1536), (512, 1536, 1536), (2048, 3584, 512), (256, 3584, 3584)]
 
 
 @pytest.mark.parametrize("m,k,n", LINEAR_CASES)
@@ -115,6 +118,31 @@ def test_linear_parity(m, k, n, engine):
     tol = (2e-5 if dt == torch.float32 else 1.2e-2) * ref.abs().max().item()
     assert err <= tol, (err, tol)
     assert obuf[:, :128].abs().max().item() == 0.0  # nothing written outside the view
+
+
+@pytest.mark.parametrize("m,k,n", [(512, 3584, 512), (256, 3584, 1536), (16, 2048, 1536), (512, 1536, 1536)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_linear_splitk_is_deterministic_and_matches_unsplit(m, k, n, out_dtype):
+    """Split-K of the small-M GEMMs: the fp32 partial tiles are added in a fixed order, so repeated
+    launches are BIT-identical; against the unsplit kernel (RMV_SPLITK=0) only the fp32 summation
+    order differs."""
+    from rotmv_b200 import functional as RF, _lib as L
+
+    g = torch.Generator(device="cuda").manual_seed(m * 3 + k + n)
+    x = torch.randn((m, k), device="cuda", generator=g).bfloat16()
+    wt = (torch.randn((n, k), device="cuda", generator=g) / math.sqrt(k)).bfloat16()
+    b = torch.randn((n,), device="cuda", generator=g)
+    outs = [RF.linear(x, wt, b, relu=True, out_dtype=out_dtype, engine=L.ENGINE_TC).clone() for _ in range(3)]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    L.check(L.load().rmv_set_tuning(b"SPLITK", 0), "rmv_set_tuning")
+    try:
+        plain = RF.linear(x, wt, b, relu=True, out_dtype=out_dtype, engine=L.ENGINE_TC)
+    finally:
+        L.check(L.load().rmv_set_tuning(b"SPLITK", 1), "rmv_set_tuning")
+    ref = torch.relu(x.float() @ wt.float().t() + b)
+    tol = (2e-5 if out_dtype == torch.float32 else 1.2e-2) * ref.abs().max().item() + 1e-5
+    assert (outs[0].float() - ref).abs().max().item() <= tol
+    assert (outs[0].float() - plain.float()).abs().max().item() <= tol
 
 
 def test_maxpool_avgpool():
