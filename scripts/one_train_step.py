@@ -19,7 +19,11 @@ gt = torch.rand((B, V, 2), device="cuda") - 0.5
 for i in range(3):
     n0 = L.STATS["launches"]
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    if i == 2:
+        torch.cuda.profiler.start()     # ncu --profile-from-start off: only the third (warm) step
     e0.record()
     eng.step(images, rot, gt)
     e1.record(); torch.cuda.synchronize()
+    if i == 2:
+        torch.cuda.profiler.stop()
     print(f"step {i}: {L.STATS['launches'] - n0} launches, {e0.elapsed_time(e1):.3f} ms, loss {eng.loss.item():.4f}")

@@ -25,7 +25,7 @@ def short(name):
     t = re.search(r"igemm_kernel<([^>]*)>", name)
     if t:
         base += "<" + t.group(1).replace("(int)", "").replace("(bool)", "").replace(" ", "") + ">"
-    t = re.search(r"(bn_\w+|wgrad_kernel|maxpool\w*|relu_bwd_kernel|colsum_kernel|avgpool\w*|rotate_gather_kernel|head_loss\w*)<([^>]*)>", name)
+    t = re.search(r"(bn_\w+|wgrad_kernel|maxpool\w*|relu_bwd_kernel|colsum_kernel|avgpool\w*|rotate_gather_kernel|head_loss\w*|tstat_kernel|splitk_reduce_kernel|mask_bits_kernel)<([^>]*)>", name)
     if t and "igemm" not in base:
         base = t.group(1) + "<" + t.group(2).replace("__nv_bfloat16", "bf16").replace("(int)", "").replace("(bool)", "").replace(" ", "") + ">"
     return base

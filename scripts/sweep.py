@@ -20,6 +20,10 @@ ap.add_argument("--views", default="2,4,8")
 ap.add_argument("--batches", default="64,128,256,512,1024,2048")
 ap.add_argument("--modes", default="infer,train")
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--global-batches", default="", help="GLOBAL batch sizes (configs[4]: 64..2048 over all GPUs); "
+                "each GPU runs global/world samples; overrides --batches")
+ap.add_argument("--cpu", action="store_true", help="rank 0 also times the CPU oracle (reference PyTorch CPU path "
+                "port) per view count and mode, B=8 samples, all host cores: the CPU column of configs[4]")
 ap.add_argument("--max-images", type=int, default=4096, help="skip points with batch*views above this (memory)")
 ap.add_argument("--max-train-images", type=int, default=1024)
 args = ap.parse_args()
@@ -45,9 +49,41 @@ def timed(fn, steps):
     return t.item()
 
 
+cpu = {}
+if args.cpu and rank == 0:
+    # the reference's CPU path beside every GPU point (throughput is flat in B on the CPU: B = 8)
+    import time
+    from oracle import rotmv_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    for mode in args.modes.split(","):
+        for v in [int(x) for x in args.views.split(",")]:
+            om = O.build_model(num_iter=3, depth=50, seed=0)
+            im, pose, gtc = O.synthetic_batch(8, v, seed=1)
+            rotc = O.pairwise_rotations(pose)
+            if mode == "train":
+                om.train(); opt = O.make_adam(om, lr=1e-6)
+                fn = lambda: O.train_step(om, opt, im, rotc, gtc)  # noqa: E731
+            else:
+                om.eval()
+                def fn():
+                    with torch.no_grad():
+                        om.forward_views(im, rotc)
+            fn()
+            t0 = time.perf_counter(); n = 0
+            while n < 3 or time.perf_counter() - t0 < 4.0:
+                fn(); n += 1
+            cpu[(mode, v)] = 8 * n / (time.perf_counter() - t0)
+    print(json.dumps({"cpu_reference": {f"{m}_v{v}": round(x, 2) for (m, v), x in cpu.items()},
+                      "cores": torch.get_num_threads(), "sample": "oracle port, B=8, fp32"}), flush=True)
+if world > 1:
+    dist.barrier()
+
+batches = [int(x) for x in args.batches.split(",")]
+if args.global_batches:
+    batches = [int(x) // world for x in args.global_batches.split(",") if int(x) // world >= 1]
 for mode in args.modes.split(","):
     for v in [int(x) for x in args.views.split(",")]:
-        for b in [int(x) for x in args.batches.split(",")]:
+        for b in batches:
             cap = args.max_images if mode == "infer" else args.max_train_images
             if b * v > cap:
                 continue
@@ -71,7 +107,12 @@ for mode in args.modes.split(","):
             del model
             torch.cuda.empty_cache()
             if rank == 0:
-                print(json.dumps({"mode": mode, "views": v, "batch_per_gpu": b, "n_gpus": world, "ms_per_step": round(ms, 3),
-                                  "samples_per_s": round(world * b / ms * 1e3, 1), "images_per_s": round(world * b * v / ms * 1e3, 1)}), flush=True)
+                rec = {"mode": mode, "views": v, "batch_per_gpu": b, "global_batch": b * world, "n_gpus": world,
+                       "ms_per_step": round(ms, 3), "samples_per_s": round(world * b / ms * 1e3, 1),
+                       "images_per_s": round(world * b * v / ms * 1e3, 1)}
+                if (mode, v) in cpu:
+                    rec["cpu_samples_per_s"] = round(cpu[(mode, v)], 2)
+                    rec["gpu_over_cpu"] = round(rec["samples_per_s"] / cpu[(mode, v)], 1)
+                print(json.dumps(rec), flush=True)
 if world > 1:
     dist.destroy_process_group()
