@@ -191,17 +191,19 @@ tstat_kernel(const __grid_constant__ TStatArgs a) {
         dyt = smem_dy + slot * C::kDyBytes + dy_box + dy_el;
       }
       float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+      // all of this thread's accumulator columns in one go (kChunks loads in flight, one wait), then
+      // the accumulator goes straight back to the MMA warp
+      uint32_t vv[kChunks][32];
+#pragma unroll
+      for (int ch = 0; ch < kChunks; ++ch)
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * N_PX + half * kCols + ch * 32,
+                           vv[ch]);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&tmem_empty[accb]);
 #pragma unroll
       for (int ch = 0; ch < kChunks; ++ch) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * N_PX +
-                               half * kCols + ch * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr, v);
-        tmem_ld_wait();
-        if (ch == kChunks - 1) {   // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before_sync();
-          mbar_arrive(&tmem_empty[accb]);
-        }
+        const uint32_t* v = vv[ch];
         float d[32];
         if (BWD) {
           const int p0 = half * kCols + ch * 32;

@@ -112,8 +112,11 @@ struct Cfg {
   static constexpr int kResBytes = HAS_RES ? kResSlots * kChunkBytes : 0;
   // scale + shift of the current N tile; BNM: 2 (a, b) or 3 (a, b, c) tables for each of the 2 views
   static constexpr int kVecBytes = (BNM == 1 ? 4 : (BNM == 2 ? 6 : 2)) * BLOCK_N * 4;
+  // BNM 1 / 3: the packed ReLU-mask words of one tile, [128 rows][BLOCK_N / 32], staged so that global
+  // memory sees whole 32-byte sectors per row instead of one 4-byte access per thread and chunk
+  static constexpr int kBitsBytes = (BNM == 1 || BNM == 3) ? 128 * (BLOCK_N / 32) * 4 : 0;
   static constexpr int kSmemBytes = kStages * kStageBytes + kResidentB + kOutBytes + kResBytes +
-                                    kVecBytes + 256 /*barriers*/ + 1024 /*align*/;
+                                    kVecBytes + kBitsBytes + 256 /*barriers*/ + 1024 /*align*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 };
 
@@ -162,7 +165,8 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   uint8_t* smem_res = smem_out + C::kOutBytes;           // [2][128 rows][128 B], SW128
   float* s_scale = reinterpret_cast<float*>(smem_res + C::kResBytes);
   float* s_shift = s_scale + (BNT ? 2 : 1) * BLOCK_N;   // BNT: [2 views][BLOCK_N] per table
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_res + C::kResBytes + C::kVecBytes);
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem_res + C::kResBytes + C::kVecBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_res + C::kResBytes + C::kVecBytes + C::kBitsBytes);
   uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + C::kStages;        // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * C::kStages;    // [2]        MMA -> epilogue
@@ -423,23 +427,52 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       bool row_ok = true;
       int row_view = 0;
       long long row_off = 0;
-      if (BNM != 0) {
-        int ow, oh, n;
+      // (validity, image, element offset) of tile row r
+      auto row_info = [&](int r, bool& ok, int& img, long long& off) {
         if (args.stat_pix > 0) {
-          const long long p = (long long)tw * args.box_w + row;
-          row_ok = p < args.stat_rows;
-          n = (int)(p / args.stat_pix);
-          ow = (int)p; oh = 0;
-          row_off = p * args.m_sw + args.mask_off;
+          const long long p = (long long)tw * args.box_w + r;
+          ok = p < args.stat_rows;
+          img = (int)(p / args.stat_pix);
+          off = p * args.m_sw + args.mask_off;
         } else {
-          ow = tw * args.box_w + (row & (args.box_w - 1));
-          oh = th * args.box_h + ((row >> args.stat_bw_shift) & (args.box_h - 1));
-          n = tn * args.box_n + (row >> args.stat_ppi_shift);
-          row_ok = ow < args.stat_w && oh < args.stat_h && n < args.stat_n;
-          row_off = (long long)n * args.m_sn + (long long)oh * args.m_sh + (long long)ow * args.m_sw +
-                    args.mask_off;
+          const int ow = tw * args.box_w + (r & (args.box_w - 1));
+          const int oh = th * args.box_h + ((r >> args.stat_bw_shift) & (args.box_h - 1));
+          img = tn * args.box_n + (r >> args.stat_ppi_shift);
+          ok = ow < args.stat_w && oh < args.stat_h && img < args.stat_n;
+          off = (long long)img * args.m_sn + (long long)oh * args.m_sh + (long long)ow * args.m_sw +
+                args.mask_off;
         }
-        row_view = n & 1;
+      };
+      if (BNT) {
+        int img;
+        row_info(row, row_ok, img, row_off);
+        row_view = img & 1;
+      }
+      // mask words of this tile <-> global memory: thread = (row fr, half fq of its BLOCK_N/32 words)
+      constexpr int kBitW = BLOCK_N / 32;        // words per row: 2 / 4 / 8
+      constexpr int kBitH = kBitW / 2;           // words per thread: 1 / 2 / 4
+      const int fr = tid_e >> 1, fq = tid_e & 1;
+      bool f_ok = false;
+      long long f_word = 0;
+      if (BNM == 1 || MASK) {
+        int img; long long off;
+        row_info(fr, f_ok, img, off);
+        f_ok = f_ok && (n_tile * BLOCK_N + fq * kBitH * 32 < args.n_total);
+        f_word = (off + n_tile * BLOCK_N) / 32 + fq * kBitH;
+      }
+      if (MASK) {
+        // (the previous tile's readers are behind its last epi_bar_sync(2); the first use below is
+        // behind this tile's first epi_bar_sync(1))
+        uint32_t* dst = s_bits + fr * kBitW + fq * kBitH;
+        if (kBitH == 4) {
+          *reinterpret_cast<uint4*>(dst) = f_ok ? __ldg(reinterpret_cast<const uint4*>(args.mask_bits + f_word))
+                                                : make_uint4(0, 0, 0, 0);
+        } else if (kBitH == 2) {
+          *reinterpret_cast<uint2*>(dst) = f_ok ? __ldg(reinterpret_cast<const uint2*>(args.mask_bits + f_word))
+                                                : make_uint2(0, 0);
+        } else {
+          *dst = f_ok ? __ldg(args.mask_bits + f_word) : 0u;
+        }
       }
       const float* t_a = s_scale + row_view * BLOCK_N;
       const float* t_b = s_shift + row_view * BLOCK_N;
@@ -509,16 +542,16 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
           }
         }
         if (BNM == 1 || MASK) {
-          // packed ReLU masks: 32 consecutive channels of this row = one 32-bit word
-          const long long woff = (row_off + n_tile * BLOCK_N + col_in_tile) >> 5;
-          if (BNM == 1 && args.bn_bits != nullptr && row_ok) {
+          // packed ReLU masks: 32 consecutive channels of this row = one 32-bit word, staged in s_bits
+          uint32_t* wp = s_bits + row * kBitW + (col_in_tile >> 5);
+          if (BNM == 1) {
             uint32_t word = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) word |= (f[j] > 0.f ? 1u : 0u) << j;
-            args.bn_bits[woff] = word;
+            *wp = word;
           }
           if (MASK) {
-            const uint32_t word = row_ok ? __ldg(args.mask_bits + woff) : 0u;
+            const uint32_t word = *wp;
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = (word >> j) & 1u ? f[j] : 0.f;
           }
@@ -607,6 +640,16 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
               s_stat[((size_t)(q >> 1) * args.n_total + col) * 2 + (q & 1)] += sum;
           }
           // the slots are rewritten only after the next chunk's epi_bar_sync(1)/(2): ordered
+        }
+      }
+      if (BNM == 1 && args.bn_bits != nullptr) {
+        // the tile's sign-mask words leave as whole sectors: 16 / 8 / 4 bytes per thread, rows contiguous
+        epi_bar_sync(3);
+        if (f_ok) {
+          const uint32_t* src = s_bits + fr * kBitW + fq * kBitH;
+          if (kBitH == 4) *reinterpret_cast<uint4*>(args.bn_bits + f_word) = *reinterpret_cast<const uint4*>(src);
+          else if (kBitH == 2) *reinterpret_cast<uint2*>(args.bn_bits + f_word) = *reinterpret_cast<const uint2*>(src);
+          else args.bn_bits[f_word] = *src;
         }
       }
     }
@@ -1285,10 +1328,10 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
     }
   }
   if (p.bn_mode != 0 || p.mask_bits != nullptr) {
-    RMV_CHECK_ARG(!out_f32 && !halo && p.c_out % 32 == 0 && p.y_sw % 32 == 0 && p.y_sh % 32 == 0 &&
-                      p.y_sn % 32 == 0 && p.mask_off % 32 == 0,
+    RMV_CHECK_ARG(!out_f32 && !halo && p.c_out % 128 == 0 && p.y_sw % 128 == 0 && p.y_sh % 128 == 0 &&
+                      p.y_sn % 128 == 0 && p.mask_off % 128 == 0,
                   "tcgen05 conv: BatchNorm-apply modes / ReLU masks need bf16 output and channel counts, "
-                  "strides and mask offsets that are multiples of 32");
+                  "strides and mask offsets that are multiples of 128 (whole 16-byte mask units per row)");
     RMV_CHECK_ARG(p.bn_mode == 0 || (p.bn_a != nullptr && p.bn_b != nullptr && p.scale == nullptr &&
                                      p.shift == nullptr && p.mask_bits == nullptr),
                   "tcgen05 conv: bn_mode needs bn_a/bn_b, no scale/shift, no mask_bits");
@@ -1299,9 +1342,9 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
     a.bn_a = p.bn_a; a.bn_b = p.bn_b; a.bn_c = p.bn_c;
     a.bn_bits = reinterpret_cast<uint32_t*>(p.bn_bits);
     a.mask_bits = reinterpret_cast<const uint32_t*>(p.mask_bits);
-    RMV_CHECK_ARG((reinterpret_cast<uintptr_t>(p.bn_bits) & 3) == 0 &&
-                      (reinterpret_cast<uintptr_t>(p.mask_bits) & 3) == 0,
-                  "tcgen05 conv: mask pointers must be 4-byte aligned");
+    RMV_CHECK_ARG((reinterpret_cast<uintptr_t>(p.bn_bits) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.mask_bits) & 15) == 0,
+                  "tcgen05 conv: mask pointers must be 16-byte aligned");
   }
   if (halo) {
     a.halo_base_mode = halo_mode() == 2;

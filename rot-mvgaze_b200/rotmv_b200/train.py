@@ -85,6 +85,13 @@ class TrainEngine:
         # downsample) never materialises the conv output -- statistics and apply passes recompute it on
         # the tensor cores (RMV_BN_RECOMPUTE=0: the conv writes z and the HBM-bound passes read it)
         self.recompute_bn = os.environ.get("RMV_BN_RECOMPUTE", "1") != "0" and trunk.kind == "bottleneck"
+        # ... where the recomputed GEMM is cheap next to the tensor it avoids: reduction depth c_in <= 256
+        # (layer1-3). Measured per block (four passes, B=128, kernels alone, cold L2): 56^2 (K=64) 586 us
+        # recomputed vs 777 us materialised; 14^2 (K=256) 219 vs ~237; 7^2 (K=512) 203 vs ~133 -- at 7^2
+        # the passes are bound by re-streaming the 2 MB of filters per tile, not by the 51 MB tensor.
+        # Whole step, same box: threshold 512 -> 20.10 ms, 128 -> 20.16, 256 -> 19.97.
+        # RMV_BN_RECOMPUTE_MAXC overrides the threshold.
+        self.recompute_max_cin = int(os.environ.get("RMV_BN_RECOMPUTE_MAXC", "256"))
         # data parallel: all-reduce the fusion-stage gradients while the trunk backward runs
         # (RMV_DP_OVERLAP=0: one all-reduce of the whole buffer after the backward pass)
         self.dp_overlap = os.environ.get("RMV_DP_OVERLAP", "1") != "0"
@@ -303,7 +310,8 @@ class TrainEngine:
     # ---- BatchNorm over a recomputed 1x1 convolution (conv3 / downsample of the bottlenecks) ------
     def _use_recompute(self, conv) -> bool:
         return (self.recompute_bn and self.precision == "bf16" and self.views == 2
-                and conv.kernel_size[0] == 1 and conv.out_channels % 128 == 0 and conv.in_channels % 64 == 0)
+                and conv.kernel_size[0] == 1 and conv.out_channels % 128 == 0 and conv.in_channels % 64 == 0
+                and conv.in_channels <= self.recompute_max_cin)
 
     def _conv_bn_fwd(self, bn: _BN, x, w, stride, residual, relu, tag):
         """y = relu?(BN_train(conv1x1(x, w)) + residual) without writing the conv output: statistics
@@ -872,9 +880,11 @@ class TrainEngine:
                 dyr = d_out
             else:
                 dz, dyr = self._bn_bwd(bns[-1], zs[-1], d_out, out, (bi, n_st), want_dyr=True)
-            # the data gradient this block hands to the previous one is masked by that block's ReLU
-            # when its packed mask exists (bf16 engine); blocks of the old path mask again (idempotent)
-            in_bits = self._bits.get(id(x_in)) if (self.precision == "bf16" and bi > 0) else None
+            # the data gradient this block hands to the previous one is multiplied by that block's ReLU
+            # derivative (its packed mask) when that block's BatchNorm backward expects it that way
+            in_bits = None
+            if bi > 0 and self._use_recompute(self.blocks[bi - 1]["convs"][-1]):
+                in_bits = self._bits.get(id(x_in))     # the previous block runs the recomputed BatchNorm
             pre_masked = in_bits is not None
             for si in reversed(range(n_st)):
                 cv = convs[si]

@@ -236,8 +236,9 @@ def test_bn_mode2_backward_apply(case):
     (4, 14, 1024, 256, 1, 1, 0),     # data gradient of a reducing conv1: expanding, HBM-bound class
     (3, 28, 512, 128, 1, 1, 0),
     (4, 14, 128, 128, 3, 2, 1),      # stride 2: four parity classes with doubled strides / mask offsets
-    (2, 15, 64, 64, 3, 2, 1),        # odd extent
-    (3, 14, 64, 128, 3, 1, 1),
+    (2, 15, 128, 64, 3, 2, 1),       # odd extent
+    (3, 14, 256, 128, 3, 1, 1),
+    (5, 7, 2048, 512, 1, 1, 0),      # 7x7: ragged last tile, 16 N tiles
 ])
 def test_dgrad_mask_bits(case):
     """rmv_conv2d_dgrad with mask_bits: dx = (conv_transpose(dy, w) + residual) * mask, against
@@ -301,6 +302,7 @@ def test_recompute_step_matches_materialised_step():
         model = model.cuda().train()
         eng = TrainEngine(model, precision="fp32" if mode == "fp32" else "bf16", lr=1e-3, weight_decay=1e-6)
         eng.recompute_bn = mode == "recompute"
+        eng.recompute_max_cin = 4096      # every bottleneck's conv3 / downsample, not only layer1-2
         eng.forward_backward(images.cuda(), rot.cuda(), gt.cuda())
         torch.cuda.synchronize()
         named = dict(model.named_parameters())
