@@ -165,6 +165,7 @@ tstat_kernel(const __grid_constant__ TStatArgs a) {
     const int ch_in_tile = quarter * 32 + lane;
     constexpr int kCols = N_PX / 2, kChunks = kCols / 32;
     double t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0};   // [view]: sums across tiles
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};    // fp32 sums of up to 4 tiles (<= 512 values each)
     // BWD: this thread's channel inside the two swizzled [N_PX][64 ch] boxes of the dy tile
     const uint32_t dy_box = (uint32_t)(ch_in_tile >> 6) * (uint32_t)(N_PX * 128);
     const uint32_t dy_unit = (uint32_t)(ch_in_tile & 63) >> 3, dy_el = (uint32_t)(ch_in_tile & 7) * 2;
@@ -190,7 +191,6 @@ tstat_kernel(const __grid_constant__ TStatArgs a) {
         mbar_wait(&dy_full[slot], dphase);
         dyt = smem_dy + slot * C::kDyBytes + dy_box + dy_el;
       }
-      float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
       // all of this thread's accumulator columns in one go (kChunks loads in flight, one wait), then
       // the accumulator goes straight back to the MMA warp
       uint32_t vv[kChunks][32];
@@ -217,15 +217,18 @@ tstat_kernel(const __grid_constant__ TStatArgs a) {
         }
         const uint32_t m = vm[ch];
         if (m == 0u || m == 0xffffffffu) {   // whole chunk in one view (the common case)
-          float x1 = 0.f, x2 = 0.f;
+          // four independent partial sums per statistic: the 4-cycle FADD/FFMA latency chains of a
+          // single accumulator left the two warps of a scheduler idle half of the time
+          float x1[4] = {0.f, 0.f, 0.f, 0.f}, x2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float z = __uint_as_float(v[j]);
-            if (BWD) { x1 += d[j]; x2 = fmaf(d[j], z, x2); }
-            else { x1 += z; x2 = fmaf(z, z, x2); }
+            if (BWD) { x1[j & 3] += d[j]; x2[j & 3] = fmaf(d[j], z, x2[j & 3]); }
+            else { x1[j & 3] += z; x2[j & 3] = fmaf(z, z, x2[j & 3]); }
           }
           const int vi = m != 0u;
-          s1[vi] += x1; s2[vi] += x2;
+          s1[vi] += (x1[0] + x1[1]) + (x1[2] + x1[3]);
+          s2[vi] += (x2[0] + x2[1]) + (x2[2] + x2[3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -241,9 +244,14 @@ tstat_kernel(const __grid_constant__ TStatArgs a) {
         mbar_arrive(&dy_empty[slot]);
         if (++slot == C::kDySlots) { slot = 0; dphase ^= 1; }
       }
-      t1[0] += (double)s1[0]; t1[1] += (double)s1[1];
-      t2[0] += (double)s2[0]; t2[1] += (double)s2[1];
+      if ((local & 3) == 3) {   // the fp64 pipe is narrow: one hand-over per four tiles
+        t1[0] += (double)s1[0]; t1[1] += (double)s1[1];
+        t2[0] += (double)s2[0]; t2[1] += (double)s2[1];
+        s1[0] = s1[1] = s2[0] = s2[1] = 0.f;
+      }
     }
+    t1[0] += (double)s1[0]; t1[1] += (double)s1[1];
+    t2[0] += (double)s2[0]; t2[1] += (double)s2[1];
     const int chn = ct * 128 + ch_in_tile;
 #pragma unroll
     for (int vi = 0; vi < 2; ++vi) {
