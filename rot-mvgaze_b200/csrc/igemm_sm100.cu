@@ -26,6 +26,9 @@ namespace rmv {
 
 namespace {
 
+#ifndef RMV_EPI_PREFETCH
+#define RMV_EPI_PREFETCH 1   // 0: round-1 epilogue (one TMEM load per chunk, waited for at once)
+#endif
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
@@ -479,7 +482,14 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       const float* t_c = s_shift + (2 + row_view) * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
-#pragma unroll 1
+      // bf16 output: the chunk loop is unrolled and the TMEM load of chunk c+1 is issued as soon as
+      // chunk c has landed, so its latency hides behind chunk c's arithmetic, staging and barriers
+      // (the epilogue of the HBM-bound layers is a latency chain with two warps per scheduler)
+      constexpr bool kPrefetch = !OUT_F32 && RMV_EPI_PREFETCH;
+      uint32_t vbuf[kPrefetch ? 2 : 1][32];
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * kWarpCols;
+      if (kPrefetch) tmem_ld_32x32b_x32(taddr0, vbuf[0]);
+#pragma unroll(kPrefetch ? kChunks : 1)
       for (int c = 0; c < kChunks; ++c, ++cc) {
         uint8_t* obuf = smem_out + (cc & 1) * kChunkBytes;
         // (1) staging buffer free: the store issued two chunks ago has finished reading it
@@ -489,11 +499,14 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
         const uint8_t* rbuf = smem_res + rslot * kChunkBytes;
         // (2) TMEM -> registers -> scale/shift(/residual)/ReLU -> swizzled smem
         const int col_in_tile = c * kChunkCols + half * kWarpCols;
-        const uint32_t taddr =
-            tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + col_in_tile;
-        uint32_t v[32];
-        if (OUT_F32) tmem_ld_32x32b_x16(taddr, v); else tmem_ld_32x32b_x32(taddr, v);
+        uint32_t* v = vbuf[kPrefetch ? (c & 1) : 0];
+        if (!kPrefetch) {
+          if (OUT_F32) tmem_ld_32x32b_x16(taddr0 + c * kChunkCols, v);
+          else tmem_ld_32x32b_x32(taddr0 + c * kChunkCols, v);
+        }
         tmem_ld_wait();
+        if (kPrefetch && c + 1 < kChunks)
+          tmem_ld_32x32b_x32(taddr0 + (c + 1) * kChunkCols, vbuf[(c + 1) & 1]);
         if (c == kChunks - 1) {
           // accumulator fully read: hand the TMEM buffer back to the MMA warp early
           tc_fence_before_sync();

@@ -22,36 +22,19 @@ ap.add_argument("--modes", default="infer,train")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--global-batches", default="", help="GLOBAL batch sizes (configs[4]: 64..2048 over all GPUs); "
                 "each GPU runs global/world samples; overrides --batches")
-ap.add_argument("--cpu", action="store_true", help="rank 0 also times the CPU oracle (reference PyTorch CPU path "
-                "port) per view count and mode, B=8 samples, all host cores: the CPU column of configs[4]")
+ap.add_argument("--cpu-only", action="store_true", help="time ONLY the CPU oracle (reference PyTorch CPU path port) "
+                "per view count and mode, B=8 samples, all host cores -- the CPU column of configs[4]. Run it "
+                "as its own single process: with 8 ranks spinning in NCCL the host cores are not free "
+                "(measured: 1.5 instead of 61 samples/s)")
+ap.add_argument("--cpu-json", default="", help="JSON line written by a --cpu-only run: adds cpu_samples_per_s / "
+                "gpu_over_cpu to every point")
 ap.add_argument("--max-images", type=int, default=4096, help="skip points with batch*views above this (memory)")
 ap.add_argument("--max-train-images", type=int, default=1024)
 args = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
-torch.cuda.set_device(local); dev = torch.device("cuda", local)
-if world > 1:
-    dist.init_process_group("nccl", device_id=dev)
-
-
-def timed(fn, steps):
-    for _ in range(3): fn()
-    if world > 1: dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    e0.record()
-    for _ in range(steps): fn()
-    e1.record()
-    if world > 1: dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
-    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return t.item()
-
-
 cpu = {}
-if args.cpu and rank == 0:
-    # the reference's CPU path beside every GPU point (throughput is flat in B on the CPU: B = 8)
+if args.cpu_only:
     import time
     from oracle import rotmv_oracle as O
     torch.set_num_threads(os.cpu_count())
@@ -74,28 +57,50 @@ if args.cpu and rank == 0:
                 fn(); n += 1
             cpu[(mode, v)] = 8 * n / (time.perf_counter() - t0)
     print(json.dumps({"cpu_reference": {f"{m}_v{v}": round(x, 2) for (m, v), x in cpu.items()},
-                      "cores": torch.get_num_threads(), "sample": "oracle port, B=8, fp32"}), flush=True)
+                      "cores": torch.get_num_threads(), "sample": "oracle port of the reference CPU path, B=8, fp32"}), flush=True)
+    sys.exit(0)
+if args.cpu_json:
+    rec = json.loads(open(args.cpu_json).read().strip().splitlines()[-1])["cpu_reference"]
+    cpu = {tuple([k.rsplit("_v", 1)[0], int(k.rsplit("_v", 1)[1])]): x for k, x in rec.items()}
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
 if world > 1:
-    dist.barrier()
+    dist.init_process_group("nccl", device_id=dev)
+
+
+def timed(fn, steps):
+    for _ in range(3): fn()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(steps): fn()
+    e1.record()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
 
 batches = [int(x) for x in args.batches.split(",")]
 if args.global_batches:
     batches = [int(x) // world for x in args.global_batches.split(",") if int(x) // world >= 1]
+torch.manual_seed(0)
+models = {}
 for mode in args.modes.split(","):
     for v in [int(x) for x in args.views.split(",")]:
         for b in batches:
             cap = args.max_images if mode == "infer" else args.max_train_images
             if b * v > cap:
                 continue
-            torch.manual_seed(0)
             if mode == "infer":
-                model = FeatRotationSymm(50, 3).to(dev).eval()
+                model = models.setdefault("infer", FeatRotationSymm(50, 3).to(dev)).eval()
                 sess = GraphedForward(model, b, v)
                 sess.images.normal_(); sess.rotations.copy_(RF.pose_to_rotations(torch.rand((b, v, 2), device=dev) - 0.5))
                 ms = timed(sess, args.steps)
                 del sess
             else:
-                model = FeatRotationSymm(50, 3).to(dev).train()
+                model = models.setdefault("train", FeatRotationSymm(50, 3).to(dev)).train()
                 eng = TrainEngine(model, precision="bf16", lr=1e-6, weight_decay=1e-6)
                 g = GraphedTrainStep(eng, b, v)
                 g.step(torch.randn((b, v, 3, 224, 224), device=dev), RF.pose_to_rotations(torch.rand((b, v, 2), device=dev) - 0.5),
@@ -104,7 +109,6 @@ for mode in args.modes.split(","):
                 loss = eng.loss.item()
                 assert loss == loss, "non-finite loss"
                 del g, eng
-            del model
             torch.cuda.empty_cache()
             if rank == 0:
                 rec = {"mode": mode, "views": v, "batch_per_gpu": b, "global_batch": b * world, "n_gpus": world,

