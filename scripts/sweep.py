@@ -94,13 +94,17 @@ for mode in args.modes.split(","):
             if b * v > cap:
                 continue
             if mode == "infer":
-                model = models.setdefault("infer", FeatRotationSymm(50, 3).to(dev)).eval()
+                if "infer" not in models:
+                    models["infer"] = FeatRotationSymm(50, 3).to(dev)
+                model = models["infer"].eval()
                 sess = GraphedForward(model, b, v)
                 sess.images.normal_(); sess.rotations.copy_(RF.pose_to_rotations(torch.rand((b, v, 2), device=dev) - 0.5))
                 ms = timed(sess, args.steps)
                 del sess
             else:
-                model = models.setdefault("train", FeatRotationSymm(50, 3).to(dev)).train()
+                if "train" not in models:
+                    models["train"] = FeatRotationSymm(50, 3).to(dev)
+                model = models["train"].train()
                 eng = TrainEngine(model, precision="bf16", lr=1e-6, weight_decay=1e-6)
                 g = GraphedTrainStep(eng, b, v)
                 g.step(torch.randn((b, v, 3, 224, 224), device=dev), RF.pose_to_rotations(torch.rand((b, v, 2), device=dev) - 0.5),
