@@ -574,7 +574,7 @@ def bench_train(args, ctx):
         split = {"bn_ms": 0.0, "conv_ms": 0.0, "wgrad_ms": 0.0, "other_ms": 0.0}
         for engn, _, a0, a1, what, _ in recs:
             t = a0.elapsed_time(a1)
-            if what.startswith("rmv_bn"):
+            if what.startswith("rmv_bn") or engn == "tcgen05-bnstat":   # incl. the recomputed-conv reductions
                 split["bn_ms"] += t
             elif engn in ("tcgen05", "tcgen05-stem"):
                 split["conv_ms"] += t
@@ -584,7 +584,9 @@ def bench_train(args, ctx):
                 split["other_ms"] += t
         roof.update(split)
         roof["note"] = ("bn_ms/conv_ms/wgrad_ms/other_ms: per-launch CUDA-event times of one eager "
-                        "forward+backward (Adam excluded), summed per class")
+                        "forward+backward (Adam excluded), summed per class; bn_ms = the BatchNorm statistics / "
+                        "apply kernels incl. the recomputed-conv reductions, conv_ms = forward convs and data "
+                        "gradients incl. the convs that carry a BatchNorm-apply epilogue")
     block = {"metric": METRIC_TRAIN, "value": value, "unit": UNIT,
              "n_gpus": world, "steps": args.steps, "warmup": W,
              "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

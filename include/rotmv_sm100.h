@@ -124,7 +124,8 @@ typedef struct rmv_conv_args {
    * below the SM count -- the lifter / fuser / head layers of models/rot_mv.py:35-50,91-98,179-184
    * at M = B*V rows): S CTAs share one output tile along K, write fp32 partial tiles here and a
    * second kernel adds them in a fixed order (bit-reproducible). NULL or too small = no split.
-   * rmv_splitk_workspace_bytes() is always enough. 16-byte aligned device memory. */
+   * rmv_splitk_workspace_bytes() is always enough. 16-byte aligned device memory. Launches that
+   * share one workspace must be ordered by their stream (one workspace per concurrently used stream). */
   void* workspace;
   size_t workspace_bytes;
 } rmv_conv_args;
