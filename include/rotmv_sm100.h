@@ -112,7 +112,12 @@ typedef struct rmv_conv_args {
    * n*y_sn + oh*y_sh + ow*y_sw + k (+ mask_off) -> bit (off % 8) of byte off / 8.
    * mask_bits (any tcgen05 launch with bf16 output): the value about to be stored is zeroed where its
    * mask bit is 0 -- the data gradient of a block input arrives already multiplied by the ReLU
-   * derivative of that tensor (models/resnet.py:146). */
+   * derivative of that tensor (models/resnet.py:146).
+   *   bn_mode 4 (data gradients of the mid layers, rmv_conv2d_dgrad): y = dy * mask is stored AND reduced
+   *                         for the BatchNorm backward of the layer that produced the tensor:
+   *                         stat_acc += (sum dy, sum dy*xhat) per (view, channel), xhat = (z - mean)*invstd
+   *                         with z passed as `residual` (NOT added), bn_a = mean, bn_b = invstd [2][c_out];
+   *                         stat_finalize (backward fields) finalizes k0/k1/k2/dgamma/dbeta in the launch. */
   int bn_mode;
   const float* bn_a;
   const float* bn_b;

@@ -117,7 +117,7 @@ struct Cfg {
   static constexpr int kVecBytes = (BNM == 1 ? 4 : (BNM == 2 ? 6 : 2)) * BLOCK_N * 4;
   // BNM 1 / 3: the packed ReLU-mask words of one tile, [128 rows][BLOCK_N / 32], staged so that global
   // memory sees whole 32-byte sectors per row instead of one 4-byte access per thread and chunk
-  static constexpr int kBitsBytes = (BNM == 1 || BNM == 3) ? 128 * (BLOCK_N / 32) * 4 : 0;
+  static constexpr int kBitsBytes = (BNM == 1 || BNM == 3 || BNM == 4) ? 128 * (BLOCK_N / 32) * 4 : 0;
   static constexpr int kSmemBytes = kStages * kStageBytes + kResidentB + kOutBytes + kResBytes +
                                     kVecBytes + kBitsBytes + 256 /*barriers*/ + 1024 /*align*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
@@ -153,7 +153,13 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
   using C = Cfg<BLOCK_N, RES, HALO, STATS, BNM>;
   static_assert(!STATS || (!HAS_RES && !OUT_F32), "STATS: bf16 output, no residual");
   static_assert(BNM == 0 || (!OUT_F32 && !HALO && !STATS), "BNM: bf16 output, plain tiles");
-  constexpr bool MASK = BNM == 3;       // plain epilogue + packed ReLU mask applied to the stored value
+  constexpr bool MASK = BNM == 3 || BNM == 4;   // plain epilogue + packed ReLU mask applied to the stored value
+  // BNM 4 (training data gradients of the mid layers): the masked gradient dy is stored AND reduced for
+  // the BatchNorm backward of the layer below -- sum dy, sum dy*z per (view, channel), with z (the
+  // pre-BatchNorm conv output of that layer) arriving through the residual ring (not added)
+  constexpr bool BSTAT = BNM == 4;
+  constexpr bool ST = STATS || BSTAT;   // the column-statistics machinery of the epilogue
+  static_assert(!BSTAT || HAS_RES, "BNM 4 reads z through the residual ring");
   constexpr bool BNT = BNM == 1 || BNM == 2;   // per-view BatchNorm coefficient tables
   static_assert(BNM != 2 || HAS_RES, "BNM 2 reads dy through the residual ring");
   constexpr int kChunkCols = OUT_F32 ? 32 : 64;
@@ -364,7 +370,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
     uint32_t rphase = 0;
     // STATS: thread = (column pair cp, 16-row group rg) of a staged chunk
     const int st_cp = tid_e & 31, st_rg = tid_e >> 5;
-    if (STATS) {
+    if (ST) {
       for (int i = tid_e; i < 4 * args.n_total; i += kEpiThreads) s_stat[i] = 0.f;
       epi_bar_sync(1);
     }
@@ -382,7 +388,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       // belongs to view 0 / view 1 (image & 1). Rows outside the tensor must not be counted: a 3x3
       // conv gives them non-zero values when their receptive field reaches into the image.
       uint32_t st_m0 = 0, st_m1 = 0;
-      if (STATS) {
+      if (ST) {
         if (args.stat_pix > 0) {   // flattened: rows are consecutive pixels of consecutive images
           const long long p0 = (long long)tw * args.box_w + st_rg * 16;
           const int img0 = (int)(p0 / args.stat_pix);
@@ -530,7 +536,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
             f[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]), sc.w, sh.w);
           }
         }
-        if (HAS_RES) {
+        if (HAS_RES && !BSTAT) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t j = (uint32_t)(half * 4 + q);  // 16-byte unit within the 128-byte row
@@ -588,7 +594,7 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
           const uint32_t j = (uint32_t)(half * 4 + q);
           *reinterpret_cast<uint4*>(obuf + row * 128 + ((j ^ sw) << 4)) = o;
         }
-        if (HAS_RES) {
+        if (HAS_RES && !BSTAT) {
           mbar_arrive(&res_empty[rslot]);
           if (++rslot == C::kResSlots) { rslot = 0; rphase ^= 1; }
         }
@@ -600,25 +606,29 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
                        th * args.box_h, args.k_splits > 1 ? split : tn * args.box_n);
           tma_store_commit();
         }
-        if (STATS) {
+        if (ST) {
           // BatchNorm batch statistics of the chunk just staged (the bf16 values that go to HBM;
           // rows outside the tensor are exact zeros). Thread = (column pair, 16-row group):
           // conflict-free LDS.32 (a warp reads one whole 128-byte row per step). The eight row
           // groups are combined through a slot array and ONE owner thread per (view, stat, column)
           // adds into the CTA-resident sums -- no shared-memory atomics (fp32 atomicAdd on shared
           // memory is a CAS loop and tripled the time of the HBM-bound layers).
-          float a1x = 0.f, a1y = 0.f, a2x = 0.f, a2y = 0.f;  // view 0: sum, sum of squares
+          // STATS: (sum y, sum y^2). BSTAT: (sum dy, sum dy*z) with z from the residual-ring tile.
+          float a1x = 0.f, a1y = 0.f, a2x = 0.f, a2y = 0.f;  // view 0
           float b1x = 0.f, b1y = 0.f, b2x = 0.f, b2y = 0.f;  // view 1
           const uint8_t* src = obuf + st_rg * 16 * 128 + (st_cp & 3) * 4;
+          const uint8_t* zsrc = rbuf + st_rg * 16 * 128 + (st_cp & 3) * 4;
           const uint32_t unit = (uint32_t)st_cp >> 2;
           if ((st_m0 ^ st_m1) == 0xFFFFu && (st_m0 == 0u || st_m1 == 0u)) {
             // warp-uniform fast path: all 16 rows are valid pixels of one view
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float2 z = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
-                  src + i * 128 + ((unit ^ (uint32_t)(i & 7)) << 4)));
+              const uint32_t o16 = (unit ^ (uint32_t)(i & 7)) << 4;
+              const float2 z = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + i * 128 + o16));
+              float2 w = z;
+              if (BSTAT) w = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(zsrc + i * 128 + o16));
               a1x += z.x; a1y += z.y;
-              a2x = fmaf(z.x, z.x, a2x); a2y = fmaf(z.y, z.y, a2y);
+              a2x = fmaf(z.x, w.x, a2x); a2y = fmaf(z.y, w.y, a2y);
             }
             if (st_m1 != 0u) {
               b1x = a1x; b1y = a1y; b2x = a2x; b2y = a2y;
@@ -627,14 +637,20 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float2 z = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
-                  src + i * 128 + ((unit ^ (uint32_t)(i & 7)) << 4)));
+              const uint32_t o16 = (unit ^ (uint32_t)(i & 7)) << 4;
+              const float2 z = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + i * 128 + o16));
+              float2 w = z;
+              if (BSTAT) w = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(zsrc + i * 128 + o16));
               const float m0 = (float)((st_m0 >> i) & 1u), m1 = (float)((st_m1 >> i) & 1u);
               a1x = fmaf(m0, z.x, a1x); a1y = fmaf(m0, z.y, a1y);
-              a2x = fmaf(m0 * z.x, z.x, a2x); a2y = fmaf(m0 * z.y, z.y, a2y);
+              a2x = fmaf(m0 * z.x, w.x, a2x); a2y = fmaf(m0 * z.y, w.y, a2y);
               b1x = fmaf(m1, z.x, b1x); b1y = fmaf(m1, z.y, b1y);
-              b2x = fmaf(m1 * z.x, z.x, b2x); b2y = fmaf(m1 * z.y, z.y, b2y);
+              b2x = fmaf(m1 * z.x, w.x, b2x); b2y = fmaf(m1 * z.y, w.y, b2y);
             }
+          }
+          if (BSTAT) {   // the z tile has been read: hand its ring slot back
+            mbar_arrive(&res_empty[rslot]);
+            if (++rslot == C::kResSlots) { rslot = 0; rphase ^= 1; }
           }
           // slot[rg][q][64 columns], q = view*2 + stat
           float* slot = s_slot + st_rg * 256 + 2 * st_cp;
@@ -667,11 +683,23 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
       }
     }
     if (tid_e == 0) tma_store_wait_all();
-    if (STATS) {
-      epi_bar_sync(1);  // every thread's shared-memory atomics are done
-      for (int i = tid_e; i < 4 * args.n_total; i += kEpiThreads) {
-        const float v = s_stat[i];
-        if (v != 0.f) atomicAdd(args.stat_acc + i, (double)v);
+    if (ST) {
+      epi_bar_sync(1);  // every thread's additions into s_stat are done
+      if (BSTAT) {
+        // sum dy*xhat = invstd * (sum dy*z - mean * sum dy); bn_a / bn_b carry mean / invstd [2][n_total]
+        for (int i = tid_e; i < 2 * args.n_total; i += kEpiThreads) {
+          const double s1 = (double)s_stat[2 * i], t = (double)s_stat[2 * i + 1];
+          if (s1 != 0.0 || t != 0.0) {
+            const double mu = (double)__ldg(args.bn_a + i), is = (double)__ldg(args.bn_b + i);
+            atomicAdd(args.stat_acc + 2 * i, s1);
+            atomicAdd(args.stat_acc + 2 * i + 1, is * (t - mu * s1));
+          }
+        }
+      } else {
+        for (int i = tid_e; i < 4 * args.n_total; i += kEpiThreads) {
+          const float v = s_stat[i];
+          if (v != 0.f) atomicAdd(args.stat_acc + i, (double)v);
+        }
       }
     }
   }
@@ -682,9 +710,10 @@ igemm_kernel(const __grid_constant__ IgemmArgs args) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
-  if (STATS) {
+  if (ST) {
     __shared__ unsigned int s_ticket;
-    bn_last_block_finalize<false>(args.stat_acc, args.stat_fin, args.n_total, 2, gridDim.x, &s_ticket);
+    bn_last_block_finalize<BSTAT>(args.stat_acc, args.stat_fin, args.n_total, 2, gridDim.x, &s_ticket,
+                                  args.bn_a, args.bn_b);
   }
 }
 
@@ -1053,7 +1082,7 @@ int launch(const IgemmArgs& a, int total_tiles, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, RES, HALO, STATS, BNM>;
   // STATS: [2][n_total][2] floats behind the fixed regions (they replace the 1 KiB alignment slack
   // at the end of kSmemBytes, which the 1024-byte aligned base may consume: keep it as well)
-  const int stat_bytes = STATS ? (4 * a.n_total + 8 * 256) * (int)sizeof(float) + 1024 : 0;
+  const int stat_bytes = (STATS || BNM == 4) ? (4 * a.n_total + 8 * 256) * (int)sizeof(float) + 1024 : 0;
   const int smem = C::kSmemBytes + stat_bytes;
   RMV_CHECK_ARG(smem <= 232448, "tcgen05 conv: %d bytes of shared memory needed (c_out=%d)", smem,
                 a.n_total);
@@ -1083,6 +1112,7 @@ int dispatch(const IgemmArgs& a, int total, bool has_res, bool out_f32, int bn_m
     return launch<BLOCK_N, 0, false, false, false, 1>(a, total, stream);
   }
   if (bn_mode == 2) return launch<BLOCK_N, 1, false, false, false, 2>(a, total, stream);
+  if (bn_mode == 4) return launch<BLOCK_N, 1, false, false, false, 4>(a, total, stream);
   if (bn_mode == 3) {   // plain epilogue (+ residual) with the packed ReLU mask applied: training data gradients
     if (has_res) return launch<BLOCK_N, 1, false, false, false, 3>(a, total, stream);
     return launch<BLOCK_N, 0, false, false, false, 3>(a, total, stream);
@@ -1315,7 +1345,7 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
     return 0;
   }
   if (pair) return block_n == 256 ? launch_pair<256>(a, stream) : launch_pair<128>(a, stream);
-  if (p.stat_acc != nullptr)
+  if (p.stat_acc != nullptr && p.bn_mode != 4)
     RMV_CHECK_ARG(!out_f32 && p.residual == nullptr && p.stat_views == 2 && p.bn_mode == 0,
                   "tcgen05 conv: fused BatchNorm statistics need bf16 output, no residual, 2 views");
   if (p.stat_acc != nullptr || p.bn_mode != 0 || p.mask_bits != nullptr) {
@@ -1337,21 +1367,27 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
       RMV_CHECK_ARG(fp->ticket != nullptr && p.n_img % 2 == 0 &&
                         (long long)(p.n_img / 2) * p.out_h * p.out_w > 1,
                     "tcgen05 conv: stat_finalize needs a ticket counter and an even image count");
-      a.stat_fin = bn_finalize_args(fp, false, (long long)(p.n_img / 2) * p.out_h * p.out_w);
+      a.stat_fin = bn_finalize_args(fp, p.bn_mode == 4, (long long)(p.n_img / 2) * p.out_h * p.out_w);
     }
   }
   if (p.bn_mode != 0 || p.mask_bits != nullptr) {
-    RMV_CHECK_ARG(!out_f32 && !halo && p.c_out % 128 == 0 && p.y_sw % 128 == 0 && p.y_sh % 128 == 0 &&
-                      p.y_sn % 128 == 0 && p.mask_off % 128 == 0,
+    // mask words are moved in units of block_n / 64 words per thread: whole units per row
+    const int unit = 32 * (block_n / 64);
+    RMV_CHECK_ARG(!out_f32 && !halo && p.c_out % unit == 0 && p.y_sw % unit == 0 && p.y_sh % unit == 0 &&
+                      p.y_sn % unit == 0 && p.mask_off % unit == 0,
                   "tcgen05 conv: BatchNorm-apply modes / ReLU masks need bf16 output and channel counts, "
-                  "strides and mask offsets that are multiples of 128 (whole 16-byte mask units per row)");
+                  "strides and mask offsets that are multiples of %d (whole mask units per row)", unit);
     RMV_CHECK_ARG(p.bn_mode == 0 || (p.bn_a != nullptr && p.bn_b != nullptr && p.scale == nullptr &&
-                                     p.shift == nullptr && p.mask_bits == nullptr),
-                  "tcgen05 conv: bn_mode needs bn_a/bn_b, no scale/shift, no mask_bits");
-    RMV_CHECK_ARG(p.stat_acc == nullptr, "tcgen05 conv: statistics cannot be combined with bn_mode / mask_bits");
+                                     p.shift == nullptr && (p.mask_bits == nullptr || p.bn_mode == 4)),
+                  "tcgen05 conv: bn_mode needs bn_a/bn_b, no scale/shift (mask_bits only with bn_mode 4)");
+    RMV_CHECK_ARG(p.stat_acc == nullptr || p.bn_mode == 4,
+                  "tcgen05 conv: statistics cannot be combined with bn_mode 1-3 / mask_bits");
     RMV_CHECK_ARG(p.bn_mode != 2 || (p.bn_c != nullptr && p.residual != nullptr && p.relu == 0),
                   "tcgen05 conv: bn_mode 2 needs bn_c and dy in `residual`, no ReLU");
-    RMV_CHECK_ARG(p.bn_mode >= 0 && p.bn_mode <= 2, "tcgen05 conv: bad bn_mode %d", p.bn_mode);
+    RMV_CHECK_ARG(p.bn_mode != 4 || (p.stat_acc != nullptr && p.residual != nullptr && p.mask_bits != nullptr &&
+                                     p.relu == 0 && p.stat_views == 2 && block_n <= 256),
+                  "tcgen05 conv: bn_mode 4 needs stat_acc (2 views), z in `residual`, mask_bits, no ReLU");
+    RMV_CHECK_ARG(p.bn_mode >= 0 && p.bn_mode <= 4 && p.bn_mode != 3, "tcgen05 conv: bad bn_mode %d", p.bn_mode);
     a.bn_a = p.bn_a; a.bn_b = p.bn_b; a.bn_c = p.bn_c;
     a.bn_bits = reinterpret_cast<uint32_t*>(p.bn_bits);
     a.mask_bits = reinterpret_cast<const uint32_t*>(p.mask_bits);
@@ -1365,7 +1401,7 @@ int conv_taps_tc(const ConvArgs& p, const TapList* taps, cudaStream_t stream) {
     return launch<64, 0, false, true>(a, total, stream);
   }
   const bool has_res = p.residual != nullptr;
-  const int epi_mode = p.mask_bits != nullptr ? 3 : p.bn_mode;
+  const int epi_mode = p.bn_mode == 4 ? 4 : (p.mask_bits != nullptr ? 3 : p.bn_mode);
   switch (block_n) {
     case 64: return dispatch<64>(a, total, has_res, out_f32, epi_mode, stream);
     case 128: return dispatch<128>(a, total, has_res, out_f32, epi_mode, stream);
@@ -1391,6 +1427,7 @@ int conv_dgrad_tc(const ConvArgs& p, cudaStream_t stream) {
     return conv_fwd_tc(q, stream);
   }
   RMV_CHECK_ARG(p.stride == 2, "dgrad: stride %d unsupported", p.stride);
+  RMV_CHECK_ARG(p.bn_mode != 4, "dgrad: bn_mode 4 (fused BatchNorm backward reduction) needs stride 1");
   RMV_CHECK_ARG(p.kh * p.kw <= kMaxTaps, "dgrad: filter too large");
   const int y_es = p.y_dtype == RMV_DTYPE_F32 ? 4 : 2;
   TapList tl[2][2];

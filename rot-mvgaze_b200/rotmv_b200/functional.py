@@ -175,7 +175,7 @@ def conv2d(x, w, *, stride=1, pad=0, scale=None, shift=None, residual=None, relu
     return out
 
 
-def conv2d_dgrad(dy, wt, *, stride, pad, in_hw, residual=None, out=None, mask_bits=None):
+def conv2d_dgrad(dy, wt, *, stride, pad, in_hw, residual=None, out=None, mask_bits=None, bwd_bn=None):
     """dx (+ residual) of y = conv(x, w, stride, pad) on the tcgen05 engine.
 
     dy: [N, OH, OW, K] bf16; wt: [C, kh, kw, K] = w reversed and transposed
@@ -206,6 +206,19 @@ def conv2d_dgrad(dy, wt, *, stride, pad, in_hw, residual=None, out=None, mask_bi
         a.residual = residual.data_ptr()
         a.r_sn, a.r_sh, a.r_sw = residual.stride(0), residual.stride(1), residual.stride(2)
     a.mask_bits = L.ptr(mask_bits)   # dx is zeroed where the packed ReLU mask of that tensor is 0
+    if bwd_bn is not None:
+        # bn_mode 4: dx (masked) is also reduced for the BatchNorm backward of the layer that produced
+        # the tensor: bwd_bn = dict(z, mean, invstd, acc, finalize) -- z (same geometry as dx) travels as
+        # `residual` and is NOT added
+        assert residual is None and mask_bits is not None and stride == 1
+        z = bwd_bn["z"]
+        assert tuple(z.shape) == tuple(out.shape) and z.dtype == out.dtype and z.stride(3) == 1
+        a.bn_mode = 4
+        a.residual = z.data_ptr()
+        a.r_sn, a.r_sh, a.r_sw = z.stride(0), z.stride(1), z.stride(2)
+        a.bn_a, a.bn_b = bwd_bn["mean"].data_ptr(), bwd_bn["invstd"].data_ptr()
+        a.stat_acc, a.stat_views = bwd_bn["acc"].data_ptr(), 2
+        a.stat_finalize = C.addressof(bwd_bn["finalize"])
     meta = {}
     if PROFILE is not None:
         meta = {"engine": "tcgen05", "flops": 2.0 * n * oh * ow * k * kh * kw * c,

@@ -92,6 +92,13 @@ class TrainEngine:
         # Whole step, same box: threshold 512 -> 20.10 ms, 128 -> 20.16, 256 -> 19.97.
         # RMV_BN_RECOMPUTE_MAXC overrides the threshold.
         self.recompute_max_cin = int(os.environ.get("RMV_BN_RECOMPUTE_MAXC", "256"))
+        # bf16, V == 2: the backward reduction of the mid-layer BatchNorms (bn1, bn2) runs inside the
+        # epilogue of the data-gradient kernel that produces their dy (bn_mode 4), except behind the
+        # halo 3x3 kernel (no shared memory left) and stride-2 data gradients (RMV_BN_BWD_FUSE=1: on).
+        # Measured (B=128, one lease, interleaved): 19.80 / 19.75 ms without, 19.85 / 19.68 ms with -- 26
+        # launches less but no time: the fused form only saves ONE read of dy (S/4 per layer), the z read
+        # and the mask read move into the data-gradient epilogue. Kept as a tested variant, off by default.
+        self.fuse_bn_bwd = os.environ.get("RMV_BN_BWD_FUSE", "0") != "0"
         # data parallel: all-reduce the fusion-stage gradients while the trunk backward runs
         # (RMV_DP_OVERLAP=0: one all-reduce of the whole buffer after the backward pass)
         self.dp_overlap = os.environ.get("RMV_DP_OVERLAP", "1") != "0"
@@ -382,7 +389,7 @@ class TrainEngine:
                                       "flops": 2.0 * n * dy.shape[1] * dy.shape[2] * dy.shape[3] * kh * kw * c},
                  L.load().rmv_conv2d_wgrad, C.byref(a), dy.data_ptr(), grad.data_ptr(), L.stream_ptr())
 
-    def _dgrad(self, dz, conv, tag, in_shape, residual=None, mask_bits=None):
+    def _dgrad(self, dz, conv, tag, in_shape, residual=None, mask_bits=None, bwd_bn=None):
         """dx = conv_transpose(dz, w) (+ residual) via the forward kernel with flipped filters;
         `mask_bits` (bf16 engine): packed ReLU mask of the tensor dx is the gradient of -- dx is
         zeroed where that ReLU was inactive."""
@@ -392,8 +399,8 @@ class TrainEngine:
         if self.precision == "bf16":
             return RF.conv2d_dgrad(dz, wt, stride=stride, pad=pad, in_hw=in_shape[1:3],
                                    residual=residual, out=self._buf(("dx", tag), in_shape),
-                                   mask_bits=mask_bits)
-        assert mask_bits is None
+                                   mask_bits=mask_bits, bwd_bn=bwd_bn)
+        assert mask_bits is None and bwd_bn is None
         src = dz
         if stride == 2:
             n, oh, ow, k = dz.shape
@@ -892,8 +899,24 @@ class TrainEngine:
                 src = x_in if si == 0 else ys[si - 1]        # input of conv si
                 self._wgrad(src, dz, cv, k, k, st, pd)
                 if si > 0:
-                    dy = self._dgrad(dz, cv, (bi, si + 1), src.shape)
-                    dz, _ = self._bn_bwd(bns[si - 1], zs[si - 1], dy, ys[si - 1], (bi, si))
+                    bn_lo, z_lo, y_lo = bns[si - 1], zs[si - 1], ys[si - 1]
+                    bits_lo = self._bits.get(id(y_lo))
+                    halo = k == 3 and st == 1 and cv.in_channels == 64 and cv.out_channels == 64
+                    if (self.fuse_bn_bwd and self.precision == "bf16" and self.views == 2 and st == 1
+                            and not halo and bits_lo is not None and cv.in_channels % 64 == 0):
+                        # the data gradient arrives masked and already reduced (bn_mode 4): apply only
+                        dy = self._dgrad(dz, cv, (bi, si + 1), src.shape, mask_bits=bits_lo,
+                                         bwd_bn={"z": z_lo, "mean": bn_lo.mean, "invstd": bn_lo.invstd,
+                                                 "acc": self.acc, "finalize": bn_lo.params})
+                        dz = self._buf(("dz", (bi, si)), z_lo.shape)
+                        n_, h_, w_, c_ = z_lo.shape
+                        _ck("rmv_bn_bwd_apply", z_lo.data_ptr(), dy.data_ptr(), None, 0, bn_lo.k0.data_ptr(),
+                            bn_lo.k1.data_ptr(), bn_lo.k2.data_ptr(), dz.data_ptr(), None, self.dtc, n_,
+                            h_ * w_, c_, self.views,
+                            desc="rmv_bn_bwd_apply" + (f" [{n_},{h_},{w_},{c_}]" if RF.PROFILE is not None else ""))
+                    else:
+                        dy = self._dgrad(dz, cv, (bi, si + 1), src.shape)
+                        dz, _ = self._bn_bwd(bn_lo, z_lo, dy, y_lo, (bi, si))
                 else:
                     if "ds_conv" in e:
                         dc = e["ds_conv"]

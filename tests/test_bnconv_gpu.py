@@ -264,6 +264,65 @@ def test_dgrad_mask_bits(case):
     assert (dx.float()[~keep] == 0).all()
 
 
+@pytest.mark.parametrize("case", [
+    # n, h, ci (channels of dx = the mid tensor), co (channels of dy_out), k, pad
+    (4, 56, 64, 256, 1, 0),        # dgrad of layer1's conv3: 64-wide tiles
+    (6, 14, 256, 1024, 1, 0),      # dgrad of layer3's conv3
+    (4, 28, 128, 128, 3, 1),       # dgrad of a 3x3 conv2 (boxed tiles, ragged rows masked by validity)
+    (4, 7, 512, 512, 3, 1),        # 7x7: several images per tile
+])
+def test_dgrad_bn_mode4_masked_gradient_and_backward_reduction(case):
+    """bn_mode 4 of rmv_conv2d_dgrad: dx = conv_transpose(dy, w) * mask is stored and, in the same
+    launch, reduced for the BatchNorm backward of the layer below (sum dx, sum dx*xhat per view and
+    channel) and finalized (dgamma, dbeta, k0, k1, k2) -- against autograd + the torch formulas."""
+    from rotmv_b200 import functional as RF
+
+    n, hh, ci, co, k, p_ = case
+    torch.manual_seed(sum(case) + 5)
+    x = torch.randn((n, ci, hh, hh), device="cuda", requires_grad=True)
+    w = (torch.randn((co, ci, k, k), device="cuda") / (k * k * co) ** 0.5).bfloat16().float().requires_grad_(True)
+    y = F.conv2d(x, w, stride=1, padding=p_)
+    dy = torch.randn_like(y).bfloat16().float()
+    y.backward(dy)
+    keep = torch.rand((n, hh, hh, ci), device="cuda") > 0.4
+    ref_dx = x.grad.permute(0, 2, 3, 1) * keep                     # fp32, masked
+    bits = (keep.reshape(-1, 8).int() * (1 << torch.arange(8, device="cuda")).view(1, 8)).sum(1).to(torch.uint8)
+    z = torch.randn((n, hh, hh, ci), device="cuda").bfloat16()     # pre-BatchNorm output of the layer below
+    pr, t = _bn_params(ci)
+    for v in range(2):
+        zv = z[v::2].double().reshape(-1, ci)
+        t["mean"][v] = zv.mean(0).float()
+        t["invstd"][v] = (1.0 / torch.sqrt(zv.var(0, unbiased=False) + 1e-5)).float()
+    acc = torch.zeros((2, ci, 2), device="cuda", dtype=torch.float64)
+    wt = w.detach().permute(1, 2, 3, 0).flip(1, 2).contiguous().bfloat16()
+    dx = RF.conv2d_dgrad(dy.permute(0, 2, 3, 1).contiguous().bfloat16(), wt, stride=1, pad=p_, in_hw=(hh, hh),
+                         mask_bits=bits, bwd_bn={"z": z, "mean": t["mean"], "invstd": t["invstd"], "acc": acc,
+                                                 "finalize": pr})
+    torch.cuda.synchronize()
+    err = (dx.float() - ref_dx).abs().max().item()
+    assert err <= 1e-2 * ref_dx.abs().max().item() + 1e-3, (case, err)
+    assert (dx.float()[~keep] == 0).all()
+    assert float(acc.abs().max()) == 0.0 and int(t["ticket"]) == 0          # finalized and reset
+    # reductions of the STORED (bf16) gradient, as the apply pass will read it
+    d = dx.double()
+    s1 = torch.stack([d[v::2].sum(dim=(0, 1, 2)) for v in range(2)])
+    xhat = torch.empty_like(d)
+    for v in range(2):
+        xhat[v::2] = (z[v::2].double() - t["mean"][v].double()) * t["invstd"][v].double()
+    s2 = torch.stack([(d * xhat)[v::2].sum(dim=(0, 1, 2)) for v in range(2)])
+    scale1 = d.abs().sum(dim=(0, 1, 2)).max().item()
+    assert (t["dbeta"].double() - s1.sum(0)).abs().max().item() <= 1e-4 * scale1
+    assert (t["dgamma"].double() - s2.sum(0)).abs().max().item() <= 2e-4 * (d * xhat).abs().sum(dim=(0, 1, 2)).max().item()
+    count = (n // 2) * hh * hh                                             # the library's count per view (even n)
+    if n % 2 == 0:
+        k0 = t["gamma"].double() * t["invstd"].double()
+        k1 = -k0 * t["invstd"].double() * s2 / count
+        k2 = -k0 * s1 / count - k1 * t["mean"].double()
+        assert ((t["k0"].double() - k0) / k0).abs().max().item() <= 1e-5
+        assert (t["k1"].double() - k1).abs().max().item() <= 2e-4 * k1.abs().max().item() + 1e-9
+        assert (t["k2"].double() - k2).abs().max().item() <= 2e-4 * k2.abs().max().item() + 1e-9
+
+
 def test_mask_bits_kernel():
     from rotmv_b200 import _lib as L
     from rotmv_b200 import functional as RF
@@ -302,7 +361,8 @@ def test_recompute_step_matches_materialised_step():
         model = model.cuda().train()
         eng = TrainEngine(model, precision="fp32" if mode == "fp32" else "bf16", lr=1e-3, weight_decay=1e-6)
         eng.recompute_bn = mode == "recompute"
-        eng.recompute_max_cin = 4096      # every bottleneck's conv3 / downsample, not only layer1-2
+        eng.recompute_max_cin = 4096      # every bottleneck's conv3 / downsample, not only layer1-3
+        eng.fuse_bn_bwd = mode == "recompute"   # and the mid-layer backward reductions inside the data gradients
         eng.forward_backward(images.cuda(), rot.cuda(), gt.cuda())
         torch.cuda.synchronize()
         named = dict(model.named_parameters())
