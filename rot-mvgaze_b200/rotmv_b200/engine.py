@@ -88,6 +88,13 @@ class InferenceEngine:
         self.encode_rot = bool(model._encode_rotmat) and not model._ignore_rotmat
         self.share_feat = bool(model._share_feature)
         self.chunk = max(1, int(model.trunk_chunk))
+        # front chunking (bf16 bottleneck trunk): stem + max-pool + the first `front_blocks` blocks
+        # (layer1) run in groups of `front_chunk` images whose tensors fit the 126 MB L2, so that a
+        # block's output is still on chip when it is re-read as the next conv's input and as the
+        # residual; the deeper stages run on the whole chunk for tile occupancy. 0 = off.
+        import os
+        self.front_chunk = int(os.environ.get("ROTMV_FRONT_CHUNK", "0"))
+        self.front_blocks = int(os.environ.get("ROTMV_FRONT_BLOCKS", "3"))
         trunk = model._feat_extractor[0]
         dev = trunk.conv1.weight.device
         if dev.type != "cuda":
@@ -153,17 +160,63 @@ class InferenceEngine:
         return t
 
     # ------------------------------------------------------------------------------------------
-    def _conv(self, x, spec, tag, relu, residual=None):
+    def _conv(self, x, spec, tag, relu, residual=None, out=None):
         n, h, w, _ = x.shape
         oh = (h + 2 * spec.pad - spec.w.shape[1]) // spec.stride + 1
         ow = (w + 2 * spec.pad - spec.w.shape[2]) // spec.stride + 1
-        out = self._buf(tag, (n, oh, ow, spec.w.shape[0]))
+        if out is None:
+            out = self._buf(tag, (n, oh, ow, spec.w.shape[0]))
         return RF.conv2d(x, spec.w, stride=spec.stride, pad=spec.pad, scale=spec.scale,
                          shift=spec.shift, residual=residual, relu=relu, out=out)
 
     def trunk(self, imgs: torch.Tensor, feat0: torch.Tensor, feat1: torch.Tensor) -> None:
         """imgs [n,3,H,W] fp32 NCHW -> global-average-pooled features into feat0[:, :C], feat1[:, :C]
         (reference `_feat_extractor`, models/rot_mv.py:124-128,196-197)."""
+        n = imgs.shape[0]
+        g = self.front_chunk
+        if g > 0 and n > g and self.precision == "bf16" and self.kind == "bottleneck":
+            nb = min(self.front_blocks, len(self.blocks))
+            x_full = None
+            for s in range(0, n, g):
+                e = min(n, s + g)
+                x = self._stem_pool(imgs[s:e])
+                for bi in range(nb):
+                    spec = self.blocks[bi]
+                    t = self._conv(x, spec["c1"], "t1", True)
+                    t = self._conv(t, spec["c2"], "t2", True)
+                    skip = self._conv(x, spec["ds"], "ds", False) if "ds" in spec else x
+                    if bi == nb - 1:
+                        if x_full is None:
+                            k = spec["c3"].w.shape[0]
+                            x_full = self._buf(("front_out",), (n, t.shape[1], t.shape[2], k))
+                        x = self._conv(t, spec["c3"], None, True, residual=skip, out=x_full[s:e])
+                    else:
+                        x = self._conv(t, spec["c3"], ("out", bi & 1), True, residual=skip)
+            x = x_full
+            for bi in range(nb, len(self.blocks)):
+                spec = self.blocks[bi]
+                t = self._conv(x, spec["c1"], "t1", True)
+                t = self._conv(t, spec["c2"], "t2", True)
+                skip = self._conv(x, spec["ds"], "ds", False) if "ds" in spec else x
+                x = self._conv(t, spec["c3"], ("out", bi & 1), True, residual=skip)
+            RF.avgpool(x, feat0, feat1)
+            return
+        x = self._stem_pool(imgs)
+        for bi, spec in enumerate(self.blocks):
+            out_tag = ("out", bi & 1)
+            if self.kind == "bottleneck":
+                t = self._conv(x, spec["c1"], "t1", True)
+                t = self._conv(t, spec["c2"], "t2", True)
+                skip = self._conv(x, spec["ds"], "ds", False) if "ds" in spec else x
+                x = self._conv(t, spec["c3"], out_tag, True, residual=skip)
+            else:
+                t = self._conv(x, spec["c1"], "t1", True)
+                skip = self._conv(x, spec["ds"], "ds", False) if "ds" in spec else x
+                x = self._conv(t, spec["c2"], out_tag, True, residual=skip)
+        RF.avgpool(x, feat0, feat1)
+
+    def _stem_pool(self, imgs: torch.Tensor) -> torch.Tensor:
+        """conv7x7/s2 + BN + ReLU + max-pool of a group of images (models/resnet.py:184-189,262-265)."""
         n = imgs.shape[0]
         if imgs.dtype == torch.uint8:
             # raw uint8 HWC images: ToTensor + Normalize folded into the stem loader (SURVEY 8f n1)
@@ -179,19 +232,8 @@ class InferenceEngine:
         else:
             y = RF.conv2d_nchw_input(imgs, self.stem_w, stride=2, pad=3, scale=self.stem_scale,
                                      shift=self.stem_shift, relu=True)
-        x = RF.maxpool3x3s2(y)
-        for bi, spec in enumerate(self.blocks):
-            out_tag = ("out", bi & 1)
-            if self.kind == "bottleneck":
-                t = self._conv(x, spec["c1"], "t1", True)
-                t = self._conv(t, spec["c2"], "t2", True)
-                skip = self._conv(x, spec["ds"], "ds", False) if "ds" in spec else x
-                x = self._conv(t, spec["c3"], out_tag, True, residual=skip)
-            else:
-                t = self._conv(x, spec["c1"], "t1", True)
-                skip = self._conv(x, spec["ds"], "ds", False) if "ds" in spec else x
-                x = self._conv(t, spec["c2"], out_tag, True, residual=skip)
-        RF.avgpool(x, feat0, feat1)
+        ph, pw = (y.shape[1] - 1) // 2 + 1, (y.shape[2] - 1) // 2 + 1
+        return RF.maxpool3x3s2(y, out=self._buf("pool", (n, ph, pw, y.shape[3]), y.dtype))
 
     # ------------------------------------------------------------------------------------------
     def run(self, images: torch.Tensor, rotations: torch.Tensor, *, want_all: bool = True,

@@ -345,12 +345,13 @@ def nchw_to_nhwc(x_nchw, dtype):
     return y
 
 
-def maxpool3x3s2(x):
-    _need_cuda(x)
+def maxpool3x3s2(x, out=None):
+    _need_cuda(x, out)
     assert x.is_contiguous()
     n, h, w, c = x.shape
     oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-    y = torch.empty((n, oh, ow, c), dtype=x.dtype, device=x.device)
+    y = out if out is not None else torch.empty((n, oh, ow, c), dtype=x.dtype, device=x.device)
+    assert tuple(y.shape) == (n, oh, ow, c) and y.dtype == x.dtype and y.is_contiguous()
     _call("rmv_maxpool3x3s2_fwd", {"desc": "rmv_maxpool3x3s2_fwd"}, L.load().rmv_maxpool3x3s2_fwd, x.data_ptr(), y.data_ptr(), n, h, w, c,
                                           L.dtype_code(x.dtype), L.stream_ptr())
     return y
