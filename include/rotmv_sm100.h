@@ -137,6 +137,14 @@ typedef struct rmv_conv_args {
 
 int rmv_conv2d_fwd(const rmv_conv_args* args, void* stream);
 
+/* Entry points that are NOT on the product path (kept for the tests and as building blocks; the
+ * engines call the fused forms): rmv_bn_stats + rmv_bn_finalize and rmv_bn_bwd_reduce +
+ * rmv_bn_bwd_finalize (the product uses rmv_bn_stats_finalize / rmv_bn_bwd_reduce_finalize or the
+ * finalize-in-launch forms via rmv_bn_params), rmv_maxpool3x3s2_bwd (the product uses the index form
+ * rmv_maxpool3x3s2_fwd_idx / _bwd_idx), rmv_stem_im2col and rmv_nchw_to_nhwc (layout helpers of the
+ * tests; the stem kernel builds its im2col rows in shared memory). rmv_dilate2 serves the fp32 (FFMA)
+ * parity engine's stride-2 data gradient only. */
+
 /* Data gradient of y = conv(x, w, stride, pad) on the tcgen05 engine (the backward of
  * models/resnet.py:31-47 that autograd/cuDNN computes for trainer.py:142):
  *     dx[n,ih,iw,c] (+ residual) = sum_{r,s,k} dy[n,oh,ow,k] * w[k,c,r,s],   ih = oh*stride - pad + r

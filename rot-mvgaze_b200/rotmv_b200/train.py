@@ -322,7 +322,7 @@ class TrainEngine:
 
     def _conv_bn_fwd(self, bn: _BN, x, w, stride, residual, relu, tag):
         """y = relu?(BN_train(conv1x1(x, w)) + residual) without writing the conv output: statistics
-        from the transposed recompute GEMM (rmv_conv_bn_stats), coefficients (rmv_bn_finalize), then
+        from the transposed recompute GEMM (rmv_conv_bn_stats, coefficients by its last thread block), then
         the conv again with the BatchNorm-apply epilogue (bn_mode 1), which also packs the ReLU mask."""
         n, h, wd, _ = x.shape
         oh, ow = (h - 1) // stride + 1, (wd - 1) // stride + 1
@@ -338,7 +338,7 @@ class TrainEngine:
     def _conv_bn_bwd(self, bn: _BN, x, w, stride, dy, tag):
         """dz of z = conv1x1(x, w) under y = BN_train(z) for a dy that is ALREADY multiplied by the
         derivative of the ReLU behind the BatchNorm: reductions over the recomputed z
-        (rmv_conv_bn_bwd_reduce), coefficients (rmv_bn_bwd_finalize), then the conv again with the
+        (rmv_conv_bn_bwd_reduce, coefficients by its last thread block), then the conv again with the
         backward-apply epilogue (bn_mode 2: dz = k0*dy + k1*z + k2)."""
         n, oh, ow, c = dy.shape
         v = self.views
