@@ -780,8 +780,7 @@ class TrainEngine:
         (list of [B*V, 2] fp32), and on `send(ext)` runs the backward -- from the fused loss when
         `ext` is None (`gt` required), from the caller's d(loss)/d(pred) list otherwise (`gt` may be
         None: rotmv_b200.module's autograd bridge). Returns {"loss", "preds", "pool_out"}."""
-        if not images.is_cuda:
-            raise L.RotmvError("images must be CUDA tensors (there is no CPU path)")
+        self._require_device(images)
         b, v = images.shape[0], images.shape[1]
         if v > self.max_views:
             raise ValueError(f"views={v} exceeds max_views={self.max_views}")
@@ -792,29 +791,13 @@ class TrainEngine:
         imgs = images.reshape(m, *images.shape[2:]).float().contiguous()
         rot = rotations.float().contiguous()
         gt_flat = None if gt is None else gt.float().reshape(m, 2).contiguous()
-        self.flat_g.zero_()
-        self.loss.zero_()
-        if self._wjobs_ready:
-            self._run_wjobs()
+        self._begin_step()
 
         # ================================ forward ================================
         # stem (models/resnet.py:262-265)
-        if self.precision == "bf16":
-            wp = RF.stem_pack_weights(self.stem_conv.weight.detach())
-            z0 = RF.stem_conv(imgs, wp, None, None, out=self._buf("z_stem", (m, 112, 112, 64))
-                              if imgs.shape[2] == 224 and imgs.shape[3] == 224 else None, relu=False)
-            stem_x, stem_xs = None, None
-        else:
-            w7 = self._w_fwd(self.stem_conv, "stem")
-            z0 = RF.conv2d_nchw_input(imgs, w7, stride=2, pad=3)
-            xv = imgs.permute(0, 2, 3, 1)
-            stem_x, stem_xs = imgs, (tuple(xv.shape), (xv.stride(0), xv.stride(1), xv.stride(2), xv.stride(3)))
+        z0 = self._stem_fwd(imgs)
         y0 = self._bn_fwd(self.stem_bn, z0, None, True, "y_stem")
-        ph, pw = (y0.shape[1] - 1) // 2 + 1, (y0.shape[2] - 1) // 2 + 1
-        x = self._buf("pool", (m, ph, pw, 64))
-        pool_idx = self._buf("pool_idx", (m, ph, pw, 64), torch.uint8)
-        _ck("rmv_maxpool3x3s2_fwd_idx", y0.data_ptr(), x.data_ptr(), pool_idx.data_ptr(), m,
-            y0.shape[1], y0.shape[2], 64, dtc)
+        x, pool_idx = self._maxpool_fwd(y0)
         pool_out = x
         saved = []
         for bi, e in enumerate(self.blocks):
@@ -867,13 +850,10 @@ class TrainEngine:
             hook(*self.buckets[0])
         # trunk
         last = saved[-1][4]
-        d_out = self._buf(("dx", "avg"), last.shape)
-        _ck("rmv_avgpool_bwd", dimg.data_ptr(), dimg.stride(0), d_out.data_ptr(), m,
-            last.shape[1] * last.shape[2], last.shape[3], dtc)
+        d_out = self._avgpool_bwd(dimg, last)
         pre_masked = False   # d_out already multiplied by the ReLU derivative of the block output
         if self.precision == "bf16" and self._bits.get(id(last)) is not None and self._use_recompute(self.blocks[-1]["convs"][-1]):
-            _ck("rmv_mask_bits", d_out.data_ptr(), self._bits[id(last)].data_ptr(), d_out.data_ptr(),
-                d_out.numel(), dtc)
+            self._mask_grad(d_out, self._bits[id(last)])
             pre_masked = True
         for bi in reversed(range(len(self.blocks))):
             e = self.blocks[bi]
@@ -932,25 +912,80 @@ class TrainEngine:
                     d_out = self._dgrad(dz, cv, (bi, 1), x_in.shape, residual=res, mask_bits=in_bits)
             if hook is not None and self._stage_first.get(bi) in self._bucket_by_stage:
                 hook(*self._bucket_by_stage[self._stage_first[bi]])   # this stage's gradients are final
-        d_y0 = self._buf("dy_stem", y0.shape)
-        _ck("rmv_maxpool3x3s2_bwd_idx", pool_idx.data_ptr(), d_out.data_ptr(), d_y0.data_ptr(), m,
-            y0.shape[1], y0.shape[2], y0.shape[3], dtc)
+        d_y0 = self._maxpool_bwd(pool_idx, d_out, y0)
         dz0, _ = self._bn_bwd(self.stem_bn, z0, d_y0, y0, "stem")
-        if stem_x is None:   # bf16: tcgen05 stem weight gradient straight from the fp32 NCHW images
+        self._stem_wgrad(imgs, dz0)
+        if hook is not None:
+            hook(*self.buckets[3])
+        self._end_step()
+        return {"loss": self.loss, "preds": preds, "pool_out": pool_out}
+
+    # ---- the trunk's non-convolution steps as tensor-level methods (the kernels behind them are raw
+    # C-ABI calls; tests/test_train_trunk_host.py replaces these methods by their torch formulas to
+    # check the orchestration of `_fwd_bwd` on the CPU) -----------------------------------------------
+    def _require_device(self, images) -> None:
+        if not images.is_cuda:
+            raise L.RotmvError("images must be CUDA tensors (there is no CPU path)")
+
+    def _begin_step(self) -> None:
+        self.flat_g.zero_()
+        self.loss.zero_()
+        if self._wjobs_ready:
+            self._run_wjobs()
+
+    def _end_step(self) -> None:
+        if not self._wjobs_ready:
+            self._finish_wjobs()
+
+    def _stem_fwd(self, imgs):
+        """conv7x7/s2 of the fp32 NCHW images -> z0 NHWC (models/resnet.py:184-186,262), no BatchNorm yet."""
+        m = imgs.shape[0]
+        if self.precision == "bf16":
+            wp = RF.stem_pack_weights(self.stem_conv.weight.detach())
+            return RF.stem_conv(imgs, wp, None, None, out=self._buf("z_stem", (m, 112, 112, 64))
+                                if imgs.shape[2] == 224 and imgs.shape[3] == 224 else None, relu=False)
+        return RF.conv2d_nchw_input(imgs, self._w_fwd(self.stem_conv, "stem"), stride=2, pad=3)
+
+    def _stem_wgrad(self, imgs, dz0) -> None:
+        m = imgs.shape[0]
+        if self.precision == "bf16":   # tcgen05 stem weight gradient straight from the fp32 NCHW images
             RF._call("rmv_stem_wgrad", {"desc": "stem wgrad (tcgen05)", "engine": "tcgen05-wgrad",
-                                        "flops": 2.0 * m * y0.shape[1] * y0.shape[2] * 64 * 147},
+                                        "flops": 2.0 * m * dz0.shape[1] * dz0.shape[2] * 64 * 147},
                      L.load().rmv_stem_wgrad, imgs.data_ptr(), dz0.data_ptr(),
                      self._buf("stem_wg", (L.load().rmv_stem_wgrad_workspace_bytes() // 4,),
                                torch.float32).data_ptr(),
                      self.grads[id(self.stem_conv.weight)].data_ptr(), m, imgs.shape[2], imgs.shape[3],
                      L.stream_ptr())
         else:
-            self._wgrad(stem_x, dz0, self.stem_conv, 7, 7, 2, 3, x_strides=stem_xs)
-        if hook is not None:
-            hook(*self.buckets[3])
-        if not self._wjobs_ready:
-            self._finish_wjobs()
-        return {"loss": self.loss, "preds": preds, "pool_out": pool_out}
+            xv = imgs.permute(0, 2, 3, 1)
+            self._wgrad(imgs, dz0, self.stem_conv, 7, 7, 2, 3,
+                        x_strides=(tuple(xv.shape), (xv.stride(0), xv.stride(1), xv.stride(2), xv.stride(3))))
+
+    def _maxpool_fwd(self, y0):
+        """MaxPool2d(3, 2, 1) with the winning window position recorded for the backward."""
+        m, h, w, c = y0.shape
+        ph, pw = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        x = self._buf("pool", (m, ph, pw, c))
+        idx = self._buf("pool_idx", (m, ph, pw, c), torch.uint8)
+        _ck("rmv_maxpool3x3s2_fwd_idx", y0.data_ptr(), x.data_ptr(), idx.data_ptr(), m, h, w, c, self.dtc)
+        return x, idx
+
+    def _maxpool_bwd(self, idx, d_out, y0):
+        d_y0 = self._buf("dy_stem", y0.shape)
+        _ck("rmv_maxpool3x3s2_bwd_idx", idx.data_ptr(), d_out.data_ptr(), d_y0.data_ptr(), y0.shape[0],
+            y0.shape[1], y0.shape[2], y0.shape[3], self.dtc)
+        return d_y0
+
+    def _avgpool_bwd(self, dimg, last):
+        """d(block output) of the global average pool: dimg [m, C] / (H*W) broadcast over the pixels."""
+        d_out = self._buf(("dx", "avg"), last.shape)
+        _ck("rmv_avgpool_bwd", dimg.data_ptr(), dimg.stride(0), d_out.data_ptr(), last.shape[0],
+            last.shape[1] * last.shape[2], last.shape[3], self.dtc)
+        return d_out
+
+    def _mask_grad(self, d, bits) -> None:
+        """d *= ReLU derivative recorded as a packed sign mask (in place)."""
+        _ck("rmv_mask_bits", d.data_ptr(), bits.data_ptr(), d.data_ptr(), d.numel(), self.dtc)
 
 
 class GraphedTrainStep:

@@ -60,15 +60,16 @@ class HostEngine(T.TrainEngine):
         p = pred.detach().clone().requires_grad_(True)
         _head_loss_value(p, gt_flat, scale, views, cfg["reference_decay"]).backward()
         dpred.copy_(p.grad)
-        dg.copy_((g > 0).float() * (p.grad @ h2.weight.detach()))
-        self.grads[id(h2.weight)] += p.grad.t() @ g
-        self.grads[id(h2.bias)] += p.grad.sum(0)
+        dp = p.grad.to(g.dtype)
+        dg.copy_((g > 0).to(g.dtype) * (dp @ h2.weight.detach()))
+        self.grads[id(h2.weight)] += dp.t() @ g
+        self.grads[id(h2.bias)] += dp.sum(0)
 
 
     def _head_bwd_ext(self, dpred, g, h2, dg):
         """rmv_head_loss_bwd with gt == NULL (external d(loss)/d(pred)): Linear(512,2) + ReLU backward."""
-        dp = dpred.detach().float().reshape(g.shape[0], 2)
-        dg.copy_((g > 0).float() * (dp @ h2.weight.detach()))
+        dp = dpred.detach().to(g.dtype).reshape(g.shape[0], 2)
+        dg.copy_((g > 0).to(g.dtype) * (dp @ h2.weight.detach()))
         self.grads[id(h2.weight)] += dp.t() @ g
         self.grads[id(h2.bias)] += dp.sum(0)
 
