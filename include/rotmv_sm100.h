@@ -394,6 +394,31 @@ int rmv_conv2d_wgrad_tc(const rmv_conv_args* args, const void* dy, float* dw_krs
 int rmv_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                   double* hyper, long long n, int decoupled, float grad_scale, void* stream);
 
+/* ---- re-layout kernels of the constructor variants (off the path main.py builds) ---- */
+/* dst[i0,i1,i2] = (accumulate ? dst[i0,i1,i2] : 0) + src[i0,i1,i2] * (scale ? scale[i2] : 1) over an
+ * n0 x n1 x n2 index space with ELEMENT strides (ss*, ds*) and independent dtypes (RMV_DTYPE_F32 /
+ * RMV_DTYPE_BF16; arithmetic in fp32, one rounding on the store). Replaces the tensor copies of
+ * ImageRotmatFeatFuser / RotFeatFuser: zero-padded corners of the 3593-wide layers and their
+ * transposes (a source contiguous along i1 with a destination contiguous along i2 runs as 32x32
+ * shared-memory tiles), the 9 rotation entries appended per row (models/rot_mv.py:53-67,225-231),
+ * the cat(...,-1).flatten(-2,-1) interleave [3][2][nvec] of two [3][nvec] features
+ * (models/rot_mv.py:80-84,243-248), x / (running_std + eps) of IntensityBatchNorm as `scale`
+ * (:32), and the backward scatter / accumulation of all of these. src and dst must not overlap. */
+int rmv_strided_copy(const void* src, int src_dtype, long long ss0, long long ss1, long long ss2,
+                     void* dst, int dst_dtype, long long ds0, long long ds1, long long ds2, int n0,
+                     int n1, int n2, const float* scale, int accumulate, void* stream);
+/* Train-mode IntensityBatchNorm statistics of ONE call (models/rot_mv.py:13-32): feat is
+ * [rows][3][nvec] with row stride ld (elements); intensity[r][j] = ||feat[r,:,j]||_2 (detached in the
+ * reference), std_j = sqrt(max(var_r(intensity) [biased], eps)), running[j] = (1-momentum) *
+ * running[j] + momentum * std_j (the buffer the reference calls `running_mean`), scale_out[j] =
+ * 1 / (running[j] + eps): the factor this call applies (through rmv_strided_copy's `scale`). */
+int rmv_intensity_bn_train(const void* feat, long long ld, int dtype, int rows, int nvec,
+                           float* running, float momentum, float eps, float* scale_out,
+                           void* stream);
+/* Zero `bytes` bytes at dst: gradient accumulators (flat gradient buffer, split-K
+ * weight-gradient scratch; the reference's optimizer.zero_grad(), trainer.py:141) and padding. */
+int rmv_fill_zero(void* dst, size_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

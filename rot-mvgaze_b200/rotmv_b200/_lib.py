@@ -123,6 +123,10 @@ SIGNATURES = {
     "rmv_conv2d_wgrad": (_i, [C.POINTER(ConvArgs), _vp, _vp, _vp]),
     "rmv_conv2d_wgrad_tc": (_i, [C.POINTER(ConvArgs), _vp, _vp, _vp]),
     "rmv_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
+    # constructor variants: re-layout kernels
+    "rmv_strided_copy": (_i, [_vp, _i, _ll, _ll, _ll, _vp, _i, _ll, _ll, _ll, _i, _i, _i, _vp, _i, _vp]),
+    "rmv_intensity_bn_train": (_i, [_vp, _ll, _i, _i, _i, _vp, _f, _f, _vp, _vp]),
+    "rmv_fill_zero": (_i, [_vp, C.c_size_t, _vp]),
 }
 
 

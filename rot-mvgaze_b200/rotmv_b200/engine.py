@@ -246,6 +246,19 @@ class InferenceEngine:
             self.run_trunk(imgs, s, min(m, s + self.chunk))
         return self.run_fusion(b, v, rot, want_all=want_all, gt=gt)
 
+    def _per_view(self, t2d: torch.Tensor, tail, b: int, v: int):
+        """Output assembly (models/rot_mv.py:205-211,256-266): the rows of a [b*v, width] row-strided
+        buffer (sample-major, view-minor; bf16 or fp32) as v contiguous fp32 tensors [b, *tail] -- the
+        reference's per-view dict entries -- one rmv_strided_copy (gather + cast) each."""
+        width = int(t2d.shape[1])
+        src = t2d.as_strided((b, v, width), (v * t2d.stride(0), t2d.stride(0), 1), t2d.storage_offset())
+        outs = []
+        for k in range(v):
+            o = torch.empty((b,) + tuple(tail), device=self.device, dtype=torch.float32)
+            RF.strided_copy(src[:, k], o.view(b, width))
+            outs.append(o)
+        return outs
+
     def _empty_outputs(self, v: int, want_all: bool, gt) -> Dict[str, Any]:
         """An empty batch launches nothing and returns empty tensors of the reference's shapes (the
         reference in eval mode returns [0,2048] / [0,3,512] / [0,2] tensors for B = 0)."""
@@ -313,8 +326,7 @@ class InferenceEngine:
         out: Dict[str, Any] = {"num_iter": self.num_iter}
 
         def per_view(t2d, tail):
-            t = t2d.float().reshape(b, v, *tail)
-            return [t[:, k].contiguous() for k in range(v)]
+            return self._per_view(t2d, tail, b, v)
 
         if want_all:
             for k, t in enumerate(per_view(x_buf[:, :self.fc_dim], (self.fc_dim,))):
@@ -345,9 +357,8 @@ class InferenceEngine:
                          aux_decay=cfg["reference_decay"])            # Linear(512,2) (+ loss)
             if want_all or i == self.num_iter - 1:
                 it: Dict[str, Any] = {}
-                pv = pred.view(b, v, 2)
-                for k in range(v):
-                    it[f"pred_gaze_{k}"] = pv[:, k].contiguous()
+                for k, t in enumerate(per_view(pred, (2,))):
+                    it[f"pred_gaze_{k}"] = t
                 if want_all:
                     for k, t in enumerate(per_view(feat_y, (3, self.nvec))):
                         it[f"feat_{k}"] = t
@@ -359,10 +370,10 @@ class InferenceEngine:
     # ------------------------------------------------------------------------------------------
     def _run_fusion_variant(self, b: int, rot: torch.Tensor, *, want_all: bool, gt) -> Dict[str, Any]:
         """encode_rotmat / share_feature (two views). The GEMMs, the rotation gather
-        and the head/loss are the same sm_100a kernels as the default configuration; the few
-        re-layout copies these variants need (9 rotation entries per row, the [3][2][512]
-        interleave of RotFeatFuser's input) are plain tensor copies -- they are not on the path
-        main.py builds."""
+        and the head/loss are the same sm_100a kernels as the default configuration; the re-layout
+        these variants need (zero padding, 9 rotation entries per row, the [3][2][512] interleave of
+        RotFeatFuser's input with IntensityBatchNorm's factor) runs in `rmv_strided_copy` /
+        `rmv_fill_zero` (csrc/variant_glue.cu) over strided views."""
         v, m = 2, 2 * b
         fc, nv = self.fc_dim, self.nvec
         x_buf, y_buf = self._xy(m)            # [m, fc + 3*nv]; avgpool wrote the image feature
@@ -374,8 +385,7 @@ class InferenceEngine:
         out: Dict[str, Any] = {"num_iter": self.num_iter}
 
         def per_view(t2d, tail):
-            t = t2d.float().reshape(b, v, *tail)
-            return [t[:, k].contiguous() for k in range(v)]
+            return self._per_view(t2d, tail, b, v)
 
         if want_all:
             src = f_init if self.share_feat else img   # share_feature: img_feat := lifted feature (:201-203)
@@ -394,18 +404,17 @@ class InferenceEngine:
         if self.encode_rot:
             p = self.fuse_pad
             xin = self._buf("Xenc", (m, p))
-            xin.zero_()
-            xin[:, :fc].copy_(img)
+            RF.fill_zero(xin)
+            RF.strided_copy(img, xin[:, :fc])
             # row (b, view) gets R_{view <- partner}: rot[b,0,1] = rot_10, rot[b,1,0] = rot_01 (:193-194)
-            pair = torch.stack([rot[:, 0, 1], rot[:, 1, 0]], dim=1).reshape(m, 9)
-            xin[:, fc + 3 * nv: fc + 3 * nv + 9].copy_(pair)
+            RF.strided_copy(rot.view(b, v * v, 9)[:, 1:3], xin.view(b, v, p)[:, :, fc + 3 * nv: fc + 3 * nv + 9])
             h1, h2 = self._buf("Henc1", (m, p)), self._buf("Henc2", (m, p))
         else:
             xin = self._buf("Xsh", (m, 6 * nv))
             yin = self._buf("Ysh", (m, 6 * nv))
             h1, h2 = self._buf("Hsh1", (m, 6 * nv)), self._buf("Hsh2", (m, 6 * nv))
             rotf = self._buf("rotF", (m, 3 * nv))
-            yin.view(m, 3, 2, nv)[:, :, 0].copy_(f_init.view(m, 3, nv))   # head input: cat(img_feat, F, -1)
+            RF.strided_copy(f_init.view(m, 3, nv), yin.view(m, 3, 2, nv)[:, :, 0])   # head input: cat(img_feat, F, -1)
         for i in range(self.num_iter):
             f_new = self._buf(("Fnew", i & 1), (m, 3 * nv))
             f1, f2, f3 = self.fusers[i]
@@ -413,29 +422,28 @@ class InferenceEngine:
                 # partner feature, NOT rotated (the matrix itself is an input) -> xin[:, fc:fc+3nv]
                 RF.rotate_gather(f_old, rot, xin[:, fc:fc + 3 * nv], b, v, nv, False)
             else:
-                s = self.int_bn[i].to(self.dtype)
+                s = self.int_bn[i]                                           # fp32 [nv]: 1 / (running_std + eps)
                 RF.rotate_gather(f_old, rot, rotf, b, v, nv, True)          # R_{self<-partner} F_partner
                 xv = xin.view(m, 3, 2, nv)
-                xv[:, :, 0] = f_init.view(m, 3, nv) * s                      # IntensityBatchNorm(feat_0)
-                xv[:, :, 1] = rotf.view(m, 3, nv) * s                        # IntensityBatchNorm(rotated)
+                RF.strided_copy(f_init.view(m, 3, nv), xv[:, :, 0], scale=s)   # IntensityBatchNorm(feat_0)
+                RF.strided_copy(rotf.view(m, 3, nv), xv[:, :, 1], scale=s)     # IntensityBatchNorm(rotated)
             RF.linear(xin, f1.w, f1.b, relu=True, out=h1)
             RF.linear(h1, f2.w, f2.b, relu=True, out=h2)
             RF.linear(h2, f3.w, f3.b, out=f_new)
             h_lin, w2, b2 = self.heads[i]
             if self.encode_rot:
-                y_buf[:, fc:].copy_(f_new)
+                RF.strided_copy(f_new, y_buf[:, fc:])
                 RF.linear(y_buf, h_lin.w, h_lin.b, relu=True, out=g)
             else:
-                yin.view(m, 3, 2, nv)[:, :, 1].copy_(f_new.view(m, 3, nv))
+                RF.strided_copy(f_new.view(m, 3, nv), yin.view(m, 3, 2, nv)[:, :, 1])
                 RF.linear(yin, h_lin.w, h_lin.b, relu=True, out=g)
             pred = torch.empty((m, 2), device=self.device, dtype=torch.float32)
             scale = (cfg["iter_decay"] ** (self.num_iter - 1 - i)) * cfg["rel_weight"] / b
             RF.head_loss(g, w2, b2, pred, gt_flat, scale, loss, views=v, aux_decay=cfg["reference_decay"])
             if want_all or i == self.num_iter - 1:
                 it: Dict[str, Any] = {}
-                pv = pred.view(b, v, 2)
-                for k in range(v):
-                    it[f"pred_gaze_{k}"] = pv[:, k].contiguous()
+                for k, t in enumerate(per_view(pred, (2,))):
+                    it[f"pred_gaze_{k}"] = t
                 if want_all:
                     for k, t in enumerate(per_view(f_new, (3, nv))):
                         it[f"feat_{k}"] = t

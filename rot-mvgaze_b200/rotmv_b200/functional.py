@@ -424,3 +424,50 @@ def relative_rotations(rot):
     out = torch.empty((b, v, v, 3, 3), dtype=torch.float32, device=rot.device)
     _call("rmv_relative_rotations", {"desc": "rmv_relative_rotations"}, L.load().rmv_relative_rotations, rot.data_ptr(), out.data_ptr(), b, v, L.stream_ptr())
     return out
+
+
+# ---- re-layout kernels of the constructor variants (encode_rotmat / share_feature) ---------------
+def strided_copy(src, dst, scale=None, accumulate=False):
+    """dst (+)= src * scale over two equally shaped strided VIEWS of up to three dimensions (fp32 or
+    bf16 each, any strides, non-overlapping); `scale` is an fp32 vector over the last dimension.
+    One launch of rmv_strided_copy: the padded-corner, interleave and scatter copies of
+    ImageRotmatFeatFuser / RotFeatFuser (models/rot_mv.py:53-85,225-248)."""
+    _need_cuda(src, dst, scale)
+    assert tuple(src.shape) == tuple(dst.shape) and 1 <= src.dim() <= 3, (src.shape, dst.shape)
+    pad = 3 - src.dim()
+    dims = [1] * pad + [int(d) for d in src.shape]
+    ss = [0] * pad + [int(s) for s in src.stride()]
+    ds = [0] * pad + [int(s) for s in dst.stride()]
+    if scale is not None:
+        assert scale.dtype == torch.float32 and scale.is_contiguous() and scale.numel() == dims[2]
+    _call("rmv_strided_copy", {"desc": "rmv_strided_copy"}, L.load().rmv_strided_copy,
+          src.data_ptr(), L.dtype_code(src.dtype), ss[0], ss[1], ss[2],
+          dst.data_ptr(), L.dtype_code(dst.dtype), ds[0], ds[1], ds[2], dims[0], dims[1], dims[2],
+          L.ptr(scale), int(bool(accumulate)), L.stream_ptr())
+    return dst
+
+
+def intensity_bn_train(feat, running, momentum, eps, scale_out):
+    """Train-mode IntensityBatchNorm statistics of one call (models/rot_mv.py:13-32): feat is a
+    [rows, 3, nvec] view (row stride free, the [3, nvec] block contiguous); updates `running` (the
+    reference's `running_mean` buffer, fp32, nvec elements) in place and writes the factor
+    1 / (running + eps) this call applies into `scale_out` (fp32 [nvec])."""
+    _need_cuda(feat, running, scale_out)
+    rows, three, nvec = feat.shape
+    assert three == 3 and feat.stride(2) == 1 and feat.stride(1) == nvec
+    assert running.dtype == scale_out.dtype == torch.float32 and running.is_contiguous() and scale_out.is_contiguous()
+    assert running.numel() == nvec and scale_out.numel() == nvec
+    _call("rmv_intensity_bn_train", {"desc": "rmv_intensity_bn_train"}, L.load().rmv_intensity_bn_train,
+          feat.data_ptr(), feat.stride(0), L.dtype_code(feat.dtype), rows, nvec, running.data_ptr(),
+          float(momentum), float(eps), scale_out.data_ptr(), L.stream_ptr())
+    return scale_out
+
+
+def fill_zero(t):
+    """t[...] = 0 for a contiguous tensor (rmv_fill_zero; `optimizer.zero_grad()` of trainer.py:141 for
+    the flat gradient buffer, padding / accumulator buffers elsewhere)."""
+    _need_cuda(t)
+    assert t.is_contiguous()
+    _call("rmv_fill_zero", {"desc": "rmv_fill_zero"}, L.load().rmv_fill_zero, t.data_ptr(),
+          t.numel() * t.element_size(), L.stream_ptr())
+    return t

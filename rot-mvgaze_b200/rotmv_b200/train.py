@@ -378,7 +378,7 @@ class TrainEngine:
             else:
                 assert L.load().rmv_conv2d_wgrad_tc_workspace_bytes(C.byref(a)) == k * kh * kw * c * 4
                 scratch = self._buf(("wg", id(conv_or_lin)), (k, kh, kw, c), torch.float32)
-                scratch.zero_()
+                self._zero(scratch)
                 RF._call("rmv_conv2d_wgrad_tc", meta, L.load().rmv_conv2d_wgrad_tc, C.byref(a),
                          dy.data_ptr(), scratch.data_ptr(), L.stream_ptr())
                 _ck("rmv_permute_cast", scratch.data_ptr(), grad.data_ptr(), k, c, kh, kw,
@@ -492,7 +492,7 @@ class TrainEngine:
         # ================================ backward ================================
         ext = yield preds   # None: gradient of the fused loss; else d(loss)/d(pred) per iteration
         dimg = self._buf("dimg", (m, fd))
-        dimg.zero_()
+        self._zero(dimg)
         d_f_next = None
         for i in reversed(range(self.num_iter)):
             h1, h2 = self.heads[i]
@@ -523,8 +523,24 @@ class TrainEngine:
     # The GEMMs, weight gradients, rotation gathers, head/loss kernels are the sm_100a kernels of the
     # default configuration. What these variants add -- zero-padding the 3593-wide layers to a
     # multiple of 64, the 9 rotation entries per row, the [3][2][512] interleave of RotFeatFuser and
-    # IntensityBatchNorm's 512-element statistics -- is done with plain tensor copies / small torch
-    # reductions: they are not on the path main.py builds.
+    # IntensityBatchNorm's 512-element statistics -- runs in the re-layout kernels of
+    # csrc/variant_glue.cu (`rmv_strided_copy` over strided views, `rmv_intensity_bn_train`,
+    # `rmv_fill_zero`); tests/test_train_fusion_host.py replaces the three methods below by their
+    # torch formulas.
+    def _zero(self, t) -> None:
+        RF.fill_zero(t)
+
+    def _scopy(self, src, dst, scale=None, accumulate=False) -> None:
+        """dst (+)= src * scale[last dim] for equally shaped strided views (<= 3-D, fp32 or bf16 each)."""
+        RF.strided_copy(src, dst, scale, accumulate)
+
+    def _intensity_scale(self, bn, feat_bv, out):
+        """Train-mode IntensityBatchNorm (models/rot_mv.py:13-32) of one call: feat_bv [B, 3, 512].
+        Updates the running STD (buffer `running_mean`) from the batch and writes the per-vector
+        scale 1 / (running_std + eps) (fp32 [512]) that this call applies into `out`; the norm is
+        detached in the reference, so the scale is a constant of the backward pass."""
+        return RF.intensity_bn_train(feat_bv, bn.running_mean.view(-1), bn.momentum, bn.eps, out)
+
     def _colsum(self, dy, n, dst):
         """dst[:n] += column sums of dy[:, :n] (bias gradient)."""
         _ck("rmv_colsum", dy.data_ptr(), dy.stride(0), dy.shape[0], n, self.dtc, dst.data_ptr())
@@ -552,13 +568,16 @@ class TrainEngine:
         n, k = lin.weight.shape
         key = ("padw", tag)
         if key not in self._bufs:
-            self._bufs[key] = (torch.zeros((pn, pk), device=self.device, dtype=self.dt),
-                               torch.zeros((pk, pn), device=self.device, dtype=self.dt),
-                               torch.zeros((pn,), device=self.device, dtype=torch.float32))
+            self._bufs[key] = (torch.empty((pn, pk), device=self.device, dtype=self.dt),
+                               torch.empty((pk, pn), device=self.device, dtype=self.dt),
+                               torch.empty((pn,), device=self.device, dtype=torch.float32))
+            for t in self._bufs[key]:
+                self._zero(t)              # the padding stays zero; only the corners are rewritten
         w, wt, bias = self._bufs[key]
-        w[:n, :k].copy_(lin.weight.detach())
-        wt[:k, :n].copy_(lin.weight.detach().t())
-        bias[:n].copy_(lin.bias.detach())
+        src = lin.weight.detach()
+        self._scopy(src, w[:n, :k])
+        self._scopy(src.t(), wt[:k, :n])   # 32x32 shared-memory tiles (source contiguous along dim 0)
+        self._scopy(lin.bias.detach(), bias[:n])
         return w, wt, bias
 
     def _padded_lin_bwd(self, lin, wt, x, dy, dx_out):
@@ -570,11 +589,11 @@ class TrainEngine:
         pk = x.shape[1]
         self._colsum(dy, n, self.grads[id(lin.bias)])
         scratch = self._buf(("padg", pn, pk), (pn, pk), torch.float32)
-        scratch.zero_()
+        self._zero(scratch)
         x4 = x.as_strided((1, 1, m, pk), (0, 0, x.stride(0), 1), x.storage_offset())
         d4 = dy.as_strided((1, 1, m, pn), (0, 0, dy.stride(0), 1), dy.storage_offset())
         self._wgrad(x4, d4, lin, 1, 1, 1, 0, grad=scratch)
-        self.grads[id(lin.weight)].add_(scratch[:n, :k])
+        self._scopy(scratch[:n, :k], self.grads[id(lin.weight)], accumulate=True)
         if dx_out is not None:
             RF.linear(dy, wt, None, out=dx_out)
         return dx_out
@@ -597,16 +616,16 @@ class TrainEngine:
         preds = [self._buf(("pred", i), (m, 2), torch.float32) for i in range(n_it)]
         y_init = self._buf("Yinit", (m, wide))
         for t in xs:
-            t.zero_()
+            self._zero(t)
         RF.avgpool(x, y_init, xs[0])
         img = y_init[:, :fd]
         # row (b, view) gets R_{view <- partner}: rot[b,0,1] = rot_10, rot[b,1,0] = rot_01 (:193-194)
-        pair = torch.stack([rot[:, 0, 1], rot[:, 1, 0]], dim=1).reshape(m, 9)
+        pair = rot.view(b, v * v, 9)[:, 1:3]                   # [b, view, 9], strides (36, 9, 1)
         for i in range(n_it):
             if i > 0:
                 self._add(img, xs[i][:, :fd])
             self._add(img, ys[i][:, :fd])
-            xs[i][:, wide:w_true].copy_(pair)
+            self._scopy(pair, xs[i].view(b, v, p)[:, :, wide:w_true])
         l1 = self._buf("L1", (m, nv3))
         self._lin(img, self._lin_fwd(self.lift[0], "l0"), self.lift[0].bias, True, l1)
         self._lin(l1, self._lin_fwd(self.lift[1], "l1"), self.lift[1].bias, False, y_init[:, fd:])
@@ -631,7 +650,7 @@ class TrainEngine:
         # backward
         ext = yield preds   # None: gradient of the fused loss; else d(loss)/d(pred) per iteration
         dimg = self._buf("dimg", (m, fd))
-        dimg.zero_()
+        self._zero(dimg)
         d_f_next = None
         for i in reversed(range(n_it)):
             h1, h2 = self.heads[i]
@@ -660,17 +679,6 @@ class TrainEngine:
         d_img2 = self._lin_bwd(self.lift[0], "l0", img, d_l1, self._buf("dimg2", (m, fd)))
         self._add(d_img2, dimg, add=dimg)
         return dimg, preds
-
-    def _intensity_scale(self, bn, feat_bv):
-        """Train-mode IntensityBatchNorm (models/rot_mv.py:13-32) of one call: feat_bv [B, 3, 512].
-        Updates the running STD (buffer `running_mean`) from the batch and returns the per-vector
-        scale 1 / (running_std + eps) [512] that this call applies; the norm is detached in the
-        reference, so the scale is a constant of the backward pass."""
-        intensity = feat_bv.float().norm(dim=-2, keepdim=True)                      # [B, 1, 512]
-        var = intensity.var(dim=0, unbiased=False, keepdim=True)
-        std = var.clamp_min(bn.eps).sqrt()
-        bn.running_mean.copy_(bn.running_mean * (1 - bn.momentum) + std * bn.momentum)
-        return (1.0 / (bn.running_mean.reshape(-1) + bn.eps)).to(self.dt)
 
     def _fusion_share_feature(self, x, rot, gt_flat, b, cfg):
         """share_feature=True (models/rot_mv.py:70-85,160-171,201-203,243-248): the lifted feature
@@ -704,20 +712,20 @@ class TrainEngine:
             r4 = rotf.view(b, v, 3, nv)
             bn = self.model._img_fusers[i]._batchnorm
             xv = xs[i].view(b, v, 3, 2, nv)
-            sc = torch.empty((v, 2, nv), device=self.device, dtype=dt)
+            sc = self._buf(("isc", i), (v, 2, nv), torch.float32)
             for k in range(v):                                                   # view order, as the reference
-                sc[k, 0] = self._intensity_scale(bn, fi4[:, k])
-                xv[:, k, :, 0] = fi4[:, k] * sc[k, 0]
-                sc[k, 1] = self._intensity_scale(bn, r4[:, k])
-                xv[:, k, :, 1] = r4[:, k] * sc[k, 1]
+                self._intensity_scale(bn, fi4[:, k], sc[k, 0])
+                self._scopy(fi4[:, k], xv[:, k, :, 0], scale=sc[k, 0])
+                self._intensity_scale(bn, r4[:, k], sc[k, 1])
+                self._scopy(r4[:, k], xv[:, k, :, 1], scale=sc[k, 1])
             bn_scales.append(sc)
             f1, f2, f3 = self.fusers[i]
             self._lin(xs[i], self._lin_fwd(f1, ("f1", i)), f1.bias, True, h1s[i])
             self._lin(h1s[i], self._lin_fwd(f2, ("f2", i)), f2.bias, True, h2s[i])
             self._lin(h2s[i], self._lin_fwd(f3, ("f3", i)), f3.bias, False, fs[i])
             yv = ys[i].view(m, 3, 2, nv)
-            yv[:, :, 0].copy_(f_init.view(m, 3, nv))
-            yv[:, :, 1].copy_(fs[i].view(m, 3, nv))
+            self._scopy(f_init.view(m, 3, nv), yv[:, :, 0])
+            self._scopy(fs[i].view(m, 3, nv), yv[:, :, 1])
             h1, h2 = self.heads[i]
             self._lin(ys[i], self._lin_fwd(h1, ("h1", i)), h1.bias, True, gs[i])
             scale = (cfg["iter_decay"] ** (n_it - 1 - i)) * cfg["rel_weight"] / b
@@ -728,7 +736,8 @@ class TrainEngine:
         self.last_feats = {"img": f_init, "init": f_init, "iters": list(fs)}
         # backward
         ext = yield preds   # None: gradient of the fused loss; else d(loss)/d(pred) per iteration
-        d_init = torch.zeros((m, nv3), device=self.device, dtype=torch.float32)   # d loss / d F_init
+        d_init = self._buf("dInit", (m, nv3), torch.float32)                       # d loss / d F_init
+        self._zero(d_init)
         d_f_next = None
         for i in reversed(range(n_it)):
             h1, h2 = self.heads[i]
@@ -740,23 +749,26 @@ class TrainEngine:
             else:
                 self._head_bwd_ext(ext[i], gs[i], h2, dg)
             d_y = self._lin_bwd(h1, ("h1", i), ys[i], dg, self._buf("dYs", (m, w6))).view(m, 3, 2, nv)
-            d_init += d_y[:, :, 0].reshape(m, nv3)
+            self._scopy(d_y[:, :, 0], d_init.view(m, 3, nv), accumulate=True)
             d_f = self._buf("dF", (m, nv3))
-            d_f.copy_(d_y[:, :, 1].reshape(m, nv3) if d_f_next is None
-                      else d_y[:, :, 1].reshape(m, nv3) + d_f_next)
+            self._scopy(d_y[:, :, 1], d_f.view(m, 3, nv))
+            if d_f_next is not None:
+                self._scopy(d_f_next, d_f, accumulate=True)
             d_h2 = self._lin_bwd(f3, ("f3", i), h2s[i], d_f, self._buf("dHs2", (m, w6)))
             self._add(d_h2, d_h2, mask=h2s[i])
             d_h1 = self._lin_bwd(f2, ("f2", i), h1s[i], d_h2, self._buf("dHs1", (m, w6)))
             self._add(d_h1, d_h1, mask=h1s[i])
             d_x = self._lin_bwd(f1, ("f1", i), xs[i], d_h1, self._buf("dXs", (m, w6))).view(b, v, 3, 2, nv)
-            sc = bn_scales[i].float()
-            d_init += (d_x[:, :, :, 0].float() * sc[:, 0].view(1, v, 1, nv)).reshape(m, nv3)
+            sc = bn_scales[i]
             d_rotf = self._buf("dRotF", (m, nv3))
-            d_rotf.copy_((d_x[:, :, :, 1].float() * sc[:, 1].view(1, v, 1, nv)).reshape(m, nv3))
+            for k in range(v):
+                self._scopy(d_x[:, k, :, 0], d_init.view(b, v, 3, nv)[:, k], scale=sc[k, 0], accumulate=True)
+                self._scopy(d_x[:, k, :, 1], d_rotf.view(b, v, 3, nv)[:, k], scale=sc[k, 1])
             d_f_next = self._buf("dFn", (m, nv3))
             RF.rotate_gather(d_rotf, rot, d_f_next, b, v, nv, self.apply_rot, transpose=True)
         d_total = self._buf("dFinit", (m, nv3))
-        d_total.copy_(d_init + d_f_next.float())    # iteration 0 gathered F_init itself
+        self._scopy(d_f_next, d_init, accumulate=True)    # iteration 0 gathered F_init itself
+        self._scopy(d_init, d_total)
         d_l1 = self._lin_bwd(self.lift[1], "l1", l1, d_total, self._buf("dL1", (m, nv3)))
         self._add(d_l1, d_l1, mask=l1)
         dimg = self._lin_bwd(self.lift[0], "l0", img, d_l1, self._buf("dimg", (m, fd)))
@@ -928,8 +940,8 @@ class TrainEngine:
             raise L.RotmvError("images must be CUDA tensors (there is no CPU path)")
 
     def _begin_step(self) -> None:
-        self.flat_g.zero_()
-        self.loss.zero_()
+        self._zero(self.flat_g)     # optimizer.zero_grad() (trainer.py:141)
+        self._zero(self.loss)
         if self._wjobs_ready:
             self._run_wjobs()
 

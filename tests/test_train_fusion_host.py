@@ -66,6 +66,27 @@ class HostEngine(T.TrainEngine):
         self.grads[id(h2.bias)] += dp.sum(0)
 
 
+    # the re-layout kernels of the constructor variants (csrc/variant_glue.cu) as torch formulas
+    def _zero(self, t):
+        t.zero_()
+
+    def _scopy(self, src, dst, scale=None, accumulate=False):
+        """rmv_strided_copy: dst (+)= src * scale[last dim] over equally shaped strided views."""
+        assert tuple(src.shape) == tuple(dst.shape) and src.dim() <= 3
+        val = src.to(torch.float64) if scale is None else src.to(torch.float64) * scale.to(torch.float64)
+        if accumulate:
+            val = val + dst.to(torch.float64)
+        dst.copy_(val.to(dst.dtype))
+
+    def _intensity_scale(self, bn, feat_bv, out):
+        """rmv_intensity_bn_train = train-mode IntensityBatchNorm of models/rot_mv.py:13-32."""
+        intensity = feat_bv.float().norm(dim=-2, keepdim=True)                      # [B, 1, 512]
+        var = intensity.var(dim=0, unbiased=False, keepdim=True)
+        std = var.clamp_min(bn.eps).sqrt()
+        bn.running_mean.copy_(bn.running_mean * (1 - bn.momentum) + std * bn.momentum)
+        out.copy_(1.0 / (bn.running_mean.reshape(-1) + bn.eps))
+        return out
+
     def _head_bwd_ext(self, dpred, g, h2, dg):
         """rmv_head_loss_bwd with gt == NULL (external d(loss)/d(pred)): Linear(512,2) + ReLU backward."""
         dp = dpred.detach().to(g.dtype).reshape(g.shape[0], 2)
