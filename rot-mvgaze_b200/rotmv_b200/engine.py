@@ -97,10 +97,7 @@ class InferenceEngine:
         self.front_blocks = int(os.environ.get("ROTMV_FRONT_BLOCKS", "3"))
         trunk = model._feat_extractor[0]
         dev = trunk.conv1.weight.device
-        if dev.type != "cuda":
-            raise L.RotmvError("FeatRotationSymm parameters must live on a CUDA device "
-                               "(model.cuda()); there is no CPU path")
-        L.check(L.load().rmv_device_check(dev.index or 0), "rmv_device_check")
+        self._require_device(dev, "FeatRotationSymm parameters must live on a CUDA device (model.cuda())")
         self.device = dev
         self._stamp = self._version_stamp()
         dt = self.dtype
@@ -145,6 +142,14 @@ class InferenceEngine:
         self._bufs: Dict[Any, torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------
+    def _require_device(self, dev, what: str) -> None:
+        """There is no CPU path: parameters and inputs must live on an sm_100 device.
+        (tests/test_engine_host.py overrides this to run the ORCHESTRATION on the CPU with torch
+        stand-ins for the kernel wrappers.)"""
+        if dev.type != "cuda":
+            raise L.RotmvError(f"{what}; there is no CPU path")
+        L.check(L.load().rmv_device_check(dev.index or 0), "rmv_device_check")
+
     def _version_stamp(self):
         return tuple(t._version for t in list(self.model.parameters()) + list(self.model.buffers()))
 
@@ -282,8 +287,8 @@ class InferenceEngine:
         return out
 
     def _check_inputs(self, images, rotations):
-        if not images.is_cuda:
-            raise L.RotmvError("images must be a CUDA tensor (there is no CPU path)")
+        if images.device != self.device:
+            self._require_device(images.device, "images must be a CUDA tensor")
         b, v = images.shape[0], images.shape[1]
         if v < 2:
             raise ValueError("Rot-MV needs at least two views")
