@@ -54,6 +54,66 @@ strided_copy_kernel(const TS* __restrict__ src, Strides3 ss, TD* __restrict__ ds
   st_f(d, v);
 }
 
+// eight consecutive i2 elements per thread (16-byte accesses) when both innermost strides are 1 and
+// every offset is a multiple of eight elements: the interleave / padded-corner / output-assembly copies
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float* f);
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = rmv::unpack_bf16x2(w[i]);
+    f[2 * i] = v.x; f[2 * i + 1] = v.y;
+  }
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float* f);
+template <> __device__ __forceinline__ void st8<float>(float* p, const float* f) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float* f) {
+  uint4 u;
+  u.x = rmv::pack_bf16x2(f[0], f[1]); u.y = rmv::pack_bf16x2(f[2], f[3]);
+  u.z = rmv::pack_bf16x2(f[4], f[5]); u.w = rmv::pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256)
+strided_copy_vec8_kernel(const TS* __restrict__ src, Strides3 ss, TD* __restrict__ dst, Strides3 ds,
+                         int n1, int n2v, long long total, const float* __restrict__ scale,
+                         int accumulate) {
+  griddep_wait();
+  griddep_launch();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over groups of 8
+  if (idx >= total) return;
+  const int i2 = (int)(idx % n2v) * 8;
+  const long long t = idx / n2v;
+  const int i1 = (int)(t % n1);
+  const long long i0 = t / n1;
+  float v[8];
+  ld8(src + i0 * ss.s0 + i1 * ss.s1 + i2, v);
+  if (scale != nullptr) {
+    float sc[8];
+    ld8(scale + i2, sc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __fmul_rn(v[i], sc[i]);
+  }
+  TD* d = dst + i0 * ds.s0 + i1 * ds.s1 + i2;
+  if (accumulate) {
+    float a[8];
+    ld8(d, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(v[i], a[i]);
+  }
+  st8(d, v);
+}
+
 // transposing form: the source is contiguous along i1 and the destination along i2 (a weight matrix
 // and its transpose). 32 x 32 tiles through shared memory, coalesced on both sides; grid.z = i0.
 template <typename TS, typename TD>
@@ -146,7 +206,18 @@ template <typename TS, typename TD>
 int launch_copy(const void* src, Strides3 ss, void* dst, Strides3 ds, int n0, int n1, int n2,
                 const float* scale, int accumulate, cudaStream_t stream) {
   const bool transposing = ss.s2 != 1 && ss.s1 == 1 && ds.s2 == 1 && n1 >= 16 && n2 >= 16 && n0 <= 65535;
-  if (transposing) {
+  const auto mult8 = [](long long x) { return (x & 7) == 0; };
+  const bool vec8 = ss.s2 == 1 && ds.s2 == 1 && (n2 & 7) == 0 &&
+                    (n1 == 1 || (mult8(ss.s1) && mult8(ds.s1))) && (n0 == 1 || (mult8(ss.s0) && mult8(ds.s0))) &&
+                    ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) |
+                      reinterpret_cast<uintptr_t>(scale)) & 15) == 0;
+  if (vec8) {
+    const long long total = (long long)n0 * n1 * (n2 / 8);
+    const long long blocks = (total + 255) / 256;
+    RMV_CHECK_ARG(blocks <= 0x7fffffffLL, "strided_copy: too many elements");
+    RMV_CUDA(rmv::launch_pdl(strided_copy_vec8_kernel<TS, TD>, dim3((unsigned)blocks), dim3(256), 0, stream,
+                             (const TS*)src, ss, (TD*)dst, ds, n1, n2 / 8, total, scale, accumulate));
+  } else if (transposing) {
     dim3 grid((unsigned)((n1 + 31) / 32), (unsigned)((n2 + 31) / 32), (unsigned)n0);
     RMV_CHECK_ARG(grid.y <= 65535u, "strided_copy: n2 too large for the transposing form");
     RMV_CUDA(rmv::launch_pdl(strided_copy_transpose_kernel<TS, TD>, grid, dim3(256), 0, stream,

@@ -103,6 +103,28 @@ def main():
           lambda: RF.avgpool(x, o0, o1))
     del x, o0, o1
 
+    # ---- round 2: zero fill (zero_grad of the flat gradient), the strided copy of the variants /
+    # output assembly, Adam (trainer.py:141,143; models/rot_mv.py:53-85,205-211)
+    flat = torch.empty((89_591_366,), device=dev)
+    timed("fill_zero fp32 flat gradient (89.6 M elements)", flat.numel() * 4, lambda: RF.fill_zero(flat))
+    del flat
+    m = 65536
+    f0 = torch.randn((m, 1536), device=dev, generator=g).to(bf)
+    xi = torch.empty((m, 3072), device=dev, dtype=bf)
+    sc = torch.rand((512,), device=dev, generator=g) + 0.5
+    timed(f"strided_copy bf16 rows={m}: [3][512] -> slot 0 of the [3][2][512] interleave, scaled",
+          m * 1536 * 2 * 2, lambda: RF.strided_copy(f0.view(m, 3, 512), xi.view(m, 3, 2, 512)[:, :, 0], scale=sc))
+    o32 = torch.empty((m // 2, 1536), device=dev)
+    src = f0.as_strided((m // 2, 2, 1536), (2 * 1536, 1536, 1))
+    timed(f"strided_copy bf16 -> fp32 rows={m // 2}: one view's rows (output assembly)",
+          (m // 2) * 1536 * (2 + 4), lambda: RF.strided_copy(src[:, 0], o32))
+    del f0, xi, o32
+    w = torch.randn((3593 * 4, 3593), device=dev, generator=g)
+    wt = torch.empty((3648, 3648 * 4), device=dev, dtype=bf)
+    timed("strided_copy fp32 -> bf16 transposing [14372,3593] -> padded [3648,14592] (32x32 tiles)",
+          w.numel() * (4 + 2), lambda: RF.strided_copy(w.t(), wt[:3593, :3593 * 4]))
+    del w, wt
+
     print(f"# HBM-bound kernels alone, operands > L2, {args.reps} launches each, CUDA events; peak = "
           f"{peak:.0f} GB/s (MEASURED_PEAKS.json copy bandwidth)")
     print(f"{'kernel':88s} {'MB':>9s} {'us':>9s} {'GB/s':>8s} {'frac':>6s}")
