@@ -35,29 +35,22 @@ world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK"
 local = int(os.environ.get("LOCAL_RANK", "0"))
 cpu = {}
 if args.cpu_only:
-    import time
-    from oracle import rotmv_oracle as O
-    torch.set_num_threads(os.cpu_count())
-    for mode in args.modes.split(","):
-        for v in [int(x) for x in args.views.split(",")]:
-            om = O.build_model(num_iter=3, depth=50, seed=0)
-            im, pose, gtc = O.synthetic_batch(8, v, seed=1)
-            rotc = O.pairwise_rotations(pose)
-            if mode == "train":
-                om.train(); opt = O.make_adam(om, lr=1e-6)
-                fn = lambda: O.train_step(om, opt, im, rotc, gtc)  # noqa: E731
-            else:
-                om.eval()
-                def fn():
-                    with torch.no_grad():
-                        om.forward_views(im, rotc)
-            fn()
-            t0 = time.perf_counter(); n = 0
-            while n < 3 or time.perf_counter() - t0 < 4.0:
-                fn(); n += 1
-            cpu[(mode, v)] = 8 * n / (time.perf_counter() - t0)
-    print(json.dumps({"cpu_reference": {f"{m}_v{v}": round(x, 2) for (m, v), x in cpu.items()},
-                      "cores": torch.get_num_threads(), "sample": "oracle port of the reference CPU path, B=8, fp32"}), flush=True)
+    # the CPU column comes from `bench.py --impl reference` (the one program besides tests/ and smoke()
+    # that executes oracle/): one run per view count, inference + training step, B = 8 samples per step
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for v in [int(x) for x in args.views.split(",")]:
+        res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--views", str(v),
+                              "--steps", str(max(3, args.steps)), "--warmup", "1", "--mode", "both"],
+                             check=True, capture_output=True, text=True)
+        line = json.loads(res.stdout.strip().splitlines()[-1])
+        cpu[("infer", v)] = line["value"]
+        cpu[("train", v)] = line["train"]["value"]
+        cores = line["cpu_baseline"]["cores"]
+    print(json.dumps({"cpu_reference": {f"{m}_v{v}": round(x, 2) for (m, v), x in cpu.items()
+                                        if m in args.modes.split(",")},
+                      "cores": cores, "sample": "bench.py --impl reference (oracle port of the reference CPU path), "
+                                                "B=8 samples per step, fp32"}), flush=True)
     sys.exit(0)
 if args.cpu_json:
     rec = json.loads(open(args.cpu_json).read().strip().splitlines()[-1])["cpu_reference"]
